@@ -1,0 +1,61 @@
+"""Seeded synthetic inputs shared by the golden generator and the tests.
+
+Only elementwise float32 arithmetic and numpy's RandomState are used (no BLAS),
+so the arrays are bit-identical on every machine with the same numpy.
+"""
+import numpy as np
+
+
+def synthetic_clip_features(seed, num_frames, h, w, channels, num_objects, n_blocks=3,
+                            sigma=0.15, texture=0.6, kind="objects"):
+    """Returns a list of ``n_blocks`` arrays [2F, h*w, C] float32 (uncond rows first),
+    mimicking the stashed attn1.q of output blocks 8/7/6, plus the ground-truth
+    object map [F, h, w].
+
+    kind="objects": moving Voronoi regions, a prototype vector per object and an
+    object-anchored texture so that nearest-neighbour tracking is meaningful.
+    kind="iid": pure N(0,1) features (stress case: many near-ties).
+    """
+    r = np.random.RandomState(seed)
+    F, C = num_frames, channels
+    if kind == "iid":
+        blocks = [r.standard_normal((2 * F, h * w, C)).astype(np.float32) for _ in range(n_blocks)]
+        return blocks, np.zeros((F, h, w), dtype=np.int64)
+    proto = r.standard_normal((num_objects, C)).astype(np.float32)
+    tex = r.standard_normal((num_objects, h, w, C)).astype(np.float32)
+    pos0 = np.stack([r.randint(0, h, num_objects), r.randint(0, w, num_objects)], 1)
+    vel = r.randint(-1, 2, (num_objects, 2))
+    yy, xx = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    seg = np.zeros((F, h, w), dtype=np.int64)
+    base = np.zeros((F, h, w, C), dtype=np.float32)
+    for t in range(F):
+        pos = pos0 + vel * t
+        # toroidal squared distance to every object centre (integer arithmetic)
+        dy = (yy[None] - pos[:, 0, None, None]) % h
+        dy = np.minimum(dy, h - dy)
+        dx = (xx[None] - pos[:, 1, None, None]) % w
+        dx = np.minimum(dx, w - dx)
+        seg[t] = np.argmin(dy * dy + dx * dx, axis=0)
+        for k in range(num_objects):
+            m = seg[t] == k
+            ty = (yy - pos[k, 0]) % h
+            tx = (xx - pos[k, 1]) % w
+            base[t][m] = proto[k] + np.float32(texture) * tex[k, ty[m], tx[m]]
+    base = base.reshape(F, h * w, C)
+    blocks = []
+    for _ in range(n_blocks):
+        cond = base + np.float32(sigma) * r.standard_normal(base.shape).astype(np.float32)
+        uncond = r.standard_normal(base.shape).astype(np.float32)
+        scale = np.float32(1.0 + 0.5 * r.rand())
+        blocks.append(np.concatenate([uncond, cond * scale], axis=0).astype(np.float32))
+    return blocks, seg
+
+
+# (name, seed, F, h, w, C, K, kind) -- sizes follow BASELINE.json configs 1 and 2/3
+CLUSTER_CASES = [
+    ("c1_objects", 1, 4, 16, 16, 640, 5, "objects"),
+    ("c1_iid", 2, 4, 16, 16, 640, 5, "iid"),
+    ("small_odd", 3, 3, 9, 7, 40, 4, "objects"),
+    ("mid_objects", 4, 6, 24, 24, 320, 12, "objects"),
+    ("c2_objects", 1, 14, 32, 32, 640, 20, "objects"),
+]
