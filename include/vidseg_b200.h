@@ -1,0 +1,169 @@
+/*
+ * vidseg_b200.h -- C-ABI of libvidseg_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the per-clip hot path of QianWangX/VidSeg_diffusion.
+ * The reference is pure Python on PyTorch/scikit-learn and has no FFI of its
+ * own; each entry point below names the reference call site (file:line under
+ * the reference root) whose arithmetic it replaces.  INTEGRATION.md shows the
+ * ctypes stubs a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are contiguous, row-major, dtype as declared;
+ *   - the caller owns all memory (outputs and workspaces are caller-allocated);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and
+ *     the call returns without synchronising unless stated otherwise;
+ *   - return value 0 = success, otherwise a cudaError_t or a negative VIDSEG_E_*
+ *     code; vidseg_last_error() gives the message for the calling thread.
+ */
+#ifndef VIDSEG_B200_H_
+#define VIDSEG_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIDSEG_E_INVALID   (-1)  /* bad argument (shape, alignment, null pointer) */
+#define VIDSEG_E_WORKSPACE (-2)  /* workspace too small                         */
+#define VIDSEG_E_UNSUPPORTED (-3)
+
+const char* vidseg_last_error(void);
+/* ABI version of this header; bumped on any signature change. */
+int vidseg_abi_version(void);
+/* Compute capability major*10+minor of the current device (100 on B200). */
+int vidseg_device_arch(void);
+
+/* ------------------------------------------------------------------------- *
+ * R1  feature aggregation + per-token max-abs normalisation
+ *
+ * Replaces scripts/sampling/feature_extraction.py:739-745 (torch.mean over the
+ * stacked blocks, in caller order), :38-39 (x / max|x| over channels, no
+ * epsilon) and :45-46 (keep the conditional half rows [F, 2F), flatten).
+ *   blocks[b] : float32 [2F, hw, C], b < n_blocks (1..4)
+ *   out       : float32 [F*hw, C]
+ * ------------------------------------------------------------------------- */
+int vidseg_aggregate_normalize(const float* const* blocks_host, int n_blocks,
+                               int num_frames, int hw, int channels,
+                               float* out, void* stream);
+
+/* ------------------------------------------------------------------------- *
+ * R2  K-means  (sklearn.cluster.KMeans(n_clusters=K, n_init=R).fit + .predict)
+ *
+ * Replaces scripts/sampling/feature_extraction.py:52-55.  The random decisions
+ * of k-means++ are data-independent draws from numpy's global RandomState; the
+ * host mirror draws them (same calls, same order as sklearn/_kmeans.py:231,249)
+ * and passes them in:
+ *   first_idx : int32  [R]            first centre of every run (choice(n, p))
+ *   rand      : double [R, K-1, T]    uniform(size=T) draws, T = 2 + int(ln K)
+ * All R runs advance in lock-step on the device (batched seeding, batched Lloyd).
+ * ------------------------------------------------------------------------- */
+size_t vidseg_kmeans_workspace_bytes(int n, int d, int k, int n_init, int n_trials);
+
+/* mean-centre (sequential fp32 column sums, as numpy's X.mean(axis=0)),
+ * tolerance mean(var(X,0))*tol_rel, float64 squared row norms; registers the
+ * problem shape with the workspace (host side) and resets the per-run state. */
+int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init, int n_trials,
+                          float tol_rel, int max_iter, void* workspace, size_t workspace_bytes,
+                          void* stream);
+
+/* k-means++ seeding of all runs (sklearn/_kmeans.py:180-277). */
+int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* E-step over rows [row_begin,row_end): labels = argmin_j ||c_j||^2 - 2 x.c_j
+ * (sklearn/_k_means_lloyd.pyx:_update_chunk_dense) for every unfinished run. */
+int vidseg_kmeans_assign(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                         void* stream);
+
+/* M-step part 1: per-run, per-cluster float64 sums and counts of rows
+ * [row_begin,row_end) -> partial [R, K, D+1] (column D = count) and changed
+ * int32 [R] (labels that changed in the last assign).  NULL = keep them in the
+ * workspace.  In the multi-GPU path the caller all-reduces both between part 1
+ * and part 2. */
+int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                          double* partial, int32_t* changed, void* stream);
+
+/* M-step part 2: relocate empty clusters (modifies `partial` in place; skipped
+ * when local_rows_only != 0 because it needs every label), average, centre
+ * shift, convergence flags (strict label equality, else sum(shift^2) <= tol). */
+int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double* partial,
+                         const int32_t* changed, int local_rows_only, void* stream);
+
+/* number of runs still iterating (synchronises the stream). */
+int vidseg_kmeans_active_runs(void* workspace, size_t workspace_bytes, int* n_active_host,
+                              void* stream);
+
+/* final E-step of the runs that did not converge strictly, then the inertia of
+ * rows [row_begin,row_end) -> inertia_partial double [R] (NULL = workspace). */
+int vidseg_kmeans_inertia(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                          double* inertia_partial, void* stream);
+
+/* same[a*R+b] = 1 iff labels of run a map onto labels of run b as a function on
+ * rows [row_begin,row_end) (_k_means_common.pyx:_is_same_clustering). */
+int vidseg_kmeans_same_matrix(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                              int32_t* same, void* stream);
+
+/* best-of-R rule on the host (sklearn/_kmeans.py:1529-1541). */
+int vidseg_kmeans_pick_best_host(const float* inertia_host, const int32_t* same_host, int n_init);
+
+/* un-centre run `best` -> centers_out float32 [K, D]; labels_fit_out int32 [N] or NULL. */
+int vidseg_kmeans_finish(void* workspace, size_t workspace_bytes, int best, float* centers_out,
+                         int32_t* labels_fit_out, void* stream);
+
+/* single-GPU convenience: same_matrix + pick_best + finish.  info_host int32[4] =
+ * {best run, n_iter of best, max n_iter, 0}; inertia_host float[R].  Synchronises. */
+int vidseg_kmeans_select(void* workspace, size_t workspace_bytes, const double* inertia,
+                         float* centers_out, int32_t* labels_fit_out,
+                         int32_t* info_host, float* inertia_host, void* stream);
+
+/* KMeans.predict: argmin over un-centred x against centres float32 [K, D].
+ * cnorm_scratch: double [K]. */
+int vidseg_kmeans_predict(const float* x, int n, int d, const float* centers, int k,
+                          int32_t* labels_out, double* cnorm_scratch, void* stream);
+
+/* Whole single-GPU fit+predict: prepare, seed, Lloyd (polling the convergence
+ * flags every few iterations), inertia, select, predict.
+ *   first_idx_host int32 [R], rand_host double [R, K-1, T]
+ *   labels_out int32 [N] (device), centers_out float32 [K, D] (device)
+ *   info_host int32[4] = {best run, n_iter of best, max n_iter, kernel launches}
+ * Synchronises the stream before returning. */
+int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_init, int n_trials,
+                              int max_iter, float tol_rel,
+                              const int32_t* first_idx_host, const double* rand_host,
+                              int32_t* labels_out, float* centers_out,
+                              int32_t* info_host, float* inertia_host,
+                              void* workspace, size_t workspace_bytes, void* stream);
+
+/* forget the host-side shape record of a workspace (call before freeing it). */
+int vidseg_kmeans_release(void* workspace);
+
+/* ------------------------------------------------------------------------- *
+ * R3  correspondence-based mask refinement
+ *
+ * Replaces scripts/sampling/feature_extraction.py:176-323 (dense nearest-
+ * neighbour tracking t -> t+1 with the frame-0 "aux" blend and the per-500-point
+ * re-normalisation), :326-364 and :367-461 (signed-jump filter, majority label
+ * per trajectory, last-writer-wins write-back).
+ *   feats     : float32 [2F, hw, C]  (features of ONE block, uncond rows first)
+ *   labels_in : int32   [F, hw]      K-means label maps
+ *   traj_out  : int32   [F, hw]      cell index h*W+w of every trajectory per frame
+ *   keep_out  : int32   [hw]         1 if the trajectory survives the spatial filter
+ *   labels_out: int32   [F, hw]      refined label maps
+ * ------------------------------------------------------------------------- */
+size_t vidseg_refine_workspace_bytes(int num_frames, int hw, int channels);
+int vidseg_refine_masks(const float* feats, const int32_t* labels_in,
+                        int num_frames, int height, int width, int channels,
+                        int32_t* traj_out, int32_t* keep_out, int32_t* labels_out,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of kernel launches issued by this library since load (for bench.py's
+ * gpu_launches accounting). */
+long long vidseg_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDSEG_B200_H_ */

@@ -1,0 +1,69 @@
+"""In-tree build of libvidseg_b200.so (hand-written CUDA for sm_100a, no torch linkage).
+
+``python -m vidseg_diffusion_b200.build`` or ``__graft_entry__.build()``.  nvcc cross-compiles
+without a GPU; the resulting .so sits next to this file (git-ignored, shipped to the GPU box).
+"""
+import hashlib
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libvidseg_b200.so")
+OBJ_DIR = os.path.join(HERE, "csrc", "_obj")
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+ARCH_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a"]
+CFLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
+          "-diag-suppress", "177"]
+
+
+def sources():
+    return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+
+
+def _stamp():
+    h = hashlib.sha256()
+    files = sources() + sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h")))
+    files.append(os.path.join(HERE, "..", "include", "vidseg_b200.h"))
+    for f in files:
+        with open(f, "rb") as fh:
+            h.update(f.encode() + b"\0" + fh.read())
+    h.update(" ".join(ARCH_FLAGS + CFLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile_one(src):
+    obj = os.path.join(OBJ_DIR, os.path.basename(src)[:-3] + ".o")
+    cmd = [NVCC, *ARCH_FLAGS, *CFLAGS, "-c", src, "-o", obj]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for {src}:\n{res.stdout}\n{res.stderr}")
+    return obj
+
+
+def build(force=False, verbose=True):
+    stamp_file = os.path.join(OBJ_DIR, "stamp")
+    stamp = _stamp()
+    if not force and os.path.exists(OUT) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
+        return OUT
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(_compile_one, sources()))
+    cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", OUT, *objs, "-lcuda"]
+    stub_dir = "/usr/local/cuda/lib64/stubs"
+    if os.path.isdir(stub_dir):
+        cmd += ["-L", stub_dir]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")
+    with open(stamp_file, "w") as fh:
+        fh.write(stamp)
+    if verbose:
+        print(f"built {OUT} ({os.path.getsize(OUT) / 1e6:.1f} MB) from {len(objs)} sources", file=sys.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

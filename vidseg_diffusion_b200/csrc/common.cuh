@@ -1,0 +1,84 @@
+// Shared helpers for libvidseg_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/vidseg_b200.h"
+
+#define VS_API extern "C" __attribute__((visibility("default")))
+
+namespace vidseg {
+
+extern thread_local char g_last_error[512];
+extern std::atomic<long long> g_launch_count;
+
+inline int set_error(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_last_error, sizeof(g_last_error), fmt, a, b, c);
+  return code;
+}
+
+#define VS_CHECK_CUDA(expr)                                                                   \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      snprintf(vidseg::g_last_error, sizeof(vidseg::g_last_error), "%s:%d %s -> %s", __FILE__, \
+               __LINE__, #expr, cudaGetErrorString(_e));                                      \
+      return (int)_e;                                                                         \
+    }                                                                                         \
+  } while (0)
+
+#define VS_REQUIRE(cond, msg)                                                              \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      snprintf(vidseg::g_last_error, sizeof(vidseg::g_last_error), "%s:%d %s (%s)", __FILE__, \
+               __LINE__, msg, #cond);                                                      \
+      return VIDSEG_E_INVALID;                                                             \
+    }                                                                                      \
+  } while (0)
+
+// every kernel launch in the library goes through this so that launches are counted
+#define VS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
+    vidseg::g_launch_count.fetch_add(1, std::memory_order_relaxed);       \
+  } while (0)
+
+#define VS_POST_LAUNCH() VS_CHECK_CUDA(cudaGetLastError())
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// streaming 128-bit load that does not pollute L1 (inputs are read once)
+__device__ __forceinline__ float4 ld_stream_f4(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace vidseg

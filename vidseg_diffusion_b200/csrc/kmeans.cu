@@ -1,0 +1,970 @@
+// R2: K-means (sklearn KMeans(n_clusters=K, n_init=R).fit + .predict) on the device.
+//
+// Replaces scripts/sampling/feature_extraction.py:52-55.  The algorithm is sklearn's
+// (sklearn/cluster/_kmeans.py, _k_means_lloyd.pyx, _k_means_common.pyx; see oracle/kmeans.py for
+// the line-by-line restatement).  Design for B200:
+//   * all R = n_init runs advance in lock-step: one launch does step c of the k-means++ seeding
+//     of every run, one launch does the E-step of every unfinished run (X is read once for all
+//     runs, the R*K centres are the "N" dimension of a skinny GEMM), so the whole fit is a few
+//     hundred launches instead of a few thousand and each launch fills the 148 SMs;
+//   * the random decisions are data-independent numpy draws made by the host mirror; the device
+//     reproduces the decision arithmetic that can be reproduced exactly: sequential fp32 column
+//     sums for the mean (numpy's add.reduce over axis 0), float64 distances rounded to fp32
+//     (_euclidean_distances_upcast), a *sequential* fp32 cumsum for the searchsorted sampling;
+//   * reductions that sklearn leaves to BLAS/OpenMP (potentials, centre sums, inertia) cannot be
+//     reproduced bit-for-bit on any other machine; they are computed in float64 in a fixed order
+//     (deterministic run-to-run) and rounded to fp32, i.e. at the centre of sklearn's error band.
+//   * HBM-bound streaming: per Lloyd iteration X (N*D*4 bytes) is read once by the E-step and once
+//     by the M-step; at the clip sizes of BASELINE.json X is L2-resident (36.7 MB < 126 MB).
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace vidseg {
+
+constexpr int kMaxTrials = 8;
+constexpr int kPotBlocks = 64;       // row blocks per run in the seeding distance kernel
+constexpr int kPotWarps = 8;         // warps per block there
+constexpr int kPotParts = kPotBlocks * kPotWarps;
+constexpr int kSlabs = 16;           // row slabs of the M-step partial sums
+constexpr int kColTile = 128;        // columns per M-step block
+constexpr int kScanChunk = 4096;
+
+struct KmLayout {
+  int n, d, k, r, t;
+  float tol_rel;
+  int max_iter;
+  size_t xc, mean, var, xx, closest, newdist, potpart, cand, pot, centers, cnorm, center_idx, labels, part, partcnt,
+      partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, total;
+};
+
+static KmLayout km_layout(int n, int d, int k, int r, int t) {
+  KmLayout L{};
+  L.n = n; L.d = d; L.k = k; L.r = r; L.t = t;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.xc = take((size_t)n * d * 4);
+  L.mean = take((size_t)d * 4);
+  L.var = take((size_t)d * 4);
+  L.xx = take((size_t)n * 8);
+  L.closest = take((size_t)r * n * 4);
+  L.newdist = take((size_t)r * t * n * 4);
+  L.potpart = take((size_t)r * t * kPotParts * 8);
+  L.cand = take((size_t)r * kMaxTrials * 4);
+  L.pot = take((size_t)r * 4);
+  L.centers = take((size_t)r * k * d * 4);
+  L.cnorm = take((size_t)r * k * 8);
+  L.center_idx = take((size_t)r * k * 4);
+  L.labels = take((size_t)r * n * 4);
+  L.part = take((size_t)r * kSlabs * k * d * 8);
+  L.partcnt = take((size_t)r * kSlabs * k * 4);
+  L.partial = take((size_t)r * k * (d + 1) * 8);
+  L.changed = take((size_t)r * 4);
+  L.flags = take((size_t)r * 4 * 4);  // done, strict, n_iter, reserved
+  L.tol = take(16);
+  L.inertia_part = take((size_t)r * kPotBlocks * 8);
+  L.inertia = take((size_t)r * 8);
+  L.same = take((size_t)r * r * 4);
+  L.rand = take((size_t)r * (k > 1 ? k - 1 : 1) * t * 8);
+  L.first_idx = take((size_t)r * 4);
+  L.total = off;
+  return L;
+}
+
+static std::mutex g_km_mu;
+static std::unordered_map<void*, KmLayout> g_km_registry;
+
+static bool km_lookup(void* ws, KmLayout* out) {
+  std::lock_guard<std::mutex> lk(g_km_mu);
+  auto it = g_km_registry.find(ws);
+  if (it == g_km_registry.end()) return false;
+  *out = it->second;
+  return true;
+}
+
+template <typename T>
+__host__ __device__ inline T* at(void* ws, size_t off) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(ws) + off);
+}
+
+// ------------------------------------------------------------------------------------------
+// prepare: column mean / variance exactly as numpy computes them for a C-contiguous float32
+// [N, D] array reduced over axis 0 (row-by-row sequential fp32 accumulation, then a float64
+// true_divide by the count cast back to fp32: numpy/_core/_methods.py _mean/_var).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) km_colstats_kernel(const float* __restrict__ x, int n, int d,
+                                                         float* __restrict__ mean, float* __restrict__ var) {
+  const int col = blockIdx.x * 32 + threadIdx.x;
+  if (col >= d) return;
+  const float* p = x + col;
+  float s = 0.f;
+  int i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(i + u) * d];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+  }
+  for (; i < n; ++i) s = __fadd_rn(s, p[(size_t)i * d]);
+  const float m = (float)((double)s / (double)n);
+  mean[col] = m;
+  float s2 = 0.f;
+  i = 0;
+  for (; i + 8 <= n; i += 8) {
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(i + u) * d];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float t = __fsub_rn(v[u], m);
+      s2 = __fadd_rn(s2, __fmul_rn(t, t));
+    }
+  }
+  for (; i < n; ++i) {
+    const float t = __fsub_rn(p[(size_t)i * d], m);
+    s2 = __fadd_rn(s2, __fmul_rn(t, t));
+  }
+  var[col] = (float)((double)s2 / (double)n);
+}
+
+// tol = mean(var) * tol_rel (sklearn/_kmeans.py:285-294); also resets the per-run state.
+__global__ void km_tol_reset_kernel(const float* __restrict__ var, int d, float tol_rel, float* __restrict__ tol,
+                                    int* __restrict__ flags, int* __restrict__ changed, int r) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) s += (double)var[c];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+    const float m = (float)(tot / (double)d);
+    tol[0] = __fmul_rn(m, tol_rel);
+  }
+  for (int i = threadIdx.x; i < r * 4; i += blockDim.x) flags[i] = 0;
+  for (int i = threadIdx.x; i < r; i += blockDim.x) changed[i] = 0;
+}
+
+// xc = x - mean (fp32), xx = float64 squared norm of the centred fp32 row.  Warp per row.
+__global__ void __launch_bounds__(256) km_center_kernel(const float* __restrict__ x, const float* __restrict__ mean,
+                                                        int n, int d, float* __restrict__ xc,
+                                                        double* __restrict__ xx) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * d;
+  float* o = xc + (size_t)row * d;
+  double s = 0.0;
+  for (int c = lane; c < d; c += 32) {
+    const float v = __fsub_rn(xr[c], mean[c]);
+    o[c] = v;
+    s += (double)v * (double)v;
+  }
+  s = warp_sum(s);
+  if (lane == 0) xx[row] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// k-means++ seeding
+// ------------------------------------------------------------------------------------------
+// distances of every point to the T candidates of each run, in float64 as
+// _euclidean_distances_upcast (-2 x.y + ||y||^2 + ||x||^2), rounded to fp32, clamped at 0,
+// min-ed with the current closest distances; per-warp float64 partial potentials.
+__global__ void __launch_bounds__(kPotWarps * 32)
+km_kpp_dist_kernel(const float* __restrict__ xc, const double* __restrict__ xx, int n, int d, int t_count,
+                   const int* __restrict__ cand, const float* __restrict__ closest, int use_min,
+                   float* __restrict__ newdist, double* __restrict__ potpart, int t_stride) {
+  extern __shared__ double cs[];  // [t_count][d]
+  const int r = blockIdx.y;
+  const int* my_cand = cand + r * kMaxTrials;
+  for (int e = threadIdx.x; e < t_count * d; e += blockDim.x) {
+    const int t = e / d, c = e - t * d;
+    cs[e] = (double)xc[(size_t)my_cand[t] * d + c];
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * kPotWarps + warp;
+  double cand_xx = 0.0;
+  if (lane < t_count) cand_xx = xx[my_cand[lane]];
+  double potacc = 0.0;
+  for (int row = gwarp; row < n; row += kPotParts) {
+    const float* xr = xc + (size_t)row * d;
+    double acc[kMaxTrials];
+#pragma unroll
+    for (int t = 0; t < kMaxTrials; ++t) acc[t] = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      const double xv = (double)xr[c];
+#pragma unroll
+      for (int t = 0; t < kMaxTrials; ++t)
+        if (t < t_count) acc[t] = fma(xv, cs[t * d + c], acc[t]);
+    }
+    double mine = 0.0;
+#pragma unroll
+    for (int t = 0; t < kMaxTrials; ++t) {
+      if (t < t_count) {
+        const double s = warp_sum(acc[t]);
+        if (lane == t) mine = s;
+      }
+    }
+    if (lane < t_count) {
+      double dd = -2.0 * mine;
+      dd += cand_xx;
+      dd += xx[row];
+      float f = (float)dd;
+      f = fmaxf(f, 0.f);
+      const size_t rn = (size_t)r * n + row;
+      if (use_min) f = fminf(closest[rn], f);
+      newdist[((size_t)r * t_stride + lane) * n + row] = f;
+      potacc += (double)f;
+    }
+  }
+  if (lane < t_count) potpart[((size_t)r * t_stride + lane) * kPotParts + gwarp] = potacc;
+}
+
+// one block per run: pick the best candidate of step c (np.argmin of the potentials), commit it
+// (closest distances, centre row), then draw the candidates of step c+1:
+//   rand_vals = u * pot;  ids = searchsorted(cumsum_fp32(closest), rand_vals)  (side='left')
+// The cumsum is a strictly sequential fp32 accumulation (np.cumsum), done by one thread over
+// shared-memory chunks; the searchsorted of a non-decreasing array is a count of elements < v.
+__global__ void __launch_bounds__(1024)
+km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int t_count, int t_stride, int c,
+                          int prev_t, const double* __restrict__ potpart, const float* __restrict__ newdist,
+                          float* __restrict__ closest, int* __restrict__ cand, float* __restrict__ pot,
+                          float* __restrict__ centers, int* __restrict__ center_idx, const double* __restrict__ rand) {
+  __shared__ float buf[kScanChunk];
+  __shared__ float s_pot[kMaxTrials];
+  __shared__ double s_vals[kMaxTrials];
+  __shared__ int s_cnt[kMaxTrials];
+  __shared__ int s_best;
+  __shared__ float s_run;
+  const int r = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < prev_t) {
+    const double* pp = potpart + ((size_t)r * t_stride + tid) * kPotParts;
+    double s = 0.0;
+    for (int i = 0; i < kPotParts; ++i) s += pp[i];
+    s_pot[tid] = (float)s;
+  }
+  if (tid < kMaxTrials) s_cnt[tid] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    int best = 0;
+    for (int t = 1; t < prev_t; ++t)
+      if (s_pot[t] < s_pot[best]) best = t;
+    s_best = best;
+    pot[r] = s_pot[best];
+    center_idx[r * k + c] = cand[r * kMaxTrials + best];
+    s_run = 0.f;
+  }
+  __syncthreads();
+  const int best = s_best;
+  const int best_row = cand[r * kMaxTrials + best];
+  const bool more = (c + 1 < k);
+  if (tid < t_count && more) s_vals[tid] = rand[((size_t)r * (k - 1) + c) * t_count + tid] * (double)s_pot[best];
+  for (int cc = tid; cc < d; cc += blockDim.x)
+    centers[((size_t)r * k + c) * d + cc] = xc[(size_t)best_row * d + cc];
+  __syncthreads();  // cand[] of this step fully consumed before it is overwritten below
+  const float* src = newdist + ((size_t)r * t_stride + best) * n;
+  float* dst = closest + (size_t)r * n;
+  int cnt[kMaxTrials];
+#pragma unroll
+  for (int t = 0; t < kMaxTrials; ++t) cnt[t] = 0;
+  for (int base = 0; base < n; base += kScanChunk) {
+    const int len = min(kScanChunk, n - base);
+    for (int j = tid; j < len; j += blockDim.x) {
+      const float v = src[base + j];
+      buf[j] = v;
+      dst[base + j] = v;
+    }
+    __syncthreads();
+    if (!more) { __syncthreads(); continue; }
+    if (tid == 0) {
+      float run = s_run;
+      int j = 0;
+      for (; j + 8 <= len; j += 8) {
+        float v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = buf[j + u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { run = __fadd_rn(run, v[u]); buf[j + u] = run; }
+      }
+      for (; j < len; ++j) { run = __fadd_rn(run, buf[j]); buf[j] = run; }
+      s_run = run;
+    }
+    __syncthreads();
+    for (int j = tid; j < len; j += blockDim.x) {
+      const double v = (double)buf[j];
+#pragma unroll
+      for (int t = 0; t < kMaxTrials; ++t)
+        if (t < t_count) cnt[t] += (v < s_vals[t]) ? 1 : 0;
+    }
+    __syncthreads();
+  }
+  if (!more) return;
+#pragma unroll
+  for (int t = 0; t < kMaxTrials; ++t) {
+    if (t < t_count) {
+      const int s = warp_sum(cnt[t]);
+      if ((tid & 31) == 0 && s) atomicAdd(&s_cnt[t], s);
+    }
+  }
+  __syncthreads();
+  if (tid < t_count) cand[r * kMaxTrials + tid] = min(s_cnt[tid], n - 1);  // np.clip(.., None, n-1)
+}
+
+// ------------------------------------------------------------------------------------------
+// Lloyd E-step: labels = argmin_j ( ||c_j||^2 - 2 x.c_j ), float64 accumulation, lowest j on ties.
+// Block tile 64 rows x (all K centres of one run, 64 at a time), k-chunks of 32 staged in shared
+// memory as doubles.  256 threads: tx = centre lane (16), ty = row group (16 x 4 rows).
+// ------------------------------------------------------------------------------------------
+constexpr int kBM = 64, kBK = 32, kBJ = 64;
+
+__global__ void __launch_bounds__(256)
+km_assign_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin, int row_end,
+                 const float* __restrict__ centers, const double* __restrict__ cnorm, int* __restrict__ labels,
+                 int labels_stride, int* __restrict__ changed, const int* __restrict__ flags, int count_changes,
+                 int only_nonstrict) {
+  __shared__ double xs[kBM][kBK + 1];
+  __shared__ double cs[kBJ][kBK + 1];
+  const int r = blockIdx.y;
+  if (flags) {
+    const int done = flags[r * 4 + 0], strict = flags[r * 4 + 1];
+    if (only_nonstrict) { if (strict) return; }
+    else if (done) return;
+  }
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int row0 = row_begin + blockIdx.x * kBM;
+  const float* cr = centers + (size_t)r * k * d;
+  const double* cn = cnorm + (size_t)r * k;
+  double best_s[4];
+  int best_j[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { best_s[q] = 1e300; best_j[q] = 0x7fffffff; }
+  for (int j0 = 0; j0 < k; j0 += kBJ) {
+    double acc[4][4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+#pragma unroll
+      for (int jt = 0; jt < 4; ++jt) acc[q][jt] = 0.0;
+    for (int k0 = 0; k0 < d; k0 += kBK) {
+      __syncthreads();
+#pragma unroll
+      for (int q = 0; q < (kBM * kBK) / 256; ++q) {
+        const int e = tid + 256 * q;
+        const int rr = e >> 5, cc = e & 31;
+        const int grow = row0 + rr, gcol = k0 + cc;
+        xs[rr][cc] = (grow < row_end && gcol < d) ? (double)x[(size_t)grow * d + gcol] : 0.0;
+      }
+#pragma unroll
+      for (int q = 0; q < (kBJ * kBK) / 256; ++q) {
+        const int e = tid + 256 * q;
+        const int jj = e >> 5, cc = e & 31;
+        const int gj = j0 + jj, gcol = k0 + cc;
+        cs[jj][cc] = (gj < k && gcol < d) ? (double)cr[(size_t)gj * d + gcol] : 0.0;
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < kBK; ++kk) {
+        double xv[4], cv[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xv[q] = xs[ty * 4 + q][kk];
+#pragma unroll
+        for (int jt = 0; jt < 4; ++jt) cv[jt] = cs[tx + 16 * jt][kk];
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int jt = 0; jt < 4; ++jt) acc[q][jt] = fma(xv[q], cv[jt], acc[q][jt]);
+      }
+    }
+#pragma unroll
+    for (int jt = 0; jt < 4; ++jt) {
+      const int gj = j0 + tx + 16 * jt;
+      if (gj < k) {
+        const double cnj = cn[gj];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const double s = cnj - 2.0 * acc[q][jt];
+          if (s < best_s[q] || (s == best_s[q] && gj < best_j[q])) { best_s[q] = s; best_j[q] = gj; }
+        }
+      }
+    }
+  }
+  int nchanged = 0;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    double s = best_s[q];
+    int j = best_j[q];
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      const double so = __shfl_xor_sync(0xffffffffu, s, o);
+      const int jo = __shfl_xor_sync(0xffffffffu, j, o);
+      if (so < s || (so == s && jo < j)) { s = so; j = jo; }
+    }
+    const int grow = row0 + ty * 4 + q;
+    if (tx == 0 && grow < row_end) {
+      int* lp = labels + (size_t)r * labels_stride + grow;
+      if (count_changes && *lp != j) ++nchanged;
+      *lp = j;
+    }
+  }
+  if (count_changes) {
+    nchanged = warp_sum(nchanged);
+    if ((tid & 31) == 0 && nchanged) atomicAdd(&changed[r], nchanged);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Lloyd M-step, part 1: per (run, row slab, 128-column tile) float64 cluster sums in shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kColTile)
+km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin, int row_end,
+                  const int* __restrict__ labels, const int* __restrict__ flags, double* __restrict__ part,
+                  int* __restrict__ partcnt) {
+  extern __shared__ double acc[];  // [k][kColTile]
+  const int r = blockIdx.z;
+  if (flags[r * 4 + 0]) return;
+  const int slab = blockIdx.x, tile = blockIdx.y;
+  const int tid = threadIdx.x;
+  const int col = tile * kColTile + tid;
+  const int rows = row_end - row_begin;
+  const int per = (rows + kSlabs - 1) / kSlabs;
+  const int r0 = row_begin + slab * per;
+  const int r1 = min(row_end, r0 + per);
+  for (int j = 0; j < k; ++j) acc[j * kColTile + tid] = 0.0;
+  const int* lab = labels + (size_t)r * n;
+  if (col < d) {
+    int i = r0;
+    for (; i + 4 <= r1; i += 4) {
+      int l[4];
+      float v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { l[u] = lab[i + u]; v[u] = x[(size_t)(i + u) * d + col]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[l[u] * kColTile + tid] += (double)v[u];
+    }
+    for (; i < r1; ++i) acc[lab[i] * kColTile + tid] += (double)x[(size_t)i * d + col];
+    double* out = part + (((size_t)r * kSlabs + slab) * k) * d + col;
+    for (int j = 0; j < k; ++j) out[(size_t)j * d] = acc[j * kColTile + tid];
+  }
+  if (tile == 0) {
+    for (int j = tid; j < k; j += kColTile) {
+      int cnt = 0;
+      for (int i = r0; i < r1; ++i) cnt += (lab[i] == j);
+      partcnt[((size_t)r * kSlabs + slab) * k + j] = cnt;
+    }
+  }
+}
+
+// fixed-order reduction over slabs -> partial [R, K, D+1] (column D holds the count)
+__global__ void __launch_bounds__(256)
+km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcnt, int d, int k,
+                 const int* __restrict__ flags, double* __restrict__ partial, const int* __restrict__ changed_ws,
+                 int* __restrict__ changed_out) {
+  const int r = blockIdx.y, j = blockIdx.x;
+  if (j == 0 && threadIdx.x == 0 && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+  if (flags[r * 4 + 0]) return;
+  double* o = partial + ((size_t)r * k + j) * (d + 1);
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double s = 0.0;
+    for (int sl = 0; sl < kSlabs; ++sl) s += part[(((size_t)r * kSlabs + sl) * k + j) * d + c];
+    o[c] = s;
+  }
+  if (threadIdx.x == 0) {
+    long long cnt = 0;
+    for (int sl = 0; sl < kSlabs; ++sl) cnt += partcnt[((size_t)r * kSlabs + sl) * k + j];
+    o[d] = (double)cnt;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Lloyd M-step, part 2 (one block per run): empty-cluster relocation, averaging, centre shift,
+// convergence flags.  `partial` is updated in place by the relocation.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+km_update_kernel(const float* __restrict__ x, int n, int d, int k, double* __restrict__ partial,
+                 const int* __restrict__ changed_in, int* __restrict__ changed_ws, const int* __restrict__ labels,
+                 float* __restrict__ centers, double* __restrict__ cnorm, int* __restrict__ flags,
+                 const float* __restrict__ tol, int max_iter, float* __restrict__ scratch_dist, int can_relocate) {
+  extern __shared__ double sm[];  // [k] counts, [k] shift^2 (as float in double slots), then ints
+  const int r = blockIdx.x;
+  if (flags[r * 4 + 0]) return;
+  const int tid = threadIdx.x;
+  double* cnt = sm;
+  double* shiftsq = sm + k;
+  __shared__ int s_nempty, s_far, s_argmax;
+  __shared__ double s_red_v[256];
+  __shared__ int s_red_i[256];
+  double* pr = partial + (size_t)r * k * (d + 1);
+  float* cr = centers + (size_t)r * k * d;
+  for (int j = tid; j < k; j += blockDim.x) cnt[j] = pr[(size_t)j * (d + 1) + d];
+  __syncthreads();
+  if (tid == 0) {
+    int ne = 0;
+    for (int j = 0; j < k; ++j) ne += (cnt[j] == 0.0);
+    s_nempty = ne;
+  }
+  __syncthreads();
+  if (s_nempty > 0 && can_relocate) {
+    // _relocate_empty_clusters_dense: distances of every point to its (old) centre, the n_empty
+    // farthest points (descending) seed the empty clusters (ascending cluster id).
+    const int* lab = labels + (size_t)r * n;
+    float* dist = scratch_dist + (size_t)r * n;
+    for (int i = tid; i < n; i += blockDim.x) {
+      const float* xr = x + (size_t)i * d;
+      const float* cc = cr + (size_t)lab[i] * d;
+      double s = 0.0;
+      for (int c = 0; c < d; ++c) { const double t = (double)xr[c] - (double)cc[c]; s = fma(t, t, s); }
+      dist[i] = (float)s;
+    }
+    __syncthreads();
+    const int n_empty = s_nempty;
+    int next_empty = 0;
+    for (int e = 0; e < n_empty; ++e) {
+      double bv = -1.0; int bi = 0x7fffffff;
+      for (int i = tid; i < n; i += blockDim.x) {
+        const double v = (double)dist[i];
+        if (v > bv) { bv = v; bi = i; }
+      }
+      s_red_v[tid] = bv; s_red_i[tid] = bi;
+      __syncthreads();
+      for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+          const double v2 = s_red_v[tid + o]; const int i2 = s_red_i[tid + o];
+          if (v2 > s_red_v[tid] || (v2 == s_red_v[tid] && i2 < s_red_i[tid])) { s_red_v[tid] = v2; s_red_i[tid] = i2; }
+        }
+        __syncthreads();
+      }
+      const double maxv = s_red_v[0];
+      const int far = s_red_i[0];
+      __syncthreads();
+      if (e == 0 && maxv == 0.0) break;  // np.max(distances) == 0 -> return
+      while (cnt[next_empty] != 0.0) ++next_empty;  // uniform across the block
+      const int new_id = next_empty++;
+      const int old_id = lab[far];
+      for (int c = tid; c < d; c += blockDim.x) {
+        const double xv = (double)x[(size_t)far * d + c];
+        pr[(size_t)old_id * (d + 1) + c] -= xv;
+        pr[(size_t)new_id * (d + 1) + c] = xv;
+      }
+      __syncthreads();
+      if (tid == 0) { cnt[new_id] = 1.0; cnt[old_id] -= 1.0; dist[far] = -1.f; }
+      __syncthreads();
+    }
+  }
+  if (tid == 0) {
+    int am = 0;
+    for (int j = 1; j < k; ++j) if (cnt[j] > cnt[am]) am = j;  // np.argmax: first maximum
+    s_argmax = am;
+  }
+  __syncthreads();
+  // _average_centers + _center_shift; one warp per cluster
+  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  const int am = s_argmax;
+  for (int j = warp; j < k; j += nwarps) {
+    double ss = 0.0, nn = 0.0;
+    const bool has = cnt[j] > 0.0;
+    for (int c = lane; c < d; c += 32) {
+      float nv;
+      if (has) {
+        nv = (float)(pr[(size_t)j * (d + 1) + c] / cnt[j]);
+      } else {
+        // centers[j] = centers[argmax_weight]: averaged already if argmax < j, raw sum otherwise
+        const double raw = pr[(size_t)am * (d + 1) + c];
+        nv = (am < j && cnt[am] > 0.0) ? (float)(raw / cnt[am]) : (float)raw;
+      }
+      const float ov = cr[(size_t)j * d + c];
+      const double df = (double)nv - (double)ov;
+      ss = fma(df, df, ss);
+      nn = fma((double)nv, (double)nv, nn);
+      cr[(size_t)j * d + c] = nv;
+    }
+    ss = warp_sum(ss);
+    nn = warp_sum(nn);
+    if (lane == 0) {
+      const float sh = (float)sqrt(ss);
+      shiftsq[j] = (double)__fmul_rn(sh, sh);
+      cnorm[(size_t)r * k + j] = nn;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float tot = 0.f;
+    for (int j = 0; j < k; ++j) tot = __fadd_rn(tot, (float)shiftsq[j]);
+    const int it = flags[r * 4 + 2] + 1;
+    flags[r * 4 + 2] = it;
+    if (changed_in[r] == 0) { flags[r * 4 + 1] = 1; flags[r * 4 + 0] = 1; }
+    else if (tot <= tol[0]) { flags[r * 4 + 0] = 1; }
+    else if (it >= max_iter) { flags[r * 4 + 0] = 1; }
+    changed_ws[r] = 0;
+  }
+}
+
+// squared norms of the initial centres (after seeding)
+__global__ void km_cnorm_kernel(const float* __restrict__ centers, int d, int total, double* __restrict__ cnorm) {
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (j >= total) return;
+  double s = 0.0;
+  for (int c = lane; c < d; c += 32) { const double v = (double)centers[(size_t)j * d + c]; s = fma(v, v, s); }
+  s = warp_sum(s);
+  if (lane == 0) cnorm[j] = s;
+}
+
+// inertia: sum over rows of ||x - c_label||^2 in float64, per-block partials in a fixed order
+__global__ void __launch_bounds__(256)
+km_inertia_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin, int row_end,
+                  const float* __restrict__ centers, const int* __restrict__ labels, double* __restrict__ part) {
+  __shared__ double red[8];
+  const int r = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int gwarp = blockIdx.x * 8 + warp;
+  double acc = 0.0;
+  for (int row = row_begin + gwarp; row < row_end; row += kPotBlocks * 8) {
+    const float* xr = x + (size_t)row * d;
+    const float* cc = centers + ((size_t)r * k + labels[(size_t)r * n + row]) * d;
+    double s = 0.0;
+    for (int c = lane; c < d; c += 32) { const double t = (double)xr[c] - (double)cc[c]; s = fma(t, t, s); }
+    acc += warp_sum(s);
+  }
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    part[(size_t)r * kPotBlocks + blockIdx.x] = t;
+  }
+}
+__global__ void km_inertia_reduce_kernel(const double* __restrict__ part, double* __restrict__ out) {
+  const int r = blockIdx.x;
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int b = 0; b < kPotBlocks; ++b) t += part[(size_t)r * kPotBlocks + b];
+    out[r] = t;
+  }
+}
+
+// same[a][b] = 1 iff labels_a -> labels_b is a function on rows [row_begin,row_end)
+// (_k_means_common.pyx:_is_same_clustering(labels_a, labels_b)).  grid (R, R).
+__global__ void __launch_bounds__(256)
+km_same_kernel(const int* __restrict__ labels, int n, int k, int row_begin, int row_end, int* __restrict__ same) {
+  extern __shared__ int mapping[];  // [k]
+  __shared__ int ok;
+  const int a = blockIdx.x, b = blockIdx.y, r = gridDim.x;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) mapping[j] = -1;
+  if (threadIdx.x == 0) ok = 1;
+  __syncthreads();
+  const int* la = labels + (size_t)a * n;
+  const int* lb = labels + (size_t)b * n;
+  for (int i = row_begin + threadIdx.x; i < row_end; i += blockDim.x) {
+    const int l1 = la[i], l2 = lb[i];
+    const int old = atomicCAS(&mapping[l1], -1, l2);
+    if (old != -1 && old != l2) ok = 0;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) same[a * r + b] = ok;
+}
+
+// un-centre the winning run: centers_out = centers[best] + mean (fp32 add, sklearn :1546)
+__global__ void km_finish_kernel(const float* __restrict__ centers, const float* __restrict__ mean, int d, int k,
+                                 int best, float* __restrict__ centers_out, const int* __restrict__ labels, int n,
+                                 int* __restrict__ labels_out) {
+  const int total = k * d;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x)
+    centers_out[e] = __fadd_rn(centers[(size_t)best * total + e], mean[e % d]);
+  if (labels_out)
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+      labels_out[i] = labels[(size_t)best * n + i];
+}
+
+static int km_check_ws(void* ws, size_t bytes, KmLayout* L) {
+  if (ws == nullptr) return set_error(VIDSEG_E_INVALID, "%s", "null workspace");
+  if (!km_lookup(ws, L)) return set_error(VIDSEG_E_INVALID, "%s", "workspace not prepared (call vidseg_kmeans_prepare)");
+  if (bytes < L->total) return set_error(VIDSEG_E_WORKSPACE, "%s: need %lld bytes, got %lld", "k-means workspace", (long long)L->total, (long long)bytes);
+  return 0;
+}
+
+static int km_launch_assign(const float* x, const KmLayout& L, int runs, int row_begin, int row_end,
+                            const float* centers, const double* cnorm, int* labels, int labels_stride, int* changed,
+                            const int* flags, int count_changes, int only_nonstrict, void* stream) {
+  const int rows = row_end - row_begin;
+  if (rows <= 0) return 0;
+  dim3 grid((rows + kBM - 1) / kBM, runs);
+  VS_LAUNCH(km_assign_kernel, grid, 256, 0, stream, x, L.n, L.d, L.k, row_begin, row_end, centers, cnorm, labels,
+            labels_stride, changed, flags, count_changes, only_nonstrict);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+}  // namespace vidseg
+
+using namespace vidseg;
+
+VS_API size_t vidseg_kmeans_workspace_bytes(int n, int d, int k, int n_init, int n_trials) {
+  if (n <= 0 || d <= 0 || k <= 0 || n_init <= 0 || n_trials <= 0 || n_trials > kMaxTrials) return 0;
+  return km_layout(n, d, k, n_init, n_trials).total;
+}
+
+VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init, int n_trials, float tol_rel,
+                                     int max_iter, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(x != nullptr && workspace != nullptr, "null pointer");
+  VS_REQUIRE(n >= 1 && d >= 1 && k >= 1 && k <= n, "need 1 <= k <= n, d >= 1");
+  VS_REQUIRE(n_init >= 1 && n_init <= 64, "n_init must be 1..64");
+  VS_REQUIRE(n_trials >= 1 && n_trials <= kMaxTrials, "n_trials must be 1..8");
+  KmLayout L = km_layout(n, d, k, n_init, n_trials);
+  L.tol_rel = tol_rel;
+  L.max_iter = max_iter;
+  if (workspace_bytes < L.total)
+    return set_error(VIDSEG_E_WORKSPACE, "%s: need %lld bytes, got %lld", "k-means workspace", (long long)L.total, (long long)workspace_bytes);
+  {
+    std::lock_guard<std::mutex> lk(g_km_mu);
+    g_km_registry[workspace] = L;
+  }
+  void* ws = workspace;
+  VS_LAUNCH(km_colstats_kernel, (d + 31) / 32, 32, 0, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_tol_reset_kernel, 1, 256, 0, stream, at<float>(ws, L.var), d, tol_rel, at<float>(ws, L.tol),
+            at<int>(ws, L.flags), at<int>(ws, L.changed), n_init);
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_center_kernel, (n * 32 + 255) / 256, 256, 0, stream, x, at<float>(ws, L.mean), n, d, at<float>(ws, L.xc),
+            at<double>(ws, L.xx));
+  VS_POST_LAUNCH();
+  VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.labels), 0xFF, (size_t)n_init * n * 4, (cudaStream_t)stream));
+  return 0;
+}
+
+VS_API int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand, void* workspace,
+                                  size_t workspace_bytes, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(first_idx != nullptr && (rand != nullptr || L.k == 1), "null pointer");
+  void* ws = workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  // cand[r][0] = first_idx[r]
+  VS_CHECK_CUDA(cudaMemcpy2DAsync(at<int>(ws, L.cand), kMaxTrials * 4, first_idx, 4, 4, L.r, cudaMemcpyDeviceToDevice, st));
+  const size_t smem = (size_t)L.t * L.d * 8;
+  VS_REQUIRE(smem <= 200 * 1024, "n_trials * d too large for the seeding kernel");
+  if (smem > 48 * 1024)
+    VS_CHECK_CUDA(cudaFuncSetAttribute(km_kpp_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(kPotBlocks, L.r);
+  for (int c = 0; c < L.k; ++c) {
+    const int tc = (c == 0) ? 1 : L.t;
+    VS_LAUNCH(km_kpp_dist_kernel, grid, kPotWarps * 32, (size_t)tc * L.d * 8, st, at<float>(ws, L.xc), at<double>(ws, L.xx),
+              L.n, L.d, tc, at<int>(ws, L.cand), at<float>(ws, L.closest), c > 0 ? 1 : 0, at<float>(ws, L.newdist),
+              at<double>(ws, L.potpart), L.t);
+    VS_POST_LAUNCH();
+    VS_LAUNCH(km_kpp_select_scan_kernel, L.r, 1024, 0, st, at<float>(ws, L.xc), L.n, L.d, L.k, L.t, L.t, c, tc,
+              at<double>(ws, L.potpart), at<float>(ws, L.newdist), at<float>(ws, L.closest), at<int>(ws, L.cand),
+              at<float>(ws, L.pot), at<float>(ws, L.centers), at<int>(ws, L.center_idx), rand);
+    VS_POST_LAUNCH();
+  }
+  VS_LAUNCH(km_cnorm_kernel, (L.r * L.k * 32 + 255) / 256, 256, 0, st, at<float>(ws, L.centers), L.d, L.r * L.k,
+            at<double>(ws, L.cnorm));
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_assign(void* workspace, size_t workspace_bytes, int row_begin, int row_end, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
+  void* ws = workspace;
+  return km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers), at<double>(ws, L.cnorm),
+                          at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), at<int>(ws, L.flags), 1, 0, stream);
+}
+
+VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                                     double* partial, int32_t* changed, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
+  void* ws = workspace;
+  if (partial == nullptr) partial = at<double>(ws, L.partial);
+  if (changed == nullptr) changed = at<int>(ws, L.changed);
+  const size_t smem = (size_t)L.k * kColTile * 8;
+  VS_REQUIRE(smem <= 200 * 1024, "k too large for the M-step kernel");
+  if (smem > 48 * 1024)
+    VS_CHECK_CUDA(cudaFuncSetAttribute(km_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, L.r);
+  VS_LAUNCH(km_partial_kernel, grid, kColTile, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin, row_end,
+            at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_reduce_kernel, dim3(L.k, L.r), 256, 0, stream, at<double>(ws, L.part), at<int>(ws, L.partcnt), L.d, L.k,
+            at<int>(ws, L.flags), partial, at<int>(ws, L.changed), changed);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double* partial, const int32_t* changed,
+                                    int local_rows_only, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  void* ws = workspace;
+  if (partial == nullptr) partial = at<double>(ws, L.partial);
+  if (changed == nullptr) changed = at<int>(ws, L.changed);
+  const size_t smem = (size_t)L.k * 2 * 8;
+  VS_LAUNCH(km_update_kernel, L.r, 256, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, partial, changed,
+            at<int>(ws, L.changed), at<int>(ws, L.labels), at<float>(ws, L.centers), at<double>(ws, L.cnorm),
+            at<int>(ws, L.flags), at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.newdist), local_rows_only ? 0 : 1);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_active_runs(void* workspace, size_t workspace_bytes, int* n_active_host, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  std::vector<int> flags((size_t)L.r * 4);
+  VS_CHECK_CUDA(cudaMemcpyAsync(flags.data(), at<int>(workspace, L.flags), flags.size() * 4, cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+  VS_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int active = 0;
+  for (int r = 0; r < L.r; ++r) active += flags[(size_t)r * 4] == 0;
+  *n_active_host = active;
+  return 0;
+}
+
+VS_API int vidseg_kmeans_inertia(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                                     double* inertia_partial, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
+  void* ws = workspace;
+  if (inertia_partial == nullptr) inertia_partial = at<double>(ws, L.inertia);
+  // rerun the E-step of runs that stopped on tolerance / max_iter (sklearn/_kmeans.py:741-753)
+  if (int e = km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers),
+                               at<double>(ws, L.cnorm), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed),
+                               at<int>(ws, L.flags), 0, 1, stream))
+    return e;
+  VS_LAUNCH(km_inertia_kernel, dim3(kPotBlocks, L.r), 256, 0, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin,
+            row_end, at<float>(ws, L.centers), at<int>(ws, L.labels), at<double>(ws, L.inertia_part));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_inertia_reduce_kernel, L.r, 32, 0, stream, at<double>(ws, L.inertia_part), inertia_partial);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_same_matrix(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                                         int32_t* same, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
+  if (same == nullptr) same = at<int>(workspace, L.same);
+  VS_LAUNCH(km_same_kernel, dim3(L.r, L.r), 256, (size_t)L.k * 4, stream, at<int>(workspace, L.labels), L.n, L.k,
+            row_begin, row_end, same);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+// host-side best-of-R rule (sklearn/_kmeans.py:1529-1541)
+VS_API int vidseg_kmeans_pick_best_host(const float* inertia_host, const int32_t* same_host, int n_init) {
+  int best = 0;
+  for (int i = 1; i < n_init; ++i)
+    if (inertia_host[i] < inertia_host[best] && !same_host[i * n_init + best]) best = i;
+  return best;
+}
+
+VS_API int vidseg_kmeans_finish(void* workspace, size_t workspace_bytes, int best, float* centers_out,
+                                    int32_t* labels_fit_out, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(best >= 0 && best < L.r && centers_out != nullptr, "bad best run / null output");
+  void* ws = workspace;
+  VS_LAUNCH(km_finish_kernel, 64, 256, 0, stream, at<float>(ws, L.centers), at<float>(ws, L.mean), L.d, L.k, best,
+            centers_out, at<int>(ws, L.labels), L.n, labels_fit_out);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_select(void* workspace, size_t workspace_bytes, const double* inertia, float* centers_out,
+                                    int32_t* labels_fit_out, int32_t* info_host, float* inertia_host, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  void* ws = workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (inertia == nullptr) inertia = at<double>(ws, L.inertia);
+  if (int e = vidseg_kmeans_same_matrix(workspace, workspace_bytes, 0, L.n, nullptr, stream)) return e;
+  std::vector<double> in64(L.r);
+  std::vector<int> same((size_t)L.r * L.r), flags((size_t)L.r * 4);
+  VS_CHECK_CUDA(cudaMemcpyAsync(in64.data(), inertia, (size_t)L.r * 8, cudaMemcpyDeviceToHost, st));
+  VS_CHECK_CUDA(cudaMemcpyAsync(same.data(), at<int>(ws, L.same), same.size() * 4, cudaMemcpyDeviceToHost, st));
+  VS_CHECK_CUDA(cudaMemcpyAsync(flags.data(), at<int>(ws, L.flags), flags.size() * 4, cudaMemcpyDeviceToHost, st));
+  VS_CHECK_CUDA(cudaStreamSynchronize(st));
+  std::vector<float> in32(L.r);
+  for (int r = 0; r < L.r; ++r) in32[r] = (float)in64[r];
+  const int best = vidseg_kmeans_pick_best_host(in32.data(), same.data(), L.r);
+  if (inertia_host) for (int r = 0; r < L.r; ++r) inertia_host[r] = in32[r];
+  if (info_host) {
+    info_host[0] = best;
+    info_host[1] = flags[(size_t)best * 4 + 2];
+    int tot = 0;
+    for (int r = 0; r < L.r; ++r) tot = tot > flags[(size_t)r * 4 + 2] ? tot : flags[(size_t)r * 4 + 2];
+    info_host[2] = tot;
+    info_host[3] = 0;
+  }
+  return vidseg_kmeans_finish(workspace, workspace_bytes, best, centers_out, labels_fit_out, stream);
+}
+
+VS_API int vidseg_kmeans_predict(const float* x, int n, int d, const float* centers, int k, int32_t* labels_out,
+                                     double* cnorm_scratch, void* stream) {
+  VS_REQUIRE(x != nullptr && centers != nullptr && labels_out != nullptr && cnorm_scratch != nullptr, "null pointer");
+  VS_REQUIRE(n >= 0 && d >= 1 && k >= 1, "bad shape");
+  if (n == 0) return 0;
+  KmLayout L{};
+  L.n = n; L.d = d; L.k = k; L.r = 1;
+  VS_LAUNCH(km_cnorm_kernel, (k * 32 + 255) / 256, 256, 0, stream, centers, d, k, cnorm_scratch);
+  VS_POST_LAUNCH();
+  return km_launch_assign(x, L, 1, 0, n, centers, cnorm_scratch, labels_out, n, nullptr, nullptr, 0, 0, stream);
+}
+
+VS_API int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_init, int n_trials, int max_iter,
+                                         float tol_rel, const int32_t* first_idx_host, const double* rand_host,
+                                         int32_t* labels_out, float* centers_out, int32_t* info_host,
+                                         float* inertia_host, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(first_idx_host != nullptr && labels_out != nullptr && centers_out != nullptr, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long launches0 = g_launch_count.load();
+  if (int e = vidseg_kmeans_prepare(x, n, d, k, n_init, n_trials, tol_rel, max_iter, workspace, workspace_bytes, stream)) return e;
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  void* ws = workspace;
+  VS_CHECK_CUDA(cudaMemcpyAsync(at<int>(ws, L.first_idx), first_idx_host, (size_t)n_init * 4, cudaMemcpyHostToDevice, st));
+  if (k > 1) {
+    VS_REQUIRE(rand_host != nullptr, "null rand_host");
+    VS_CHECK_CUDA(cudaMemcpyAsync(at<double>(ws, L.rand), rand_host, (size_t)n_init * (k - 1) * n_trials * 8,
+                                  cudaMemcpyHostToDevice, st));
+  }
+  if (int e = vidseg_kmeans_seed(at<int>(ws, L.first_idx), at<double>(ws, L.rand), workspace, workspace_bytes, stream)) return e;
+  int it = 0;
+  int poll = 4;
+  while (it < max_iter) {
+    const int burst = (max_iter - it) < poll ? (max_iter - it) : poll;
+    for (int b = 0; b < burst; ++b) {
+      if (int e = vidseg_kmeans_assign(workspace, workspace_bytes, 0, n, stream)) return e;
+      if (int e = vidseg_kmeans_partial(workspace, workspace_bytes, 0, n, nullptr, nullptr, stream)) return e;
+      if (int e = vidseg_kmeans_update(workspace, workspace_bytes, nullptr, nullptr, 0, stream)) return e;
+    }
+    it += burst;
+    int active = 0;
+    if (int e = vidseg_kmeans_active_runs(workspace, workspace_bytes, &active, stream)) return e;
+    if (active == 0) break;
+    if (poll < 16) poll *= 2;
+  }
+  if (int e = vidseg_kmeans_inertia(workspace, workspace_bytes, 0, n, nullptr, stream)) return e;
+  if (int e = vidseg_kmeans_select(workspace, workspace_bytes, nullptr, centers_out, nullptr, info_host, inertia_host, stream)) return e;
+  // KMeans.predict on the un-centred data (sklearn/_kmeans.py:1075-1107)
+  if (int e = vidseg_kmeans_predict(x, n, d, centers_out, k, labels_out, at<double>(ws, L.cnorm), stream)) return e;
+  VS_CHECK_CUDA(cudaStreamSynchronize(st));
+  if (info_host) info_host[3] = (int)(g_launch_count.load() - launches0);
+  return 0;
+}
+
+VS_API int vidseg_kmeans_release(void* workspace) {
+  std::lock_guard<std::mutex> lk(g_km_mu);
+  g_km_registry.erase(workspace);
+  return 0;
+}
