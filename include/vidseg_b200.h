@@ -159,6 +159,26 @@ int vidseg_refine_masks(const float* feats, const int32_t* labels_in,
                         int32_t* traj_out, int32_t* keep_out, int32_t* labels_out,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------- *
+ * A1-A4  attention-block linear layers on the tcgen05 tensor cores
+ *
+ * Split-fp16 operands: an fp32 tensor x is carried as two fp16 tensors
+ * hi = fp16(x), lo = fp16((x - hi) * 2048), so x ~= hi + lo/2048 (22 bits).
+ * ------------------------------------------------------------------------- */
+/* elementwise split of n fp32 values (x 16-byte aligned). */
+int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
+
+/* out[M,N] = A[M,K] . W[N,K]^T (+ bias[N]) (+ residual[M,N]); three tcgen05 MMAs per product
+ * (A_hi.W_hi ; A_hi.W_lo + A_lo.W_hi), fp32 accumulation in TMEM.  Replaces the nn.Linear call
+ * sites sgm/modules/attention.py:308,315,317 (to_q/k/v; out_f32 is what the reference stashes as
+ * self.q / self.k, :330-331), :364 (to_out), :95 (GEGLU.proj), :110-112 (ff.net[2]), :903,:923
+ * (proj_in / proj_out).  a_*: fp16 [M,K]; w_*: fp16 [N,K] (nn.Linear weight layout);
+ * out_f32: fp32 [M,N] or NULL; out_hi/out_lo: fp16 [M,N] split of the result or NULL.
+ * N % 8 == 0 and K % 8 == 0. */
+int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                      const float* bias, const float* residual, float* out_f32,
+                      void* out_hi, void* out_lo, int m, int n, int k, void* stream);
+
 /* number of kernel launches issued by this library since load (for bench.py's
  * gpu_launches accounting). */
 long long vidseg_launch_count(void);

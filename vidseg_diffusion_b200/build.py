@@ -51,10 +51,7 @@ def build(force=False, verbose=True):
     os.makedirs(OBJ_DIR, exist_ok=True)
     with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(_compile_one, sources()))
-    cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", OUT, *objs, "-lcuda"]
-    stub_dir = "/usr/local/cuda/lib64/stubs"
-    if os.path.isdir(stub_dir):
-        cmd += ["-L", stub_dir]
+    cmd = [NVCC, *ARCH_FLAGS, "-shared", "-o", OUT, *objs]  # driver entry points are resolved at run time
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"link failed:\n{res.stdout}\n{res.stderr}")

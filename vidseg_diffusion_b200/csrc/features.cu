@@ -115,13 +115,13 @@ using namespace vidseg;
 
 VS_API int vidseg_aggregate_normalize(const float* const* blocks_host, int n_blocks, int num_frames, int hw,
                                           int channels, float* out, void* stream) {
-  VS_REQUIRE(blocks_host != nullptr && out != nullptr, "null pointer");
   VS_REQUIRE(n_blocks >= 1 && n_blocks <= 4, "n_blocks must be 1..4");
   VS_REQUIRE(num_frames >= 0 && hw >= 0 && channels >= 1, "bad shape");
   const long long rows_ll = (long long)num_frames * hw;
   VS_REQUIRE(rows_ll < (1ll << 26), "too many rows");
   const int rows = (int)rows_ll;
-  if (rows == 0) return 0;
+  if (rows == 0) return 0;  // empty clip: nothing to do (pointers may be null)
+  VS_REQUIRE(blocks_host != nullptr && out != nullptr, "null pointer");
   BlockPtrs bp{};
   for (int b = 0; b < n_blocks; ++b) {
     VS_REQUIRE(blocks_host[b] != nullptr, "null block pointer");

@@ -1,0 +1,69 @@
+"""Host side of the tcgen05 linear layers (csrc/gemm_tc.cu): split-fp16 operands and the
+3-MMA GEMM.  Reference call sites: the nn.Linear layers of sgm/modules/attention.py."""
+import torch
+
+from . import _lib
+
+
+class Split:
+    """An fp32 tensor carried as two fp16 tensors: x ~= hi + lo / 2048."""
+    __slots__ = ("hi", "lo")
+
+    def __init__(self, hi, lo):
+        self.hi = hi
+        self.lo = lo
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def reshape(self, *shape):
+        return Split(self.hi.reshape(*shape), self.lo.reshape(*shape))
+
+    def float(self):
+        return self.hi.float() + self.lo.float() / 2048.0
+
+
+def split(x):
+    """fp32 CUDA tensor -> Split (one streaming kernel)."""
+    x = _lib.require_cuda_tensor(x, torch.float32, "x")
+    hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.vidseg_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _lib.stream_ptr()), "split_f16")
+    return Split(hi, lo)
+
+
+def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
+    """out = a @ w.T (+ bias) (+ residual).  a: Split [.., K], w: Split [N, K] (nn.Linear layout).
+    Returns (out_f32 or None, Split or None)."""
+    k = a.hi.shape[-1]
+    lead = a.hi.shape[:-1]
+    m = a.hi.numel() // k
+    n = w.hi.shape[0]
+    if w.hi.shape[1] != k:
+        raise _lib.VidsegError(f"gemm_split: K mismatch {k} vs {w.hi.shape[1]}")
+    for t, name in ((a.hi, "a.hi"), (a.lo, "a.lo"), (w.hi, "w.hi"), (w.lo, "w.lo")):
+        _lib.require_cuda_tensor(t, torch.float16, name)
+    dev = a.hi.device
+    out = torch.empty((*lead, n), dtype=torch.float32, device=dev) if want_f32 else None
+    oh = torch.empty((*lead, n), dtype=torch.float16, device=dev) if want_split else None
+    ol = torch.empty((*lead, n), dtype=torch.float16, device=dev) if want_split else None
+    if bias is not None:
+        _lib.require_cuda_tensor(bias, torch.float32, "bias")
+    if residual is not None:
+        _lib.require_cuda_tensor(residual, torch.float32, "residual")
+        if residual.numel() != m * n:
+            raise _lib.VidsegError("gemm_split: residual shape mismatch")
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.vidseg_gemm_split(
+            a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(),
+            bias.data_ptr() if bias is not None else None,
+            residual.data_ptr() if residual is not None else None,
+            out.data_ptr() if out is not None else None,
+            oh.data_ptr() if oh is not None else None,
+            ol.data_ptr() if ol is not None else None,
+            m, n, k, _lib.stream_ptr()), "gemm_split")
+    return out, (Split(oh, ol) if want_split else None)
