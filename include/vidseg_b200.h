@@ -179,6 +179,15 @@ int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, cons
                       const float* bias, const float* residual, float* out_f32,
                       void* out_hi, void* out_lo, int m, int n, int k, void* stream);
 
+/* softmax(q k^T * scale) v per (batch, head), head dim 64, no mask: replaces
+ * F.scaled_dot_product_attention at sgm/modules/attention.py:352-356 (xformers :473-485).
+ * q_*: fp16 [B, Nq, heads*64]; k_*, v_*: fp16 [B, Nk, heads*64] (the pre-head-split layout the
+ * reference stashes); out_f32 fp32 [B, Nq, heads*64] and/or its split out_hi/out_lo. */
+int vidseg_attention_split(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo,
+                           const void* v_hi, const void* v_lo, float* out_f32, void* out_hi,
+                           void* out_lo, int batch, int heads, int nq, int nk, float scale,
+                           void* stream);
+
 /* number of kernel launches issued by this library since load (for bench.py's
  * gpu_launches accounting). */
 long long vidseg_launch_count(void);

@@ -1,0 +1,28 @@
+"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 5e-6 of the
+output scale; the parity bar of the path is 1e-3)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("b,h,nq,nk,sharp", [
+    (2, 5, 512, 512, 1.0), (1, 2, 256, 77, 1.0), (3, 1, 64, 64, 1.0), (2, 3, 300, 300, 1.0), (1, 20, 64, 1, 1.0),
+    (2, 10, 1024, 1024, 4.0), (1, 5, 4096, 4096, 1.0), (2, 2, 130, 65, 8.0), (1, 1, 1, 1, 1.0),
+])
+def test_attention_matches_fp64(cuda, b, h, nq, nk, sharp):
+    from vidseg_diffusion_b200.linear import attention_split, split
+    g = torch.Generator(device="cpu").manual_seed(b * 1000 + h * 100 + nq + nk)
+    c = h * 64
+    q = (torch.randn(b, nq, c, generator=g) * sharp).to(cuda)
+    k = torch.randn(b, nk, c, generator=g).to(cuda)
+    v = torch.randn(b, nk, c, generator=g).to(cuda)
+    qd, kd, vd = [t.double().reshape(b, -1, h, 64).permute(0, 2, 1, 3) for t in (q, k, v)]
+    want = torch.softmax(qd @ kd.transpose(-1, -2) / 8.0, dim=-1) @ vd
+    want = want.permute(0, 2, 1, 3).reshape(b, nq, c)
+    out, sp = attention_split(split(q), split(k), split(v), h, want_f32=True, want_split=True)
+    scale = want.abs().max().item()
+    err = (out.double() - want).abs().max().item() / scale
+    assert err < 5e-6, f"fp32 output rel err {err:.3e}"
+    err = (sp.float().double() - want).abs().max().item() / scale
+    assert err < 5e-6, f"split output rel err {err:.3e}"

@@ -41,6 +41,7 @@ SIGNATURES = {
     "vidseg_kmeans_release": (c_int, [c_void_p]),
     "vidseg_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
     "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
+    "vidseg_attention_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_refine_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vidseg_refine_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),

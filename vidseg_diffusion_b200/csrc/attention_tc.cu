@@ -207,19 +207,19 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         tc::tmem_wait_ld();
 #pragma unroll
         for (int i = 0; i < 32; i += 8) {
-          __align__(16) __half h[8];
-          __align__(16) __half l[8];
+          float pv[8];
 #pragma unroll
           for (int u = 0; u < 8; ++u) {
             const float s = fmaf(__uint_as_float(a1[i + u]), tc::kLoInv, __uint_as_float(a0[i + u]));
-            const float pv = (c + i + u < valid) ? exp2f(fmaf(s, p.scale_log2, -m_new)) : 0.f;
-            lsum += pv;
-            tc::split_f16(pv, h[u], l[u]);
+            pv[u] = (c + i + u < valid) ? exp2f(fmaf(s, p.scale_log2, -m_new)) : 0.f;
+            lsum += pv[u];
           }
+          uint4 hv, lv;
+          tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv, lv);
           const int chunk = (c + i) >> 3;  // 16-byte chunk index inside the 128-byte row
           const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(p_hi_tile + off) = *reinterpret_cast<uint4*>(h);
-          *reinterpret_cast<uint4*>(p_lo_tile + off) = *reinterpret_cast<uint4*>(l);
+          *reinterpret_cast<uint4*>(p_hi_tile + off) = hv;
+          *reinterpret_cast<uint4*>(p_lo_tile + off) = lv;
         }
       }
       l_run = fmaf(l_run, alpha, lsum);
@@ -258,12 +258,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       if (p.out_hi) {
 #pragma unroll
         for (int d = 0; d < kAtD; d += 8) {
-          __align__(16) __half h[8];
-          __align__(16) __half l[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) tc::split_f16(o[d + u], h[u], l[u]);
-          *reinterpret_cast<uint4*>(p.out_hi + off + d) = *reinterpret_cast<uint4*>(h);
-          *reinterpret_cast<uint4*>(p.out_lo + off + d) = *reinterpret_cast<uint4*>(l);
+          uint4 hv, lv;
+          tc::split8_f16(o[d], o[d + 1], o[d + 2], o[d + 3], o[d + 4], o[d + 5], o[d + 6], o[d + 7], hv, lv);
+          *reinterpret_cast<uint4*>(p.out_hi + off + d) = hv;
+          *reinterpret_cast<uint4*>(p.out_lo + off + d) = lv;
         }
       }
     }

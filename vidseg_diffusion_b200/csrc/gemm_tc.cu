@@ -257,12 +257,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
               if (j < ncols) {
-                __align__(16) __half h[8];
-                __align__(16) __half l[8];
-#pragma unroll
-                for (int u = 0; u < 8; ++u) tc::split_f16(v[j + u], h[u], l[u]);
-                *reinterpret_cast<uint4*>(p.out_hi + off + j) = *reinterpret_cast<uint4*>(h);
-                *reinterpret_cast<uint4*>(p.out_lo + off + j) = *reinterpret_cast<uint4*>(l);
+                uint4 hv, lv;
+                tc::split8_f16(v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7], hv, lv);
+                *reinterpret_cast<uint4*>(p.out_hi + off + j) = hv;
+                *reinterpret_cast<uint4*>(p.out_lo + off + j) = lv;
               }
           }
         }

@@ -142,6 +142,24 @@ __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
 }
 
+__device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
+// two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs, all in registers
+__device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
+  hi = h2_bits(h);
+  lo = h2_bits(l);
+}
+// eight fp32 -> one 16-byte vector of fp16 hi and one of fp16 lo
+__device__ __forceinline__ void split8_f16(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
+                                           uint4& hi, uint4& lo) {
+  split2_f16(v0, v1, hi.x, lo.x);
+  split2_f16(v2, v3, hi.y, lo.y);
+  split2_f16(v4, v5, hi.z, lo.z);
+  split2_f16(v6, v7, hi.w, lo.w);
+}
+
 }  // namespace tc
 
 // host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)

@@ -67,3 +67,27 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
             ol.data_ptr() if ol is not None else None,
             m, n, k, _lib.stream_ptr()), "gemm_split")
     return out, (Split(oh, ol) if want_split else None)
+
+
+def attention_split(q, k, v, heads, scale=None, want_f32=False, want_split=True):
+    """softmax(q k^T * scale) v per head.  q: Split [B, Nq, heads*64]; k, v: Split [B, Nk, heads*64].
+    Returns (out_f32 or None, Split or None), both [B, Nq, heads*64]."""
+    b, nq, c = q.hi.shape
+    nk = k.hi.shape[1]
+    if c != heads * 64 or k.hi.shape[2] != c or v.hi.shape != k.hi.shape or k.hi.shape[0] != b:
+        raise _lib.VidsegError(f"attention_split: bad shapes q{tuple(q.hi.shape)} k{tuple(k.hi.shape)} v{tuple(v.hi.shape)} heads={heads}")
+    for t, name in ((q.hi, "q.hi"), (q.lo, "q.lo"), (k.hi, "k.hi"), (k.lo, "k.lo"), (v.hi, "v.hi"), (v.lo, "v.lo")):
+        _lib.require_cuda_tensor(t, torch.float16, name)
+    dev = q.hi.device
+    out = torch.empty((b, nq, c), dtype=torch.float32, device=dev) if want_f32 else None
+    oh = torch.empty((b, nq, c), dtype=torch.float16, device=dev) if want_split else None
+    ol = torch.empty((b, nq, c), dtype=torch.float16, device=dev) if want_split else None
+    if scale is None:
+        scale = 64 ** -0.5
+    lib = _lib.load()
+    with torch.cuda.device(dev):
+        _lib.check(lib.vidseg_attention_split(
+            q.hi.data_ptr(), q.lo.data_ptr(), k.hi.data_ptr(), k.lo.data_ptr(), v.hi.data_ptr(), v.lo.data_ptr(),
+            out.data_ptr() if out is not None else None, oh.data_ptr() if oh is not None else None,
+            ol.data_ptr() if ol is not None else None, b, heads, nq, nk, float(scale), _lib.stream_ptr()), "attention_split")
+    return out, (Split(oh, ol) if want_split else None)
