@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""Benchmark of the VidSeg per-clip hot path on B200 (contract: see DESIGN.md section "Measurement").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+
+One "step" = one pass of the hot path over one synthetic clip per GPU: SD-2.1 UNet forward at batch 2F
+with the Q/K stash -> aggregate(out 8,7,6)/normalise -> K-means(K, n_init=10) fit+predict
+(BASELINE.json configs[1]: 14 frames, 512x512, num_masks=20, --is_aggre_attn).  Metric: frames/sec.
+Rank 0 prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "frames/sec per clip (14x512x512)"
+UNIT = "frames/s"
+
+WORKLOADS = {
+    # name: (config key, frames, latent side, context len, num_masks, aggregate, refine)
+    "c2": dict(cfg="sd21", frames=14, latent=64, ctx_len=77, num_masks=20, aggre=True, refine=False,
+               desc="SD-2.1 UNet 1 step + aggregate(out 8,7,6) + KMeans(20, n_init=10), 14 frames 512x512 (BASELINE configs[1])"),
+    "c2r": dict(cfg="sd21", frames=14, latent=64, ctx_len=77, num_masks=20, aggre=True, refine=True,
+                desc="configs[1] plus --is_refine_mask"),
+    "c1": dict(cfg="sd21", frames=4, latent=32, ctx_len=77, num_masks=5, aggre=False, refine=False,
+               desc="SD-2.1, 4 frames 256x256, num_masks=5 (BASELINE configs[0])"),
+    "tiny": dict(cfg="tiny", frames=2, latent=16, ctx_len=7, num_masks=3, aggre=True, refine=True,
+                 desc="toy-width UNet, plumbing check only"),
+}
+# algorithmic FLOPs of one UNet step (FlopCounterMode over the reference modules)
+UNET_TFLOP = {"c2": 22.519, "c2r": 22.519, "c1": 1.449}
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return {"hbm_gbs": float(d["hbm_gbs"]), "tflops": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    "source": "measured (MEASURED_PEAKS.json, sustained bf16)"}
+        except Exception:
+            pass
+    return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
+
+
+def param_shapes(cfg):
+    """{state-dict key: shape} of the architecture, from the module tree on the meta device (no allocation)."""
+    import torch
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    with torch.device("meta"):
+        model = UNetModel(**cfg)
+    return {k: tuple(v.shape) for k, v in model.state_dict().items()}
+
+
+def make_state_dict(cfg, seed=0):
+    """Random-init weights of the reference architecture: N(0, 1/fan_in) matrices, unit norms, small biases."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for key, shape in param_shapes(cfg).items():
+        if len(shape) >= 2:
+            fan_in = 1
+            for s in shape[1:]:
+                fan_in *= s
+            sd[key] = torch.randn(shape, generator=g) * fan_in ** -0.5
+        elif key.endswith(".weight"):
+            sd[key] = 1.0 + 0.1 * torch.randn(shape, generator=g)
+        else:
+            sd[key] = 0.05 * torch.randn(shape, generator=g)
+    return sd
+
+
+def make_clip(wl, cfg, seed):
+    """Host tensors of one step: x [2F,4,h,w] (uncond rows first), timesteps [2F], context [2F,L,D]."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    F, hw = wl["frames"], wl["latent"]
+    lat = torch.randn(F, cfg["in_channels"], hw, hw, generator=g)
+    ctx = torch.randn(F, wl["ctx_len"], cfg["context_dim"], generator=g)
+    x = torch.cat([lat, lat], 0)
+    context = torch.cat([torch.zeros_like(ctx), ctx], 0)
+    t = torch.full((2 * F,), 21.0)  # DiscreteDenoiser index of the last sampler step (feature_timestep 24 of 25)
+    return x, t, context
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons of one GPU every 100 ms while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake_slowdown",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def finish(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's CPU path (oracle port): bounded sample of the same workload
+# --------------------------------------------------------------------------------------------------
+def cpu_reference_step(wl, cfg, sd, clip, n_frames, seed):
+    """One pass of the reference's CPU implementation over ``n_frames`` frames of the clip: fp32 UNet forward
+    (oracle/unet.py, the same ATen CPU kernels the reference's nn.Modules dispatch to) at batch 2*n_frames,
+    3-block mean + max-abs normalise (numpy, as feature_extraction.py:38-46,745), scikit-learn
+    KMeans(K, n_init=10).fit + .predict (feature_extraction.py:52-55; the oracle's restatement if sklearn is
+    missing), and the nearest-neighbour refinement when the workload has it.  Returns seconds."""
+    import numpy as np
+    import torch
+    from oracle import features as ofeat, kmeans as okm, refine as oref, unet as ounet
+    x, t, ctx = clip
+    F = wl["frames"]
+    idx = list(range(n_frames)) + [F + i for i in range(n_frames)]
+    xs, ts, cs = x[idx], t[idx], ctx[idx]
+    t0 = time.perf_counter()
+    stash = {}
+    ounet.unet_forward(sd, cfg, xs, ts, cs, stash)
+    blocks = (8, 7, 6) if wl["aggre"] else (8,)
+    feats = [stash[(f"output_block_{i}", "spatial_self_attn_q")].numpy() for i in blocks]
+    X = ofeat.aggregate_normalize(feats, n_frames)
+    np.random.seed(seed)
+    k = min(wl["num_masks"], X.shape[0])
+    try:
+        import warnings
+        from sklearn.cluster import KMeans
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            km = KMeans(n_clusters=k, n_init=10).fit(X)
+            labels = km.predict(X)
+    except ImportError:
+        labels, _ = okm.kmeans_fit_predict(X, k)
+    if wl["refine"]:
+        fh = wl["latent"] // 2
+        oref.correct_low_res_mask(stash[("output_block_7", "spatial_self_attn_q")].numpy(), labels.reshape(n_frames, fh, fh),
+                                  fh, fh, n_frames)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, wl, cfg):
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(cfg)
+    clip = make_clip(wl, cfg, 1)
+    nf = max(1, min(args.ref_frames, wl["frames"]))
+    for _ in range(args.warmup):
+        cpu_reference_step(wl, cfg, sd, clip, nf, 1)
+    times = [cpu_reference_step(wl, cfg, sd, clip, nf, 1) for _ in range(args.steps)]
+    total = sum(times)
+    fps = nf * args.steps / total
+    sample = (f"{nf} of {wl['frames']} frames per step (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8}, "
+              f"K-means on {nf} frames' features), fp32, torch {torch.__version__} CPU + scikit-learn")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "sample": sample},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# this repo's CUDA path
+# --------------------------------------------------------------------------------------------------
+def run_b200(args, wl, cfg):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from vidseg_diffusion_b200 import _lib
+    from vidseg_diffusion_b200.pipeline import ClipSegmenter
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.load()
+
+    sd = make_state_dict(cfg)
+    with torch.device("meta"):
+        model = UNetModel(**cfg)
+    model = model.to_empty(device=dev)
+    model.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
+    model.eval()
+    seg = ClipSegmenter(model, num_masks=wl["num_masks"], is_aggre_attn=wl["aggre"], is_refine_mask=wl["refine"])
+    F = wl["frames"]
+    host = [t.pin_memory() for t in make_clip(wl, cfg, 1 + rank)]     # every rank its own clip (weak scaling)
+    devt = [t.to(dev) for t in host]
+    seed = 1
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        barrier()
+        if profile:
+            _lib.profile_enable(True)
+        launches0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        prof = None
+        if profile:
+            _lib.profile_enable(False)
+            prof = _lib.profile_read()
+        if world > 1:
+            tt = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, _lib.launch_count() - launches0, prof
+
+    step_dev = lambda: seg.segment(devt[0], devt[1], devt[2], F, seed)
+    step_e2e = lambda: seg.segment_host(host[0], host[1], host[2], F, seed)
+    for _ in range(max(args.warmup, 3)):
+        step_dev()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ms, launches, prof = timed(step_dev, args.steps, profile=True)
+    clocks = sampler.finish()
+    step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+    labels = step_e2e()
+    fps = world * F * args.steps / (ms / 1e3)
+    fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
+    h2d = sum(t.numel() * t.element_size() for t in host)
+    d2h = labels.numel() * labels.element_size()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = read_peaks()
+    # dominant kernel = the family with the most device time in the timed region
+    fam = max(prof, key=lambda k: prof[k]["ms"])
+    p = prof[fam]
+    tensor_bound = fam in ("gemm", "attention", "conv")
+    if tensor_bound:
+        achieved = p["work"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                "frac": achieved / peaks["tflops"], "traffic": None}
+    else:
+        achieved = p["work"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / peaks["hbm_gbs"], "traffic": None}
+    roof.update(kernel=fam, launches_per_step=p["launches"] / args.steps, avg_launch_us=1e3 * p["ms"] / max(p["launches"], 1),
+                peak_source=peaks["source"],
+                note="achieved = algorithmic FLOPs (2MNK of the fp32-equivalent product) / CUDA-event time per launch; "
+                     "the split-fp16 path issues 3 tensor-core MMAs per algorithmic product, so tensor-pipe work is 3x")
+    lib_ms = sum(v["ms"] for v in prof.values())
+    breakdown = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}
+    breakdown["non_library(torch glue + host gaps)"] = round((ms - lib_ms) / args.steps, 3)
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    nf = max(1, min(args.ref_frames, F))
+    t_cpu = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], nf, seed)
+    sample = (f"{nf} of {F} frames, one pass (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32 + "
+              f"K-means on those frames), {t_cpu:.1f} s")
+    line = {
+        "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (split-fp16 tensor-core operands, fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": wl["desc"], "frames": F, "clips_per_step": world,
+                   "multi_gpu": "one clip per GPU per step, no data-path collective" if world > 1 else "single GPU",
+                   "l2": "working set (3.5 GB split weights + >4 GB activations per step) exceeds the 126 MB L2; no flush needed",
+                   "unet_tflop_per_step": UNET_TFLOP.get(args.workload)},
+        "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "stage_ms_per_step": breakdown,
+        "cpu_baseline": {"value": nf / t_cpu, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    from vidseg_diffusion_b200 import configs
+    cfg = {"sd21": configs.SD21_UNET, "tiny": configs.TINY_UNET}[wl["cfg"]]
+    if args.impl == "reference":
+        run_reference(args, wl, cfg)
+    else:
+        run_b200(args, wl, cfg)
+
+
+if __name__ == "__main__":
+    main()

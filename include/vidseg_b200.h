@@ -188,6 +188,15 @@ int vidseg_attention_split(const void* q_hi, const void* q_lo, const void* k_hi,
                            void* out_lo, int batch, int heads, int nq, int nk, float scale,
                            void* stream);
 
+/* Live per-kernel timing for bench.py's roofline object: while enabled, every launch of the library is
+ * bracketed by CUDA events on the stream it is launched on.  Families: 0 other, 1 tcgen05 GEMM (linear layers),
+ * 2 tcgen05 attention, 3 tcgen05 convolution, 4 aggregate/normalise, 5 K-means, 6 refine, 7 elementwise/norm.
+ * vidseg_profile_enable(1) resets the accumulators; vidseg_profile_read synchronises on the recorded events and
+ * returns total milliseconds, launch count and total algorithmic work (FLOPs for 1-3, bytes otherwise; 0 where
+ * the launch site does not state it). */
+int vidseg_profile_enable(int on);
+int vidseg_profile_read(int family, double* ms_total_host, long long* launches_host, double* work_total_host);
+
 /* number of kernel launches issued by this library since load (for bench.py's
  * gpu_launches accounting). */
 long long vidseg_launch_count(void);

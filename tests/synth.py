@@ -59,3 +59,39 @@ CLUSTER_CASES = [
     ("mid_objects", 4, 6, 24, 24, 320, 12, "objects"),
     ("c2_objects", 1, 14, 32, 32, 640, 20, "objects"),
 ]
+
+
+# ---------------------------------------------------------------------------------------------
+# UNet: seeded weights and inputs (numpy RandomState only -> identical on every machine)
+# ---------------------------------------------------------------------------------------------
+def synthetic_unet_weights(shapes, seed=0):
+    """{key: float32 array} for a {key: shape} table with the reference's state-dict names.
+
+    Every tensor is drawn (including the layers the reference zero-initialises, which would make
+    the UNet output identically zero): matrices / conv kernels N(0, 1/fan_in), norm scales
+    1 + 0.1 N(0,1), biases 0.05 N(0,1).  Keys are visited in sorted order."""
+    r = np.random.RandomState(seed)
+    out = {}
+    for key in sorted(shapes):
+        shape = tuple(shapes[key])
+        z = r.standard_normal(shape).astype(np.float32)
+        if len(shape) >= 2:
+            fan_in = int(np.prod(shape[1:]))
+            out[key] = z * np.float32(1.0 / np.sqrt(fan_in))
+        elif key.endswith(".weight"):
+            out[key] = np.float32(1.0) + np.float32(0.1) * z
+        else:
+            out[key] = np.float32(0.05) * z
+    return out
+
+
+def synthetic_unet_inputs(seed, num_frames, latent_hw, in_channels, context_len, context_dim, timestep=261):
+    """The batch the guider builds for one step (guiders.py:33-42): uncond rows first, both halves
+    share the noisy latent; the uncond context is zero (force_uc_zero_embeddings)."""
+    r = np.random.RandomState(seed)
+    lat = r.standard_normal((num_frames, in_channels, latent_hw, latent_hw)).astype(np.float32)
+    ctx = r.standard_normal((num_frames, context_len, context_dim)).astype(np.float32)
+    x = np.concatenate([lat, lat], 0)
+    context = np.concatenate([np.zeros_like(ctx), ctx], 0)
+    t = np.full((2 * num_frames,), timestep, dtype=np.int64)
+    return x, t, context

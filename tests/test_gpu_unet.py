@@ -1,0 +1,87 @@
+"""GPU parity of the UNet forward with the Q/K stash (A1/A3/A4/A7) against (a) goldens produced by the
+UNMODIFIED reference UNetModel (tests/golden/make_unet_goldens.py) and (b) the fp32 CPU oracle run on
+this box.  Tolerance is the path's bar: max|delta| / max|ref| <= 1e-3 per tensor;
+the split-fp16 tensor-core path is expected to sit two orders of magnitude below it."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import unet as ounet
+from synth import synthetic_unet_inputs, synthetic_unet_weights
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3          # the bar
+EXPECTED = 5e-5     # what the fp32-class path should achieve; a regression past this is a bug
+
+
+def relerr(got, want):
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    return float((got - want).abs().max() / want.abs().max())
+
+
+def build(cfg, seed, cuda):
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    w = synthetic_unet_weights(ounet.param_shapes(cfg), seed)
+    sd = {k: torch.from_numpy(v) for k, v in w.items()}
+    model = UNetModel(use_checkpoint=True, use_linear_in_transformer=True, transformer_depth=1, **cfg)
+    model.load_state_dict(sd, strict=True)
+    return model.to(cuda).eval(), sd
+
+
+@pytest.mark.parametrize("name,cfg", [("tiny", ounet.TINY_CONFIG), ("sd21_c1", ounet.SD21_CONFIG)])
+def test_unet_matches_reference_golden_and_oracle(cuda, name, cfg):
+    g = np.load(os.path.join(GOLDEN, f"unet_{name}.npz"))
+    seed, F, hw, L = (int(v) for v in g["meta"])
+    assert list(g["keys"]) == sorted(ounet.param_shapes(cfg))
+    model, sd = build(cfg, seed, cuda)
+    x, t, ctx = synthetic_unet_inputs(seed, F, hw, cfg["in_channels"], L, cfg["context_dim"])
+    out = model(torch.from_numpy(x).to(cuda), timesteps=torch.from_numpy(t).to(cuda), context=torch.from_numpy(ctx).to(cuda))
+    ts, cs = (int(v) for v in g["q_stride"])
+    errs = {"out": relerr(out, g["out"])}
+    for i in (6, 7, 8):
+        layer = model.output_blocks[i][1]
+        assert "SpatialTransformer" in str(type(layer))  # how the reference's pipelines find it
+        q = layer.transformer_blocks[0].attn1.q
+        assert q.dtype == torch.float32 and q.shape[0] == 2 * F and q.is_contiguous()
+        errs[f"q{i}"] = relerr(q[:, ::ts, ::cs], g[f"q{i}"])
+    # the oracle on this box's CPU: full tensors, every stashed q/k of every attention layer
+    stash = {}
+    out_or = ounet.unet_forward(sd, cfg, torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(ctx), stash)
+    errs["out_oracle"] = relerr(out, out_or)
+    tags = {}
+    for i, blk in enumerate(model.input_blocks):
+        tags[f"input_block_{i}"] = blk
+    tags["middle_block"] = model.middle_block
+    for i, blk in enumerate(model.output_blocks):
+        tags[f"output_block_{i}"] = blk
+    n_checked = 0
+    for (tag, what), want in stash.items():
+        tb = tags[tag][1].transformer_blocks[0]
+        attn = tb.attn1 if "self" in what else tb.attn2
+        got = attn.q if what.endswith("_q") else attn.k
+        errs[f"{tag}.{what}"] = relerr(got, want)
+        n_checked += 1
+    assert n_checked == 16 * 4
+    worst = max(errs, key=errs.get)
+    print(f"{name}: worst {worst} = {errs[worst]:.2e}; out {errs['out']:.2e}, q7 {errs['q7']:.2e}")
+    assert errs[worst] <= TOL, (worst, errs[worst])
+    assert errs[worst] <= EXPECTED, f"fp32-class path regressed: {worst} {errs[worst]:.2e}"
+
+
+def test_unet_frames_are_independent(cuda):
+    """SD-2.1 has no op that mixes batch entries: running a frame subset gives the same
+    features bit for bit -- the property the multi-GPU frame sharding relies on."""
+    cfg = ounet.TINY_CONFIG
+    model, _ = build(cfg, 5, cuda)
+    x, t, ctx = synthetic_unet_inputs(5, 3, 16, cfg["in_channels"], 7, cfg["context_dim"])
+    x, t, ctx = (torch.from_numpy(a).to(cuda) for a in (x, t, ctx))
+    full = model(x, timesteps=t, context=ctx)
+    q_full = model.output_blocks[7][1].transformer_blocks[0].attn1.q.clone()
+    sel = torch.tensor([1, 4], device=cuda)  # frame 1: uncond row 1 and cond row 4
+    part = model(x[sel], timesteps=t[sel], context=ctx[sel])
+    q_part = model.output_blocks[7][1].transformer_blocks[0].attn1.q
+    assert relerr(q_part, q_full[sel]) < 1e-6 and relerr(part, full[sel]) < 1e-6  # TODO bit-exact once the convs are ours

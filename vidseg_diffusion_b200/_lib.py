@@ -22,6 +22,8 @@ SIGNATURES = {
     "vidseg_abi_version": (c_int, []),
     "vidseg_device_arch": (c_int, []),
     "vidseg_launch_count": (c_longlong, []),
+    "vidseg_profile_enable": (c_int, [c_int]),
+    "vidseg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_longlong), ctypes.POINTER(ctypes.c_double)]),
     "vidseg_aggregate_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "vidseg_kmeans_workspace_bytes": (c_size_t, [c_int] * 5),
     "vidseg_kmeans_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
@@ -80,6 +82,24 @@ def check(code, what=""):
     if code != 0:
         msg = load().vidseg_last_error().decode(errors="replace")
         raise VidsegError(f"{what or 'libvidseg_b200'} failed with code {code}: {msg}")
+
+
+KERNEL_FAMILIES = ("other", "gemm", "attention", "conv", "aggregate", "kmeans", "refine", "elementwise")
+
+
+def profile_enable(on=True):
+    check(load().vidseg_profile_enable(1 if on else 0), "profile_enable")
+
+
+def profile_read():
+    """{family: {"ms": total ms, "launches": n, "work": FLOPs or bytes}} since the last profile_enable(True)."""
+    lib = load()
+    out = {}
+    for i, name in enumerate(KERNEL_FAMILIES):
+        ms, n, w = ctypes.c_double(), c_longlong(), ctypes.c_double()
+        check(lib.vidseg_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(w)), "profile_read")
+        out[name] = {"ms": ms.value, "launches": n.value, "work": w.value}
+    return out
 
 
 def launch_count():

@@ -1,0 +1,13 @@
+"""UNet hyper-parameters of the two inference configs the pipelines use (reference: configs/inference/)."""
+
+# configs/inference/sd_2_1.yaml:18-30 (network_config.params of sgm...openaimodel.UNetModel)
+SD21_UNET = dict(
+    use_checkpoint=True, in_channels=4, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+    num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_head_channels=64, use_linear_in_transformer=True,
+    transformer_depth=1, context_dim=1024)
+
+# same topology at toy width (head dim stays 64): plumbing checks and fast tests
+TINY_UNET = dict(
+    use_checkpoint=True, in_channels=4, out_channels=4, model_channels=64, attention_resolutions=[4, 2, 1],
+    num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_head_channels=64, use_linear_in_transformer=True,
+    transformer_depth=1, context_dim=96)

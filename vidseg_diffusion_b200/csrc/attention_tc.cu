@@ -16,6 +16,7 @@
 // TMA (warp 0) streams K/V blocks through a 2-stage ring.  TMEM: 2 tiles x (S 128 + PV 128) = 512 columns.
 #include <mutex>
 
+#define VS_FAMILY vidseg::kFamAttention
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -300,7 +301,7 @@ VS_API int vidseg_attention_split(const void* q_hi, const void* q_lo, const void
   VS_CHECK_CUDA(attr_err);
   AttnParams p{batch, heads, nq, nk, scale * 1.4426950408889634f, out_f32, (__half*)out_hi, (__half*)out_lo};
   dim3 grid((nq + kAtBQ * kAtTiles - 1) / (kAtBQ * kAtTiles), heads, batch);
-  VS_LAUNCH(attn_split_kernel, grid, kAtThreads, kAtSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
+  VS_LAUNCH_W(4.0 * batch * heads * (double)nq * nk * kAtD, attn_split_kernel, grid, kAtThreads, kAtSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
   VS_POST_LAUNCH();
   return 0;
 }

@@ -38,12 +38,31 @@ inline int set_error(int code, const char* fmt, const char* a = "", long long b 
     }                                                                                      \
   } while (0)
 
-// every kernel launch in the library goes through this so that launches are counted
-#define VS_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
-  do {                                                                    \
-    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__); \
-    vidseg::g_launch_count.fetch_add(1, std::memory_order_relaxed);       \
+// Kernel families for the live per-kernel timing bench.py asks for (vidseg_profile_*).
+enum KernelFamily {
+  kFamOther = 0, kFamGemm = 1, kFamAttention = 2, kFamConv = 3, kFamAggregate = 4, kFamKMeans = 5, kFamRefine = 6,
+  kFamElementwise = 7, kNumFamilies = 8
+};
+extern std::atomic<int> g_profile_on;
+void profile_before(int family, double work, cudaStream_t stream);
+void profile_after(cudaStream_t stream);
+
+#ifndef VS_FAMILY
+#define VS_FAMILY vidseg::kFamOther
+#endif
+
+// every kernel launch in the library goes through this so that launches are counted; when profiling
+// is enabled the launch is bracketed by CUDA events on its own stream (work = algorithmic FLOPs or bytes)
+#define VS_LAUNCH_W(work, kernel, grid, block, smem, stream, ...)                                  \
+  do {                                                                                             \
+    const bool _prof = vidseg::g_profile_on.load(std::memory_order_relaxed) != 0;                  \
+    if (_prof) vidseg::profile_before(VS_FAMILY, (double)(work), (cudaStream_t)(stream));          \
+    kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                      \
+    if (_prof) vidseg::profile_after((cudaStream_t)(stream));                                      \
+    vidseg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                \
   } while (0)
+#define VS_LAUNCH(kernel, grid, block, smem, stream, ...) \
+  VS_LAUNCH_W(0.0, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 #define VS_POST_LAUNCH() VS_CHECK_CUDA(cudaGetLastError())
 

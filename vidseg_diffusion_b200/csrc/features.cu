@@ -5,6 +5,7 @@
 // division, no epsilon) and :45-46 (rows [F, 2F) only).  HBM-bound streaming kernel: one warp
 // per token row, 128-bit loads, the row stays in registers between the max reduction and the
 // divide, so every input byte is read once and every output byte written once.
+#define VS_FAMILY vidseg::kFamAggregate
 #include "common.cuh"
 
 namespace vidseg {

@@ -18,6 +18,7 @@
 // tile i overlaps the MMAs of tile i+1.
 #include <mutex>
 
+#define VS_FAMILY vidseg::kFamGemm
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -279,6 +280,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
 
 using namespace vidseg;
 
+#undef VS_FAMILY
+#define VS_FAMILY vidseg::kFamElementwise
 VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, void* stream) {
   VS_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
@@ -286,11 +289,13 @@ VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, voi
   VS_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "unaligned pointer");
   const size_t n4 = (size_t)n / 4;
   int grid = (int)std::min<size_t>((n4 + 255) / 256 + 1, (size_t)kNumSMs * 8);
-  VS_LAUNCH(split_f16_kernel, grid, 256, 0, stream, x, (__half*)hi, (__half*)lo, n4, (size_t)n);
+  VS_LAUNCH_W(8.0 * n, split_f16_kernel, grid, 256, 0, stream, x, (__half*)hi, (__half*)lo, n4, (size_t)n);
   VS_POST_LAUNCH();
   return 0;
 }
 
+#undef VS_FAMILY
+#define VS_FAMILY vidseg::kFamGemm
 VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                              const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
                              void* stream) {
@@ -314,7 +319,7 @@ VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_h
   GemmParams p{m, n, k, bias, residual, out_f32, (__half*)out_hi, (__half*)out_lo};
   const int m_tiles = (m + kGemmBM - 1) / kGemmBM, n_tiles = (n + kGemmBN - 1) / kGemmBN;
   const int grid = std::min(m_tiles * n_tiles, kNumSMs);
-  VS_LAUNCH(gemm_split_kernel, grid, 256, kGemmSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
+  VS_LAUNCH_W(2.0 * m * n * k, gemm_split_kernel, grid, 256, kGemmSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
   VS_POST_LAUNCH();
   return 0;
 }

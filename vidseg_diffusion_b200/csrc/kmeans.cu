@@ -20,6 +20,7 @@
 #include <unordered_map>
 #include <vector>
 
+#define VS_FAMILY vidseg::kFamKMeans
 #include "common.cuh"
 
 namespace vidseg {

@@ -13,6 +13,7 @@
 //     ascending point order, i.e. the highest point index wins a contested cell.
 // The reference round-trips every cosine map to the host for np.argpartition; here the arg-max is
 // fused into the similarity kernel and positions never leave HBM.
+#define VS_FAMILY vidseg::kFamRefine
 #include "common.cuh"
 
 namespace vidseg {

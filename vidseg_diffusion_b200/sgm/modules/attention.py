@@ -1,0 +1,204 @@
+"""Attention operators of the UNet transformer blocks on B200 (reference: sgm/modules/attention.py).
+
+``CrossAttention`` (:257-364) keeps the reference's constructor, forward signature and the Q/K
+"hook": after every forward ``self.q`` / ``self.k`` hold the projected, pre-head-split activations
+[B, N, heads*64] in fp32 (:330-331) -- written by the epilogue of the projection GEMM, so harvesting
+them costs no extra pass.  ``BasicTransformerBlock`` (:504-759), ``SpatialTransformer`` (:806-927),
+``FeedForward`` / ``GEGLU`` (:89-115) keep their attribute names so that state dicts and
+``output_blocks[i][1].transformer_blocks[0].attn1.q`` resolve exactly as in the reference.
+
+Every Linear runs as a split-fp16 3-MMA tcgen05 GEMM and the softmax attention as the tcgen05 flash
+kernel (csrc/gemm_tc.cu, csrc/attention_tc.cu); normalisations and the GEGLU gate are fused
+streaming kernels (csrc/elementwise.cu).  There is no eager-PyTorch fallback.
+"""
+import torch
+import torch.nn as nn
+
+from ... import _lib
+from ... import kernels as K
+from ...linear import Split
+
+
+def _unsupported(name):
+    raise NotImplementedError(f"{name}: not on the B200 hot path (SURVEY.md section 8f, next rows)")
+
+
+class GEGLU(nn.Module):
+    """reference :89-96.  proj -> chunk(2) -> value * gelu(gate), computed in the GEMM's consumer kernel."""
+
+    def __init__(self, dim_in, dim_out):
+        super().__init__()
+        self.proj = nn.Linear(dim_in, dim_out * 2)
+
+    def forward_split(self, xs):
+        h, _ = K.linear(xs, self.proj.weight, self.proj.bias, want_f32=True)
+        return K.geglu_split(h)
+
+    def forward(self, x):
+        return self.forward_split(K.split(x)).float()
+
+
+class FeedForward(nn.Module):
+    """reference :99-115 (only the gated form is on the path: BasicTransformerBlock uses glu=True)."""
+
+    def __init__(self, dim, dim_out=None, mult=4, glu=False, dropout=0.0):
+        super().__init__()
+        if not glu:
+            _unsupported("FeedForward(glu=False)")
+        inner_dim = int(dim * mult)
+        dim_out = dim if dim_out is None else dim_out
+        self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
+
+    def forward_split(self, xs, residual=None):
+        hs = self.net[0].forward_split(xs)
+        out, _ = K.linear(hs, self.net[2].weight, self.net[2].bias, residual=residual, want_f32=True)
+        return out
+
+    def forward(self, x):
+        return self.forward_split(K.split(x))
+
+
+class CrossAttention(nn.Module):
+    """reference :257-364.  Self-attention when ``context`` is None."""
+
+    def __init__(self, query_dim, context_dim=None, heads=8, dim_head=64, dropout=0.0, backend=None):
+        super().__init__()
+        if dim_head != 64:
+            raise _lib.VidsegError(f"CrossAttention: the tcgen05 attention kernel is built for head dim 64, got {dim_head}")
+        inner_dim = dim_head * heads
+        context_dim = query_dim if context_dim is None else context_dim
+        self.scale = dim_head ** -0.5
+        self.heads = heads
+        self.to_q = nn.Linear(query_dim, inner_dim, bias=False)
+        self.to_k = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
+        self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
+        self.backend = backend
+        self.q = None
+        self.k = None
+
+    def forward_split(self, xs, context=None, residual=None, injected_q=None, injected_k=None, injected_v=None):
+        """xs: Split [B, N, C] (already normalised); context: Split [B, L, Cctx] or None.
+        Returns to_out(attention) (+ residual) as fp32 [B, N, C]."""
+        cs = xs if context is None else context
+        if injected_q is not None:
+            q, qs = injected_q, K.split(injected_q.float().contiguous())
+        else:
+            q, qs = K.linear(xs, self.to_q.weight, want_f32=True, want_split=True)
+        if injected_k is not None:
+            k, ks = injected_k, K.split(injected_k.float().contiguous())
+        else:
+            k, ks = K.linear(cs, self.to_k.weight, want_f32=True, want_split=True)
+        if injected_v is not None:
+            vs = K.split(injected_v.float().contiguous())
+        else:
+            _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True)
+        self.q = q
+        self.k = k
+        _, os_ = K.attention(qs, ks, vs, self.heads, self.scale)
+        lin = self.to_out[0]
+        out, _ = K.linear(os_, lin.weight, lin.bias, residual=residual, want_f32=True)
+        return out
+
+    def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
+                injected_q=None, injected_k=None, injected_v=None):
+        if mask is not None or additional_tokens is not None or n_times_crossframe_attn_in_self:
+            _unsupported("CrossAttention(mask / additional_tokens / n_times_crossframe_attn_in_self)")
+        xs = x if isinstance(x, Split) else K.split(x)
+        if context is not None and not isinstance(context, Split):
+            context = K.split(context)
+        return self.forward_split(xs, context, None, injected_q, injected_k, injected_v)
+
+
+class BasicTransformerBlock(nn.Module):
+    """reference :504-759 (inference path; modulation :646-663,:697-719 is a next row)."""
+    ATTENTION_MODES = {"softmax": CrossAttention, "softmax-xformers": CrossAttention}  # one kernel serves both
+
+    def __init__(self, dim, n_heads, d_head, dropout=0.0, context_dim=None, gated_ff=True, checkpoint=True,
+                 disable_self_attn=False, attn_mode="softmax", sdp_backend=None):
+        super().__init__()
+        if attn_mode not in self.ATTENTION_MODES:
+            raise AssertionError(attn_mode)
+        attn_cls = self.ATTENTION_MODES[attn_mode]
+        self.disable_self_attn = disable_self_attn
+        self.attn1 = attn_cls(query_dim=dim, heads=n_heads, dim_head=d_head, dropout=dropout,
+                              context_dim=context_dim if disable_self_attn else None, backend=sdp_backend)
+        self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
+        self.attn2 = attn_cls(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
+                              dropout=dropout, backend=sdp_backend)
+        self.norm1 = nn.LayerNorm(dim)
+        self.norm2 = nn.LayerNorm(dim)
+        self.norm3 = nn.LayerNorm(dim)
+        self.checkpoint = checkpoint  # inference only: torch.utils.checkpoint is a no-op without grad
+
+    def forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
+                is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        return self._forward(x, context, additional_tokens, n_times_crossframe_attn_in_self, is_modulate_step,
+                             is_injected_step, modulate_params)
+
+    def _forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
+                 is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        if is_modulate_step:
+            _unsupported("BasicTransformerBlock(is_modulate_step=True)")
+        if additional_tokens is not None or n_times_crossframe_attn_in_self:
+            _unsupported("BasicTransformerBlock(additional_tokens / n_times_crossframe_attn_in_self)")
+        inj = {"self": [None] * 3, "cross": [None] * 3}
+        if is_injected_step:  # reference :616-623, :674-681: lookup by substring of the dict key
+            for key, val in modulate_params["injected_features_group"].items():
+                for kind in ("self", "cross"):
+                    for i, name in enumerate("qkv"):
+                        if f"spatial_{kind}_attn_{name}" in key:
+                            inj[kind][i] = val
+        if context is not None and not isinstance(context, Split):
+            context = K.split(context.float().contiguous())
+        x = x.float().contiguous()
+        ctx1 = context if self.disable_self_attn else None
+        x = self.attn1.forward_split(K.layer_norm_split(x, self.norm1), ctx1, x, *inj["self"])
+        self.attn1_out = None  # the reference keeps attn1_out / attn2_out / ff_out for modulation only
+        x = self.attn2.forward_split(K.layer_norm_split(x, self.norm2), context, x, *inj["cross"])
+        x = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x)
+        return x
+
+
+class SpatialTransformer(nn.Module):
+    """reference :806-927 (``use_linear=True`` form used by sd_2_1.yaml / svd.yaml)."""
+
+    def __init__(self, in_channels, n_heads, d_head, depth=1, dropout=0.0, context_dim=None, disable_self_attn=False,
+                 use_linear=False, attn_type="softmax", use_checkpoint=True, sdp_backend=None):
+        super().__init__()
+        if not use_linear:
+            _unsupported("SpatialTransformer(use_linear=False)")
+        if context_dim is not None and not isinstance(context_dim, (list, tuple)):
+            context_dim = [context_dim]
+        if context_dim is None:
+            context_dim = [None] * depth
+        elif len(context_dim) != depth:
+            context_dim = depth * [context_dim[0]]
+        self.in_channels = in_channels
+        inner_dim = n_heads * d_head
+        self.norm = nn.GroupNorm(num_groups=32, num_channels=in_channels, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(in_channels, inner_dim)
+        self.transformer_blocks = nn.ModuleList([
+            BasicTransformerBlock(inner_dim, n_heads, d_head, dropout=dropout, context_dim=context_dim[d],
+                                  disable_self_attn=disable_self_attn, attn_mode=attn_type, checkpoint=use_checkpoint,
+                                  sdp_backend=sdp_backend) for d in range(depth)])
+        self.proj_out = nn.Linear(inner_dim, in_channels)
+        self.use_linear = use_linear
+
+    def forward(self, x, context=None, is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        if is_modulate_step:
+            _unsupported("SpatialTransformer(is_modulate_step=True)")
+        if not isinstance(context, (list, tuple)):
+            context = [context]
+        context = [c if (c is None or isinstance(c, Split)) else K.split(c.float().contiguous()) for c in context]
+        b, c, h, w = x.shape
+        x = x.float()
+        # GroupNorm (eps 1e-6) + 'b c h w -> b (h w) c' + operand split in one kernel; tokens stay channels-last
+        x_tok, xs = K.group_norm_tokens_split(x, self.norm, silu=False)
+        t, _ = K.linear(xs, self.proj_in.weight, self.proj_in.bias, want_f32=True)
+        for i, block in enumerate(self.transformer_blocks):
+            ctx = context[0] if (i > 0 and len(context) == 1) else context[i]
+            t = block(t, context=ctx, is_injected_step=is_injected_step, modulate_params=modulate_params)
+        # proj_out + residual x_in (token layout), then back to b c h w
+        out, _ = K.linear(K.split(t), self.proj_out.weight, self.proj_out.bias, residual=x_tok, want_f32=True)
+        return K.tokens_to_nchw(out, b, c, h, w)
