@@ -160,33 +160,67 @@ int vidseg_refine_masks(const float* feats, const int32_t* labels_in,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
- * A1-A4  attention-block linear layers on the tcgen05 tensor cores
+ * A1-A8  UNet forward on the tcgen05 tensor cores
  *
- * Split-fp16 operands: an fp32 tensor x is carried as two fp16 tensors
- * hi = fp16(x), lo = fp16((x - hi) * 2048), so x ~= hi + lo/2048 (22 bits).
+ * Split operands: an fp32 tensor x is carried as hi = fp16(x) and lo = fp16(x - hi), x ~= hi + lo (22 significant
+ * bits for |x| >= 0.25, absolute error <= 3e-8 below).  Every product is three tensor-core MMAs
+ * (lo.hi + hi.lo + hi.hi) accumulated in one fp32 TMEM accumulator.  Tensors of systematically small values are
+ * split pre-scaled by a power of two (weights: 2^8) and the GEMM multiplies its accumulator by the exact inverse
+ * (acc_scale).  Activations are channels-last ([B, H, W, C] / [B, N, C]).
  * ------------------------------------------------------------------------- */
-/* elementwise split of n fp32 values (x 16-byte aligned). */
-int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, void* stream);
+/* elementwise split of n fp32 values times `scale` (x 16-byte aligned). */
+int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, float scale, void* stream);
 
-/* out[M,N] = A[M,K] . W[N,K]^T (+ bias[N]) (+ residual[M,N]); three tcgen05 MMAs per product
- * (A_hi.W_hi ; A_hi.W_lo + A_lo.W_hi), fp32 accumulation in TMEM.  Replaces the nn.Linear call
- * sites sgm/modules/attention.py:308,315,317 (to_q/k/v; out_f32 is what the reference stashes as
- * self.q / self.k, :330-331), :364 (to_out), :95 (GEGLU.proj), :110-112 (ff.net[2]), :903,:923
- * (proj_in / proj_out).  a_*: fp16 [M,K]; w_*: fp16 [N,K] (nn.Linear weight layout);
- * out_f32: fp32 [M,N] or NULL; out_hi/out_lo: fp16 [M,N] split of the result or NULL.
- * N % 8 == 0 and K % 8 == 0. */
+/* out[M,N] = A[M,K] . W[N,K]^T (+ bias[N]) (+ residual[M,N]).  Replaces the nn.Linear call sites
+ * sgm/modules/attention.py:308,315,317 (to_q/k/v; out_f32 is what the reference stashes as self.q / self.k,
+ * :330-331), :364 (to_out), :95 (GEGLU.proj), :110-112 (ff.net[2]), :903,:923 (proj_in / proj_out) and the
+ * time-embedding Linears (openaimodel.py:552-556, :281-287).  a_*: [M,K]; w_*: [N,K] (nn.Linear weight layout);
+ * out_f32: fp32 [M,N] or NULL; out_hi/out_lo: split of the result or NULL.  N % 4 == 0 (8 with a split output),
+ * K % 8 == 0. */
 int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                       const float* bias, const float* residual, float* out_f32,
-                      void* out_hi, void* out_lo, int m, int n, int k, void* stream);
+                      void* out_hi, void* out_lo, int m, int n, int k, float acc_scale, void* stream);
+
+/* nn.Conv2d as an implicit GEMM (no im2col: the taps are shifted TMA boxes, zero padding is the TMA out-of-bounds
+ * fill).  Replaces the 3x3 / 1x1 convolutions of ResBlock (openaimodel.py:267-315), Downsample (:202-209, stride 2),
+ * Upsample (:145-147), the input conv (:587-593) and the output conv (:825-829).
+ *   x_*: [B, H, W, Cin] split;  w_*: [Cout, ksize*ksize*Cin] split, tap-major (ky, kx, cin) = weight.permute(0,2,3,1);
+ *   bias [Cout] or NULL; chan_bias [B, Cout] or NULL (ResBlock time embedding, :352-362); residual [B,Ho,Wo,Cout] or NULL;
+ *   out_f32 [B, Ho, Wo, Cout] and/or its split.  ksize 1|3 (padding ksize/2), stride 1|2 (3x3 only; Ho = H/2).
+ *   Cin % 8 == 0 (64 for stride 2), Cout % 4 == 0. */
+int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                        const float* chan_bias, const float* residual, float* out_f32, void* out_hi, void* out_lo,
+                        int batch, int height, int width, int cin, int cout, int ksize, int stride, float acc_scale,
+                        void* stream);
 
 /* softmax(q k^T * scale) v per (batch, head), head dim 64, no mask: replaces
  * F.scaled_dot_product_attention at sgm/modules/attention.py:352-356 (xformers :473-485).
- * q_*: fp16 [B, Nq, heads*64]; k_*, v_*: fp16 [B, Nk, heads*64] (the pre-head-split layout the
+ * q_*: [B, Nq, heads*64] split; k_*, v_*: [B, Nk, heads*64] split (the pre-head-split layout the
  * reference stashes); out_f32 fp32 [B, Nq, heads*64] and/or its split out_hi/out_lo. */
 int vidseg_attention_split(const void* q_hi, const void* q_lo, const void* k_hi, const void* k_lo,
                            const void* v_hi, const void* v_lo, float* out_f32, void* out_hi,
                            void* out_lo, int batch, int heads, int nq, int nk, float scale,
                            void* stream);
+
+/* nn.LayerNorm over the last dim (attention.py:567-569) -> split operand.  x fp32 [rows, C]; C % 4 == 0, <= 2048. */
+int vidseg_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, void* out_hi,
+                           void* out_lo, long long rows, int channels, void* stream);
+
+/* GEGLU gate (attention.py:95-96): h fp32 [rows, 2*D] = (value | gate) -> split(value * gelu_erf(gate)) [rows, D]. */
+int vidseg_geglu_split(const float* h, void* out_hi, void* out_lo, long long rows, int d, void* stream);
+
+/* GroupNorm (+ SiLU) over the channel concatenation [x1 (c1) | x2 (c2)] of channels-last fp32 tensors [B, HW, c]
+ * -> split operand [B, HW, c1+c2]; raw_hi/raw_lo (optional) receive the split of the un-normalised concatenation
+ * (operand of the ResBlock's 1x1 skip convolution).  Replaces GroupNorm32+SiLU (openaimodel.py:267-271, 300-303,
+ * 825-827; util.py:276-278), Normalize (attention.py:127-130) and th.cat([h, hs.pop()], 1) (openaimodel.py:911).
+ * x2 may be NULL (c2 = 0).  Deterministic (fixed summation order). */
+size_t vidseg_groupnorm_workspace_bytes(int batch, int groups);
+int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int c2, const float* gamma, const float* beta,
+                           float eps, int groups, int silu, void* out_hi, void* out_lo, void* raw_hi, void* raw_lo,
+                           int batch, int hw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* nearest x2 upsampling (openaimodel.py:153) -> split operand.  x fp32 [B, H, W, C] -> [B, 2H, 2W, C]. */
+int vidseg_upsample2x_split(const float* x, void* out_hi, void* out_lo, int batch, int h, int w, int c, void* stream);
 
 /* Live per-kernel timing for bench.py's roofline object: while enabled, every launch of the library is
  * bracketed by CUDA events on the stream it is launched on.  Families: 0 other, 1 tcgen05 GEMM (linear layers),

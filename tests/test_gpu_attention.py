@@ -1,4 +1,4 @@
-"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 5e-6 of the
+"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 1e-5 of the
 output scale; the parity bar of the path is 1e-3)."""
 import pytest
 import torch
@@ -23,6 +23,6 @@ def test_attention_matches_fp64(cuda, b, h, nq, nk, sharp):
     out, sp = attention_split(split(q), split(k), split(v), h, want_f32=True, want_split=True)
     scale = want.abs().max().item()
     err = (out.double() - want).abs().max().item() / scale
-    assert err < 5e-6, f"fp32 output rel err {err:.3e}"
+    assert err < 1e-5, f"fp32 output rel err {err:.3e}"
     err = (sp.float().double() - want).abs().max().item() / scale
-    assert err < 5e-6, f"split output rel err {err:.3e}"
+    assert err < 1e-5, f"split output rel err {err:.3e}"

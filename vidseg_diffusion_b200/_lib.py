@@ -41,8 +41,15 @@ SIGNATURES = {
     "vidseg_kmeans_fit_predict": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidseg_kmeans_release": (c_int, [c_void_p]),
-    "vidseg_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_void_p]),
-    "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_void_p]),
+    "vidseg_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
+    "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "vidseg_conv2d_split": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p]),
+    "vidseg_layernorm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "vidseg_geglu_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
+    "vidseg_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "vidseg_groupnorm_split": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_float, c_int, c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "vidseg_upsample2x_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vidseg_attention_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_refine_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vidseg_refine_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,

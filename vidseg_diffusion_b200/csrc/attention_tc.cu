@@ -9,11 +9,11 @@
 // One CTA = 256 queries of one (batch, head): two 128-row query tiles, each owned by a softmax
 // warpgroup (128 threads = 128 TMEM lanes); the two groups ping-pong so that the tensor pipe works on
 // one tile while the CUDA cores exponentiate the other.  Per 64-key block and tile:
-//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x64x16: hi.hi -> S_main, hi.lo + lo.hi -> S_cross)
+//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x64x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator)
 //   softmax  : tcgen05.ld S, online max / exp2 / row sum, P -> fp16 hi/lo into swizzled smem
 //   MMA warp : PV = P V    (12 x tcgen05.mma 128x64x16, V is the MN-major B operand)
 //   softmax  : tcgen05.ld PV, O = O * alpha + PV   (O lives in registers, 64 fp32 per thread)
-// TMA (warp 0) streams K/V blocks through a 2-stage ring.  TMEM: 2 tiles x (S 128 + PV 128) = 512 columns.
+// TMA (warp 0) streams K/V blocks through a 2-stage ring.  TMEM: 2 tiles x (S 64 + PV 64) = 256 columns.
 #include <mutex>
 
 #define VS_FAMILY vidseg::kFamAttention
@@ -79,7 +79,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     for (int g = 0; g < kAtTiles; ++g) { tc::mbar_init(&s_full[g], 1); tc::mbar_init(&p_full[g], 128); tc::mbar_init(&o_full[g], 1); }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<512>(tmem_base_ptr);
+  if (warp == 1) tc::tmem_alloc<256>(tmem_base_ptr);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -116,14 +116,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         const uint32_t ka = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes);
         const uint64_t q_hi = tc::make_sw128_desc(qa), q_lo = tc::make_sw128_desc(qa + kAtQTileBytes);
         const uint64_t k_hi = tc::make_sw128_desc(ka), k_lo = tc::make_sw128_desc(ka + kAtKTileBytes);
-        const uint32_t d_main = tmem_base + (uint32_t)(g * 256);
-        const uint32_t d_cross = d_main + 64;
+        const uint32_t d_s = tmem_base + (uint32_t)(g * 128);
 #pragma unroll
         for (int ks = 0; ks < kAtD / 16; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);
-          tc::umma_f16(d_main, q_hi + adv, k_hi + adv, idesc_s, ks > 0);
-          tc::umma_f16(d_cross, q_hi + adv, k_lo + adv, idesc_s, ks > 0);
-          tc::umma_f16(d_cross, q_lo + adv, k_hi + adv, idesc_s, 1u);
+          tc::umma_f16(d_s, q_lo + adv, k_hi + adv, idesc_s, ks > 0);
+          tc::umma_f16(d_s, q_hi + adv, k_lo + adv, idesc_s, 1u);
+          tc::umma_f16(d_s, q_hi + adv, k_hi + adv, idesc_s, 1u);
         }
         tc::umma_commit(&s_full[g]);
       };
@@ -132,15 +131,14 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         const uint32_t va = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes + 2 * kAtKTileBytes);
         const uint64_t p_hi = tc::make_sw128_desc(pa), p_lo = tc::make_sw128_desc(pa + kAtPTileBytes);
         const uint64_t v_hi = tc::make_sw128_desc(va), v_lo = tc::make_sw128_desc(va + kAtKTileBytes);
-        const uint32_t d_main = tmem_base + (uint32_t)(g * 256 + 128);
-        const uint32_t d_cross = d_main + 64;
+        const uint32_t d_o = tmem_base + (uint32_t)(g * 128 + 64);
 #pragma unroll
         for (int ks = 0; ks < kAtBK / 16; ++ks) {
           const uint64_t adv_a = (uint64_t)(ks * 32 >> 4);          // 16 keys along K inside P's swizzle atom
           const uint64_t adv_b = (uint64_t)(ks * 16 * 128 >> 4);    // 16 key rows of 128 B in the V tile
-          tc::umma_f16(d_main, p_hi + adv_a, v_hi + adv_b, idesc_o, ks > 0);
-          tc::umma_f16(d_cross, p_hi + adv_a, v_lo + adv_b, idesc_o, ks > 0);
-          tc::umma_f16(d_cross, p_lo + adv_a, v_hi + adv_b, idesc_o, 1u);
+          tc::umma_f16(d_o, p_lo + adv_a, v_hi + adv_b, idesc_o, ks > 0);
+          tc::umma_f16(d_o, p_hi + adv_a, v_lo + adv_b, idesc_o, 1u);
+          tc::umma_f16(d_o, p_hi + adv_a, v_hi + adv_b, idesc_o, 1u);
         }
         tc::umma_commit(&o_full[g]);
       };
@@ -171,7 +169,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     const int g = (warp - 2) >> 2;       // query tile of this warpgroup
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
     const int r = quarter * 32 + lane;   // row inside the tile
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 256);
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 128);
     uint8_t* p_hi_tile = sm_p + (g * 2 + 0) * kAtPTileBytes;
     uint8_t* p_lo_tile = sm_p + (g * 2 + 1) * kAtPTileBytes;
     float o[kAtD];
@@ -182,46 +180,39 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       const int valid = min(kAtBK, p.nk - j * kAtBK);
       tc::mbar_wait(&s_full[g], (uint32_t)(j & 1));
       tc::tc_fence_after();
-      // pass 1: row maximum
+      // the 64 scores of this row stay in registers between the max pass and the exp pass
+      uint32_t sc[kAtBK];
+      {
+        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[0]);
+        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[32]);
+        tc::tmem_ld_32x32(t_row, s0);
+        tc::tmem_ld_32x32(t_row + 32, s1);
+        tc::tmem_wait_ld();
+      }
       float mx = -INFINITY;
 #pragma unroll
-      for (int c = 0; c < kAtBK; c += 32) {
-        uint32_t a0[32], a1[32];
-        tc::tmem_ld_32x32(t_row + c, a0);
-        tc::tmem_ld_32x32(t_row + 64 + c, a1);
-        tc::tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float s = fmaf(__uint_as_float(a1[i]), tc::kLoInv, __uint_as_float(a0[i]));
-          if (c + i < valid) mx = fmaxf(mx, s);
-        }
-      }
+      for (int i = 0; i < kAtBK; ++i)
+        if (i < valid) mx = fmaxf(mx, __uint_as_float(sc[i]));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
       const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
       float lsum = 0.f;
-      // pass 2: probabilities -> fp16 hi/lo -> swizzled smem (A operand of the PV product)
+      // probabilities -> fp16 hi / lo -> swizzled smem (A operand of the PV product)
 #pragma unroll
-      for (int c = 0; c < kAtBK; c += 32) {
-        uint32_t a0[32], a1[32];
-        tc::tmem_ld_32x32(t_row + c, a0);
-        tc::tmem_ld_32x32(t_row + 64 + c, a1);
-        tc::tmem_wait_ld();
+      for (int i = 0; i < kAtBK; i += 8) {
+        float pv[8];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float pv[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float s = fmaf(__uint_as_float(a1[i + u]), tc::kLoInv, __uint_as_float(a0[i + u]));
-            pv[u] = (c + i + u < valid) ? exp2f(fmaf(s, p.scale_log2, -m_new)) : 0.f;
-            lsum += pv[u];
-          }
-          uint4 hv, lv;
-          tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv, lv);
-          const int chunk = (c + i) >> 3;  // 16-byte chunk index inside the 128-byte row
-          const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-          *reinterpret_cast<uint4*>(p_hi_tile + off) = hv;
-          *reinterpret_cast<uint4*>(p_lo_tile + off) = lv;
+        for (int u = 0; u < 8; ++u) {
+          // probabilities are carried scaled by 2^12 (<= 4096) so that their fp16 residuals stay normal numbers;
+          // the row sum carries the same factor, which cancels in the final O / l
+          pv[u] = (i + u < valid) ? exp2f(fmaf(__uint_as_float(sc[i + u]), p.scale_log2, 12.0f - m_new)) : 0.f;
+          lsum += pv[u];
         }
+        uint4 hv, lv;
+        tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv, lv);
+        const int chunk = i >> 3;  // 16-byte chunk index inside the 128-byte row
+        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(p_hi_tile + off) = hv;
+        *reinterpret_cast<uint4*>(p_lo_tile + off) = lv;
       }
       l_run = fmaf(l_run, alpha, lsum);
       m_run = m_new;
@@ -234,15 +225,11 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       tc::tc_fence_after();
 #pragma unroll
       for (int c = 0; c < kAtD; c += 32) {
-        uint32_t a0[32], a1[32];
-        tc::tmem_ld_32x32(t_row + 128 + c, a0);
-        tc::tmem_ld_32x32(t_row + 192 + c, a1);
+        uint32_t a0[32];
+        tc::tmem_ld_32x32(t_row + 64 + c, a0);
         tc::tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float pvv = fmaf(__uint_as_float(a1[i]), tc::kLoInv, __uint_as_float(a0[i]));
-          o[c + i] = fmaf(o[c + i], alpha, pvv);
-        }
+        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(a0[i]));
       }
     }
     const int q = q0 + g * kAtBQ + r;
@@ -269,7 +256,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<512>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
 }
 
 }  // namespace vidseg

@@ -53,16 +53,18 @@ void profile_after(cudaStream_t stream);
 
 // every kernel launch in the library goes through this so that launches are counted; when profiling
 // is enabled the launch is bracketed by CUDA events on its own stream (work = algorithmic FLOPs or bytes)
-#define VS_LAUNCH_W(work, kernel, grid, block, smem, stream, ...)                                  \
+#define VS_LAUNCH_FW(family, work, kernel, grid, block, smem, stream, ...)                         \
   do {                                                                                             \
     const bool _prof = vidseg::g_profile_on.load(std::memory_order_relaxed) != 0;                  \
-    if (_prof) vidseg::profile_before(VS_FAMILY, (double)(work), (cudaStream_t)(stream));          \
+    if (_prof) vidseg::profile_before((family), (double)(work), (cudaStream_t)(stream));           \
     kernel<<<(grid), (block), (smem), (cudaStream_t)(stream)>>>(__VA_ARGS__);                      \
     if (_prof) vidseg::profile_after((cudaStream_t)(stream));                                      \
     vidseg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                \
   } while (0)
+#define VS_LAUNCH_W(work, kernel, grid, block, smem, stream, ...) \
+  VS_LAUNCH_FW(VS_FAMILY, work, kernel, grid, block, smem, stream, __VA_ARGS__)
 #define VS_LAUNCH(kernel, grid, block, smem, stream, ...) \
-  VS_LAUNCH_W(0.0, kernel, grid, block, smem, stream, __VA_ARGS__)
+  VS_LAUNCH_FW(VS_FAMILY, 0.0, kernel, grid, block, smem, stream, __VA_ARGS__)
 
 #define VS_POST_LAUNCH() VS_CHECK_CUDA(cudaGetLastError())
 

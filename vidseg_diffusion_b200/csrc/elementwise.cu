@@ -1,0 +1,314 @@
+// Streaming (HBM-bound) kernels between the tensor-core GEMMs of the UNet: every one of them reads fp32
+// channels-last activations once and writes the split operand pair (hi | lo fp16) the next GEMM /
+// convolution consumes through TMA, so normalisation, activation, concatenation and operand conversion
+// cost one pass instead of four.
+//
+//   layernorm_split   nn.LayerNorm (sgm/modules/attention.py:567-569, norm1/2/3)                 one warp per token
+//   geglu_split       GEGLU: value * gelu(gate), erf form (attention.py:95-96)
+//   groupnorm_split   GroupNorm32 + SiLU of the ResBlocks (openaimodel.py:267-271, 300-303, util.py:276-278),
+//                     Normalize of SpatialTransformer (attention.py:127-130), over the channel concatenation of two
+//                     sources (the th.cat([h, hs.pop()], 1) of openaimodel.py:911) without materialising it
+//   upsample2x_split  nearest x2 (openaimodel.py:153) fused with the operand conversion of the following conv
+#define VS_FAMILY vidseg::kFamElementwise
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace vidseg {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm -> split.  One warp per row; the row lives in registers (C <= 32 * 4 * kLnMaxQuads).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLnMaxQuads = 16;  // C <= 2048
+
+__global__ void __launch_bounds__(256)
+layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                       float eps, __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nq = c >> 2;  // float4 per row
+  const float4* xr = reinterpret_cast<const float4*>(x + row * c);
+  float4 v[kLnMaxQuads];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) {
+      v[i] = ld_stream_f4(xr + q);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / (float)c;
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) {
+      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
+      s2 += (a * a + b * b) + (cc * cc + d * d);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(s2) / (float)c + eps);
+  uint2* hr = reinterpret_cast<uint2*>(hi + row * c);
+  uint2* lr = reinterpret_cast<uint2*>(lo + row * c);
+#pragma unroll
+  for (int i = 0; i < kLnMaxQuads; ++i) {
+    const int q = lane + 32 * i;
+    if (q < nq) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+      uint2 h, l;
+      tc::split4_f16((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y,
+                     (v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w, h, l);
+      hr[q] = h;
+      lr[q] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEGLU -> split.  h [rows, 2*d] = (value | gate); out [rows, d].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+geglu_split_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half* __restrict__ lo, long long rows,
+                   int d) {
+  const int dq = d >> 2;
+  const long long total = rows * dq;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / dq;
+    const int q = (int)(i - row * dq);
+    const float4* hr = reinterpret_cast<const float4*>(h + row * 2 * d);
+    const float4 val = ld_stream_f4(hr + q);
+    const float4 gate = ld_stream_f4(hr + dq + q);
+    uint2 a, b;
+    tc::split4_f16(val.x * gelu_erf_f(gate.x), val.y * gelu_erf_f(gate.y), val.z * gelu_erf_f(gate.z),
+                   val.w * gelu_erf_f(gate.w), a, b);
+    reinterpret_cast<uint2*>(hi + row * d)[q] = a;
+    reinterpret_cast<uint2*>(lo + row * d)[q] = b;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm (+SiLU) -> split over the channel concatenation [x1 (c1) | x2 (c2)], channels-last.
+// Pass 1: per (sample, pixel chunk) per-group sum and sum of squares, fixed summation order (deterministic).
+// Pass 2: normalise, affine, activation, operand split.
+// ---------------------------------------------------------------------------------------------
+constexpr int kGnChunks = 32;     // pixel chunks per sample in pass 1
+constexpr int kGnThreads = 256;
+constexpr int kGnMaxGroups = 32;
+
+__device__ __forceinline__ float4 gn_load(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
+                                          long long pix, int ch) {
+  if (ch < c1) return ld_stream_f4(reinterpret_cast<const float4*>(x1 + pix * c1 + ch));
+  return ld_stream_f4(reinterpret_cast<const float4*>(x2 + pix * c2 + (ch - c1)));
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int hw, int groups,
+                       double* __restrict__ partial /* [B, kGnChunks, groups, 2] */) {
+  extern __shared__ float sm[];  // [lanes][C][2]
+  const int c = c1 + c2;
+  const int nq = c >> 2;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  const int per = (hw + kGnChunks - 1) / kGnChunks;
+  const int p0 = chunk * per, p1 = min(hw, p0 + per);
+  // thread -> (pixel lane, first channel quad); with nq >= 256 every thread strides over the quads of one pixel
+  const int lanes = (nq >= kGnThreads) ? 1 : kGnThreads / nq;
+  const int qpl = (nq >= kGnThreads) ? kGnThreads : nq;  // threads per pixel lane
+  const int pl = threadIdx.x / qpl, q0 = threadIdx.x % qpl;
+  const bool active = pl < lanes;
+  const long long base = (long long)b * hw;
+  for (int q = q0; q < nq && active; q += qpl) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), s2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int pp = p0 + pl; pp < p1; pp += lanes) {
+      const float4 v = gn_load(x1, c1, x2, c2, base + pp, q * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      s2.x = fmaf(v.x, v.x, s2.x); s2.y = fmaf(v.y, v.y, s2.y); s2.z = fmaf(v.z, v.z, s2.z); s2.w = fmaf(v.w, v.w, s2.w);
+    }
+    float* dst = sm + ((size_t)pl * c + q * 4) * 2;
+    dst[0] = s.x; dst[1] = s2.x; dst[2] = s.y; dst[3] = s2.y; dst[4] = s.z; dst[5] = s2.z; dst[6] = s.w; dst[7] = s2.w;
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    const int g = threadIdx.x, cpg = c / groups;
+    double a = 0.0, a2 = 0.0;
+    for (int l = 0; l < lanes; ++l)
+      for (int ch = g * cpg; ch < (g + 1) * cpg; ++ch) {
+        a += (double)sm[((size_t)l * c + ch) * 2];
+        a2 += (double)sm[((size_t)l * c + ch) * 2 + 1];
+      }
+    double* out = partial + (((size_t)b * kGnChunks + chunk) * groups + g) * 2;
+    out[0] = a;
+    out[1] = a2;
+  }
+}
+
+__global__ void __launch_bounds__(kGnThreads)
+groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int hw, int groups,
+                       const double* __restrict__ partial, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out_hi,
+                       __half* __restrict__ out_lo, __half* __restrict__ raw_hi, __half* __restrict__ raw_lo,
+                       int pix_per_block) {
+  __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
+  const int c = c1 + c2;
+  const int nq = c >> 2;
+  const int b = blockIdx.y;
+  if (threadIdx.x < groups) {
+    double a = 0.0, a2 = 0.0;
+    for (int ch = 0; ch < kGnChunks; ++ch) {
+      const double* pp = partial + (((size_t)b * kGnChunks + ch) * groups + threadIdx.x) * 2;
+      a += pp[0];
+      a2 += pp[1];
+    }
+    const double cnt = (double)hw * (double)(c / groups);
+    const double mean = a / cnt;
+    double var = a2 / cnt - mean * mean;
+    if (var < 0.0) var = 0.0;
+    s_mean[threadIdx.x] = (float)mean;
+    s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+  __syncthreads();
+  const int cpg = c / groups;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
+  const long long total = (long long)(p1 - p0) * nq;
+  for (long long i = threadIdx.x; i < total; i += kGnThreads) {
+    const int pp = p0 + (int)(i / nq);
+    const int q = (int)(i % nq);
+    const int ch = q * 4;
+    const long long pix = (long long)b * hw + pp;
+    const float4 v = gn_load(x1, c1, x2, c2, pix, ch);
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+    const int g0 = ch / cpg, g1 = (ch + 1) / cpg, g2 = (ch + 2) / cpg, g3 = (ch + 3) / cpg;
+    float y0 = (v.x - s_mean[g0]) * s_rstd[g0] * g.x + bt.x;
+    float y1 = (v.y - s_mean[g1]) * s_rstd[g1] * g.y + bt.y;
+    float y2 = (v.z - s_mean[g2]) * s_rstd[g2] * g.z + bt.z;
+    float y3 = (v.w - s_mean[g3]) * s_rstd[g3] * g.w + bt.w;
+    if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
+    uint2 h, l;
+    tc::split4_f16(y0, y1, y2, y3, h, l);
+    reinterpret_cast<uint2*>(out_hi + pix * c)[q] = h;
+    reinterpret_cast<uint2*>(out_lo + pix * c)[q] = l;
+    if (raw_hi) {
+      tc::split4_f16(v.x, v.y, v.z, v.w, h, l);
+      reinterpret_cast<uint2*>(raw_hi + pix * c)[q] = h;
+      reinterpret_cast<uint2*>(raw_lo + pix * c)[q] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest-neighbour x2 upsampling -> split.  x [B, H, W, C] fp32 -> out [B, 2H, 2W, C].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int batch,
+                        int h, int w, int c) {
+  const int nq = c >> 2;
+  const long long total = (long long)batch * h * w * nq;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int q = (int)(i % nq);
+    const long long pix = i / nq;
+    const int xw = (int)(pix % w);
+    const int yh = (int)((pix / w) % h);
+    const int b = (int)(pix / ((long long)w * h));
+    const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(x + pix * c) + q);
+    uint2 a, bb;
+    tc::split4_f16(v.x, v.y, v.z, v.w, a, bb);
+#pragma unroll
+    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 2; ++dx) {
+        const long long op = ((long long)b * 2 * h + 2 * yh + dy) * (2 * w) + 2 * xw + dx;
+        reinterpret_cast<uint2*>(hi + op * c)[q] = a;
+        reinterpret_cast<uint2*>(lo + op * c)[q] = bb;
+      }
+  }
+}
+
+static int grid_for(long long work_items, int threads) {
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 16;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+}  // namespace vidseg
+
+using namespace vidseg;
+
+VS_API int vidseg_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, void* out_hi,
+                                  void* out_lo, long long rows, int channels, void* stream) {
+  VS_REQUIRE(x && gamma && beta && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(rows >= 0 && channels >= 4 && channels % 4 == 0 && channels <= 128 * kLnMaxQuads, "C must be a multiple of 4, <= 2048");
+  if (rows == 0) return 0;
+  const int warps = 8;
+  const long long grid = (rows + warps - 1) / warps;
+  VS_REQUIRE(grid <= 0x7fffffffLL, "too many rows");
+  VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel, (int)grid, warps * 32, 0, stream, x, gamma, beta, eps,
+              (__half*)out_hi, (__half*)out_lo, rows, channels);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_geglu_split(const float* h, void* out_hi, void* out_lo, long long rows, int d, void* stream) {
+  VS_REQUIRE(h && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(rows >= 0 && d >= 4 && d % 4 == 0, "D must be a multiple of 4");
+  if (rows == 0) return 0;
+  VS_LAUNCH_W(12.0 * rows * d, geglu_split_kernel, grid_for(rows * (d / 4), 256), 256, 0, stream, h, (__half*)out_hi,
+              (__half*)out_lo, rows, d);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API size_t vidseg_groupnorm_workspace_bytes(int batch, int groups) {
+  if (batch <= 0 || groups <= 0) return 0;
+  return (size_t)batch * kGnChunks * groups * 2 * sizeof(double);
+}
+
+VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int c2, const float* gamma, const float* beta,
+                                  float eps, int groups, int silu, void* out_hi, void* out_lo, void* raw_hi, void* raw_lo,
+                                  int batch, int hw, void* workspace, size_t workspace_bytes, void* stream) {
+  VS_REQUIRE(x1 && gamma && beta && out_hi && out_lo && workspace, "null pointer");
+  VS_REQUIRE((x2 == nullptr) == (c2 == 0), "x2 and c2 go together");
+  VS_REQUIRE((raw_hi == nullptr) == (raw_lo == nullptr), "raw_hi and raw_lo go together");
+  const int c = c1 + c2;
+  VS_REQUIRE(batch >= 0 && hw >= 1 && c1 >= 4 && c1 % 4 == 0 && c2 % 4 == 0, "channel counts must be multiples of 4");
+  VS_REQUIRE(groups >= 1 && groups <= kGnMaxGroups && c % groups == 0, "groups must divide C, <= 32");
+  VS_REQUIRE(batch <= 65535, "batch exceeds the grid limit");
+  if (batch == 0) return 0;
+  VS_REQUIRE(workspace_bytes >= vidseg_groupnorm_workspace_bytes(batch, groups), "group-norm workspace too small");
+  const int nq = c / 4;
+  const int lanes = (nq >= kGnThreads) ? 1 : kGnThreads / nq;
+  const size_t smem = (size_t)lanes * c * 2 * sizeof(float);
+  VS_REQUIRE(smem <= 48 * 1024, "C too large for the group-norm statistics kernel");
+  double* partial = reinterpret_cast<double*>(workspace);
+  const double bytes = 4.0 * batch * hw * c;
+  VS_LAUNCH_W(bytes, groupnorm_stats_kernel, dim3(kGnChunks, batch), kGnThreads, smem, stream, x1, c1, x2, c2, hw, groups,
+              partial);
+  VS_POST_LAUNCH();
+  // pass 2: ~16K quads per block
+  int pix_per_block = (16384 + nq - 1) / nq;
+  if (pix_per_block > hw) pix_per_block = hw;
+  const int blocks = (hw + pix_per_block - 1) / pix_per_block;
+  VS_LAUNCH_W(bytes * (raw_hi ? 3.0 : 2.0), groupnorm_apply_kernel, dim3(blocks, batch), kGnThreads, 0, stream, x1, c1, x2,
+              c2, hw, groups, partial, gamma, beta, eps, silu, (__half*)out_hi, (__half*)out_lo, (__half*)raw_hi,
+              (__half*)raw_lo, pix_per_block);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_upsample2x_split(const float* x, void* out_hi, void* out_lo, int batch, int h, int w, int c,
+                                   void* stream) {
+  VS_REQUIRE(x && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(batch >= 0 && h >= 1 && w >= 1 && c >= 4 && c % 4 == 0, "C must be a multiple of 4");
+  if (batch == 0) return 0;
+  const long long items = (long long)batch * h * w * (c / 4);
+  VS_LAUNCH_W(4.0 * batch * h * w * c * 5.0, upsample2x_split_kernel, grid_for(items, 256), 256, 0, stream, x,
+              (__half*)out_hi, (__half*)out_lo, batch, h, w, c);
+  VS_POST_LAUNCH();
+  return 0;
+}

@@ -44,7 +44,7 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-static int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                            const uint32_t* box) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return set_error(VIDSEG_E_UNSUPPORTED, "%s", "cuTensorMapEncodeTiled entry point not available");
@@ -53,7 +53,7 @@ static int encode_tmap_f16(CUtensorMap* out, const void* base, int rank, const u
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16 /* bf16 tiles move identically */, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(VIDSEG_E_INVALID, "%s: CUresult %lld (rank %lld)", "cuTensorMapEncodeTiled failed", (long long)r, (long long)rank);
@@ -65,77 +65,102 @@ int encode_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint6
   const uint64_t dims[2] = {inner, outer};
   const uint64_t strides[1] = {outer_stride_bytes};
   const uint32_t box[2] = {box_inner, box_outer};
-  return encode_tmap_f16(out, base, 2, dims, strides, box);
+  return encode_tmap_16bit(out, base, 2, dims, strides, box);
 }
 int encode_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                        uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
   const uint64_t dims[3] = {d0, d1, d2};
   const uint64_t strides[2] = {stride1_bytes, stride2_bytes};
   const uint32_t box[3] = {b0, b1, b2};
-  return encode_tmap_f16(out, base, 3, dims, strides, box);
+  return encode_tmap_16bit(out, base, 3, dims, strides, box);
 }
 
 // ---------------------------------------------------------------------------------------------
-// fp32 -> (hi, lo) fp16 split, elementwise, 128-bit loads / 64-bit stores
+// fp32 -> (hi, lo) fp16 split of x * scale, elementwise, 128-bit loads / 64-bit stores
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict__ x, __half* __restrict__ hi,
-                                                        __half* __restrict__ lo, size_t n4, size_t n) {
+                                                        __half* __restrict__ lo, size_t n4, size_t n, float scale) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 v = reinterpret_cast<const float4*>(x)[i];
-    __half h[4], l[4];
-    tc::split_f16(v.x, h[0], l[0]);
-    tc::split_f16(v.y, h[1], l[1]);
-    tc::split_f16(v.z, h[2], l[2]);
-    tc::split_f16(v.w, h[3], l[3]);
-    reinterpret_cast<uint2*>(hi)[i] = *reinterpret_cast<uint2*>(h);
-    reinterpret_cast<uint2*>(lo)[i] = *reinterpret_cast<uint2*>(l);
+    uint2 h, l;
+    tc::split4_f16(v.x * scale, v.y * scale, v.z * scale, v.w * scale, h, l);
+    reinterpret_cast<uint2*>(hi)[i] = h;
+    reinterpret_cast<uint2*>(lo)[i] = l;
   }
   // tail (n not a multiple of 4)
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-    __half h, l;
-    tc::split_f16(x[i], h, l);
+    __half h;
+    __half l;
+    tc::split_f16(x[i] * scale, h, l);
     hi[i] = h;
     lo[i] = l;
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// split GEMM
+// split GEMM / implicit-GEMM convolution
+//
+// out[p, n] = sum_{tap, c} A[pixel p shifted by tap, c] * W[n, tap*Cin + c]  (+ bias[n]) (+ chan_bias[b(p), n])
+//             (+ residual[p, n])
+// The A operand is a channels-last activation tensor seen through a rank-5 TMA map
+// (C', W', P, H', B): a 128-pixel tile is a bw x bh x bb patch of the OUTPUT grid, and the tile of tap (dy, dx) is
+// the same patch shifted by the tap offset -- out-of-range pixels (the zero padding of the convolution) are
+// filled by the TMA unit, so no im2col matrix ever exists.  A plain Linear is the 1-tap case with W' = M.
+// Stride-2 convolutions view [B, H, W, C] as [B, H/2, 2, W/2, 2C] so that the row/column parity of a tap becomes
+// a coordinate (P) / channel offset.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGemmBM = 128, kGemmBN = 128, kGemmBK = 64, kGemmStages = 3, kGemmAccStages = 2;
+constexpr int kGemmBM = 128, kGemmBK = 64, kGemmAccStages = 2;
 constexpr int kTileABytes = kGemmBM * kGemmBK * 2;  // 16 KB
-constexpr int kTileBBytes = kGemmBN * kGemmBK * 2;  // 16 KB
-constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
-constexpr int kGemmSmemBytes = kGemmStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int kMaxTaps = 9;
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kTileBBytes = BN * kGemmBK * 2;
+  static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
+  static constexpr int kStages = (BN <= 128) ? 3 : (BN <= 160 ? 3 : 2);
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
+  static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
+};
 
 struct GemmParams {
-  int m, n, k;
-  const float* bias;      // [N] or null
-  const float* residual;  // [M, N] or null
-  float* out_f32;         // [M, N] or null
-  __half* out_hi;         // [M, N] or null
+  int n, k;                 // GEMM N and K (K = taps * cin)
+  int taps, cin, kc_per_tap;
+  int bw, bh, bb;           // tile patch (bw * bh * bb == 128)
+  int wo, ho, nb;           // output pixel grid; M = nb * ho * wo
+  int tiles_w, tiles_h, tiles_b;
+  int c_off[kMaxTaps], w_off[kMaxTaps], p_idx[kMaxTaps], h_off[kMaxTaps];
+  float acc_scale;          // exact power-of-two inverse of the operand pre-scaling (weights carry 2^8)
+  const float* bias;        // [N] or null
+  const float* chan_bias;   // [nb, N] or null (per-sample channel bias: the ResBlock time embedding)
+  const float* residual;    // [M, N] or null
+  float* out_f32;           // [M, N] or null
+  __half* out_hi;           // [M, N] or null
   __half* out_lo;
 };
 
+template <int BN>
 __global__ void __launch_bounds__(256, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                   const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
-                  const GemmParams p) {
+                  const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kGemmStages * kStageBytes);
-  uint64_t* empty_bar = full_bar + kGemmStages;
-  uint64_t* tmem_full_bar = empty_bar + kGemmStages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kGemmAccStages;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + kGemmAccStages);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.m + kGemmBM - 1) / kGemmBM;
-  const int n_tiles = (p.n + kGemmBN - 1) / kGemmBN;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
+  const int n_tiles = (p.n + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int k_blocks = (p.k + kGemmBK - 1) / kGemmBK;
+  const int k_blocks = p.taps * p.kc_per_tap;
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a_hi);
@@ -144,11 +169,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     tc::prefetch_tmap(&tmap_b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kGemmStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 128); }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc<512>(tmem_base_ptr);
+  if (warp == 2) tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -160,25 +185,32 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kGemmBM;
-        const int n0 = (tile % n_tiles) * kGemmBN;
-        for (int kb = 0; kb < k_blocks; ++kb) {
-          tc::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* st = smem + stage * kStageBytes;
-          tc::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          const int k0 = kb * kGemmBK;
-          tc::tma_load_2d(st, &tmap_a_hi, &full_bar[stage], k0, m0);
-          tc::tma_load_2d(st + kTileABytes, &tmap_a_lo, &full_bar[stage], k0, m0);
-          tc::tma_load_2d(st + 2 * kTileABytes, &tmap_b_hi, &full_bar[stage], k0, n0);
-          tc::tma_load_2d(st + 2 * kTileABytes + kTileBBytes, &tmap_b_lo, &full_bar[stage], k0, n0);
-          if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+        const int mt = tile / n_tiles;
+        const int n0 = (tile % n_tiles) * BN;
+        const int w0 = (mt % p.tiles_w) * p.bw;
+        const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
+        const int b0 = (mt / (p.tiles_w * p.tiles_h)) * p.bb;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int cw = w0 + p.w_off[tap], ch = h0 + p.h_off[tap], cp = p.p_idx[tap];
+          for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+            tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* st = smem + stage * Cfg::kStageBytes;
+            tc::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+            const int ca = p.c_off[tap] + kc * kGemmBK;
+            const int kb0 = tap * p.cin + kc * kGemmBK;
+            tc::tma_load_5d(st, &tmap_a_hi, &full_bar[stage], ca, cw, cp, ch, b0);
+            tc::tma_load_5d(st + kTileABytes, &tmap_a_lo, &full_bar[stage], ca, cw, cp, ch, b0);
+            tc::tma_load_2d(st + 2 * kTileABytes, &tmap_b_hi, &full_bar[stage], kb0, n0);
+            tc::tma_load_2d(st + 2 * kTileABytes + Cfg::kTileBBytes, &tmap_b_lo, &full_bar[stage], kb0, n0);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_f16(kGemmBM, kGemmBN, 0, 0);
+      constexpr uint32_t idesc = tc::make_idesc_f16(kGemmBM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -186,27 +218,26 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
-        const uint32_t d_main = tmem_base + (uint32_t)(acc * 2 * kGemmBN);
-        const uint32_t d_cross = d_main + kGemmBN;
+        const uint32_t d_acc = tmem_base + (uint32_t)(acc * Cfg::kAccStride);
         for (int kb = 0; kb < k_blocks; ++kb) {
           tc::mbar_wait(&full_bar[stage], phase);
           tc::tc_fence_after();
-          const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+          const uint32_t sa = tc::smem_u32(smem + stage * Cfg::kStageBytes);
           const uint64_t a_hi = tc::make_sw128_desc(sa);
           const uint64_t a_lo = tc::make_sw128_desc(sa + kTileABytes);
           const uint64_t b_hi = tc::make_sw128_desc(sa + 2 * kTileABytes);
-          const uint64_t b_lo = tc::make_sw128_desc(sa + 2 * kTileABytes + kTileBBytes);
+          const uint64_t b_lo = tc::make_sw128_desc(sa + 2 * kTileABytes + Cfg::kTileBBytes);
 #pragma unroll
           for (int ks = 0; ks < kGemmBK / 16; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 fp16 = 32 bytes along K inside the swizzle atom
-            const uint32_t accum = (kb > 0 || ks > 0) ? 1u : 0u;
-            tc::umma_f16(d_main, a_hi + adv, b_hi + adv, idesc, accum);
-            tc::umma_f16(d_cross, a_hi + adv, b_lo + adv, idesc, accum);
-            tc::umma_f16(d_cross, a_lo + adv, b_hi + adv, idesc, 1u);
+            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 elements = 32 bytes along K inside the swizzle atom
+            // small terms first, so that they are not absorbed one by one into a large partial sum
+            tc::umma_f16(d_acc, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+            tc::umma_f16(d_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+            tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
           }
           tc::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
           if (kb == k_blocks - 1) tc::umma_commit(&tmem_full_bar[acc]);
-          if (++stage == kGemmStages) { stage = 0; phase ^= 1; }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
       }
@@ -214,39 +245,57 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   } else if (warp >= 4) {
     // ===================== epilogue =====================
     const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+    const int r = ew * 32 + lane;  // row of the tile = pixel of the patch
+    const int pw = r % p.bw, ph = (r / p.bw) % p.bh, pb = r / (p.bw * p.bh);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile / n_tiles) * kGemmBM;
-      const int n0 = (tile % n_tiles) * kGemmBN;
+      const int mt = tile / n_tiles;
+      const int n0 = (tile % n_tiles) * BN;
+      const int w = (mt % p.tiles_w) * p.bw + pw;
+      const int h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + ph;
+      const int b = (mt / (p.tiles_w * p.tiles_h)) * p.bb + pb;
+      const bool row_ok = (w < p.wo) && (h < p.ho) && (b < p.nb);
+      const size_t pix = ((size_t)b * p.ho + h) * p.wo + w;
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
-      const int row = m0 + ew * 32 + lane;
-      const uint32_t t_main = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * 2 * kGemmBN);
+      const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
 #pragma unroll 1
-      for (int c = 0; c < kGemmBN; c += 32) {
-        uint32_t r0[32], r1[32];
-        tc::tmem_ld_32x32(t_main + c, r0);
-        tc::tmem_ld_32x32(t_main + kGemmBN + c, r1);
-        tc::tmem_wait_ld();
+      for (int c = 0; c < BN; c += 32) {
         const int col0 = n0 + c;
-        if (row < p.m && col0 < p.n) {
+        if (col0 >= p.n) break;  // warp-uniform
+        uint32_t rr[32];
+        tc::tmem_ld_32x32(t_acc + c, rr);
+        tc::tmem_wait_ld();
+        if (row_ok) {
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r1[j]), tc::kLoInv, __uint_as_float(r0[j]));
-          const int ncols = min(32, p.n - col0);  // N % 8 == 0 is required by the host wrapper
-          const size_t off = (size_t)row * p.n + col0;
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.acc_scale;
+          const int ncols = min(32, p.n - col0);  // N % 4 == 0 is required by the host wrapper
+          const size_t off = pix * p.n + col0;
           if (p.bias) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (j < ncols) v[j] += __ldg(p.bias + col0 + j);
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) {
+                const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
+              }
+          }
+          if (p.chan_bias) {
+            const float* cb = p.chan_bias + (size_t)b * p.n + col0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) {
+                const float4 bb4 = __ldg(reinterpret_cast<const float4*>(cb + j));
+                v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
+              }
           }
           if (p.residual) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (j < ncols) {
-                const float4 rr = *reinterpret_cast<const float4*>(p.residual + off + j);
-                v[j] += rr.x; v[j + 1] += rr.y; v[j + 2] += rr.z; v[j + 3] += rr.w;
+                const float4 q = *reinterpret_cast<const float4*>(p.residual + off + j);
+                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
               }
           }
           if (p.out_f32) {
@@ -273,7 +322,57 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 2) tc::tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tc::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+// 128-pixel tile = bw x bh x bb patch (powers of two) of the output grid that pads the grid the least;
+// ties go to the widest, then tallest patch (longest contiguous runs for TMA and for the epilogue stores)
+static void pick_patch(int wo, int ho, int nb, int* bw_out, int* bh_out, int* bb_out) {
+  long best = -1;
+  for (int bw = 128; bw >= 1; bw /= 2)
+    for (int bh = 128 / bw; bh >= 1; bh /= 2) {
+      const int bb = 128 / (bw * bh);
+      const long vol = (long)((wo + bw - 1) / bw) * bw * ((ho + bh - 1) / bh) * bh * ((nb + bb - 1) / bb) * bb;
+      if (best < 0 || vol < best) { best = vol; *bw_out = bw; *bh_out = bh; *bb_out = bb; }
+    }
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const void* w_hi, const void* w_lo,
+                       const GemmParams& p, double flops, int family, void* stream) {
+  using Cfg = GemmCfg<BN>;
+  CUtensorMap tb_hi, tb_lo;
+  if (int e = encode_tmap_2d_f16(&tb_hi, w_hi, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN)) return e;
+  if (int e = encode_tmap_2d_f16(&tb_lo, w_lo, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN)) return e;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  VS_CHECK_CUDA(attr_err);
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b, n_tiles = (p.n + BN - 1) / BN;
+  const int grid = std::min(m_tiles * n_tiles, kNumSMs);
+  VS_LAUNCH_FW(family, flops, gemm_split_kernel<BN>, grid, 256, Cfg::kSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+// shared host path of the Linear and convolution entry points
+static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, const uint64_t* astrides, GemmParams p,
+                    const void* w_hi, const void* w_lo, int family, void* stream) {
+  pick_patch(p.wo, p.ho, p.nb, &p.bw, &p.bh, &p.bb);
+  p.tiles_w = (p.wo + p.bw - 1) / p.bw;
+  p.tiles_h = (p.ho + p.bh - 1) / p.bh;
+  p.tiles_b = (p.nb + p.bb - 1) / p.bb;
+  p.kc_per_tap = (p.cin + kGemmBK - 1) / kGemmBK;
+  const uint32_t box[5] = {(uint32_t)kGemmBK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
+  CUtensorMap ta_hi, ta_lo;
+  if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
+  if (int e = encode_tmap_16bit(&ta_lo, a_lo, 5, adims, astrides, box)) return e;
+  const double flops = 2.0 * (double)p.nb * p.ho * p.wo * (double)p.n * (double)p.k;
+  if (p.n % 256 == 0) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  if (p.n % 160 == 0) return launch_gemm<160>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
 }
 
 }  // namespace vidseg
@@ -282,14 +381,14 @@ using namespace vidseg;
 
 #undef VS_FAMILY
 #define VS_FAMILY vidseg::kFamElementwise
-VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, void* stream) {
+VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, float scale, void* stream) {
   VS_REQUIRE(n >= 0, "negative size");
   if (n == 0) return 0;
   VS_REQUIRE(x && hi && lo, "null pointer");
   VS_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)hi % 8 == 0) && ((uintptr_t)lo % 8 == 0), "unaligned pointer");
   const size_t n4 = (size_t)n / 4;
   int grid = (int)std::min<size_t>((n4 + 255) / 256 + 1, (size_t)kNumSMs * 8);
-  VS_LAUNCH_W(8.0 * n, split_f16_kernel, grid, 256, 0, stream, x, (__half*)hi, (__half*)lo, n4, (size_t)n);
+  VS_LAUNCH_W(8.0 * n, split_f16_kernel, grid, 256, 0, stream, x, (__half*)hi, (__half*)lo, n4, (size_t)n, scale);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -298,28 +397,73 @@ VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, voi
 #define VS_FAMILY vidseg::kFamGemm
 VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                              const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
-                             void* stream) {
+                             float acc_scale, void* stream) {
   VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null operand pointer");
   VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
   VS_REQUIRE(m >= 0 && n >= 1 && k >= 1, "bad shape");
-  VS_REQUIRE(n % 8 == 0 && k % 8 == 0, "N and K must be multiples of 8 (16-byte rows for TMA and vector stores)");
+  VS_REQUIRE(n % 4 == 0 && k % 8 == 0, "N must be a multiple of 4 and K of 8 (16-byte rows for TMA and vector stores)");
+  VS_REQUIRE(out_hi == nullptr || n % 8 == 0, "split output needs N % 8 == 0");
   if (m == 0) return 0;
-  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
-  if (int e = encode_tmap_2d_f16(&ta_hi, a_hi, k, m, (uint64_t)k * 2, kGemmBK, kGemmBM)) return e;
-  if (int e = encode_tmap_2d_f16(&ta_lo, a_lo, k, m, (uint64_t)k * 2, kGemmBK, kGemmBM)) return e;
-  if (int e = encode_tmap_2d_f16(&tb_hi, w_hi, k, n, (uint64_t)k * 2, kGemmBK, kGemmBN)) return e;
-  if (int e = encode_tmap_2d_f16(&tb_lo, w_lo, k, n, (uint64_t)k * 2, kGemmBK, kGemmBN)) return e;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmemBytes);
-  });
-  VS_CHECK_CUDA(attr_err);
-  GemmParams p{m, n, k, bias, residual, out_f32, (__half*)out_hi, (__half*)out_lo};
-  const int m_tiles = (m + kGemmBM - 1) / kGemmBM, n_tiles = (n + kGemmBN - 1) / kGemmBN;
-  const int grid = std::min(m_tiles * n_tiles, kNumSMs);
-  VS_LAUNCH_W(2.0 * m * n * k, gemm_split_kernel, grid, 256, kGemmSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
-  VS_POST_LAUNCH();
-  return 0;
+  GemmParams p{};
+  p.n = n; p.k = k; p.taps = 1; p.cin = k;
+  p.wo = m; p.ho = 1; p.nb = 1;
+  p.acc_scale = acc_scale;
+  p.bias = bias; p.residual = residual; p.out_f32 = out_f32;
+  p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
+  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
+  const uint64_t row = (uint64_t)k * 2;
+  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
+  return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, kFamGemm, stream);
+}
+
+#undef VS_FAMILY
+#define VS_FAMILY vidseg::kFamConv
+VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               const float* chan_bias, const float* residual, float* out_f32, void* out_hi, void* out_lo,
+                               int batch, int height, int width, int cin, int cout, int ksize, int stride, float acc_scale,
+                               void* stream) {
+  VS_REQUIRE(x_hi && x_lo && w_hi && w_lo, "null operand pointer");
+  VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
+  VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
+  VS_REQUIRE(batch >= 0 && height >= 1 && width >= 1 && cin >= 1 && cout >= 1, "bad shape");
+  VS_REQUIRE((ksize == 1 || ksize == 3) && (stride == 1 || stride == 2), "kernel 1 or 3, stride 1 or 2");
+  VS_REQUIRE(ksize == 3 || stride == 1, "1x1 convolutions are stride 1");
+  VS_REQUIRE(cin % 8 == 0 && cout % 4 == 0, "Cin must be a multiple of 8 and Cout of 4");
+  VS_REQUIRE(out_hi == nullptr || cout % 8 == 0, "split output needs Cout % 8 == 0");
+  if (batch == 0) return 0;
+  GemmParams p{};
+  p.taps = ksize * ksize;
+  p.cin = cin;
+  p.n = cout; p.k = p.taps * cin;
+  p.bias = bias; p.chan_bias = chan_bias; p.residual = residual; p.out_f32 = out_f32;
+  p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
+  p.nb = batch;
+  p.acc_scale = acc_scale;
+  uint64_t adims[5], astrides[4];
+  const uint64_t px = (uint64_t)cin * 2;  // bytes per pixel
+  if (stride == 1) {
+    p.wo = width; p.ho = height;
+    adims[0] = cin; adims[1] = width; adims[2] = 1; adims[3] = height; adims[4] = batch;
+    astrides[0] = px; astrides[1] = px * width; astrides[2] = px * width; astrides[3] = px * width * height;
+    for (int t = 0; t < p.taps; ++t) {
+      const int dy = (ksize == 3) ? t / 3 - 1 : 0, dx = (ksize == 3) ? t % 3 - 1 : 0;
+      p.c_off[t] = 0; p.w_off[t] = dx; p.p_idx[t] = 0; p.h_off[t] = dy;
+    }
+  } else {
+    VS_REQUIRE(height % 2 == 0 && width % 2 == 0, "stride-2 convolution needs even H and W");
+    VS_REQUIRE(cin % 64 == 0, "stride-2 convolution needs Cin % 64 == 0 (a 64-channel chunk must not straddle pixels)");
+    p.wo = width / 2; p.ho = height / 2;
+    // [B, H, W, C] viewed as (2C, W/2, 2, H/2, B): input row 2*ho + dy - 1 -> (parity, index) = dy==1 ? (0, ho) : (1, ho + (dy-1)/2 ...)
+    adims[0] = 2 * (uint64_t)cin; adims[1] = width / 2; adims[2] = 2; adims[3] = height / 2; adims[4] = batch;
+    astrides[0] = 2 * px; astrides[1] = px * width; astrides[2] = 2 * px * width; astrides[3] = px * width * height;
+    for (int t = 0; t < 9; ++t) {
+      const int dy = t / 3, dx = t % 3;  // input row = 2*ho + dy - 1, column = 2*wo + dx - 1
+      p.p_idx[t] = (dy == 1) ? 0 : 1;
+      p.h_off[t] = (dy == 0) ? -1 : 0;
+      p.c_off[t] = (dx == 1) ? 0 : cin;
+      p.w_off[t] = (dx == 0) ? -1 : 0;
+    }
+  }
+  return run_gemm(x_hi, x_lo, adims, astrides, p, w_hi, w_lo, kFamConv, stream);
 }

@@ -2,6 +2,7 @@
 // tcgen05 MMA / TMEM, shared-memory matrix descriptors.  Raw PTX, no CUTLASS dependency.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -69,6 +70,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+__device__ __forceinline__ void tma_load_5d(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+
 // ---- TMEM ----
 template <int NCOLS>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {
@@ -115,9 +125,12 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr_bytes) {
 // Instruction descriptor for kind::f16 with fp16 operands and fp32 accumulation
 // (cute::UMMA::InstrDescriptor): c_format[4,6)=1 (F32), a/b_format=0 (F16), a_major bit15, b_major bit16,
 // n_dim[17,23)=N>>3, m_dim[24,29)=M>>4.
-__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major, int b_mn_major) {
-  return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) |
-         ((uint32_t)(m >> 4) << 24);
+// a_bf16 / b_bf16 select the operand element type (a_format bits [7,10), b_format bits [10,13): 0 = F16, 1 = BF16);
+// the hardware requires both operands of one MMA to have the same format.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int a_mn_major, int b_mn_major, int a_bf16 = 0,
+                                                      int b_bf16 = 0) {
+  return (1u << 4) | ((uint32_t)a_bf16 << 7) | ((uint32_t)b_bf16 << 10) | ((uint32_t)a_mn_major << 15) |
+         ((uint32_t)b_mn_major << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -134,22 +147,27 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
                : "memory");
 }
 
-// split an fp32 value into fp16 hi + fp16 lo*2^11 (x ~= hi + lo / 2048, ~22 significant bits)
-constexpr float kLoScale = 2048.0f;
-constexpr float kLoInv = 1.0f / 2048.0f;
+// Split an fp32 value into hi = fp16(x) and lo = fp16(x - hi): x ~= hi + lo.  All three products
+// lo.hi + hi.lo + hi.hi of a split GEMM accumulate in ONE fp32 TMEM accumulator.  (tcgen05 kind::f16 rejects an
+// fp16 x bf16 operand mix -- illegal instruction, measured -- so lo cannot borrow bf16's exponent range.)
+// |lo| <= 2^-12 |x| is a normal fp16 number for |x| >= ~0.25 (22 significant bits); below that the residual falls
+// into fp16's subnormals and the absolute error of the pair is bounded by 2^-25 ~ 3e-8.  Operands whose values
+// are systematically tiny are therefore carried pre-scaled by a power of two and the exact inverse is applied to
+// the fp32 accumulator: weights x 2^8 (kWeightScale), softmax probabilities x 2^12 (cancels in the normalisation).
+// Activations are unscaled, so the overflow threshold is fp16's 65504 -- the same as the reference's own
+// fp16-autocast GPU path.
+constexpr float kWeightScale = 256.0f;
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   hi = __float2half_rn(x);
-  lo = __float2half_rn((x - __half2float(hi)) * kLoScale);
+  lo = __float2half_rn(x - __half2float(hi));
 }
-
 __device__ __forceinline__ uint32_t h2_bits(__half2 h) { return *reinterpret_cast<uint32_t*>(&h); }
 // two fp32 -> packed (hi, hi) and (lo, lo) fp16 pairs, all in registers
 __device__ __forceinline__ void split2_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __half2 h = __floats2half2_rn(a, b);
   const float2 hf = __half22float2(h);
-  const __half2 l = __floats2half2_rn((a - hf.x) * kLoScale, (b - hf.y) * kLoScale);
   hi = h2_bits(h);
-  lo = h2_bits(l);
+  lo = h2_bits(__floats2half2_rn(a - hf.x, b - hf.y));
 }
 // eight fp32 -> one 16-byte vector of fp16 hi and one of fp16 lo
 __device__ __forceinline__ void split8_f16(float v0, float v1, float v2, float v3, float v4, float v5, float v6, float v7,
@@ -159,6 +177,10 @@ __device__ __forceinline__ void split8_f16(float v0, float v1, float v2, float v
   split2_f16(v4, v5, hi.z, lo.z);
   split2_f16(v6, v7, hi.w, lo.w);
 }
+__device__ __forceinline__ void split4_f16(float v0, float v1, float v2, float v3, uint2& hi, uint2& lo) {
+  split2_f16(v0, v1, hi.x, lo.x);
+  split2_f16(v2, v3, hi.y, lo.y);
+}
 
 }  // namespace tc
 
@@ -167,5 +189,8 @@ int encode_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint6
                        uint32_t box_inner, uint32_t box_outer);
 int encode_tmap_3d_f16(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
                        uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+// generic rank-1..5 map of 16-bit elements (fp16 and bf16 tiles move identically), 128-byte swizzle, zero OOB fill
+int encode_tmap_16bit(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                      const uint32_t* box);
 
 }  // namespace vidseg

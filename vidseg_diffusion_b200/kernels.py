@@ -1,18 +1,21 @@
 """Functional layer between the ``sgm`` operator mirrors and libvidseg_b200.
 
-Every function takes / returns CUDA tensors and launches on the caller's current stream.  Weights
-are nn.Parameters owned by the modules; their tensor-core operand form (fp16 hi/lo split, conv
-kernels re-laid as [Cout, taps*Cin]) is derived once and cached until the parameter changes.
+Every function takes / returns CUDA tensors and launches on the caller's current stream.  Image-shaped
+activations are ``[B, C, H, W]`` tensors in ``torch.channels_last`` memory format, i.e. the memory the
+kernels see is ``[B, H, W, C]``: tokens of the transformer blocks and pixels of the convolutions are the
+same rows, no transposes exist anywhere in the forward.  Weights are nn.Parameters owned by the modules;
+their tensor-core operand form (hi | lo fp16 split, conv kernels re-laid tap-major as
+[Cout, ky*kx*Cin]) is derived once and cached until the parameter changes.
 """
 import weakref
 
 import torch
-import torch.nn.functional as F
 
 from . import _lib
-from .linear import Split, attention_split, gemm_split, split
+from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, split
 
 _WEIGHT_CACHE = {}
+_WORKSPACES = {}
 
 
 def _cached(param, tag, make):
@@ -30,14 +33,76 @@ def clear_weight_cache():
     _WEIGHT_CACHE.clear()
 
 
+def _f32(param, tag="f32"):
+    return _cached(param, tag, lambda t: t.float().contiguous())
+
+
 def weight_split(param):
     """[N, K] nn.Linear weight -> cached Split."""
-    return _cached(param, "lin", lambda w: split(w.float().contiguous()))
+    return _cached(param, "lin", lambda w: split(w.float().contiguous(), WEIGHT_SCALE))
 
 
+def conv_weight_split(param, cin_pad=None):
+    """[Cout, Cin, kh, kw] nn.Conv2d weight -> cached Split of [Cout, kh*kw*Cin'] (tap-major, Cin padded)."""
+    def make(w):
+        w = w.float().permute(0, 2, 3, 1)  # [Cout, kh, kw, Cin]
+        if cin_pad is not None and cin_pad != w.shape[-1]:
+            w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
+        return split(w.reshape(w.shape[0], -1).contiguous(), WEIGHT_SCALE)
+    return _cached(param, f"conv{cin_pad}", make)
+
+
+def _workspace(device, nbytes):
+    key = (device.type, device.index)
+    ws = _WORKSPACES.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _WORKSPACES[key] = ws
+    return ws
+
+
+def _require(x, name):
+    return _lib.require_cuda_tensor(x, torch.float32, name)
+
+
+def nhwc(x, name="x"):
+    """[B, C, H, W] fp32 CUDA tensor (any memory format) -> contiguous [B, H, W, C] view / copy."""
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise _lib.VidsegError(f"{name}: expected a CUDA tensor (the hot path has no CPU fallback)")
+    if x.dtype != torch.float32 or x.dim() != 4:
+        raise _lib.VidsegError(f"{name}: expected a 4-d float32 tensor, got {x.dtype} {tuple(x.shape)}")
+    return x.permute(0, 2, 3, 1).contiguous()
+
+
+def as_nchw(t):
+    """contiguous [B, H, W, C] -> [B, C, H, W] view (channels_last strides)."""
+    return t.permute(0, 3, 1, 2)
+
+
+class ChannelCat:
+    """``torch.cat([a, b], dim=1)`` that is never materialised: the consuming GroupNorm kernel reads both sources."""
+
+    def __init__(self, a, b):
+        if a.shape[0] != b.shape[0] or a.shape[2:] != b.shape[2:]:
+            raise _lib.VidsegError(f"concat_channels: shape mismatch {tuple(a.shape)} vs {tuple(b.shape)}")
+        self.a, self.b = a, b
+        self.shape = (a.shape[0], a.shape[1] + b.shape[1], a.shape[2], a.shape[3])
+        self.device = a.device
+
+    def materialize(self):
+        return torch.cat([self.a, self.b], dim=1)
+
+
+def concat_channels(a, b):
+    return ChannelCat(a, b)
+
+
+# ------------------------------------------------------------------------------------------------
+# tensor-core ops
+# ------------------------------------------------------------------------------------------------
 def linear(xs, weight, bias=None, residual=None, want_f32=True, want_split=False):
     """nn.Linear on a Split activation: xs [.., K] x weight[N, K]^T (+ bias) (+ residual)."""
-    b = None if bias is None else _cached(bias, "bias", lambda t: t.float().contiguous())
+    b = None if bias is None else _f32(bias)
     return gemm_split(xs, weight_split(weight), b, residual, want_f32=want_f32, want_split=want_split)
 
 
@@ -45,75 +110,125 @@ def attention(qs, ks, vs, heads, scale):
     return attention_split(qs, ks, vs, heads, scale, want_f32=False, want_split=True)
 
 
-def _require(x, name):
-    return _lib.require_cuda_tensor(x, torch.float32, name)
+def conv2d(xs, conv, chan_bias=None, residual=None):
+    """nn.Conv2d on a Split activation xs [B, H, W, Cin'] -> fp32 [B, Cout, Ho, Wo] (channels_last memory).
+    chan_bias [B, Cout] is added per sample and channel; residual is an image-shaped fp32 tensor."""
+    k, stride = conv.kernel_size[0], conv.stride[0]
+    if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or conv.padding[0] != k // 2 or stride not in (1, 2):
+        raise _lib.VidsegError(f"conv2d: unsupported geometry {conv}")
+    b, h, w, cin = xs.hi.shape
+    cout = conv.out_channels
+    ws = conv_weight_split(conv.weight, cin)
+    if ws.hi.shape[1] != k * k * cin:
+        raise _lib.VidsegError(f"conv2d: activation has {cin} channels, weight expects {conv.in_channels}")
+    ho, wo = h // stride, w // stride
+    out = torch.empty((b, ho, wo, cout), dtype=torch.float32, device=xs.hi.device)
+    res = None
+    if residual is not None:
+        res = nhwc(residual, "residual")
+        if res.shape != out.shape:
+            raise _lib.VidsegError("conv2d: residual shape mismatch")
+    if chan_bias is not None:
+        _require(chan_bias, "chan_bias")
+        if tuple(chan_bias.shape) != (b, cout):
+            raise _lib.VidsegError("conv2d: chan_bias must be [B, Cout]")
+    bias = None if conv.bias is None else _f32(conv.bias)
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.vidseg_conv2d_split(
+            xs.hi.data_ptr(), xs.lo.data_ptr(), ws.hi.data_ptr(), ws.lo.data_ptr(),
+            bias.data_ptr() if bias is not None else None,
+            chan_bias.data_ptr() if chan_bias is not None else None,
+            res.data_ptr() if res is not None else None,
+            out.data_ptr(), None, None, b, h, w, cin, cout, k, stride, 1.0 / (xs.scale * ws.scale), _lib.stream_ptr()), "conv2d_split")
+    return as_nchw(out)
 
 
 # ------------------------------------------------------------------------------------------------
-# normalisation / gating kernels
+# normalisation / gating / resampling kernels (all emit the split operand of the next GEMM)
 # ------------------------------------------------------------------------------------------------
+def _empty_split(shape, device):
+    return Split(torch.empty(shape, dtype=torch.float16, device=device), torch.empty(shape, dtype=torch.float16, device=device))
+
+
 def layer_norm_split(x, ln):
-    """LayerNorm over the last dim (eps from the module) -> Split operand of the next GEMM."""
+    """LayerNorm over the last dim -> Split operand of the next GEMM."""
     _require(x, "x")
-    y = F.layer_norm(x, (x.shape[-1],), ln.weight, ln.bias, ln.eps)
-    return split(y)
+    c = x.shape[-1]
+    out = _empty_split(x.shape, x.device)
+    lib = _lib.load()
+    with torch.cuda.device(x.device):
+        _lib.check(lib.vidseg_layernorm_split(x.data_ptr(), _f32(ln.weight).data_ptr(), _f32(ln.bias).data_ptr(), float(ln.eps),
+                                              out.hi.data_ptr(), out.lo.data_ptr(), x.numel() // c, c, _lib.stream_ptr()),
+                   "layernorm_split")
+    return out
 
 
 def geglu_split(h):
     """h [.., 2*D] = (value | gate) -> Split(value * gelu(gate)) (erf form, attention.py:95-96)."""
     _require(h, "h")
-    val, gate = h.chunk(2, dim=-1)
-    return split((val * F.gelu(gate)).contiguous())
+    d = h.shape[-1] // 2
+    out = _empty_split((*h.shape[:-1], d), h.device)
+    lib = _lib.load()
+    with torch.cuda.device(h.device):
+        _lib.check(lib.vidseg_geglu_split(h.data_ptr(), out.hi.data_ptr(), out.lo.data_ptr(), h.numel() // (2 * d), d,
+                                          _lib.stream_ptr()), "geglu_split")
+    return out
 
 
-def group_norm_tokens_split(x, gn, silu=False):
-    """x [B, C, H, W] -> (x as tokens [B, H*W, C] fp32, Split(GroupNorm(x)) as tokens)."""
-    _require(x.contiguous(), "x")
-    b, c, h, w = x.shape
-    y = F.group_norm(x, gn.num_groups, gn.weight, gn.bias, gn.eps)
-    if silu:
-        y = F.silu(y)
-    tok = lambda t: t.permute(0, 2, 3, 1).reshape(b, h * w, c).contiguous()
-    return tok(x), split(tok(y))
+def group_norm_split(x, gn, silu, want_raw=False):
+    """GroupNorm (+ SiLU) of an image-shaped fp32 tensor or a ChannelCat of two.
+
+    Returns (Split [B, H, W, C] of the normalised activation, Split of the raw input or None, [B, H, W, Ca] fp32
+    view of the first source)."""
+    if isinstance(x, ChannelCat):
+        a, bsrc = nhwc(x.a, "x.a"), nhwc(x.b, "x.b")
+    else:
+        a, bsrc = nhwc(x), None
+    b, h, w, c1 = a.shape
+    c2 = 0 if bsrc is None else bsrc.shape[3]
+    c = c1 + c2
+    if c != gn.num_channels:
+        raise _lib.VidsegError(f"group_norm: {c} channels, module expects {gn.num_channels}")
+    out = _empty_split((b, h, w, c), a.device)
+    raw = _empty_split((b, h, w, c), a.device) if want_raw else None
+    lib = _lib.load()
+    nbytes = lib.vidseg_groupnorm_workspace_bytes(b, gn.num_groups)
+    ws = _workspace(a.device, nbytes)
+    with torch.cuda.device(a.device):
+        _lib.check(lib.vidseg_groupnorm_split(
+            a.data_ptr(), c1, bsrc.data_ptr() if bsrc is not None else None, c2,
+            _f32(gn.weight).data_ptr(), _f32(gn.bias).data_ptr(), float(gn.eps), gn.num_groups, 1 if silu else 0,
+            out.hi.data_ptr(), out.lo.data_ptr(), raw.hi.data_ptr() if raw else None, raw.lo.data_ptr() if raw else None,
+            b, h * w, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "groupnorm_split")
+    return out, raw, a
 
 
-def tokens_to_nchw(t, b, c, h, w):
-    return t.reshape(b, h, w, c).permute(0, 3, 1, 2).contiguous()
+def upsample_nearest2x_split(x):
+    """[B, C, H, W] fp32 -> Split [B, 2H, 2W, C] of the nearest-neighbour x2 upsampling."""
+    a = nhwc(x)
+    b, h, w, c = a.shape
+    out = _empty_split((b, 2 * h, 2 * w, c), a.device)
+    lib = _lib.load()
+    with torch.cuda.device(a.device):
+        _lib.check(lib.vidseg_upsample2x_split(a.data_ptr(), out.hi.data_ptr(), out.lo.data_ptr(), b, h, w, c,
+                                               _lib.stream_ptr()), "upsample2x_split")
+    return out
 
 
-def group_norm_silu(x, gn):
-    _require(x.contiguous(), "x")
-    return F.silu(F.group_norm(x, gn.num_groups, gn.weight, gn.bias, gn.eps))
-
-
-def conv2d(x, conv, stride=1, padding=1, channel_bias=None, residual=None):
-    """nn.Conv2d (+ per-(sample, channel) bias [B, Cout]) (+ residual [B, Cout, Ho, Wo])."""
-    _require(x.contiguous(), "x")
-    prev = torch.backends.cudnn.allow_tf32
-    torch.backends.cudnn.allow_tf32 = False
-    try:
-        y = F.conv2d(x, conv.weight, conv.bias, stride=stride, padding=padding)
-    finally:
-        torch.backends.cudnn.allow_tf32 = prev
-    if channel_bias is not None:
-        y = y + channel_bias[:, :, None, None]
-    if residual is not None:
-        y = y + residual
-    return y
-
-
-def upsample_nearest2x(x):
-    return F.interpolate(x, scale_factor=2, mode="nearest")
-
-
-def concat_channels(a, b):
-    return torch.cat([a, b], dim=1)
+def image_split(x, pad_to=8):
+    """[B, C, H, W] fp32 -> Split [B, H, W, C'] with C padded up to a multiple of ``pad_to`` (input conv: 4 -> 8)."""
+    a = nhwc(x)
+    c = a.shape[3]
+    if c % pad_to:
+        a = torch.nn.functional.pad(a, (0, pad_to - c % pad_to))
+    return split(a)
 
 
 def dense(x, lin, act_silu_in=False):
     """Small host-latency-bound Linear on [B, K] fp32 (time embedding MLP, ResBlock emb_layers)."""
     _require(x, "x")
     if act_silu_in:
-        x = F.silu(x)
+        x = torch.nn.functional.silu(x)
     out, _ = linear(split(x.contiguous()), lin.weight, lin.bias, want_f32=True)
     return out

@@ -6,33 +6,37 @@ from . import _lib
 
 
 class Split:
-    """An fp32 tensor carried as two fp16 tensors: x ~= hi + lo / 2048."""
-    __slots__ = ("hi", "lo")
+    """An fp32 tensor carried as two fp16 tensors: x * scale ~= hi + lo (scale is a power of two, 1 for activations)."""
+    __slots__ = ("hi", "lo", "scale")
 
-    def __init__(self, hi, lo):
+    def __init__(self, hi, lo, scale=1.0):
         self.hi = hi
         self.lo = lo
+        self.scale = scale
 
     @property
     def shape(self):
         return self.hi.shape
 
     def reshape(self, *shape):
-        return Split(self.hi.reshape(*shape), self.lo.reshape(*shape))
+        return Split(self.hi.reshape(*shape), self.lo.reshape(*shape), self.scale)
 
     def float(self):
-        return self.hi.float() + self.lo.float() / 2048.0
+        return (self.hi.float() + self.lo.float()) / self.scale
 
 
-def split(x):
-    """fp32 CUDA tensor -> Split (one streaming kernel)."""
+WEIGHT_SCALE = 256.0  # tc::kWeightScale
+
+
+def split(x, scale=1.0):
+    """fp32 CUDA tensor -> Split of x * scale (one streaming kernel)."""
     x = _lib.require_cuda_tensor(x, torch.float32, "x")
     hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        _lib.check(lib.vidseg_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), _lib.stream_ptr()), "split_f16")
-    return Split(hi, lo)
+        _lib.check(lib.vidseg_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), float(scale), _lib.stream_ptr()), "split_f16")
+    return Split(hi, lo, float(scale))
 
 
 def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
@@ -44,7 +48,9 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
     n = w.hi.shape[0]
     if w.hi.shape[1] != k:
         raise _lib.VidsegError(f"gemm_split: K mismatch {k} vs {w.hi.shape[1]}")
-    for t, name in ((a.hi, "a.hi"), (a.lo, "a.lo"), (w.hi, "w.hi"), (w.lo, "w.lo")):
+    for t, name in ((a.hi, "a.hi"), (w.hi, "w.hi")):
+        _lib.require_cuda_tensor(t, torch.float16, name)
+    for t, name in ((a.lo, "a.lo"), (w.lo, "w.lo")):
         _lib.require_cuda_tensor(t, torch.float16, name)
     dev = a.hi.device
     out = torch.empty((*lead, n), dtype=torch.float32, device=dev) if want_f32 else None
@@ -65,7 +71,7 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
             out.data_ptr() if out is not None else None,
             oh.data_ptr() if oh is not None else None,
             ol.data_ptr() if ol is not None else None,
-            m, n, k, _lib.stream_ptr()), "gemm_split")
+            m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split")
     return out, (Split(oh, ol) if want_split else None)
 
 
@@ -76,7 +82,9 @@ def attention_split(q, k, v, heads, scale=None, want_f32=False, want_split=True)
     nk = k.hi.shape[1]
     if c != heads * 64 or k.hi.shape[2] != c or v.hi.shape != k.hi.shape or k.hi.shape[0] != b:
         raise _lib.VidsegError(f"attention_split: bad shapes q{tuple(q.hi.shape)} k{tuple(k.hi.shape)} v{tuple(v.hi.shape)} heads={heads}")
-    for t, name in ((q.hi, "q.hi"), (q.lo, "q.lo"), (k.hi, "k.hi"), (k.lo, "k.lo"), (v.hi, "v.hi"), (v.lo, "v.lo")):
+    for t, name in ((q.hi, "q.hi"), (k.hi, "k.hi"), (v.hi, "v.hi")):
+        _lib.require_cuda_tensor(t, torch.float16, name)
+    for t, name in ((q.lo, "q.lo"), (k.lo, "k.lo"), (v.lo, "v.lo")):
         _lib.require_cuda_tensor(t, torch.float16, name)
     dev = q.hi.device
     out = torch.empty((b, nq, c), dtype=torch.float32, device=dev) if want_f32 else None

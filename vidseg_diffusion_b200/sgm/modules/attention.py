@@ -16,7 +16,7 @@ import torch.nn as nn
 
 from ... import _lib
 from ... import kernels as K
-from ...linear import Split
+from ...linear import Split, split as _split
 
 
 def _unsupported(name):
@@ -192,13 +192,14 @@ class SpatialTransformer(nn.Module):
             context = [context]
         context = [c if (c is None or isinstance(c, Split)) else K.split(c.float().contiguous()) for c in context]
         b, c, h, w = x.shape
-        x = x.float()
-        # GroupNorm (eps 1e-6) + 'b c h w -> b (h w) c' + operand split in one kernel; tokens stay channels-last
-        x_tok, xs = K.group_norm_tokens_split(x, self.norm, silu=False)
-        t, _ = K.linear(xs, self.proj_in.weight, self.proj_in.bias, want_f32=True)
+        # GroupNorm (eps 1e-6) + operand split in one kernel; activations are channels-last, so the reference's
+        # 'b c h w -> b (h w) c' is a view and the tokens of the transformer are the pixels of the convolutions
+        xs, _, x_nhwc = K.group_norm_split(x.float(), self.norm, silu=False)
+        x_tok = x_nhwc.reshape(b, h * w, c)
+        t, _ = K.linear(xs.reshape(b, h * w, c), self.proj_in.weight, self.proj_in.bias, want_f32=True)
         for i, block in enumerate(self.transformer_blocks):
             ctx = context[0] if (i > 0 and len(context) == 1) else context[i]
             t = block(t, context=ctx, is_injected_step=is_injected_step, modulate_params=modulate_params)
-        # proj_out + residual x_in (token layout), then back to b c h w
+        # proj_out + residual x_in, still in token layout; the result is handed on as b c h w (channels_last view)
         out, _ = K.linear(K.split(t), self.proj_out.weight, self.proj_out.bias, residual=x_tok, want_f32=True)
-        return K.tokens_to_nchw(out, b, c, h, w)
+        return K.as_nchw(out.reshape(b, h, w, c))

@@ -30,8 +30,8 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
                           modulate_params=modulate_params)
             elif isinstance(layer, TimestepBlock):
                 x = layer(x, emb)
-            elif isinstance(layer, nn.Conv2d):
-                x = K.conv2d(x, layer, stride=layer.stride[0], padding=layer.padding[0])
+            elif isinstance(layer, nn.Conv2d):  # input_blocks[0]: 4 latent channels, zero-padded to 8 for the TMA rows
+                x = K.conv2d(K.image_split(x), layer)
             else:
                 x = layer(x)
         return x
@@ -54,8 +54,9 @@ class Upsample(nn.Module):
 
     def forward(self, x):
         assert x.shape[1] == self.channels
-        x = K.upsample_nearest2x(x)
-        return K.conv2d(x, self.conv) if self.use_conv else x
+        if not self.use_conv:
+            _unsupported("Upsample(use_conv=False)")
+        return K.conv2d(K.upsample_nearest2x_split(x), self.conv)
 
 
 class Downsample(nn.Module):
@@ -73,7 +74,7 @@ class Downsample(nn.Module):
 
     def forward(self, x):
         assert x.shape[1] == self.channels
-        return K.conv2d(x, self.op, stride=2)
+        return K.conv2d(K.image_split(x), self.op)
 
 
 class ResBlock(TimestepBlock):
@@ -107,14 +108,16 @@ class ResBlock(TimestepBlock):
         return self._forward(x, emb)
 
     def _forward(self, x, emb):
+        """x: image-shaped fp32 tensor or a K.ChannelCat (the skip concatenation of the output blocks)."""
         emb_out = K.dense(emb, self.emb_layers[1], act_silu_in=True)  # [B, Cout], added per (sample, channel)
-        h = K.conv2d(K.group_norm_silu(x, self.in_layers[0]), self.in_layers[2], channel_bias=emb_out)
-        if isinstance(self.skip_connection, nn.Identity):
-            skip = x
-        else:
-            sc = self.skip_connection
-            skip = K.conv2d(x, sc, padding=sc.padding[0])
-        return K.conv2d(K.group_norm_silu(h, self.out_layers[0]), self.out_layers[3], residual=skip)
+        identity_skip = isinstance(self.skip_connection, nn.Identity)
+        if identity_skip and isinstance(x, K.ChannelCat):
+            x = x.materialize()
+        hs, raw, _ = K.group_norm_split(x, self.in_layers[0], silu=True, want_raw=not identity_skip)
+        h = K.conv2d(hs, self.in_layers[2], chan_bias=emb_out)
+        skip = x if identity_skip else K.conv2d(raw, self.skip_connection)
+        hs2, _, _ = K.group_norm_split(h, self.out_layers[0], silu=True)
+        return K.conv2d(hs2, self.out_layers[3], residual=skip)
 
 
 class UNetModel(nn.Module):
@@ -219,5 +222,6 @@ class UNetModel(nn.Module):
         for module in self.output_blocks:
             h = K.concat_channels(h, hs.pop())
             h = module(h, emb, context=context)
-        h = K.conv2d(K.group_norm_silu(h, self.out[0]), self.out[2])
-        return h.to(in_dtype)
+        hs_out, _, _ = K.group_norm_split(h, self.out[0], silu=True)
+        h = K.conv2d(hs_out, self.out[2])
+        return h.contiguous().to(in_dtype)
