@@ -375,6 +375,22 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
 }
 
+// internal entry for other translation units (the K-means E-step): plain split GEMM with an explicit family tag
+int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, float* out_f32, int m, int n,
+                   int k, float acc_scale, int family, void* stream) {
+  VS_REQUIRE(a_hi && a_lo && w_hi && w_lo && out_f32, "null pointer");
+  VS_REQUIRE(m >= 1 && n >= 4 && n % 4 == 0 && k >= 8 && k % 8 == 0, "bad shape");
+  GemmParams p{};
+  p.n = n; p.k = k; p.taps = 1; p.cin = k;
+  p.wo = m; p.ho = 1; p.nb = 1;
+  p.acc_scale = acc_scale;
+  p.out_f32 = out_f32;
+  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
+  const uint64_t row = (uint64_t)k * 2;
+  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
+  return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, family, stream);
+}
+
 }  // namespace vidseg
 
 using namespace vidseg;

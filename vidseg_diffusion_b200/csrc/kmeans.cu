@@ -22,6 +22,7 @@
 
 #define VS_FAMILY vidseg::kFamKMeans
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vidseg {
 
@@ -29,7 +30,7 @@ constexpr int kMaxTrials = 8;
 constexpr int kPotBlocks = 64;       // row blocks per run in the seeding distance kernel
 constexpr int kPotWarps = 8;         // warps per block there
 constexpr int kPotParts = kPotBlocks * kPotWarps;
-constexpr int kSlabs = 16;           // row slabs of the M-step partial sums
+constexpr int kSlabs = 32;           // row slabs of the M-step partial sums
 constexpr int kColTile = 128;        // columns per M-step block
 constexpr int kScanChunk = 4096;
 
@@ -38,7 +39,10 @@ struct KmLayout {
   float tol_rel;
   int max_iter;
   size_t xc, mean, var, xx, closest, newdist, potpart, cand, pot, centers, cnorm, center_idx, labels, part, partcnt,
-      partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, total;
+      partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, xs_hi, xs_lo, cs_hi, cs_lo, sdot,
+      absmax, amb_list, total;
+  int rk_pad;   // R*K rounded up to a multiple of 8 (row length of the tensor-core score matrix)
+  int use_tc;   // E-step on the tensor cores (needs D % 8 == 0)
 };
 
 static KmLayout km_layout(int n, int d, int k, int r, int t) {
@@ -70,6 +74,17 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
   L.same = take((size_t)r * r * 4);
   L.rand = take((size_t)r * (k > 1 ? k - 1 : 1) * t * 8);
   L.first_idx = take((size_t)r * 4);
+  L.rk_pad = (r * k + 7) / 8 * 8;
+  L.use_tc = (d % 8 == 0 && n >= 512 && (size_t)r * k * 16 <= 48 * 1024) ? 1 : 0;
+  L.absmax = take(16);
+  if (L.use_tc) {
+    L.xs_hi = take((size_t)n * d * 2);
+    L.xs_lo = take((size_t)n * d * 2);
+    L.cs_hi = take((size_t)L.rk_pad * d * 2);
+    L.cs_lo = take((size_t)L.rk_pad * d * 2);
+    L.sdot = take((size_t)n * L.rk_pad * 4);
+    L.amb_list = take((size_t)n * r * 8);
+  }
   L.total = off;
   return L;
 }
@@ -133,6 +148,7 @@ __global__ void __launch_bounds__(32) km_colstats_kernel(const float* __restrict
 
 // tol = mean(var) * tol_rel (sklearn/_kmeans.py:285-294); also resets the per-run state.
 __global__ void km_tol_reset_kernel(const float* __restrict__ var, int d, float tol_rel, float* __restrict__ tol,
+                                    unsigned* __restrict__ absmax,
                                     int* __restrict__ flags, int* __restrict__ changed, int r) {
   __shared__ double red[32];
   double s = 0.0;
@@ -148,25 +164,32 @@ __global__ void km_tol_reset_kernel(const float* __restrict__ var, int d, float 
   }
   for (int i = threadIdx.x; i < r * 4; i += blockDim.x) flags[i] = 0;
   for (int i = threadIdx.x; i < r; i += blockDim.x) changed[i] = 0;
+  if (threadIdx.x == 0) absmax[0] = 0u;
 }
 
 // xc = x - mean (fp32), xx = float64 squared norm of the centred fp32 row.  Warp per row.
 __global__ void __launch_bounds__(256) km_center_kernel(const float* __restrict__ x, const float* __restrict__ mean,
                                                         int n, int d, float* __restrict__ xc,
-                                                        double* __restrict__ xx) {
+                                                        double* __restrict__ xx, unsigned* __restrict__ absmax) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
   const float* xr = x + (size_t)row * d;
   float* o = xc + (size_t)row * d;
   double s = 0.0;
+  float mx = 0.f;
   for (int c = lane; c < d; c += 32) {
     const float v = __fsub_rn(xr[c], mean[c]);
     o[c] = v;
     s += (double)v * (double)v;
+    mx = fmaxf(mx, fabsf(v));
   }
   s = warp_sum(s);
-  if (lane == 0) xx[row] = s;
+  mx = warp_max(mx);
+  if (lane == 0) {
+    xx[row] = s;
+    atomicMax(absmax, __float_as_uint(mx));  // non-negative floats order like their bit patterns; max is order-free
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -421,6 +444,146 @@ km_assign_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin
 }
 
 // ------------------------------------------------------------------------------------------
+// E-step on the tensor cores, exact by construction.
+//
+// The dot products x_i . c_j of all runs are one skinny GEMM [N, D] x [D, R*K] (what sklearn hands to BLAS,
+// _k_means_lloyd.pyx:_update_chunk_dense).  It runs as a split-fp16 tcgen05 GEMM whose result is only used as a
+// FILTER: with |S_ij - x_i.c_j| <= (D 2^-22 + 2^-20) |x_i| |c_j| (operand split + worst-case fp32 accumulation of D
+// products inside the tensor core) every centre whose approximate score is within the error band of the best one is a candidate,
+// and only candidates are re-evaluated with the float64 FMA chain of km_assign_kernel (same order over d, same
+// score cn_j - 2 acc, same lowest-index tie rule).  Almost every point has a single candidate, so the labels are
+// bit-identical to the float64 kernel at a fraction of its cost.
+// Operands are carried scaled by s = 2^(11 - exponent(max |xc|)) so that the fp16 pairs keep 22 bits; centres are
+// means of rows, hence bounded by the same maximum.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float km_operand_scale(unsigned absmax_bits) {
+  const float m = __uint_as_float(absmax_bits);
+  if (!(m > 0.f) || !isfinite(m)) return 1.f;
+  int e;
+  frexpf(m, &e);               // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(11-e) < 2048
+  return ldexpf(1.f, 11 - e);
+}
+
+__global__ void __launch_bounds__(256)
+km_split_scaled_kernel(const float* __restrict__ x, size_t n_valid, size_t n_total, const unsigned* __restrict__ absmax,
+                       __half* __restrict__ hi, __half* __restrict__ lo) {
+  const float s = km_operand_scale(absmax[0]);
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_total; i += stride) {
+    __half h = __float2half_rn(0.f), l = h;
+    if (i < n_valid) tc::split_f16(x[i] * s, h, l);
+    hi[i] = h;
+    lo[i] = l;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* __restrict__ cnorm,
+                    const double* __restrict__ xx, const float* __restrict__ sdot, int ld,
+                    const unsigned* __restrict__ absmax, int* __restrict__ labels, int labels_stride,
+                    int* __restrict__ changed, const int* __restrict__ flags, int count_changes, int only_nonstrict,
+                    double band, int* __restrict__ amb_count, int2* __restrict__ amb_list) {
+  extern __shared__ double sm_cn[];  // [runs*k] squared centre norms, then [runs*k] error radii per unit |x|
+  double* sm_tau = sm_cn + runs * k;
+  for (int i = threadIdx.x; i < runs * k; i += blockDim.x) {
+    const double c = cnorm[i];
+    sm_cn[i] = c;
+    sm_tau[i] = band * sqrt(c);
+  }
+  __syncthreads();
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)(row_end - row_begin) * runs;
+  if (idx >= total) return;
+  const int row = row_begin + (int)(idx / runs);
+  const int r = (int)(idx % runs);
+  if (flags) {
+    const int done = flags[r * 4 + 0], strict = flags[r * 4 + 1];
+    if (only_nonstrict ? (strict != 0) : (done != 0)) return;
+  }
+  const float s = km_operand_scale(absmax[0]);
+  const double inv = 1.0 / ((double)s * (double)s);
+  const float* sr = sdot + (size_t)row * ld + (size_t)r * k;
+  const double* cn = sm_cn + r * k;
+  const double* tau = sm_tau + r * k;
+  const double xn = sqrt(xx[row]);
+  double best = 1e300, best_tau = 0.0;
+  int best_j = 0;
+  for (int j = 0; j < k; ++j) {
+    const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+    if (sc < best) { best = sc; best_tau = tau[j]; best_j = j; }
+  }
+  int ncand = 0;
+  for (int j = 0; j < k; ++j) {
+    const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+    ncand += (sc <= best + (best_tau + tau[j]) * xn) ? 1 : 0;
+  }
+  if (ncand > 1) {  // rare: defer to the exact float64 resolver, one warp per pair
+    const int slot = atomicAdd(amb_count, 1);
+    amb_list[slot] = make_int2(row, r);
+    return;
+  }
+  int* lp = labels + (size_t)r * labels_stride + row;
+  if (count_changes && *lp != best_j) atomicAdd(&changed[r], 1);
+  *lp = best_j;
+}
+
+// exact float64 evaluation of the candidates of every ambiguous pair, identical to km_assign_kernel:
+// acc = fma(x[c], centre[c], acc) over ascending c, score cn_j - 2 acc, lowest index wins ties.
+// One warp per pair, lane = candidate centre (k <= 32 per pass).
+__global__ void __launch_bounds__(256)
+km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float* __restrict__ centers,
+                         const double* __restrict__ cnorm, const double* __restrict__ xx, const float* __restrict__ sdot,
+                         int ld, const unsigned* __restrict__ absmax, int* __restrict__ labels, int labels_stride,
+                         int* __restrict__ changed, int count_changes, double band, const int* __restrict__ amb_count,
+                         const int2* __restrict__ amb_list) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int count = *amb_count;
+  const float s = km_operand_scale(absmax[0]);
+  const double inv = 1.0 / ((double)s * (double)s);
+  for (int e = warp; e < count; e += nwarps) {
+    const int row = amb_list[e].x, r = amb_list[e].y;
+    const float* sr = sdot + (size_t)row * ld + (size_t)r * k;
+    const double* cn = cnorm + (size_t)r * k;
+    const double xn = sqrt(xx[row]);
+    double best = 1e300, best_tau = 0.0;
+    for (int j = 0; j < k; ++j) {
+      const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+      if (sc < best) { best = sc; best_tau = band * sqrt(cn[j]); }
+    }
+    const float* xr = x + (size_t)row * d;
+    double bs = 1e300;
+    int bj = 0x7fffffff;
+    for (int j0 = 0; j0 < k; j0 += 32) {
+      const int j = j0 + lane;
+      double es = 1e300;
+      if (j < k) {
+        const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+        if (sc <= best + (best_tau + band * sqrt(cn[j])) * xn) {
+          const float* cr = centers + ((size_t)r * k + j) * d;
+          double acc = 0.0;
+          for (int c = 0; c < d; ++c) acc = fma((double)xr[c], (double)cr[c], acc);
+          es = cn[j] - 2.0 * acc;
+        }
+      }
+      if (es < bs || (es == bs && j < bj)) { bs = es; bj = j; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double so = __shfl_xor_sync(0xffffffffu, bs, o);
+      const int jo = __shfl_xor_sync(0xffffffffu, bj, o);
+      if (so < bs || (so == bs && jo < bj)) { bs = so; bj = jo; }
+    }
+    if (lane == 0) {
+      int* lp = labels + (size_t)r * labels_stride + row;
+      if (count_changes && *lp != bj) atomicAdd(&changed[r], 1);
+      *lp = bj;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // Lloyd M-step, part 1: per (run, row slab, 128-column tile) float64 cluster sums in shared memory.
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kColTile)
@@ -441,13 +604,14 @@ km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int row_begi
   const int* lab = labels + (size_t)r * n;
   if (col < d) {
     int i = r0;
-    for (; i + 4 <= r1; i += 4) {
-      int l[4];
-      float v[4];
+    // 16 rows in flight per thread: the loop is bound by L2 latency, not by the shared-memory adds
+    for (; i + 16 <= r1; i += 16) {
+      int l[16];
+      float v[16];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) { l[u] = lab[i + u]; v[u] = x[(size_t)(i + u) * d + col]; }
+      for (int u = 0; u < 16; ++u) { l[u] = lab[i + u]; v[u] = x[(size_t)(i + u) * d + col]; }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) acc[l[u] * kColTile + tid] += (double)v[u];
+      for (int u = 0; u < 16; ++u) acc[l[u] * kColTile + tid] += (double)v[u];
     }
     for (; i < r1; ++i) acc[lab[i] * kColTile + tid] += (double)x[(size_t)i * d + col];
     double* out = part + (((size_t)r * kSlabs + slab) * k) * d + col;
@@ -702,6 +866,48 @@ static int km_launch_assign(const float* x, const KmLayout& L, int runs, int row
   return 0;
 }
 
+
+// defined in gemm_tc.cu: out[M,N] = acc_scale * A[M,K] . W[N,K]^T on the split operands, tagged with `family`
+int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, float* out_f32, int m, int n,
+                   int k, float acc_scale, int family, void* stream);
+
+// E-step of every unfinished run over rows [row_begin, row_end) of the centred data held in the workspace
+static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_end, int count_changes, int only_nonstrict,
+                          void* stream) {
+  const int rows = row_end - row_begin;
+  if (rows <= 0) return 0;
+  if (!L.use_tc)
+    return km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers),
+                            at<double>(ws, L.cnorm), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed),
+                            at<int>(ws, L.flags), count_changes, only_nonstrict, stream);
+  const size_t c_valid = (size_t)L.r * L.k * L.d, c_total = (size_t)L.rk_pad * L.d;
+  VS_LAUNCH(km_split_scaled_kernel, (int)((c_total + 255) / 256), 256, 0, stream, at<float>(ws, L.centers), c_valid, c_total,
+            at<unsigned>(ws, L.absmax), at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo));
+  VS_POST_LAUNCH();
+  if (int e = gemm_split_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
+                             at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo),
+                             at<float>(ws, L.sdot) + (size_t)row_begin * L.rk_pad, rows, L.rk_pad, L.d, 1.0f, kFamKMeans, stream))
+    return e;
+  // error radius of the filter per unit |x||c|: the score is cn - 2 S; S carries the operand split (2^-21) and the
+  // fp32 accumulation of d products inside the tensor core (<= d * 2^-22 with truncating alignment)
+  const double band = 2.0 * ((double)L.d * 0x1p-22 + 0x1p-20);
+  const long long total = (long long)rows * L.r;
+  int* amb_count = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
+  VS_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, 4, (cudaStream_t)stream));
+  const size_t smem = (size_t)L.r * L.k * 16;
+  VS_REQUIRE(smem <= 48 * 1024, "n_init * k too large for the tensor-core E-step");
+  VS_LAUNCH(km_assign_tc_kernel, (int)((total + 255) / 256), 256, smem, stream, L.k, L.r, row_begin, row_end,
+            at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
+            at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), at<int>(ws, L.flags), count_changes, only_nonstrict, band,
+            amb_count, at<int2>(ws, L.amb_list));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
+            at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
+            at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band, amb_count, at<int2>(ws, L.amb_list));
+  VS_POST_LAUNCH();
+  return 0;
+}
+
 }  // namespace vidseg
 
 using namespace vidseg;
@@ -730,12 +936,18 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
   VS_LAUNCH(km_colstats_kernel, (d + 31) / 32, 32, 0, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
   VS_POST_LAUNCH();
   VS_LAUNCH(km_tol_reset_kernel, 1, 256, 0, stream, at<float>(ws, L.var), d, tol_rel, at<float>(ws, L.tol),
-            at<int>(ws, L.flags), at<int>(ws, L.changed), n_init);
+            at<unsigned>(ws, L.absmax), at<int>(ws, L.flags), at<int>(ws, L.changed), n_init);
   VS_POST_LAUNCH();
   VS_LAUNCH(km_center_kernel, (n * 32 + 255) / 256, 256, 0, stream, x, at<float>(ws, L.mean), n, d, at<float>(ws, L.xc),
-            at<double>(ws, L.xx));
+            at<double>(ws, L.xx), at<unsigned>(ws, L.absmax));
   VS_POST_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.labels), 0xFF, (size_t)n_init * n * 4, (cudaStream_t)stream));
+  if (L.use_tc) {
+    const size_t tot = (size_t)n * d;
+    VS_LAUNCH(km_split_scaled_kernel, (int)std::min<size_t>((tot + 255) / 256, (size_t)kNumSMs * 16), 256, 0, stream,
+              at<float>(ws, L.xc), tot, tot, at<unsigned>(ws, L.absmax), at<__half>(ws, L.xs_hi), at<__half>(ws, L.xs_lo));
+    VS_POST_LAUNCH();
+  }
   return 0;
 }
 
@@ -775,8 +987,7 @@ VS_API int vidseg_kmeans_assign(void* workspace, size_t workspace_bytes, int row
   if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
   VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
   void* ws = workspace;
-  return km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers), at<double>(ws, L.cnorm),
-                          at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), at<int>(ws, L.flags), 1, 0, stream);
+  return km_assign_runs(ws, L, row_begin, row_end, 1, 0, stream);
 }
 
 VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
@@ -837,10 +1048,7 @@ VS_API int vidseg_kmeans_inertia(void* workspace, size_t workspace_bytes, int ro
   void* ws = workspace;
   if (inertia_partial == nullptr) inertia_partial = at<double>(ws, L.inertia);
   // rerun the E-step of runs that stopped on tolerance / max_iter (sklearn/_kmeans.py:741-753)
-  if (int e = km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers),
-                               at<double>(ws, L.cnorm), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed),
-                               at<int>(ws, L.flags), 0, 1, stream))
-    return e;
+  if (int e = km_assign_runs(ws, L, row_begin, row_end, 0, 1, stream)) return e;
   VS_LAUNCH(km_inertia_kernel, dim3(kPotBlocks, L.r), 256, 0, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin,
             row_end, at<float>(ws, L.centers), at<int>(ws, L.labels), at<double>(ws, L.inertia_part));
   VS_POST_LAUNCH();
