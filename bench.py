@@ -29,13 +29,17 @@ WORKLOADS = {
                desc="SD-2.1 UNet 1 step + aggregate(out 8,7,6) + KMeans(20, n_init=10), 14 frames 512x512 (BASELINE configs[1])"),
     "c2r": dict(cfg="sd21", frames=14, latent=64, ctx_len=77, num_masks=20, aggre=True, refine=True,
                 desc="configs[1] plus --is_refine_mask"),
+    "c3": dict(cfg="svd", frames=14, latent=64, ctx_len=1, num_masks=20, aggre=True, refine=True,
+               desc="SVD VideoUNet 1 step + aggregate(out 8,7,6) + KMeans(20, n_init=10) + mask refinement, 14 frames 512x512 (BASELINE configs[2])"),
     "c1": dict(cfg="sd21", frames=4, latent=32, ctx_len=77, num_masks=5, aggre=False, refine=False,
                desc="SD-2.1, 4 frames 256x256, num_masks=5 (BASELINE configs[0])"),
     "tiny": dict(cfg="tiny", frames=2, latent=16, ctx_len=7, num_masks=3, aggre=True, refine=True,
                  desc="toy-width UNet, plumbing check only"),
+    "tinyv": dict(cfg="tinyv", frames=3, latent=16, ctx_len=1, num_masks=3, aggre=True, refine=True,
+                  desc="toy-width VideoUNet, plumbing check only"),
 }
 # algorithmic FLOPs of one UNet step (FlopCounterMode over the reference modules)
-UNET_TFLOP = {"c2": 22.519, "c2r": 22.519, "c1": 1.449}
+UNET_TFLOP = {"c2": 22.519, "c2r": 22.519, "c1": 1.449, "c3": 35.542}
 
 
 def read_peaks():
@@ -50,12 +54,23 @@ def read_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1590.0, "source": "fallback (B200_PROFILING.md: 6.65 TB/s, 1.59 PFLOP/s)"}
 
 
+def is_video(cfg):
+    return "video_kernel_size" in cfg
+
+
+def model_class(cfg):
+    if is_video(cfg):
+        from vidseg_diffusion_b200.sgm.modules.diffusionmodules.video_model import VideoUNet
+        return VideoUNet
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
+    return UNetModel
+
+
 def param_shapes(cfg):
     """{state-dict key: shape} of the architecture, from the module tree on the meta device (no allocation)."""
     import torch
-    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
     with torch.device("meta"):
-        model = UNetModel(**cfg)
+        model = model_class(cfg)(**cfg)
     return {k: tuple(v.shape) for k, v in model.state_dict().items()}
 
 
@@ -78,10 +93,21 @@ def make_state_dict(cfg, seed=0):
 
 
 def make_clip(wl, cfg, seed):
-    """Host tensors of one step: x [2F,4,h,w] (uncond rows first), timesteps [2F], context [2F,L,D]."""
+    """Host tensors of one step: x [2F,C,h,w] (uncond rows first), timesteps [2F], context [2F,L,D] (+ y [2F,adm] for
+    the SVD VideoUNet: noisy latent | conditioning-frame latent, one CLIP image token, vector conditioning)."""
     import torch
     g = torch.Generator().manual_seed(seed)
     F, hw = wl["frames"], wl["latent"]
+    if is_video(cfg):
+        half = cfg["in_channels"] // 2
+        lat = torch.randn(F, half, hw, hw, generator=g)
+        cond = torch.randn(1, half, hw, hw, generator=g).expand(F, -1, -1, -1)
+        ctx = torch.randn(1, 1, cfg["context_dim"], generator=g).expand(F, -1, -1)
+        yv = torch.randn(1, cfg["adm_in_channels"], generator=g).expand(F, -1)
+        x = torch.cat([torch.cat([lat, torch.zeros_like(cond)], 1), torch.cat([lat, cond], 1)], 0).contiguous()
+        context = torch.cat([torch.zeros_like(ctx), ctx], 0).contiguous()
+        t = torch.full((2 * F,), 0.8)   # c_noise = 0.25 ln(sigma) (denoiser_scaling.py:58)
+        return x, t, context, torch.cat([yv, yv], 0).contiguous()
     lat = torch.randn(F, cfg["in_channels"], hw, hw, generator=g)
     ctx = torch.randn(F, wl["ctx_len"], cfg["context_dim"], generator=g)
     x = torch.cat([lat, lat], 0)
@@ -151,13 +177,20 @@ def cpu_reference_step(wl, cfg, sd, clip, n_frames, seed):
     import numpy as np
     import torch
     from oracle import features as ofeat, kmeans as okm, refine as oref, unet as ounet
-    x, t, ctx = clip
     F = wl["frames"]
     idx = list(range(n_frames)) + [F + i for i in range(n_frames)]
-    xs, ts, cs = x[idx], t[idx], ctx[idx]
+    sub = [a[idx] for a in clip]
     t0 = time.perf_counter()
     stash = {}
-    ounet.unet_forward(sd, cfg, xs, ts, cs, stash)
+    if is_video(cfg):
+        from oracle import video_unet as ovid
+        ocfg = dict(in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], model_channels=cfg["model_channels"],
+                    attention_resolutions=tuple(cfg["attention_resolutions"]), num_res_blocks=cfg["num_res_blocks"],
+                    channel_mult=tuple(cfg["channel_mult"]), num_head_channels=cfg["num_head_channels"],
+                    context_dim=cfg["context_dim"], adm_in_channels=cfg["adm_in_channels"])
+        ovid.video_unet_forward(sd, ocfg, sub[0], sub[1], sub[2], sub[3], n_frames, None, stash)
+    else:
+        ounet.unet_forward(sd, cfg, sub[0], sub[1], sub[2], stash)
     blocks = (8, 7, 6) if wl["aggre"] else (8,)
     feats = [stash[(f"output_block_{i}", "spatial_self_attn_q")].numpy() for i in blocks]
     X = ofeat.aggregate_normalize(feats, n_frames)
@@ -217,7 +250,6 @@ def run_b200(args, wl, cfg):
     import torch.distributed as dist
     from vidseg_diffusion_b200 import _lib
     from vidseg_diffusion_b200.pipeline import ClipSegmenter
-    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.openaimodel import UNetModel
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -232,7 +264,7 @@ def run_b200(args, wl, cfg):
 
     sd = make_state_dict(cfg)
     with torch.device("meta"):
-        model = UNetModel(**cfg)
+        model = model_class(cfg)(**cfg)
     model = model.to_empty(device=dev)
     model.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
     model.eval()
@@ -269,8 +301,9 @@ def run_b200(args, wl, cfg):
             ms = float(tt.item())
         return ms, _lib.launch_count() - launches0, prof
 
-    step_dev = lambda: seg.segment(devt[0], devt[1], devt[2], F, seed)
-    step_e2e = lambda: seg.segment_host(host[0], host[1], host[2], F, seed)
+    vkw = dict(num_video_frames=F) if is_video(cfg) else {}
+    step_dev = lambda: seg.segment(devt[0], devt[1], devt[2], F, seed, **(dict(vkw, y=devt[3]) if vkw else {}))
+    step_e2e = lambda: seg.segment_host(host[0], host[1], host[2], F, seed, **(dict(vkw, y=host[3]) if vkw else {}))
     for _ in range(max(args.warmup, 3)):
         step_dev()
     sampler = ClockSampler(local_rank)
@@ -290,22 +323,46 @@ def run_b200(args, wl, cfg):
             dist.destroy_process_group()
         return
     peaks = read_peaks()
-    # dominant kernel = the family with the most device time in the timed region
-    fam = max(prof, key=lambda k: prof[k]["ms"])
-    p = prof[fam]
-    tensor_bound = fam in ("gemm", "attention", "conv")
-    if tensor_bound:
+    # dominant KERNEL of the step.  Profile families map onto kernels: "gemm" and "conv" are both launches of
+    # gemm_split_kernel (the Linear and the implicit-GEMM convolution form of one tcgen05 kernel), "attention" is
+    # attn_split_kernel; "kmeans" / "elementwise" / "refine" are groups of several small kernels and are listed in
+    # stage_ms_per_step, not as one kernel.
+    kernels = {
+        "gemm_split_kernel (tcgen05 split-fp16 GEMM + implicit-GEMM conv)": ("tensor", ["gemm", "conv"]),
+        "attn_split_kernel (tcgen05 flash attention)": ("tensor", ["attention"]),
+        "aggregate_normalize_kernel": ("hbm", ["aggregate"]),
+    }
+    agg = {}
+    for name, (bound, fams) in kernels.items():
+        agg[name] = {"bound": bound, "ms": sum(prof[f]["ms"] for f in fams), "work": sum(prof[f]["work"] for f in fams),
+                     "launches": sum(prof[f]["launches"] for f in fams)}
+    kname = max(agg, key=lambda k: agg[k]["ms"])
+    p = agg[kname]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
+    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+        try:
+            tj = json.load(open(tpath))
+            if tj.get("workload") == args.workload and tj.get("kernel", "") in kname:
+                traffic = tj["dram_bytes_per_launch"]
+        except Exception:
+            traffic = None
+    if p["bound"] == "tensor":
         achieved = p["work"] / (p["ms"] * 1e-3) / 1e12 if p["ms"] > 0 else 0.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["tflops"], "traffic": None}
+                "frac": achieved / peaks["tflops"], "traffic": traffic,
+                "tensor_pipe_tflops": 3.0 * achieved, "tensor_pipe_frac": 3.0 * achieved / peaks["tflops"]}
     else:
         achieved = p["work"] / (p["ms"] * 1e-3) / 1e9 if p["ms"] > 0 else 0.0
         roof = {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / peaks["hbm_gbs"], "traffic": None}
-    roof.update(kernel=fam, launches_per_step=p["launches"] / args.steps, avg_launch_us=1e3 * p["ms"] / max(p["launches"], 1),
+                "frac": achieved / peaks["hbm_gbs"], "traffic": traffic}
+    roof.update(kernel=kname, launches_per_step=p["launches"] / args.steps,
+                avg_launch_us=1e3 * p["ms"] / max(p["launches"], 1), share_of_step=p["ms"] / ms,
                 peak_source=peaks["source"],
-                note="achieved = algorithmic FLOPs (2MNK of the fp32-equivalent product) / CUDA-event time per launch; "
-                     "the split-fp16 path issues 3 tensor-core MMAs per algorithmic product, so tensor-pipe work is 3x")
+                note="achieved = algorithmic FLOPs (2MNK of the fp32-equivalent product) / CUDA-event time over all "
+                     "launches of the kernel in the timed region; the split-fp16 path issues 3 tensor-core MMAs per "
+                     "algorithmic product (fp32-class accuracy is the parity bar), so the tensor pipe runs at "
+                     "tensor_pipe_tflops = 3 x achieved and frac can not exceed 1/3")
     lib_ms = sum(v["ms"] for v in prof.values())
     breakdown = {k: round(v["ms"] / args.steps, 3) for k, v in prof.items() if v["launches"]}
     breakdown["non_library(torch glue + host gaps)"] = round((ms - lib_ms) / args.steps, 3)
@@ -313,9 +370,12 @@ def run_b200(args, wl, cfg):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nf = max(1, min(args.ref_frames, F))
-    t_cpu = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], nf, seed)
-    sample = (f"{nf} of {F} frames, one pass (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32 + "
-              f"K-means on those frames), {t_cpu:.1f} s")
+    if args.no_cpu_baseline:
+        t_cpu, sample = float("nan"), "skipped (--no-cpu-baseline)"
+    else:
+        t_cpu = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], nf, seed)
+        sample = (f"{nf} of {F} frames, one pass (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32 + "
+                  f"K-means on those frames), {t_cpu:.1f} s")
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -329,7 +389,7 @@ def run_b200(args, wl, cfg):
         "gpu_launches": int(launches),
         "roofline": roof,
         "stage_ms_per_step": breakdown,
-        "cpu_baseline": {"value": nf / t_cpu, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": (nf / t_cpu if t_cpu == t_cpu else None), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -344,11 +404,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the CPU leg (profiling runs)")
     ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     from vidseg_diffusion_b200 import configs
-    cfg = {"sd21": configs.SD21_UNET, "tiny": configs.TINY_UNET}[wl["cfg"]]
+    cfg = {"sd21": configs.SD21_UNET, "tiny": configs.TINY_UNET, "svd": configs.SVD_UNET,
+           "tinyv": configs.TINY_VIDEO_UNET}[wl["cfg"]]
     if args.impl == "reference":
         run_reference(args, wl, cfg)
     else:

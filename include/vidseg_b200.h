@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);
+int vidseg_abi_version(void);  /* 2: + gemm_split_ex, conv_temporal_split, temporal_attention, layernorm_bias_split */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -181,6 +181,20 @@ int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, cons
                       const float* bias, const float* residual, float* out_f32,
                       void* out_hi, void* out_lo, int m, int n, int k, float acc_scale, void* stream);
 
+/* vidseg_gemm_split with the epilogue terms of the SVD temporal layers:
+ *   row_bias [M / rows_per_bias, N]: one bias row per group of rows_per_bias consecutive output rows -- the
+ *     frame-position embedding 'x_mix = x + emb' (sgm/modules/video_attention.py:417-427, 452-453; group = the
+ *     h*w tokens of a frame) and the single-token cross-attention output, which is one vector per sample;
+ *   blend, blend_alpha [M / rows_per_alpha]: out = a * blend + (1 - a) * out -- AlphaBlender
+ *     (sgm/modules/diffusionmodules/util.py:368-391) as used by SpatialVideoTransformer.time_mixer
+ *     (video_attention.py:472-476).
+ * Order: acc * acc_scale + bias + row_bias + residual, then the blend.  NULL disables a term. */
+int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
+                         const float* bias, const float* residual, const float* row_bias,
+                         long long rows_per_bias, const float* blend, const float* blend_alpha,
+                         long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
+                         int m, int n, int k, float acc_scale, void* stream);
+
 /* nn.Conv2d as an implicit GEMM (no im2col: the taps are shifted TMA boxes, zero padding is the TMA out-of-bounds
  * fill).  Replaces the 3x3 / 1x1 convolutions of ResBlock (openaimodel.py:267-315), Downsample (:202-209, stride 2),
  * Upsample (:145-147), the input conv (:587-593) and the output conv (:825-829).
@@ -193,6 +207,20 @@ int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w_hi, co
                         int batch, int height, int width, int cin, int cout, int ksize, int stride, float acc_scale,
                         void* stream);
 
+/* Conv3d with a (3,1,1) kernel, padding (1,0,0), over the frame axis of a clip: the time_stack ResBlock of
+ * VideoResBlock (sgm/modules/diffusionmodules/video_model.py:45-58, 75-80).  Implicit GEMM like vidseg_conv2d_split;
+ * the three taps are the same pixel patch shifted by -1 / 0 / +1 frames.
+ *   x_*: [V, T, HW, Cin] split (the '(b t) h w c' channels-last memory of the 2-D layers, no rearrange);
+ *   w_*: [Cout, 3*Cin] split, tap-major = weight[:, :, :, 0, 0].permute(0, 2, 1);
+ *   frame_bias [V*T, Cout] or NULL: the per-frame time embedding (exchange_temb_dims, openaimodel.py:364-366);
+ *   residual [V, T, HW, Cout] or NULL; blend / blend_alpha [V*T]: AlphaBlender 'b t -> b 1 t 1 1'
+ *   (video_model.py:59-63, 81-85): out = a * blend + (1 - a) * out. */
+int vidseg_conv_temporal_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                               const float* bias, const float* frame_bias, const float* residual,
+                               const float* blend, const float* blend_alpha, float* out_f32, void* out_hi,
+                               void* out_lo, int videos, int frames, int hw, int cin, int cout, float acc_scale,
+                               void* stream);
+
 /* softmax(q k^T * scale) v per (batch, head), head dim 64, no mask: replaces
  * F.scaled_dot_product_attention at sgm/modules/attention.py:352-356 (xformers :473-485).
  * q_*: [B, Nq, heads*64] split; k_*, v_*: [B, Nk, heads*64] split (the pre-head-split layout the
@@ -202,9 +230,24 @@ int vidseg_attention_split(const void* q_hi, const void* q_lo, const void* k_hi,
                            void* out_lo, int batch, int heads, int nq, int nk, float scale,
                            void* stream);
 
+/* Self-attention over the T <= 32 frames of every spatial site: VideoTransformerBlock.attn1 on the '(b s) t c'
+ * layout (sgm/modules/video_attention.py:152, 195; CrossAttention.forward attention.py:286-364).  q, k, v, out are
+ * fp32 / split tensors in the frame-major layout [V, T, S, heads*64] of the spatial layers; the reference's
+ * '(b t) s c -> (b s) t c' rearrange is index arithmetic inside the kernel.  HBM-bound (16 bytes per element). */
+int vidseg_temporal_attention(const float* q, const float* k, const float* v, float* out_f32, void* out_hi,
+                              void* out_lo, int videos, int frames, int sites, int heads, float scale,
+                              void* stream);
+
 /* nn.LayerNorm over the last dim (attention.py:567-569) -> split operand.  x fp32 [rows, C]; C % 4 == 0, <= 2048. */
 int vidseg_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, void* out_hi,
                            void* out_lo, long long rows, int channels, void* stream);
+
+/* LayerNorm(x + row_bias[row / rows_per_bias]) -> split operand: the norms that follow a per-frame / per-sample
+ * broadcast add in the temporal layers (norm_in after 'x + emb', video_attention.py:155-157, 452; norm3 after a
+ * single-token cross-attention).  row_bias NULL = vidseg_layernorm_split. */
+int vidseg_layernorm_bias_split(const float* x, const float* row_bias, long long rows_per_bias, const float* gamma,
+                                const float* beta, float eps, void* out_hi, void* out_lo, long long rows,
+                                int channels, void* stream);
 
 /* GEGLU gate (attention.py:95-96): h fp32 [rows, 2*D] = (value | gate) -> split(value * gelu_erf(gate)) [rows, D]. */
 int vidseg_geglu_split(const float* h, void* out_hi, void* out_lo, long long rows, int d, void* stream);

@@ -95,3 +95,21 @@ def synthetic_unet_inputs(seed, num_frames, latent_hw, in_channels, context_len,
     context = np.concatenate([np.zeros_like(ctx), ctx], 0)
     t = np.full((2 * num_frames,), timestep, dtype=np.int64)
     return x, t, context
+
+
+def synthetic_video_unet_inputs(seed, num_frames, latent_hw, in_channels, context_dim, adm_channels, c_noise=0.8):
+    """The batch the SVD guider builds for one step (guiders.py:60-100): uncond rows first; each row is the noisy
+    latent (4 channels) concatenated with the conditioning-frame latent (4 channels, zero in the uncond half);
+    context is one CLIP image token per frame (zero in the uncond half); y = the vector conditioning
+    (fps / motion bucket / cond_aug embeddings), identical in both halves; timesteps = c_noise = 0.25 ln(sigma)
+    (denoiser_scaling.py:58)."""
+    r = np.random.RandomState(seed)
+    half = in_channels // 2
+    lat = r.standard_normal((num_frames, half, latent_hw, latent_hw)).astype(np.float32)
+    cond = r.standard_normal((1, half, latent_hw, latent_hw)).astype(np.float32).repeat(num_frames, 0)
+    ctx = r.standard_normal((1, 1, context_dim)).astype(np.float32).repeat(num_frames, 0)
+    y = r.standard_normal((1, adm_channels)).astype(np.float32).repeat(num_frames, 0)
+    x = np.concatenate([np.concatenate([lat, np.zeros_like(cond)], 1), np.concatenate([lat, cond], 1)], 0)
+    context = np.concatenate([np.zeros_like(ctx), ctx], 0)
+    t = np.full((2 * num_frames,), c_noise, dtype=np.float32)
+    return x, t, context, np.concatenate([y, y], 0)

@@ -1,0 +1,112 @@
+"""GPU parity of the SVD VideoUNet forward with the spatial and temporal Q/K stash (A2/A5/A6/A8) against (a) goldens
+produced by the UNMODIFIED reference VideoUNet (tests/golden/make_video_unet_goldens.py) and (b) the fp32 CPU oracle
+run on this box.  Tolerance: max|delta| / max|ref| <= 1e-3 per tensor."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import video_unet as ov
+from synth import synthetic_unet_weights, synthetic_video_unet_inputs
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+TOL = 1e-3
+EXPECTED = 2e-4
+
+
+def relerr(got, want):
+    got = torch.as_tensor(got).double().cpu()
+    want = torch.as_tensor(want).double().cpu()
+    return float((got - want).abs().max() / want.abs().max())
+
+
+def build(cfg, seed, cuda):
+    from vidseg_diffusion_b200 import configs
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.video_model import VideoUNet
+    kw = dict(configs.SVD_UNET)
+    kw.update(model_channels=cfg["model_channels"], context_dim=cfg["context_dim"], adm_in_channels=cfg["adm_in_channels"])
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ov.param_shapes(cfg), seed).items()}
+    model = VideoUNet(**kw)
+    model.load_state_dict(sd, strict=True)
+    return model.to(cuda).eval(), sd
+
+
+@pytest.mark.parametrize("name,cfg", [("video_tiny", ov.TINY_VIDEO_CONFIG), ("svd_c1", ov.SVD_CONFIG)])
+def test_video_unet_matches_reference_golden_and_oracle(cuda, name, cfg):
+    g = np.load(os.path.join(GOLDEN, f"unet_{name}.npz"))
+    seed, F, hw = (int(v) for v in g["meta"])
+    assert list(g["keys"]) == sorted(ov.param_shapes(cfg))
+    model, sd = build(cfg, seed, cuda)
+    x, t, ctx, y = synthetic_video_unet_inputs(seed, F, hw, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"])
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    ind = torch.zeros(2, F, device=cuda)
+    out = model(dev(x), timesteps=dev(t), context=dev(ctx), y=dev(y), num_video_frames=F, image_only_indicator=ind)
+    ts, cs = (int(v) for v in g["q_stride"])
+    errs = {"out": relerr(out, g["out"])}
+    for i in (6, 7, 8):
+        layer = model.output_blocks[i][1]
+        assert "SpatialVideoTransformer" in str(type(layer))  # how the reference's SVD pipelines find it
+        q = layer.transformer_blocks[0].attn1.q
+        assert q.dtype == torch.float32 and q.shape[0] == 2 * F
+        errs[f"q{i}"] = relerr(q[:, ::ts, ::cs], g[f"q{i}"])
+    tq = model.output_blocks[7][1].time_stack[0].attn1.q
+    tk2 = model.output_blocks[7][1].time_stack[0].attn2.k
+    assert tq.shape[1] == F and tk2.shape[1] == 1 and tq.shape[0] == tk2.shape[0]     # the '(b s) t c' layout
+    errs["tq7"] = relerr(tq[::ts, :, ::cs], g["tq7"])
+    errs["tk2_7"] = relerr(tk2[::ts, :, ::cs], g["tk2_7"])
+    # the oracle on this box's CPU: full tensors, every stashed spatial and temporal q/k of every attention layer
+    stash = {}
+    out_or = ov.video_unet_forward(sd, cfg, torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(ctx),
+                                   torch.from_numpy(y), F, torch.zeros(2, F), stash)
+    errs["out_oracle"] = relerr(out, out_or)
+    tags = {}
+    for i, blk in enumerate(model.input_blocks):
+        tags[f"input_block_{i}"] = blk
+    tags["middle_block"] = model.middle_block
+    for i, blk in enumerate(model.output_blocks):
+        tags[f"output_block_{i}"] = blk
+    n_checked = 0
+    for (tag, what), want in stash.items():
+        layer = tags[tag][1]
+        tb = layer.transformer_blocks[0] if what.startswith("spatial") else layer.time_stack[0]
+        attn = tb.attn1 if "_self_" in what else tb.attn2
+        got = attn.q if what.endswith("_q") else attn.k
+        assert tuple(got.shape) == tuple(want.shape), (tag, what, tuple(got.shape), tuple(want.shape))
+        errs[f"{tag}.{what}"] = relerr(got, want)
+        n_checked += 1
+    assert n_checked == 16 * 8
+    worst = max(errs, key=errs.get)
+    print(f"{name}: worst {worst} = {errs[worst]:.2e}; out {errs['out']:.2e}, q7 {errs['q7']:.2e}, tq7 {errs['tq7']:.2e}")
+    assert errs[worst] <= TOL, (worst, errs[worst])
+    assert errs[worst] <= EXPECTED, f"fp32-class path regressed: {worst} {errs[worst]:.2e}"
+
+
+def test_temporal_attention_kernel_matches_torch(cuda):
+    """The strided small-sequence kernel against fp32 torch attention on the rearranged tensors (T = 14 and 25)."""
+    from vidseg_diffusion_b200 import kernels as K
+    for (v, T, s, heads) in [(2, 14, 33, 5), (1, 25, 7, 2), (3, 1, 5, 1)]:
+        g = torch.Generator(device="cpu").manual_seed(T)
+        q, k, val = (torch.randn(v * T, s, heads * 64, generator=g).to(cuda) for _ in range(3))
+        got = K.temporal_attention(q, k, val, v, T, heads, 0.125).float()
+        def site_major(t):
+            return t.view(v, T, s, heads, 64).permute(0, 2, 3, 1, 4).double()    # v s h T d
+        w = torch.softmax(site_major(q) @ site_major(k).transpose(-1, -2) * 0.125, dim=-1)
+        want = (w @ site_major(val)).permute(0, 3, 1, 2, 4).reshape(v * T, s, heads * 64)
+        assert relerr(got, want) < 2e-6
+
+
+def test_video_image_only_indicator_switches_the_temporal_branch_off(cuda):
+    """AlphaBlender 'learned_with_images' (util.py:357-366): alpha = 1 where the indicator is set, so the temporal
+    branches contribute nothing and frames become independent (checked against the oracle with the same flag)."""
+    cfg = ov.TINY_VIDEO_CONFIG
+    model, sd = build(cfg, 9, cuda)
+    F = 2
+    x, t, ctx, y = synthetic_video_unet_inputs(9, F, 16, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"])
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    ind = torch.tensor([[1.0, 0.0], [1.0, 1.0]])
+    out = model(dev(x), timesteps=dev(t), context=dev(ctx), y=dev(y), num_video_frames=F, image_only_indicator=ind.to(cuda))
+    want = ov.video_unet_forward(sd, cfg, torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(ctx),
+                                 torch.from_numpy(y), F, ind)
+    assert relerr(out, want) < EXPECTED

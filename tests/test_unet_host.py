@@ -58,3 +58,54 @@ def test_unet_rejects_cpu_tensors_and_unbuilt_rows():
         model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=None, is_modulate_step=True)
     with pytest.raises(NotImplementedError):
         UNetModel(use_linear_in_transformer=False, **cfg)
+
+
+@pytest.mark.parametrize("name", ["video_tiny", "svd_c1"])
+def test_video_state_dict_keys_match_reference(name):
+    from oracle import video_unet as ov
+    from vidseg_diffusion_b200 import configs
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.video_model import VideoUNet
+    cfg = {"video_tiny": configs.TINY_VIDEO_UNET, "svd_c1": configs.SVD_UNET}[name]
+    ocfg = {"video_tiny": ov.TINY_VIDEO_CONFIG, "svd_c1": ov.SVD_CONFIG}[name]
+    g = np.load(os.path.join(GOLDEN, f"unet_{name}.npz"))
+    ref = {k: tuple(int(v) for v in s.split(",")) for k, s in zip(g["keys"], g["shapes"])}
+    with torch.device("meta"):
+        model = VideoUNet(**cfg)
+    assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == ref
+    assert ov.param_shapes(ocfg) == ref
+    for i in (3, 4, 5, 6, 7, 8, 9, 10, 11):
+        layer = model.output_blocks[i][1]
+        assert "SpatialVideoTransformer" in str(type(layer))     # svd_single_video_inference.py:117
+        for blk in (layer.transformer_blocks[0], layer.time_stack[0]):
+            assert hasattr(blk.attn1, "q") and hasattr(blk.attn2, "k")
+
+
+def test_oracle_video_unet_matches_reference_golden_tiny():
+    from oracle import video_unet as ov
+    from synth import synthetic_unet_weights, synthetic_video_unet_inputs
+    cfg = ov.TINY_VIDEO_CONFIG
+    g = np.load(os.path.join(GOLDEN, "unet_video_tiny.npz"))
+    seed, F, hw = (int(v) for v in g["meta"])
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ov.param_shapes(cfg), seed).items()}
+    x, t, ctx, y = (torch.from_numpy(a) for a in
+                    synthetic_video_unet_inputs(seed, F, hw, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"]))
+    stash = {}
+    out = ov.video_unet_forward(sd, cfg, x, t, ctx, y, F, torch.zeros(2, F), stash)
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert rel(out.numpy(), g["out"]) < 2e-5
+    for i in (6, 7, 8):
+        assert rel(stash[(f"output_block_{i}", "spatial_self_attn_q")].numpy(), g[f"q{i}"]) < 2e-5
+    assert rel(stash[("output_block_7", "temporal_self_attn_q")].numpy(), g["tq7"]) < 2e-5
+    assert rel(stash[("output_block_7", "temporal_cross_attn_k")].numpy(), g["tk2_7"]) < 2e-5
+
+
+def test_video_unet_rejects_cpu_tensors_and_unbuilt_rows():
+    from vidseg_diffusion_b200 import _lib, configs
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.video_model import VideoUNet
+    with torch.device("meta"):
+        model = VideoUNet(**configs.TINY_VIDEO_UNET)
+    args = dict(timesteps=torch.zeros(4), context=torch.zeros(4, 1, 96), y=torch.zeros(4, 48), num_video_frames=2)
+    with pytest.raises(_lib.VidsegError):
+        model(torch.zeros(4, 8, 16, 16), **args)
+    with pytest.raises(NotImplementedError):
+        model(torch.zeros(4, 8, 16, 16), is_modulate_step=True, **args)

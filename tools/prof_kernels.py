@@ -1,0 +1,40 @@
+"""Launch the hot tensor-core kernels at their config-2 shapes a few times each (target of `ncu --set full`).
+Also prints CUDA-event timings when run without a profiler."""
+import os, sys, json
+import torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from vidseg_diffusion_b200.linear import gemm_split, split, attention_split, Split
+from vidseg_diffusion_b200 import kernels as K
+
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+res = {}
+
+def ev(fn, it=3, warm=1):
+    for _ in range(warm): fn()
+    torch.cuda.synchronize()
+    a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(it): fn()
+    b.record(); torch.cuda.synchronize()
+    return a.elapsed_time(b) / it
+
+which = sys.argv[1:] or ["attn", "gemm", "conv"]
+if "attn" in which:
+    for (B, H, N, Nk) in [(28, 5, 4096, 4096), (28, 10, 1024, 1024), (28, 5, 4096, 77)]:
+        q = split(torch.randn(B, N, H * 64, device=dev)); k = split(torch.randn(B, Nk, H * 64, device=dev)); v = split(torch.randn(B, Nk, H * 64, device=dev))
+        ms = ev(lambda: attention_split(q, k, v, H, 0.125))
+        res[f"attn_B{B}_H{H}_N{N}_Nk{Nk}"] = {"ms": ms, "alg_TFLOPs": 4.0 * B * H * N * Nk * 64 / ms / 1e9}
+if "gemm" in which:
+    for (m, n, kk) in [(28 * 4096, 2560, 320), (28 * 4096, 320, 1280), (28 * 1024, 5120, 640), (28 * 4096, 320, 320)]:
+        a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0)
+        ms = ev(lambda: gemm_split(a, w))
+        res[f"gemm_{m}x{n}x{kk}"] = {"ms": ms, "alg_TFLOPs": 2.0 * m * n * kk / ms / 1e9}
+if "conv" in which:
+    for (B, H, C, Co) in [(28, 64, 320, 320), (28, 32, 640, 640), (28, 64, 640, 320)]:
+        conv = torch.nn.Conv2d(C, Co, 3, padding=1).to(dev)
+        x = split(torch.randn(B, H, H, C, device=dev))
+        ms = ev(lambda: K.conv2d(x, conv))
+        res[f"conv3x3_B{B}_{H}x{H}_{C}to{Co}"] = {"ms": ms, "alg_TFLOPs": 2.0 * B * H * H * Co * 9 * C / ms / 1e9}
+print(json.dumps(res, indent=1))

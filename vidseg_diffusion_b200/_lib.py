@@ -43,6 +43,12 @@ SIGNATURES = {
     "vidseg_kmeans_release": (c_int, [c_void_p]),
     "vidseg_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
     "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
+    "vidseg_gemm_split_ex": (c_int, [c_void_p] * 7 + [c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
+                                     c_int, c_int, c_int, c_float, c_void_p]),
+    "vidseg_conv_temporal_split": (c_int, [c_void_p] * 12 + [c_int] * 5 + [c_float, c_void_p]),
+    "vidseg_temporal_attention": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),
+    "vidseg_layernorm_bias_split": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
+                                            c_longlong, c_int, c_void_p]),
     "vidseg_conv2d_split": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p]),
     "vidseg_layernorm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vidseg_geglu_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),

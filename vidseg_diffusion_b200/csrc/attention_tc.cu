@@ -36,6 +36,13 @@ constexpr int kAtSmemP = kAtTiles * 2 * kAtPTileBytes;          // 64 KB
 constexpr int kAtSmemBytes = kAtSmemQ + kAtSmemKV + kAtSmemP + 1024 + 256;
 constexpr int kAtThreads = 64 + kAtTiles * 128;  // producer warp, MMA warp, 2 softmax warpgroups
 
+// 2^x on the SFU, flush-to-zero: one MUFU.EX2 (exp2f() adds a denormal-range rescale: two FMUL and a compare per call)
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 struct AttnParams {
   int batch, heads, nq, nk;
   float scale_log2;  // softmax scale * log2(e)
@@ -189,24 +196,36 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         tc::tmem_ld_32x32(t_row + 32, s1);
         tc::tmem_wait_ld();
       }
-      float mx = -INFINITY;
+      if (valid < kAtBK) {  // warp-uniform: only the last key block of a ragged Nk (e.g. the 77 context tokens)
 #pragma unroll
-      for (int i = 0; i < kAtBK; ++i)
-        if (i < valid) mx = fmaxf(mx, __uint_as_float(sc[i]));
+        for (int i = 0; i < kAtBK; ++i)
+          if (i >= valid) sc[i] = 0xff800000u;  // -inf: exp2 -> 0, max unaffected
+      }
+      // four independent chains for the row maximum and the row sum (one thread owns the whole row, so a single
+      // chain would serialise 64 dependent operations at the ALU latency)
+      float mx0 = __uint_as_float(sc[0]), mx1 = __uint_as_float(sc[1]), mx2 = __uint_as_float(sc[2]),
+            mx3 = __uint_as_float(sc[3]);
+#pragma unroll
+      for (int i = 4; i < kAtBK; i += 4) {
+        mx0 = fmaxf(mx0, __uint_as_float(sc[i]));
+        mx1 = fmaxf(mx1, __uint_as_float(sc[i + 1]));
+        mx2 = fmaxf(mx2, __uint_as_float(sc[i + 2]));
+        mx3 = fmaxf(mx3, __uint_as_float(sc[i + 3]));
+      }
+      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = exp2f(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      float lsum = 0.f;
+      const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
+      // probabilities are carried scaled by 2^12 (<= 4096) so that their fp16 residuals stay normal numbers;
+      // the row sum carries the same factor, which cancels in the final O / l
+      const float bias = 12.0f - m_new;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
       // probabilities -> fp16 hi / lo -> swizzled smem (A operand of the PV product)
 #pragma unroll
       for (int i = 0; i < kAtBK; i += 8) {
         float pv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          // probabilities are carried scaled by 2^12 (<= 4096) so that their fp16 residuals stay normal numbers;
-          // the row sum carries the same factor, which cancels in the final O / l
-          pv[u] = (i + u < valid) ? exp2f(fmaf(__uint_as_float(sc[i + u]), p.scale_log2, 12.0f - m_new)) : 0.f;
-          lsum += pv[u];
-        }
+        for (int u = 0; u < 8; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[i + u]), p.scale_log2, bias));
+        ls0 += pv[0] + pv[4]; ls1 += pv[1] + pv[5]; ls2 += pv[2] + pv[6]; ls3 += pv[3] + pv[7];
         uint4 hv, lv;
         tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv, lv);
         const int chunk = i >> 3;  // 16-byte chunk index inside the 128-byte row
@@ -214,6 +233,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         *reinterpret_cast<uint4*>(p_hi_tile + off) = hv;
         *reinterpret_cast<uint4*>(p_lo_tile + off) = lv;
       }
+      const float lsum = (ls0 + ls1) + (ls2 + ls3);
       l_run = fmaf(l_run, alpha, lsum);
       m_run = m_new;
       // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal

@@ -74,7 +74,7 @@ VS_API int vidseg_profile_read(int family, double* ms_total, long long* launches
 }
 
 VS_API const char* vidseg_last_error(void) { return vidseg::g_last_error; }
-VS_API int vidseg_abi_version(void) { return 1; }
+VS_API int vidseg_abi_version(void) { return 2; }
 VS_API long long vidseg_launch_count(void) { return vidseg::g_launch_count.load(); }
 VS_API int vidseg_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

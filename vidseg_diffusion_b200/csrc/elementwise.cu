@@ -24,13 +24,17 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 constexpr int kLnMaxQuads = 16;  // C <= 2048
 
 __global__ void __launch_bounds__(256)
-layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                       float eps, __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c) {
+layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ row_bias, long long rows_per_bias,
+                       const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                       __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int nq = c >> 2;  // float4 per row
   const float4* xr = reinterpret_cast<const float4*>(x + row * c);
+  // optional bias shared by groups of rows_per_bias consecutive rows, added BEFORE the normalisation: the
+  // frame-position embedding / single-token cross-attention output of the temporal layers
+  const float4* br = row_bias ? reinterpret_cast<const float4*>(row_bias + (row / rows_per_bias) * c) : nullptr;
   float4 v[kLnMaxQuads];
   float s = 0.f;
 #pragma unroll
@@ -38,6 +42,10 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ga
     const int q = lane + 32 * i;
     if (q < nq) {
       v[i] = ld_stream_f4(xr + q);
+      if (br) {
+        const float4 bb = __ldg(br + q);
+        v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+      }
       s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
@@ -97,7 +105,7 @@ geglu_split_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half*
 // Pass 1: per (sample, pixel chunk) per-group sum and sum of squares, fixed summation order (deterministic).
 // Pass 2: normalise, affine, activation, operand split.
 // ---------------------------------------------------------------------------------------------
-constexpr int kGnChunks = 32;     // pixel chunks per sample in pass 1
+constexpr int kGnMaxChunks = 256; // pixel chunks per sample in pass 1 (chosen per call so that the grid fills the GPU)
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxGroups = 32;
 
@@ -109,7 +117,8 @@ __device__ __forceinline__ float4 gn_load(const float* __restrict__ x1, int c1, 
 
 __global__ void __launch_bounds__(kGnThreads)
 groupnorm_stats_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2, int hw, int groups,
-                       double* __restrict__ partial /* [B, kGnChunks, groups, 2] */) {
+                       double* __restrict__ partial /* [B, chunks, groups, 2] */) {
+  const int kGnChunks = gridDim.x;
   extern __shared__ float sm[];  // [lanes][C][2]
   const int c = c1 + c2;
   const int nq = c >> 2;
@@ -152,7 +161,7 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
                        const double* __restrict__ partial, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out_hi,
                        __half* __restrict__ out_lo, __half* __restrict__ raw_hi, __half* __restrict__ raw_lo,
-                       int pix_per_block) {
+                       int pix_per_block, int kGnChunks) {
   __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
   const int c = c1 + c2;
   const int nq = c >> 2;
@@ -240,15 +249,32 @@ static int grid_for(long long work_items, int threads) {
 
 using namespace vidseg;
 
+static int layernorm_entry(const float* x, const float* row_bias, long long rows_per_bias, const float* gamma,
+                           const float* beta, float eps, void* out_hi, void* out_lo, long long rows, int channels,
+                           void* stream);
+
 VS_API int vidseg_layernorm_split(const float* x, const float* gamma, const float* beta, float eps, void* out_hi,
                                   void* out_lo, long long rows, int channels, void* stream) {
+  return layernorm_entry(x, nullptr, 1, gamma, beta, eps, out_hi, out_lo, rows, channels, stream);
+}
+
+VS_API int vidseg_layernorm_bias_split(const float* x, const float* row_bias, long long rows_per_bias, const float* gamma,
+                                       const float* beta, float eps, void* out_hi, void* out_lo, long long rows,
+                                       int channels, void* stream) {
+  VS_REQUIRE(row_bias == nullptr || rows_per_bias >= 1, "rows_per_bias must be positive");
+  return layernorm_entry(x, row_bias, rows_per_bias, gamma, beta, eps, out_hi, out_lo, rows, channels, stream);
+}
+
+static int layernorm_entry(const float* x, const float* row_bias, long long rows_per_bias, const float* gamma,
+                           const float* beta, float eps, void* out_hi, void* out_lo, long long rows, int channels,
+                           void* stream) {
   VS_REQUIRE(x && gamma && beta && out_hi && out_lo, "null pointer");
   VS_REQUIRE(rows >= 0 && channels >= 4 && channels % 4 == 0 && channels <= 128 * kLnMaxQuads, "C must be a multiple of 4, <= 2048");
   if (rows == 0) return 0;
   const int warps = 8;
   const long long grid = (rows + warps - 1) / warps;
   VS_REQUIRE(grid <= 0x7fffffffLL, "too many rows");
-  VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel, (int)grid, warps * 32, 0, stream, x, gamma, beta, eps,
+  VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel, (int)grid, warps * 32, 0, stream, x, row_bias, rows_per_bias, gamma, beta, eps,
               (__half*)out_hi, (__half*)out_lo, rows, channels);
   VS_POST_LAUNCH();
   return 0;
@@ -266,7 +292,7 @@ VS_API int vidseg_geglu_split(const float* h, void* out_hi, void* out_lo, long l
 
 VS_API size_t vidseg_groupnorm_workspace_bytes(int batch, int groups) {
   if (batch <= 0 || groups <= 0) return 0;
-  return (size_t)batch * kGnChunks * groups * 2 * sizeof(double);
+  return (size_t)batch * kGnMaxChunks * groups * 2 * sizeof(double);
 }
 
 VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int c2, const float* gamma, const float* beta,
@@ -287,7 +313,11 @@ VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int 
   VS_REQUIRE(smem <= 48 * 1024, "C too large for the group-norm statistics kernel");
   double* partial = reinterpret_cast<double*>(workspace);
   const double bytes = 4.0 * batch * hw * c;
-  VS_LAUNCH_W(bytes, groupnorm_stats_kernel, dim3(kGnChunks, batch), kGnThreads, smem, stream, x1, c1, x2, c2, hw, groups,
+  // more chunks for long samples (the video ResBlocks normalise over whole clips: batch 2, hw = T*h*w); a function
+  // of hw only, so that a sample's statistics do not depend on which other samples share the batch
+  int chunks = 32;
+  while (chunks < kGnMaxChunks && hw / (chunks * 2) >= 256) chunks *= 2;
+  VS_LAUNCH_W(bytes, groupnorm_stats_kernel, dim3(chunks, batch), kGnThreads, smem, stream, x1, c1, x2, c2, hw, groups,
               partial);
   VS_POST_LAUNCH();
   // pass 2: ~16K quads per block
@@ -296,7 +326,7 @@ VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int 
   const int blocks = (hw + pix_per_block - 1) / pix_per_block;
   VS_LAUNCH_W(bytes * (raw_hi ? 3.0 : 2.0), groupnorm_apply_kernel, dim3(blocks, batch), kGnThreads, 0, stream, x1, c1, x2,
               c2, hw, groups, partial, gamma, beta, eps, silu, (__half*)out_hi, (__half*)out_lo, (__half*)raw_hi,
-              (__half*)raw_lo, pix_per_block);
+              (__half*)raw_lo, pix_per_block, chunks);
   VS_POST_LAUNCH();
   return 0;
 }

@@ -133,8 +133,13 @@ struct GemmParams {
   int c_off[kMaxTaps], w_off[kMaxTaps], p_idx[kMaxTaps], h_off[kMaxTaps];
   float acc_scale;          // exact power-of-two inverse of the operand pre-scaling (weights carry 2^8)
   const float* bias;        // [N] or null
-  const float* chan_bias;   // [nb, N] or null (per-sample channel bias: the ResBlock time embedding)
+  const float* chan_bias;   // [M / cb_div, N] or null: bias per group of cb_div consecutive output rows (the ResBlock
+                            // time embedding per sample; per-frame / per-video vectors of the temporal layers)
+  long long cb_div;
   const float* residual;    // [M, N] or null
+  const float* blend;       // [M, N] or null: out = a * blend + (1 - a) * out, a = blend_alpha[row / ba_div] (AlphaBlender)
+  const float* blend_alpha;
+  long long ba_div;
   float* out_f32;           // [M, N] or null
   __half* out_hi;           // [M, N] or null
   __half* out_lo;
@@ -257,6 +262,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       const int b = (mt / (p.tiles_w * p.tiles_h)) * p.bb + pb;
       const bool row_ok = (w < p.wo) && (h < p.ho) && (b < p.nb);
       const size_t pix = ((size_t)b * p.ho + h) * p.wo + w;
+      const size_t cb_row = p.chan_bias ? (size_t)((long long)pix / p.cb_div) : 0;
+      const float blend_a = (p.blend && row_ok) ? __ldg(p.blend_alpha + (long long)pix / p.ba_div) : 0.f;
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
@@ -282,7 +289,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               }
           }
           if (p.chan_bias) {
-            const float* cb = p.chan_bias + (size_t)b * p.n + col0;
+            const float* cb = p.chan_bias + cb_row * p.n + col0;
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
               if (j < ncols) {
@@ -296,6 +303,16 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               if (j < ncols) {
                 const float4 q = *reinterpret_cast<const float4*>(p.residual + off + j);
                 v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+              }
+          }
+          if (p.blend) {
+            const float a = blend_a, na = 1.0f - a;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              if (j < ncols) {
+                const float4 q = *reinterpret_cast<const float4*>(p.blend + off + j);
+                v[j] = a * q.x + na * v[j]; v[j + 1] = a * q.y + na * v[j + 1];
+                v[j + 2] = a * q.z + na * v[j + 2]; v[j + 3] = a * q.w + na * v[j + 3];
               }
           }
           if (p.out_f32) {
@@ -365,6 +382,8 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   p.tiles_h = (p.ho + p.bh - 1) / p.bh;
   p.tiles_b = (p.nb + p.bb - 1) / p.bb;
   p.kc_per_tap = (p.cin + kGemmBK - 1) / kGemmBK;
+  if (p.cb_div <= 0) p.cb_div = (long long)p.ho * p.wo;  // default: one bias row per sample
+  if (p.ba_div <= 0) p.ba_div = 1;
   const uint32_t box[5] = {(uint32_t)kGemmBK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
   CUtensorMap ta_hi, ta_lo;
   if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
@@ -411,26 +430,47 @@ VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, flo
 
 #undef VS_FAMILY
 #define VS_FAMILY vidseg::kFamGemm
-VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
-                             const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
-                             float acc_scale, void* stream) {
+static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                      const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
+                      const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
+                      int m, int n, int k, float acc_scale, void* stream) {
   VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null operand pointer");
   VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
   VS_REQUIRE(m >= 0 && n >= 1 && k >= 1, "bad shape");
   VS_REQUIRE(n % 4 == 0 && k % 8 == 0, "N must be a multiple of 4 and K of 8 (16-byte rows for TMA and vector stores)");
   VS_REQUIRE(out_hi == nullptr || n % 8 == 0, "split output needs N % 8 == 0");
+  VS_REQUIRE(row_bias == nullptr || rows_per_bias >= 1, "rows_per_bias must be positive");
+  VS_REQUIRE((blend == nullptr) == (blend_alpha == nullptr), "blend and blend_alpha go together");
+  VS_REQUIRE(blend == nullptr || rows_per_alpha >= 1, "rows_per_alpha must be positive");
   if (m == 0) return 0;
   GemmParams p{};
   p.n = n; p.k = k; p.taps = 1; p.cin = k;
   p.wo = m; p.ho = 1; p.nb = 1;
   p.acc_scale = acc_scale;
   p.bias = bias; p.residual = residual; p.out_f32 = out_f32;
+  p.chan_bias = row_bias; p.cb_div = rows_per_bias;
+  p.blend = blend; p.blend_alpha = blend_alpha; p.ba_div = rows_per_alpha;
   p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
   const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
   const uint64_t row = (uint64_t)k * 2;
   const uint64_t astrides[4] = {row, row * m, row * m, row * m};
   return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, kFamGemm, stream);
+}
+
+VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                             const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
+                             float acc_scale, void* stream) {
+  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, out_f32, out_hi, out_lo, m, n,
+                    k, acc_scale, stream);
+}
+
+VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
+                                const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi,
+                                void* out_lo, int m, int n, int k, float acc_scale, void* stream) {
+  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, row_bias, rows_per_bias, blend, blend_alpha, rows_per_alpha,
+                    out_f32, out_hi, out_lo, m, n, k, acc_scale, stream);
 }
 
 #undef VS_FAMILY
@@ -481,5 +521,38 @@ VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w
       p.w_off[t] = (dx == 0) ? -1 : 0;
     }
   }
+  return run_gemm(x_hi, x_lo, adims, astrides, p, w_hi, w_lo, kFamConv, stream);
+}
+
+
+// (3,1,1) convolution over the frame axis of a video tensor [V, T, HW, C] (channels-last '(b t) h w c' memory):
+// the three taps are the same pixel patch shifted by -1 / 0 / +1 frames, out-of-range frames are the TMA zero fill.
+VS_API int vidseg_conv_temporal_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                                      const float* bias, const float* frame_bias, const float* residual,
+                                      const float* blend, const float* blend_alpha, float* out_f32, void* out_hi,
+                                      void* out_lo, int videos, int frames, int hw, int cin, int cout, float acc_scale,
+                                      void* stream) {
+  VS_REQUIRE(x_hi && x_lo && w_hi && w_lo, "null operand pointer");
+  VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
+  VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
+  VS_REQUIRE(videos >= 0 && frames >= 1 && hw >= 1 && cin >= 1 && cout >= 1, "bad shape");
+  VS_REQUIRE(cin % 8 == 0 && cout % 4 == 0, "Cin must be a multiple of 8 and Cout of 4");
+  VS_REQUIRE(out_hi == nullptr || cout % 8 == 0, "split output needs Cout % 8 == 0");
+  VS_REQUIRE((blend == nullptr) == (blend_alpha == nullptr), "blend and blend_alpha go together");
+  if (videos == 0) return 0;
+  GemmParams p{};
+  p.taps = 3;
+  p.cin = cin;
+  p.n = cout; p.k = 3 * cin;
+  p.bias = bias; p.residual = residual; p.out_f32 = out_f32;
+  p.chan_bias = frame_bias; p.cb_div = hw;           // [V*T, Cout]: one row per frame
+  p.blend = blend; p.blend_alpha = blend_alpha; p.ba_div = hw;  // alpha[V*T]
+  p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
+  p.nb = videos; p.ho = frames; p.wo = hw;
+  p.acc_scale = acc_scale;
+  const uint64_t px = (uint64_t)cin * 2;
+  const uint64_t adims[5] = {(uint64_t)cin, (uint64_t)hw, 1, (uint64_t)frames, (uint64_t)videos};
+  const uint64_t astrides[4] = {px, px * hw, px * hw, px * hw * frames};
+  for (int t = 0; t < 3; ++t) { p.c_off[t] = 0; p.w_off[t] = 0; p.p_idx[t] = 0; p.h_off[t] = t - 1; }
   return run_gemm(x_hi, x_lo, adims, astrides, p, w_hi, w_lo, kFamConv, stream);
 }

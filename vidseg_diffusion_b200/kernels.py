@@ -100,10 +100,11 @@ def concat_channels(a, b):
 # ------------------------------------------------------------------------------------------------
 # tensor-core ops
 # ------------------------------------------------------------------------------------------------
-def linear(xs, weight, bias=None, residual=None, want_f32=True, want_split=False):
-    """nn.Linear on a Split activation: xs [.., K] x weight[N, K]^T (+ bias) (+ residual)."""
+def linear(xs, weight, bias=None, residual=None, want_f32=True, want_split=False, **epilogue):
+    """nn.Linear on a Split activation: xs [.., K] x weight[N, K]^T (+ bias) (+ residual); ``epilogue`` = the
+    row_bias / blend terms of linear.gemm_split (temporal layers of the SVD UNet)."""
     b = None if bias is None else _f32(bias)
-    return gemm_split(xs, weight_split(weight), b, residual, want_f32=want_f32, want_split=want_split)
+    return gemm_split(xs, weight_split(weight), b, residual, want_f32=want_f32, want_split=want_split, **epilogue)
 
 
 def attention(qs, ks, vs, heads, scale):
@@ -144,6 +145,61 @@ def conv2d(xs, conv, chan_bias=None, residual=None):
     return as_nchw(out)
 
 
+def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blend=None, blend_alpha=None):
+    """nn.Conv3d with a (3,1,1) kernel over the frame axis.  xs: Split [(V T), H, W, Cin] (the 2-D layers' layout);
+    frame_bias [(V T), Cout]; residual / blend: image-shaped fp32 [(V T), Cout, H, W]; blend_alpha [(V T)].
+    Returns fp32 [(V T), Cout, H, W] (channels_last memory)."""
+    if tuple(conv.kernel_size) != (3, 1, 1) or tuple(conv.padding) != (1, 0, 0) or tuple(conv.stride) != (1, 1, 1):
+        raise _lib.VidsegError(f"conv_temporal: unsupported geometry {conv}")
+    bt, h, w, cin = xs.hi.shape
+    if bt != videos * frames or cin != conv.in_channels:
+        raise _lib.VidsegError("conv_temporal: shape mismatch")
+    cout = conv.out_channels
+    ws = _cached(conv.weight, "conv_t", lambda t: split(t.float()[:, :, :, 0, 0].permute(0, 2, 1).reshape(cout, 3 * cin).contiguous(), WEIGHT_SCALE))
+    out = torch.empty((bt, h, w, cout), dtype=torch.float32, device=xs.hi.device)
+    res = None if residual is None else nhwc(residual, "residual")
+    bl = None if blend is None else nhwc(blend, "blend")
+    for t, name in ((res, "residual"), (bl, "blend")):
+        if t is not None and t.shape != out.shape:
+            raise _lib.VidsegError(f"conv_temporal: {name} shape mismatch")
+    if frame_bias is not None:
+        _require(frame_bias, "frame_bias")
+        if tuple(frame_bias.shape) != (bt, cout):
+            raise _lib.VidsegError("conv_temporal: frame_bias must be [(V T), Cout]")
+    if (bl is None) != (blend_alpha is None):
+        raise _lib.VidsegError("conv_temporal: blend and blend_alpha go together")
+    if blend_alpha is not None:
+        _require(blend_alpha, "blend_alpha")
+        if blend_alpha.numel() != bt:
+            raise _lib.VidsegError("conv_temporal: blend_alpha must have one entry per frame")
+    bias = None if conv.bias is None else _f32(conv.bias)
+    ptr = lambda t: t.data_ptr() if t is not None else None
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.vidseg_conv_temporal_split(
+            xs.hi.data_ptr(), xs.lo.data_ptr(), ws.hi.data_ptr(), ws.lo.data_ptr(), ptr(bias), ptr(frame_bias), ptr(res),
+            ptr(bl), ptr(blend_alpha), out.data_ptr(), None, None, videos, frames, h * w, cin, cout,
+            1.0 / (xs.scale * ws.scale), _lib.stream_ptr()), "conv_temporal_split")
+    return as_nchw(out)
+
+
+def temporal_attention(q, k, v, videos, frames, heads, scale):
+    """Self-attention over the frames of every spatial site.  q, k, v: fp32 [(V T), S, heads*64] in the frame-major
+    layout of the spatial layers.  Returns the Split operand [(V T), S, heads*64] of the to_out GEMM."""
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        _require(t, name)
+    bt, s, c = q.shape
+    if bt != videos * frames or c != heads * 64 or k.shape != q.shape or v.shape != q.shape:
+        raise _lib.VidsegError(f"temporal_attention: bad shapes q{tuple(q.shape)} k{tuple(k.shape)} v{tuple(v.shape)}")
+    out = _empty_split(q.shape, q.device)
+    lib = _lib.load()
+    with torch.cuda.device(q.device):
+        _lib.check(lib.vidseg_temporal_attention(q.data_ptr(), k.data_ptr(), v.data_ptr(), None, out.hi.data_ptr(),
+                                                 out.lo.data_ptr(), videos, frames, s, heads, float(scale),
+                                                 _lib.stream_ptr()), "temporal_attention")
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 # normalisation / gating / resampling kernels (all emit the split operand of the next GEMM)
 # ------------------------------------------------------------------------------------------------
@@ -151,16 +207,26 @@ def _empty_split(shape, device):
     return Split(torch.empty(shape, dtype=torch.float16, device=device), torch.empty(shape, dtype=torch.float16, device=device))
 
 
-def layer_norm_split(x, ln):
-    """LayerNorm over the last dim -> Split operand of the next GEMM."""
+def layer_norm_split(x, ln, row_bias=None, rows_per_bias=1):
+    """LayerNorm over the last dim of (x + row_bias[row // rows_per_bias]) -> Split operand of the next GEMM."""
     _require(x, "x")
     c = x.shape[-1]
+    rows = x.numel() // c
     out = _empty_split(x.shape, x.device)
     lib = _lib.load()
     with torch.cuda.device(x.device):
-        _lib.check(lib.vidseg_layernorm_split(x.data_ptr(), _f32(ln.weight).data_ptr(), _f32(ln.bias).data_ptr(), float(ln.eps),
-                                              out.hi.data_ptr(), out.lo.data_ptr(), x.numel() // c, c, _lib.stream_ptr()),
-                   "layernorm_split")
+        if row_bias is None:
+            _lib.check(lib.vidseg_layernorm_split(x.data_ptr(), _f32(ln.weight).data_ptr(), _f32(ln.bias).data_ptr(),
+                                                  float(ln.eps), out.hi.data_ptr(), out.lo.data_ptr(), rows, c,
+                                                  _lib.stream_ptr()), "layernorm_split")
+        else:
+            _require(row_bias, "row_bias")
+            if rows_per_bias < 1 or row_bias.numel() != -(-rows // rows_per_bias) * c:
+                raise _lib.VidsegError(f"layer_norm: row_bias {tuple(row_bias.shape)} does not cover {rows} rows in groups of {rows_per_bias}")
+            _lib.check(lib.vidseg_layernorm_bias_split(x.data_ptr(), row_bias.data_ptr(), int(rows_per_bias),
+                                                       _f32(ln.weight).data_ptr(), _f32(ln.bias).data_ptr(), float(ln.eps),
+                                                       out.hi.data_ptr(), out.lo.data_ptr(), rows, c, _lib.stream_ptr()),
+                       "layernorm_bias_split")
     return out
 
 
@@ -176,7 +242,7 @@ def geglu_split(h):
     return out
 
 
-def group_norm_split(x, gn, silu, want_raw=False):
+def group_norm_split(x, gn, silu, want_raw=False, samples=None):
     """GroupNorm (+ SiLU) of an image-shaped fp32 tensor or a ChannelCat of two.
 
     Returns (Split [B, H, W, C] of the normalised activation, Split of the raw input or None, [B, H, W, Ca] fp32
@@ -193,6 +259,11 @@ def group_norm_split(x, gn, silu, want_raw=False):
     out = _empty_split((b, h, w, c), a.device)
     raw = _empty_split((b, h, w, c), a.device) if want_raw else None
     lib = _lib.load()
+    hw = h * w
+    if samples is not None:  # statistics over groups of b // samples consecutive images (GroupNorm on 'b c t h w')
+        if b % samples:
+            raise _lib.VidsegError(f"group_norm: {b} images do not split into {samples} clips")
+        hw, b = hw * (b // samples), samples
     nbytes = lib.vidseg_groupnorm_workspace_bytes(b, gn.num_groups)
     ws = _workspace(a.device, nbytes)
     with torch.cuda.device(a.device):
@@ -200,7 +271,7 @@ def group_norm_split(x, gn, silu, want_raw=False):
             a.data_ptr(), c1, bsrc.data_ptr() if bsrc is not None else None, c2,
             _f32(gn.weight).data_ptr(), _f32(gn.bias).data_ptr(), float(gn.eps), gn.num_groups, 1 if silu else 0,
             out.hi.data_ptr(), out.lo.data_ptr(), raw.hi.data_ptr() if raw else None, raw.lo.data_ptr() if raw else None,
-            b, h * w, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "groupnorm_split")
+            b, hw, ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "groupnorm_split")
     return out, raw, a
 
 

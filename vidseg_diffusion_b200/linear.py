@@ -24,6 +24,9 @@ class Split:
     def float(self):
         return (self.hi.float() + self.lo.float()) / self.scale
 
+    def __getitem__(self, idx):
+        return Split(self.hi[idx].contiguous(), self.lo[idx].contiguous(), self.scale)
+
 
 WEIGHT_SCALE = 256.0  # tc::kWeightScale
 
@@ -39,9 +42,11 @@ def split(x, scale=1.0):
     return Split(hi, lo, float(scale))
 
 
-def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
-    """out = a @ w.T (+ bias) (+ residual).  a: Split [.., K], w: Split [N, K] (nn.Linear layout).
-    Returns (out_f32 or None, Split or None)."""
+def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, row_bias=None, rows_per_bias=1,
+               blend=None, blend_alpha=None, rows_per_alpha=1):
+    """out = a @ w.T (+ bias) (+ row_bias[row // rows_per_bias]) (+ residual), then optionally
+    out = alpha * blend + (1 - alpha) * out with alpha = blend_alpha[row // rows_per_alpha].
+    a: Split [.., K], w: Split [N, K] (nn.Linear layout).  Returns (out_f32 or None, Split or None)."""
     k = a.hi.shape[-1]
     lead = a.hi.shape[:-1]
     m = a.hi.numel() // k
@@ -62,16 +67,29 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False):
         _lib.require_cuda_tensor(residual, torch.float32, "residual")
         if residual.numel() != m * n:
             raise _lib.VidsegError("gemm_split: residual shape mismatch")
+    if row_bias is not None:
+        _lib.require_cuda_tensor(row_bias, torch.float32, "row_bias")
+        if rows_per_bias < 1 or row_bias.numel() != -(-m // rows_per_bias) * n:
+            raise _lib.VidsegError(f"gemm_split: row_bias {tuple(row_bias.shape)} does not cover {m} rows in groups of {rows_per_bias}")
+    if (blend is None) != (blend_alpha is None):
+        raise _lib.VidsegError("gemm_split: blend and blend_alpha go together")
+    if blend is not None:
+        _lib.require_cuda_tensor(blend, torch.float32, "blend")
+        _lib.require_cuda_tensor(blend_alpha, torch.float32, "blend_alpha")
+        if blend.numel() != m * n or rows_per_alpha < 1 or blend_alpha.numel() != -(-m // rows_per_alpha):
+            raise _lib.VidsegError("gemm_split: blend / blend_alpha shape mismatch")
     lib = _lib.load()
+    ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(dev):
-        _lib.check(lib.vidseg_gemm_split(
-            a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(),
-            bias.data_ptr() if bias is not None else None,
-            residual.data_ptr() if residual is not None else None,
-            out.data_ptr() if out is not None else None,
-            oh.data_ptr() if oh is not None else None,
-            ol.data_ptr() if ol is not None else None,
-            m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split")
+        if row_bias is None and blend is None:
+            _lib.check(lib.vidseg_gemm_split(
+                a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
+                ptr(out), ptr(oh), ptr(ol), m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split")
+        else:
+            _lib.check(lib.vidseg_gemm_split_ex(
+                a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
+                ptr(row_bias), int(rows_per_bias), ptr(blend), ptr(blend_alpha), int(rows_per_alpha),
+                ptr(out), ptr(oh), ptr(ol), m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split_ex")
     return out, (Split(oh, ol) if want_split else None)
 
 

@@ -24,8 +24,9 @@ def harvest_self_attn_q(model, blocks):
     feats = []
     for i in blocks:
         layer = model.output_blocks[i][1]
-        if "SpatialTransformer" not in str(type(layer)):
-            raise _lib.VidsegError(f"output_blocks[{i}][1] is not a SpatialTransformer")
+        kind = str(type(layer))  # the reference's own test: sd_pipeline_vspw.py:112 / svd_single_video_inference.py:117
+        if "SpatialTransformer" not in kind and "SpatialVideoTransformer" not in kind:
+            raise _lib.VidsegError(f"output_blocks[{i}][1] is not a Spatial(Video)Transformer")
         q = layer.transformer_blocks[0].attn1.q
         if q is None:
             raise _lib.VidsegError(f"output_blocks[{i}] has no stashed q: run the UNet first")
@@ -84,5 +85,6 @@ class ClipSegmenter:
         x = x_host.to(dev, non_blocking=True)
         t = timesteps_host.to(dev, non_blocking=True)
         c = context_host.to(dev, non_blocking=True)
+        unet_kwargs = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in unet_kwargs.items()}
         labels, _ = self.segment(x, t, c, num_frames, seed, **unet_kwargs)
         return labels.cpu()

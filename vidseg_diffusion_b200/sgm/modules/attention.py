@@ -49,10 +49,13 @@ class FeedForward(nn.Module):
         dim_out = dim if dim_out is None else dim_out
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
-    def forward_split(self, xs, residual=None):
+    def forward_split(self, xs, residual=None, want_split=False, **epilogue):
+        """``epilogue``: row_bias / blend terms of the output GEMM (linear.gemm_split).  Returns fp32, or
+        (fp32, Split) with ``want_split``."""
         hs = self.net[0].forward_split(xs)
-        out, _ = K.linear(hs, self.net[2].weight, self.net[2].bias, residual=residual, want_f32=True)
-        return out
+        out, outs = K.linear(hs, self.net[2].weight, self.net[2].bias, residual=residual, want_f32=True,
+                             want_split=want_split, **epilogue)
+        return (out, outs) if want_split else out
 
     def forward(self, x):
         return self.forward_split(K.split(x))
@@ -74,8 +77,31 @@ class CrossAttention(nn.Module):
         self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
         self.backend = backend
-        self.q = None
-        self.k = None
+        self._stash = {"q": None, "k": None}
+
+    # the Q/K "hook" (reference :330-331): plain attributes there; here the temporal layers keep their activations in
+    # the frame-major layout and hand out the reference's '(b s) t c' view on first access
+    def _get_stash(self, name):
+        v = self._stash[name]
+        if callable(v):
+            v = self._stash[name] = v()
+        return v
+
+    q = property(lambda self: self._get_stash("q"), lambda self, v: self._stash.__setitem__("q", v))
+    k = property(lambda self: self._get_stash("k"), lambda self, v: self._stash.__setitem__("k", v))
+
+    def forward_single_token(self, xs, context):
+        """Cross-attention to a context of ONE token (SVD: the CLIP image embedding, svd.yaml): softmax over a single
+        key is exactly 1, so every query of a sample receives to_out(to_v(context)).  Returns that vector per sample,
+        fp32 [B, C]; the caller adds it as a row bias.  q is still projected because the pipelines dump it."""
+        q, _ = K.linear(xs, self.to_q.weight, want_f32=True)
+        k, _ = K.linear(context, self.to_k.weight, want_f32=True)
+        _, vs = K.linear(context, self.to_v.weight, want_f32=False, want_split=True)
+        self.q = q
+        self.k = k
+        lin = self.to_out[0]
+        out, _ = K.linear(vs, lin.weight, lin.bias, want_f32=True)
+        return out.reshape(out.shape[0], out.shape[-1])
 
     def forward_split(self, xs, context=None, residual=None, injected_q=None, injected_k=None, injected_v=None):
         """xs: Split [B, N, C] (already normalised); context: Split [B, L, Cctx] or None.
@@ -155,6 +181,12 @@ class BasicTransformerBlock(nn.Module):
         ctx1 = context if self.disable_self_attn else None
         x = self.attn1.forward_split(K.layer_norm_split(x, self.norm1), ctx1, x, *inj["self"])
         self.attn1_out = None  # the reference keeps attn1_out / attn2_out / ff_out for modulation only
+        if context is not None and context.hi.shape[1] == 1 and not any(v is not None for v in inj["cross"]):
+            # one context token: attn2's output is one vector per sample, carried as a row bias of norm3 / ff
+            n = x.shape[1]
+            a = self.attn2.forward_single_token(K.layer_norm_split(x, self.norm2), context)
+            return self.ff.forward_split(K.layer_norm_split(x, self.norm3, row_bias=a, rows_per_bias=n), x,
+                                         row_bias=a, rows_per_bias=n)
         x = self.attn2.forward_split(K.layer_norm_split(x, self.norm2), context, x, *inj["cross"])
         x = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x)
         return x

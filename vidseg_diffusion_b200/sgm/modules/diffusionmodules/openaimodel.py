@@ -24,13 +24,21 @@ class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
 
     def forward(self, x, emb, context=None, image_only_indicator=None, time_context=None, num_video_frames=None,
                 is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        from ..video_attention import SpatialVideoTransformer
+        from .video_model import VideoResBlock
         for layer in self:
-            if isinstance(layer, SpatialTransformer):
+            if isinstance(layer, VideoResBlock):
+                x = layer(x, emb, num_video_frames, image_only_indicator)
+            elif isinstance(layer, SpatialVideoTransformer):
+                x = layer(x, context, time_context, num_video_frames, image_only_indicator,
+                          is_modulate_step=is_modulate_step, is_injected_step=is_injected_step,
+                          modulate_params=modulate_params)
+            elif isinstance(layer, SpatialTransformer):
                 x = layer(x, context, is_modulate_step=is_modulate_step, is_injected_step=is_injected_step,
                           modulate_params=modulate_params)
             elif isinstance(layer, TimestepBlock):
                 x = layer(x, emb)
-            elif isinstance(layer, nn.Conv2d):  # input_blocks[0]: 4 latent channels, zero-padded to 8 for the TMA rows
+            elif isinstance(layer, nn.Conv2d):  # input_blocks[0]: 4 (SD) / 8 (SVD) latent channels, padded to 8 for the TMA rows
                 x = K.conv2d(K.image_split(x), layer)
             else:
                 x = layer(x)
@@ -84,21 +92,31 @@ class ResBlock(TimestepBlock):
                  dims=2, use_checkpoint=False, up=False, down=False, kernel_size=3, exchange_temb_dims=False,
                  skip_t_emb=False):
         super().__init__()
-        if up or down or use_scale_shift_norm or dims != 2 or kernel_size != 3 or skip_t_emb or exchange_temb_dims:
-            _unsupported("ResBlock(up / down / scale-shift / dims != 2 / kernel != 3 / skip_t_emb)")
+        video = dims == 3
+        if up or down or use_scale_shift_norm or skip_t_emb or dims not in (2, 3):
+            _unsupported("ResBlock(up / down / scale-shift / skip_t_emb / dims not in (2, 3))")
+        if video and not (list(kernel_size) == [3, 1, 1] and exchange_temb_dims and not use_conv):
+            _unsupported("ResBlock(dims=3) other than the (3,1,1) time_stack of VideoResBlock")
+        if not video and (kernel_size != 3 or exchange_temb_dims):
+            _unsupported("ResBlock(dims=2, kernel != 3 / exchange_temb_dims)")
+        self.dims = dims
+        self.exchange_temb_dims = exchange_temb_dims
         self.channels = channels
         self.emb_channels = emb_channels
         self.dropout = dropout
         self.out_channels = out_channels or channels
         self.use_conv = use_conv
         self.use_checkpoint = use_checkpoint
-        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
-                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        conv = (lambda ci, co: nn.Conv3d(ci, co, (3, 1, 1), padding=(1, 0, 0))) if video else \
+            (lambda ci, co: nn.Conv2d(ci, co, 3, padding=1))
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), conv(channels, self.out_channels))
         self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
         self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
-                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+                                        zero_module(conv(self.out_channels, self.out_channels)))
         if self.out_channels == channels:
             self.skip_connection = nn.Identity()
+        elif video:
+            _unsupported("ResBlock(dims=3) with a channel change")
         elif use_conv:
             self.skip_connection = nn.Conv2d(channels, self.out_channels, 3, padding=1)
         else:
@@ -107,8 +125,21 @@ class ResBlock(TimestepBlock):
     def forward(self, x, emb):
         return self._forward(x, emb)
 
+    def forward_video(self, x, emb, videos, frames, blend_alpha):
+        """The dims=3 form as VideoResBlock uses it (video_model.py:75-85): x is the '(b t) c h w' output of the 2-D
+        block (the 'b c t h w' rearrange is index arithmetic in the kernels), GroupNorm statistics run over whole
+        clips, the convolutions are (3,1,1) over frames, the embedding is per frame (exchange_temb_dims), and the
+        AlphaBlender mix with the block input is the epilogue of the second convolution."""
+        emb_out = K.dense(emb, self.emb_layers[1], act_silu_in=True)  # [(b t), Cout]
+        hs, _, _ = K.group_norm_split(x, self.in_layers[0], silu=True, samples=videos)
+        h = K.conv_temporal(hs, self.in_layers[2], videos, frames, frame_bias=emb_out)
+        hs2, _, _ = K.group_norm_split(h, self.out_layers[0], silu=True, samples=videos)
+        return K.conv_temporal(hs2, self.out_layers[3], videos, frames, residual=x, blend=x, blend_alpha=blend_alpha)
+
     def _forward(self, x, emb):
         """x: image-shaped fp32 tensor or a K.ChannelCat (the skip concatenation of the output blocks)."""
+        if self.dims != 2:
+            _unsupported("ResBlock(dims=3).forward outside VideoResBlock")
         emb_out = K.dense(emb, self.emb_layers[1], act_silu_in=True)  # [B, Cout], added per (sample, channel)
         identity_skip = isinstance(self.skip_connection, nn.Identity)
         if identity_skip and isinstance(x, K.ChannelCat):

@@ -31,3 +31,36 @@ def zero_module(module):
     for p in module.parameters():
         p.detach().zero_()
     return module
+
+
+class AlphaBlender(nn.Module):
+    """reference :314-391.  Holds ``mix_factor`` under the reference's name; the blend itself
+    (alpha * x_spatial + (1 - alpha) * x_temporal) runs in the epilogue of the GEMM / convolution that produces
+    x_temporal, so this module only supplies alpha per frame."""
+    strategies = ["learned", "fixed", "learned_with_images"]
+
+    def __init__(self, alpha, merge_strategy="learned_with_images", rearrange_pattern="b t -> (b t) 1 1"):
+        super().__init__()
+        assert merge_strategy in self.strategies, f"merge_strategy needs to be in {self.strategies}"
+        self.merge_strategy = merge_strategy
+        self.rearrange_pattern = rearrange_pattern
+        if merge_strategy == "fixed":
+            self.register_buffer("mix_factor", torch.Tensor([alpha]))
+        else:
+            self.register_parameter("mix_factor", nn.Parameter(torch.Tensor([alpha])))
+
+    def frame_alpha(self, image_only_indicator, videos, frames):
+        """alpha of every frame, fp32 [(b t)] on the device (reference get_alpha :357-366; both rearrange patterns
+        index the same (b, t) entry)."""
+        mf = self.mix_factor.detach().float()
+        if self.merge_strategy == "fixed":
+            a = mf.expand(videos, frames)
+        elif self.merge_strategy == "learned":
+            a = torch.sigmoid(mf).expand(videos, frames)
+        else:
+            assert image_only_indicator is not None, "need image_only_indicator ..."
+            if tuple(image_only_indicator.shape) != (videos, frames):
+                raise ValueError(f"image_only_indicator must be [{videos}, {frames}], got {tuple(image_only_indicator.shape)}")
+            a = torch.where(image_only_indicator.to(mf.device).bool(), torch.ones(1, 1, device=mf.device),
+                            torch.sigmoid(mf)[..., None])
+        return a.reshape(-1).contiguous()
