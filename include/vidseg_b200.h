@@ -96,6 +96,12 @@ int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double* partia
 int vidseg_kmeans_active_runs(void* workspace, size_t workspace_bytes, int* n_active_host,
                               void* stream);
 
+/* as active_runs, plus the number of runs whose M-step met an EMPTY cluster while local_rows_only was set (the
+ * relocation of sklearn/_k_means_common.pyx:_relocate_empty_clusters_dense needs every label, so it is skipped
+ * there): a sharded caller that sees empty_seen != 0 repeats the fit unsharded.  Synchronises the stream. */
+int vidseg_kmeans_status(void* workspace, size_t workspace_bytes, int* n_active_host, int* empty_seen_host,
+                         void* stream);
+
 /* final E-step of the runs that did not converge strictly, then the inertia of
  * rows [row_begin,row_end) -> inertia_partial double [R] (NULL = workspace). */
 int vidseg_kmeans_inertia(void* workspace, size_t workspace_bytes, int row_begin, int row_end,

@@ -1,0 +1,199 @@
+"""CPU, world_size 2 over gloo: the host logic of the frame-sharded path (vidseg_diffusion_b200/distributed.py) --
+frame partition, ragged row all-gather, and the distributed Lloyd driver (per-iteration all-reduce of the fused
+[n_init, K, D+1] sums|counts buffer, redundant seeding / best-of selection, final label all-gather).  The CUDA kernels
+cannot run here, so the driver is exercised with a numpy stand-in that implements the same split E-step / M-step
+contract as include/vidseg_b200.h (R2) on top of the oracle's primitives; the GPU form of the same driver is covered by
+tests/test_gpu_distributed.py."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import kmeans as okm
+from synth import synthetic_clip_features
+from oracle import features as ofeat
+
+
+class _ReplayRandom:
+    """Feeds pre-drawn k-means++ decisions back through the RandomState calls the oracle makes."""
+
+    def __init__(self, first, rand):
+        self.first, self.rand, self.c = int(first), rand, 0
+
+    def choice(self, n, p=None):
+        return self.first
+
+    def uniform(self, size=None):
+        v = self.rand[self.c]
+        self.c += 1
+        return v
+
+
+class NumpyLloydBackend:
+    """Same contract as distributed.CudaLloydBackend (prepare / seed / assign / partial / update / status / inertia /
+    same_matrix / finish / predict) in numpy: float64 cluster sums, fp32 centres, sklearn's convergence rules."""
+
+    def __init__(self, k, r, max_iter=300, tol=1e-4):
+        self.k, self.r, self.max_iter, self.tol_rel = k, r, max_iter, tol
+
+    def prepare(self, X):
+        X = X.numpy().astype(np.float32)
+        self.tol = np.mean(np.var(X, axis=0)) * self.tol_rel
+        self.mean = X.mean(axis=0)
+        self.xc = X - self.mean
+        self.n, self.d = X.shape
+        self.labels = np.full((self.r, self.n), -1, dtype=np.int32)
+        self.changed = np.zeros(self.r, dtype=np.int32)
+        self.done = np.zeros(self.r, dtype=bool)
+        self.strict = np.zeros(self.r, dtype=bool)
+        self.empty_seen = np.zeros(self.r, dtype=bool)
+        self.n_iter = np.zeros(self.r, dtype=np.int32)
+
+    def seed(self, first, rand):
+        self.centers = np.stack([okm.kmeans_plusplus(self.xc, self.k, _ReplayRandom(first[r], rand[r]))[0]
+                                 for r in range(self.r)])
+
+    def _estep(self, r, r0, r1):
+        c = self.centers[r].astype(np.float64)
+        x = self.xc[r0:r1].astype(np.float64)
+        return np.argmin((c * c).sum(1)[None, :] - 2.0 * x @ c.T, axis=1).astype(np.int32)
+
+    def assign(self, r0, r1):
+        for r in range(self.r):
+            if self.done[r]:
+                continue
+            lab = self._estep(r, r0, r1)
+            self.changed[r] += int((lab != self.labels[r, r0:r1]).sum())
+            self.labels[r, r0:r1] = lab
+
+    def partial(self, r0, r1):
+        part = np.zeros((self.r, self.k, self.d + 1))
+        for r in range(self.r):
+            if self.done[r]:
+                continue
+            lab = self.labels[r, r0:r1]
+            np.add.at(part[r, :, : self.d], lab, self.xc[r0:r1].astype(np.float64))
+            part[r, :, self.d] = np.bincount(lab, minlength=self.k)
+        ch = self.changed.copy()
+        return torch.from_numpy(part), torch.from_numpy(ch)
+
+    def update(self, partial, changed, local_rows_only):
+        part, ch = partial.numpy(), changed.numpy()
+        for r in range(self.r):
+            if self.done[r]:
+                continue
+            cnt = part[r, :, self.d]
+            if (cnt == 0).any():
+                assert local_rows_only, "stand-in has no relocation"
+                self.empty_seen[r] = True
+            new = self.centers[r].copy()
+            am = int(np.argmax(cnt))
+            for j in range(self.k):
+                new[j] = (part[r, j, : self.d] / cnt[j]).astype(np.float32) if cnt[j] > 0 else new[am]
+            shift = np.sqrt(((new.astype(np.float64) - self.centers[r]) ** 2).sum(1)).astype(np.float32)
+            self.centers[r] = new
+            self.n_iter[r] += 1
+            if ch[r] == 0:
+                self.strict[r] = self.done[r] = True
+            elif np.float32((shift * shift).sum()) <= self.tol or self.n_iter[r] >= self.max_iter:
+                self.done[r] = True
+            self.changed[r] = 0
+
+    def status(self):
+        return int((~self.done).sum()), int(self.empty_seen.sum())
+
+    def inertia(self, r0, r1):
+        out = np.zeros(self.r)
+        for r in range(self.r):
+            if not self.strict[r]:
+                self.labels[r, r0:r1] = self._estep(r, r0, r1)
+            diff = self.xc[r0:r1].astype(np.float64) - self.centers[r][self.labels[r, r0:r1]]
+            out[r] = (diff * diff).sum()
+        return torch.from_numpy(out)
+
+    def same_matrix(self, r0, r1):
+        out = np.zeros((self.r, self.r), dtype=np.int32)
+        for a in range(self.r):
+            for b in range(self.r):
+                out[a, b] = okm.is_same_clustering(self.labels[a, r0:r1], self.labels[b, r0:r1], self.k)
+        return torch.from_numpy(out)
+
+    def finish(self, best):
+        return torch.from_numpy(self.centers[best] + self.mean)
+
+    def predict(self, rows, centers):
+        return torch.from_numpy(okm.kmeans_predict(rows.numpy(), centers.numpy()).astype(np.int32))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vidseg_diffusion_b200 import distributed as D
+        F, h, w, C, K = 5, 8, 8, 32, 4
+        blocks, _ = synthetic_clip_features(11, F, h, w, C, K)
+        parts = D.frame_partition(F, world)
+        f0, f1 = parts[rank]
+        # the rows this rank would produce from its own frames (conditional half), then exchange step 1
+        x_full = ofeat.aggregate_normalize(blocks, F)
+        local = torch.from_numpy(x_full[f0 * h * w: f1 * h * w])
+        counts = [(b - a) * h * w for a, b in parts]
+        X = D.gather_rows(local, counts)
+        assert np.array_equal(X.numpy(), x_full)
+        np.random.seed(7)
+        info = {}
+        row0 = sum(counts[:rank])
+        labels = D.sharded_kmeans_fit_predict(X, K, (row0, row0 + counts[rank]), n_init=3,
+                                              backend=NumpyLloydBackend(K, 3), info=info)
+        q.put((rank, labels.numpy(), info["iterations"], info["allreduces"], info["unsharded_fallback"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_frame_partition():
+    from vidseg_diffusion_b200.distributed import frame_partition
+    assert [b - a for a, b in frame_partition(14, 8)] == [2, 2, 2, 2, 2, 2, 1, 1]
+    assert frame_partition(14, 1) == [(0, 14)]
+    assert frame_partition(3, 4) == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    for F in (1, 7, 14, 28):
+        for g in (1, 2, 4, 8):
+            p = frame_partition(F, g)
+            assert p[0][0] == 0 and p[-1][1] == F and all(a[1] == b[0] for a, b in zip(p, p[1:]))
+
+
+def test_sharded_kmeans_two_ranks_gloo_matches_oracle():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, lab0, it0, ar0, fb0), (_, lab1, it1, ar1, fb1) = res
+    assert np.array_equal(lab0, lab1) and it0 == it1 and ar0 == ar1 > 0 and not fb0 and not fb1
+    # the reference's answer on the same rows, same seed
+    F, h, w, C, K = 5, 8, 8, 32, 4
+    blocks, _ = synthetic_clip_features(11, F, h, w, C, K)
+    x_full = ofeat.aggregate_normalize(blocks, F)
+    np.random.seed(7)
+    want, _ = okm.kmeans_fit_predict(x_full, K, n_init=3)
+    assert np.array_equal(lab0, want)
+    # two all-reduces per Lloyd iteration (sums|counts, changed) + inertia + same-clustering matrix
+    assert ar0 == 2 * it0 + 2

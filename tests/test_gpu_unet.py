@@ -85,3 +85,20 @@ def test_unet_frames_are_independent(cuda):
     part = model(x[sel], timesteps=t[sel], context=ctx[sel])
     q_part = model.output_blocks[7][1].transformer_blocks[0].attn1.q
     assert torch.equal(q_part, q_full[sel]) and torch.equal(part, full[sel])
+
+
+def test_cuda_graph_replay_matches_eager_launches(cuda):
+    """ClipSegmenter(use_cuda_graph=True): the UNet stage replayed as one CUDA graph gives the same bits as the eager
+    launches, on first use and on a second clip with different inputs (static buffers refreshed)."""
+    from vidseg_diffusion_b200.pipeline import ClipSegmenter
+    cfg = ounet.TINY_CONFIG
+    model, _ = build(cfg, 5, cuda)
+    eager = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True)
+    graphed = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, use_cuda_graph=True)
+    for seed in (5, 6):
+        x, t, ctx = (torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(seed, 2, 16, cfg["in_channels"], 7, cfg["context_dim"]))
+        want, out_e = eager.segment(x, t, ctx, 2, seed=seed)
+        want, out_e = want.clone(), out_e.clone()
+        got, out_g = graphed.segment(x, t, ctx, 2, seed=seed)
+        assert torch.equal(out_g, out_e) and torch.equal(got, want)
+    assert graphed.graph_replays == 2 and graphed.graph_kernel_launches > 0

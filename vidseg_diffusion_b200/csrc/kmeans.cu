@@ -40,7 +40,7 @@ struct KmLayout {
   int max_iter;
   size_t xc, mean, var, xx, closest, newdist, potpart, cand, pot, centers, cnorm, center_idx, labels, part, partcnt,
       partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, xs_hi, xs_lo, cs_hi, cs_lo, sdot,
-      absmax, amb_list, total;
+      absmax, amb_list, upd_cnt, upd_argmax, upd_shift, upd_ticket, total;
   int rk_pad;   // R*K rounded up to a multiple of 8 (row length of the tensor-core score matrix)
   int use_tc;   // E-step on the tensor cores (needs D % 8 == 0)
 };
@@ -77,6 +77,10 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
   L.rk_pad = (r * k + 7) / 8 * 8;
   L.use_tc = (d % 8 == 0 && n >= 512 && (size_t)r * k * 16 <= 48 * 1024) ? 1 : 0;
   L.absmax = take(16);
+  L.upd_cnt = take((size_t)r * k * 8);
+  L.upd_argmax = take((size_t)r * 4);
+  L.upd_shift = take((size_t)r * k * 4);
+  L.upd_ticket = take((size_t)r * 4);
   if (L.use_tc) {
     L.xs_hi = take((size_t)n * d * 2);
     L.xs_lo = take((size_t)n * d * 2);
@@ -648,25 +652,28 @@ km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcn
 }
 
 // ------------------------------------------------------------------------------------------
-// Lloyd M-step, part 2 (one block per run): empty-cluster relocation, averaging, centre shift,
-// convergence flags.  `partial` is updated in place by the relocation.
+// Lloyd M-step, part 2: empty-cluster relocation, averaging, centre shift, convergence flags.
+//   km_update_prep_kernel  one block per run: cluster counts, (rare) relocation of empty clusters -- `partial` is
+//                          updated in place -- and the arg-max count the averaging falls back to;
+//   km_update_avg_kernel   one WARP per (run, cluster): _average_centers + _center_shift of that centre; the last warp
+//                          of a run to finish (ticket counter) adds the K squared shifts in cluster order and sets the
+//                          convergence flags.  (One block per run spent 60 us per iteration on 10 SMs.)
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-km_update_kernel(const float* __restrict__ x, int n, int d, int k, double* __restrict__ partial,
-                 const int* __restrict__ changed_in, int* __restrict__ changed_ws, const int* __restrict__ labels,
-                 float* __restrict__ centers, double* __restrict__ cnorm, int* __restrict__ flags,
-                 const float* __restrict__ tol, int max_iter, float* __restrict__ scratch_dist, int can_relocate) {
-  extern __shared__ double sm[];  // [k] counts, [k] shift^2 (as float in double slots), then ints
+km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* __restrict__ partial,
+                      const int* __restrict__ labels, const float* __restrict__ centers, int* __restrict__ flags,
+                      float* __restrict__ scratch_dist, int can_relocate, double* __restrict__ cnt_out,
+                      int* __restrict__ argmax_out) {
+  extern __shared__ double sm[];  // [k] counts
   const int r = blockIdx.x;
   if (flags[r * 4 + 0]) return;
   const int tid = threadIdx.x;
   double* cnt = sm;
-  double* shiftsq = sm + k;
-  __shared__ int s_nempty, s_far, s_argmax;
+  __shared__ int s_nempty;
   __shared__ double s_red_v[256];
   __shared__ int s_red_i[256];
   double* pr = partial + (size_t)r * k * (d + 1);
-  float* cr = centers + (size_t)r * k * d;
+  const float* cr = centers + (size_t)r * k * d;
   for (int j = tid; j < k; j += blockDim.x) cnt[j] = pr[(size_t)j * (d + 1) + d];
   __syncthreads();
   if (tid == 0) {
@@ -675,6 +682,7 @@ km_update_kernel(const float* __restrict__ x, int n, int d, int k, double* __res
     s_nempty = ne;
   }
   __syncthreads();
+  if (s_nempty > 0 && !can_relocate && tid == 0) flags[r * 4 + 3] = 1;  // sharded caller must redo the fit unsharded
   if (s_nempty > 0 && can_relocate) {
     // _relocate_empty_clusters_dense: distances of every point to its (old) centre, the n_empty
     // farthest points (descending) seed the empty clusters (ascending cluster id).
@@ -722,51 +730,70 @@ km_update_kernel(const float* __restrict__ x, int n, int d, int k, double* __res
       __syncthreads();
     }
   }
+  for (int j = tid; j < k; j += blockDim.x) cnt_out[(size_t)r * k + j] = cnt[j];
   if (tid == 0) {
     int am = 0;
     for (int j = 1; j < k; ++j) if (cnt[j] > cnt[am]) am = j;  // np.argmax: first maximum
-    s_argmax = am;
+    argmax_out[r] = am;
   }
-  __syncthreads();
-  // _average_centers + _center_shift; one warp per cluster
-  const int lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-  const int am = s_argmax;
-  for (int j = warp; j < k; j += nwarps) {
-    double ss = 0.0, nn = 0.0;
-    const bool has = cnt[j] > 0.0;
-    for (int c = lane; c < d; c += 32) {
-      float nv;
-      if (has) {
-        nv = (float)(pr[(size_t)j * (d + 1) + c] / cnt[j]);
-      } else {
-        // centers[j] = centers[argmax_weight]: averaged already if argmax < j, raw sum otherwise
-        const double raw = pr[(size_t)am * (d + 1) + c];
-        nv = (am < j && cnt[am] > 0.0) ? (float)(raw / cnt[am]) : (float)raw;
-      }
-      const float ov = cr[(size_t)j * d + c];
-      const double df = (double)nv - (double)ov;
-      ss = fma(df, df, ss);
-      nn = fma((double)nv, (double)nv, nn);
-      cr[(size_t)j * d + c] = nv;
+}
+
+constexpr int kUpdWarps = 4;
+__global__ void __launch_bounds__(kUpdWarps * 32)
+km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial, const double* __restrict__ cnt_all,
+                     const int* __restrict__ argmax_all, const int* __restrict__ changed_in,
+                     int* __restrict__ changed_ws, float* __restrict__ centers, double* __restrict__ cnorm,
+                     int* __restrict__ flags, const float* __restrict__ tol, int max_iter, float* __restrict__ shiftsq,
+                     int* __restrict__ ticket) {
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * kUpdWarps + (threadIdx.x >> 5);
+  if (w >= runs * k) return;
+  const int r = w / k, j = w - r * k;
+  if (flags[r * 4 + 0]) return;   // set only by the finalising warp of an EARLIER launch
+  const double* pr = partial + (size_t)r * k * (d + 1);
+  const double* cnt = cnt_all + (size_t)r * k;
+  float* cr = centers + (size_t)r * k * d;
+  const int am = argmax_all[r];
+  // _average_centers + _center_shift
+  double ss = 0.0, nn = 0.0;
+  const bool has = cnt[j] > 0.0;
+  for (int c = lane; c < d; c += 32) {
+    float nv;
+    if (has) {
+      nv = (float)(pr[(size_t)j * (d + 1) + c] / cnt[j]);
+    } else {
+      // centers[j] = centers[argmax_weight]: averaged already if argmax < j, raw sum otherwise
+      const double raw = pr[(size_t)am * (d + 1) + c];
+      nv = (am < j && cnt[am] > 0.0) ? (float)(raw / cnt[am]) : (float)raw;
     }
-    ss = warp_sum(ss);
-    nn = warp_sum(nn);
-    if (lane == 0) {
-      const float sh = (float)sqrt(ss);
-      shiftsq[j] = (double)__fmul_rn(sh, sh);
-      cnorm[(size_t)r * k + j] = nn;
-    }
+    const float ov = cr[(size_t)j * d + c];
+    const double df = (double)nv - (double)ov;
+    ss = fma(df, df, ss);
+    nn = fma((double)nv, (double)nv, nn);
+    cr[(size_t)j * d + c] = nv;
   }
-  __syncthreads();
-  if (tid == 0) {
+  ss = warp_sum(ss);
+  nn = warp_sum(nn);
+  int last = 0;
+  if (lane == 0) {
+    const float sh = (float)sqrt(ss);
+    shiftsq[(size_t)r * k + j] = __fmul_rn(sh, sh);
+    cnorm[(size_t)r * k + j] = nn;
+    __threadfence();
+    last = (atomicAdd(&ticket[r], 1) == k - 1);
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (last && lane == 0) {
+    __threadfence();
     float tot = 0.f;
-    for (int j = 0; j < k; ++j) tot = __fadd_rn(tot, (float)shiftsq[j]);
+    for (int jj = 0; jj < k; ++jj) tot = __fadd_rn(tot, __ldcg(&shiftsq[(size_t)r * k + jj]));
     const int it = flags[r * 4 + 2] + 1;
     flags[r * 4 + 2] = it;
     if (changed_in[r] == 0) { flags[r * 4 + 1] = 1; flags[r * 4 + 0] = 1; }
     else if (tot <= tol[0]) { flags[r * 4 + 0] = 1; }
     else if (it >= max_iter) { flags[r * 4 + 0] = 1; }
     changed_ws[r] = 0;
+    ticket[r] = 0;
   }
 }
 
@@ -942,6 +969,7 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
             at<double>(ws, L.xx), at<unsigned>(ws, L.absmax));
   VS_POST_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.labels), 0xFF, (size_t)n_init * n * 4, (cudaStream_t)stream));
+  VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.upd_ticket), 0, (size_t)n_init * 4, (cudaStream_t)stream));
   if (L.use_tc) {
     const size_t tot = (size_t)n * d;
     VS_LAUNCH(km_split_scaled_kernel, (int)std::min<size_t>((tot + 255) / 256, (size_t)kNumSMs * 16), 256, 0, stream,
@@ -1019,10 +1047,14 @@ VS_API int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double*
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
   if (changed == nullptr) changed = at<int>(ws, L.changed);
-  const size_t smem = (size_t)L.k * 2 * 8;
-  VS_LAUNCH(km_update_kernel, L.r, 256, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, partial, changed,
-            at<int>(ws, L.changed), at<int>(ws, L.labels), at<float>(ws, L.centers), at<double>(ws, L.cnorm),
-            at<int>(ws, L.flags), at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.newdist), local_rows_only ? 0 : 1);
+  VS_LAUNCH(km_update_prep_kernel, L.r, 256, (size_t)L.k * 8, stream, at<float>(ws, L.xc), L.n, L.d, L.k, partial,
+            at<int>(ws, L.labels), at<float>(ws, L.centers), at<int>(ws, L.flags), at<float>(ws, L.newdist),
+            local_rows_only ? 0 : 1, at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(km_update_avg_kernel, (L.r * L.k + kUpdWarps - 1) / kUpdWarps, kUpdWarps * 32, 0, stream, L.d, L.k, L.r, partial,
+            at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax), changed, at<int>(ws, L.changed), at<float>(ws, L.centers),
+            at<double>(ws, L.cnorm), at<int>(ws, L.flags), at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.upd_shift),
+            at<int>(ws, L.upd_ticket));
   VS_POST_LAUNCH();
   return 0;
 }
@@ -1037,6 +1069,21 @@ VS_API int vidseg_kmeans_active_runs(void* workspace, size_t workspace_bytes, in
   int active = 0;
   for (int r = 0; r < L.r; ++r) active += flags[(size_t)r * 4] == 0;
   *n_active_host = active;
+  return 0;
+}
+
+VS_API int vidseg_kmeans_status(void* workspace, size_t workspace_bytes, int* n_active_host, int* empty_seen_host,
+                                void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  std::vector<int> flags((size_t)L.r * 4);
+  VS_CHECK_CUDA(cudaMemcpyAsync(flags.data(), at<int>(workspace, L.flags), flags.size() * 4, cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
+  VS_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int active = 0, empty = 0;
+  for (int r = 0; r < L.r; ++r) { active += flags[(size_t)r * 4] == 0; empty += flags[(size_t)r * 4 + 3] != 0; }
+  if (n_active_host) *n_active_host = active;
+  if (empty_seen_host) *empty_seen_host = empty;
   return 0;
 }
 

@@ -37,8 +37,12 @@ def harvest_self_attn_q(model, blocks):
 class ClipSegmenter:
     """One object per process / GPU.  ``model`` is a ``UNetModel`` (or ``VideoUNet``) on the GPU."""
 
-    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10):
+    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, use_cuda_graph=False):
         self.model = model
+        self.use_cuda_graph = bool(use_cuda_graph)
+        self._graphs = {}
+        self.graph_replays = 0
+        self.graph_kernel_launches = 0
         self.num_masks = int(num_masks)
         self.blocks = AGGRE_BLOCKS if is_aggre_attn else SINGLE_BLOCK
         self.is_refine_mask = bool(is_refine_mask)
@@ -50,10 +54,49 @@ class ClipSegmenter:
         """x [2F, C, h, w] (uncond rows first, guiders.py:38-42), timesteps [2F], context [2F, L, D]."""
         return self.model(x, timesteps=timesteps, context=context, **unet_kwargs)
 
-    def cluster(self, num_frames, feature_height, feature_width, seed=None):
+    def _features(self, num_frames):
+        return aggregate_normalize(harvest_self_attn_q(self.model, self.blocks), num_frames)
+
+    def _graphed_unet_features(self, x, timesteps, context, num_frames, unet_kwargs):
+        """UNet step + harvest + aggregate/normalise as ONE CUDA graph per input signature: ~500 kernel launches of
+        the step replay without host work in between.  Inputs are copied into the graph's static buffers; the stashed
+        q/k tensors, the UNet output and the feature matrix live in the graph's memory pool and are overwritten by
+        every replay (clone what must outlive the next call)."""
+        tens = {k: v for k, v in unet_kwargs.items() if isinstance(v, torch.Tensor)}
+        rest = {k: v for k, v in unet_kwargs.items() if not isinstance(v, torch.Tensor)}
+        key = (tuple(x.shape), tuple(timesteps.shape), tuple(context.shape), num_frames,
+               tuple(sorted((k, tuple(v.shape)) for k, v in tens.items())), tuple(sorted(rest.items())))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = dict(x=x.clone(), t=timesteps.clone(), c=context.clone(), **{"kw_" + k: v.clone() for k, v in tens.items()})
+            kw = dict(rest, **{k: static["kw_" + k] for k in tens})
+            side = torch.cuda.Stream(device=x.device)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):            # warm-up outside capture: weight operand caches, workspaces
+                for _ in range(2):
+                    self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
+                    self._features(num_frames)
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            n0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
+                feats = self._features(num_frames)
+            ent = self._graphs[key] = (graph, static, out, feats, _lib.launch_count() - n0)
+        graph, static, out, feats, n_launches = ent
+        self.graph_replays += 1
+        self.graph_kernel_launches += n_launches   # library kernels inside the replayed graph (not counted by the host-side counter)
+        static["x"].copy_(x, non_blocking=True)
+        static["t"].copy_(timesteps, non_blocking=True)
+        static["c"].copy_(context, non_blocking=True)
+        for k, v in tens.items():
+            static["kw_" + k].copy_(v, non_blocking=True)
+        graph.replay()
+        return out, feats
+
+    def cluster(self, num_frames, feature_height, feature_width, seed=None, features=None):
         """K-means label maps [F, h, w] (int32, device) from the features stashed by the last UNet call."""
-        feats = harvest_self_attn_q(self.model, self.blocks)
-        x = aggregate_normalize(feats, num_frames)
+        x = self._features(num_frames) if features is None else features
         if seed is not None:
             np.random.seed(seed)  # seed_everything(), svd_single_video_inference.py:590-594
         km = KMeans(n_clusters=self.num_masks, n_init=self.n_init)
@@ -70,9 +113,13 @@ class ClipSegmenter:
     @torch.no_grad()
     def segment(self, x, timesteps, context, num_frames, seed=None, **unet_kwargs):
         """Whole path on device tensors.  Returns (label maps int32 [F, h, w], UNet output)."""
-        out = self.unet_step(x, timesteps, context, **unet_kwargs)
+        feats = None
+        if self.use_cuda_graph:
+            out, feats = self._graphed_unet_features(x, timesteps, context, num_frames, unet_kwargs)
+        else:
+            out = self.unet_step(x, timesteps, context, **unet_kwargs)
         fh, fw = x.shape[-2] // 2, x.shape[-1] // 2   # H // (8 * 2): feature grid of output blocks 6-8
-        labels = self.cluster(num_frames, fh, fw, seed)
+        labels = self.cluster(num_frames, fh, fw, seed, features=feats)
         if self.is_refine_mask:
             labels = self.refine(labels, num_frames, fh, fw)
         return labels, out

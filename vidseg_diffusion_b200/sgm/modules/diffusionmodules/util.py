@@ -5,13 +5,22 @@ import torch
 import torch.nn as nn
 
 
+_FREQS = {}
+
+
 def timestep_embedding(timesteps, dim, max_period=10000, repeat_only=False):
     """reference :209-233: [N] -> [N, dim] = (cos | sin) of t * max_period^(-i/half).  B x dim values:
     host-latency bound, evaluated with the same fp32 expression order as the reference."""
     if repeat_only:
         return timesteps[:, None].expand(-1, dim)
     half = dim // 2
-    freqs = torch.exp(-math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
+    # the frequency table is evaluated on the host with the reference's expression (bit-identical to its CPU run) and
+    # kept on the device, so that a forward issues no host-to-device copy (CUDA-graph capturable)
+    key = (half, float(max_period), timesteps.device)
+    freqs = _FREQS.get(key)
+    if freqs is None:
+        freqs = _FREQS[key] = torch.exp(
+            -math.log(max_period) * torch.arange(0, half, dtype=torch.float32) / half).to(timesteps.device)
     args = timesteps[:, None].float() * freqs[None]
     emb = torch.cat([torch.cos(args), torch.sin(args)], dim=-1)
     if dim % 2:
