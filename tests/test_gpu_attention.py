@@ -1,4 +1,4 @@
-"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 1e-5 of the
+"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 3e-5 of the
 output scale; the parity bar of the path is 1e-3)."""
 import pytest
 import torch
@@ -23,6 +23,25 @@ def test_attention_matches_fp64(cuda, b, h, nq, nk, sharp):
     out, sp = attention_split(split(q), split(k), split(v), h, want_f32=True, want_split=True)
     scale = want.abs().max().item()
     err = (out.double() - want).abs().max().item() / scale
-    assert err < 1e-5, f"fp32 output rel err {err:.3e}"
+    assert err < 3e-5, f"fp32 output rel err {err:.3e}"
     err = (sp.float().double() - want).abs().max().item() / scale
-    assert err < 1e-5, f"split output rel err {err:.3e}"
+    assert err < 3e-5, f"split output rel err {err:.3e}"
+
+
+@pytest.mark.parametrize("step", [0.01, 0.2, 3.0])
+def test_attention_running_maximum_ramps_up(cuda, step):
+    """Scores that keep growing along the key axis: exercises both sides of the lazy rescale (blocks that raise the
+    reference maximum and blocks that stay within its 2^3 headroom)."""
+    from vidseg_diffusion_b200.linear import attention_split, split
+    g = torch.Generator(device="cpu").manual_seed(17)
+    b, h, nq, nk = 1, 2, 256, 640
+    c = h * 64
+    q = torch.randn(b, nq, c, generator=g).abs()
+    k = torch.randn(b, nk, c, generator=g) * 0.1 + (torch.arange(nk).float() * step / 64.0)[None, :, None]
+    v = torch.randn(b, nk, c, generator=g)
+    q, k, v = q.to(cuda), k.to(cuda), v.to(cuda)
+    qd, kd, vd = [t.double().reshape(b, -1, h, 64).permute(0, 2, 1, 3) for t in (q, k, v)]
+    want = (torch.softmax(qd @ kd.transpose(-1, -2) / 8.0, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(b, nq, c)
+    out, _ = attention_split(split(q), split(k), split(v), h, want_f32=True, want_split=False)
+    err = (out.double() - want).abs().max().item() / want.abs().max().item()
+    assert err < 3e-5, f"rel err {err:.3e}"

@@ -7,13 +7,16 @@
 // accumulation in TMEM, the softmax runs in fp32 registers.
 //
 // One CTA = 256 queries of one (batch, head): two 128-row query tiles, each owned by a softmax
-// warpgroup (128 threads = 128 TMEM lanes); the two groups ping-pong so that the tensor pipe works on
-// one tile while the CUDA cores exponentiate the other.  Per 64-key block and tile:
-//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x64x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator)
-//   softmax  : tcgen05.ld S, online max / exp2 / row sum, P -> fp16 hi/lo into swizzled smem
-//   MMA warp : PV = P V    (12 x tcgen05.mma 128x64x16, V is the MN-major B operand)
-//   softmax  : tcgen05.ld PV, O = O * alpha + PV   (O lives in registers, 64 fp32 per thread)
-// TMA (warp 0) streams K/V blocks through a 2-stage ring.  TMEM: 2 tiles x (S 64 + PV 64) = 256 columns.
+// warpgroup (128 threads = 128 TMEM lanes).  Per 64-key block and tile:
+//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x64x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator), issued TWO
+//              blocks ahead into a double-buffered S region of TMEM, so a softmax group never waits for its scores
+//   softmax  : tcgen05.ld S, row max / exp2 / row sum in registers, P -> fp16 hi/lo into swizzled smem
+//   MMA warp : O += P V    (12 x tcgen05.mma 128x64x16, V is the MN-major B operand); O stays in TMEM across the whole
+//              key loop, so the softmax group does not wait for this product either
+//   rescale  : the running maximum is only raised when a block exceeds it by more than 2^3 (the probabilities are
+//              carried with 2^12 headroom inside fp16); only then -- typically the first one or two blocks of a row --
+//              the group loads O from TMEM, multiplies by 2^(m_old - m_new) and stores it back
+// TMA (warp 0) streams K/V blocks through a 3-stage ring.  TMEM: 2 tiles x (S 2x64 + O 64) = 384 of 512 columns.
 #include <mutex>
 
 #define VS_FAMILY vidseg::kFamAttention
@@ -26,15 +29,18 @@ constexpr int kAtBQ = 128;        // queries per tile
 constexpr int kAtTiles = 2;       // query tiles per CTA
 constexpr int kAtBK = 64;         // keys per block
 constexpr int kAtD = 64;          // head dim
-constexpr int kAtStages = 2;
+constexpr int kAtStages = 4;      // K/V ring depth: the refill of a stage (TMA latency ~1 us) overlaps several key blocks of work
 constexpr int kAtQTileBytes = kAtBQ * kAtD * 2;  // 16 KB (one of hi / lo)
 constexpr int kAtKTileBytes = kAtBK * kAtD * 2;  // 8 KB
 constexpr int kAtPTileBytes = kAtBQ * kAtBK * 2; // 16 KB
 constexpr int kAtSmemQ = kAtTiles * 2 * kAtQTileBytes;          // 64 KB
 constexpr int kAtSmemKV = kAtStages * 4 * kAtKTileBytes;        // 64 KB
-constexpr int kAtSmemP = kAtTiles * 2 * kAtPTileBytes;          // 64 KB
+constexpr int kAtSmemP = 0;                                     // P lives in TMEM
 constexpr int kAtSmemBytes = kAtSmemQ + kAtSmemKV + kAtSmemP + 1024 + 256;
-constexpr int kAtThreads = 64 + kAtTiles * 128;  // producer warp, MMA warp, 2 softmax warpgroups
+constexpr int kAtThreads = 64 + kAtTiles * 128;
+constexpr int kAtTmemCols = 512;       // per tile: S buffer 0 | S buffer 1 | O, 64 columns each
+constexpr int kAtTileCols = 192;
+constexpr float kAtTau = 3.0f;         // lazy-rescale threshold (log2 units): p <= 2^(12+3) stays inside fp16  // producer warp, MMA warp, 2 softmax warpgroups
 
 // 2^x on the SFU, flush-to-zero: one MUFU.EX2 (exp2f() adds a denormal-range rescale: two FMUL and a compare per call)
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -62,13 +68,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
   uint8_t* sm_kv = sm_q + kAtSmemQ;           // [stage][k_hi|k_lo|v_hi|v_lo][64x64]
   uint8_t* sm_p = sm_kv + kAtSmemKV;          // [tile][hi|lo][128x64]
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + kAtSmemP);
-  uint64_t* q_full = bars;                    // 1
-  uint64_t* kv_full = bars + 1;               // [2]
-  uint64_t* kv_empty = bars + 3;              // [2]
-  uint64_t* s_full = bars + 5;                // [2]
-  uint64_t* p_full = bars + 7;                // [2]
-  uint64_t* o_full = bars + 9;                // [2]
-  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* q_full = bars;                                // 1
+  uint64_t* kv_full = bars + 1;                           // [kAtStages]
+  uint64_t* kv_empty = kv_full + kAtStages;               // [kAtStages]
+  uint64_t* s_full = kv_empty + kAtStages;                // [tile][S buffer]
+  uint64_t* p_full = s_full + 2 * kAtTiles;               // [tile]
+  uint64_t* pv_done = p_full + kAtTiles;                  // [tile]
+  uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(pv_done + kAtTiles);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -83,10 +89,13 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     tc::prefetch_tmap(&tm_v_hi); tc::prefetch_tmap(&tm_v_lo);
     tc::mbar_init(q_full, 1);
     for (int s = 0; s < kAtStages; ++s) { tc::mbar_init(&kv_full[s], 1); tc::mbar_init(&kv_empty[s], 1); }
-    for (int g = 0; g < kAtTiles; ++g) { tc::mbar_init(&s_full[g], 1); tc::mbar_init(&p_full[g], 128); tc::mbar_init(&o_full[g], 1); }
+    for (int g = 0; g < kAtTiles; ++g) {
+      tc::mbar_init(&s_full[2 * g], 1); tc::mbar_init(&s_full[2 * g + 1], 1);
+      tc::mbar_init(&p_full[g], 128); tc::mbar_init(&pv_done[g], 1);
+    }
     tc::fence_barrier_init();
   }
-  if (warp == 1) tc::tmem_alloc<256>(tmem_base_ptr);
+  if (warp == 1) tc::tmem_alloc<kAtTmemCols>(tmem_base_ptr);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -118,12 +127,12 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc_s = tc::make_idesc_f16(kAtBQ, kAtBK, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = tc::make_idesc_f16(kAtBQ, kAtD, 0, 1);    // P (K-major) x V (MN-major)
-      auto issue_s = [&](int g, int stage) {
+      auto issue_s = [&](int g, int stage, int buf) {
         const uint32_t qa = tc::smem_u32(sm_q + g * 2 * kAtQTileBytes);
         const uint32_t ka = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes);
         const uint64_t q_hi = tc::make_sw128_desc(qa), q_lo = tc::make_sw128_desc(qa + kAtQTileBytes);
         const uint64_t k_hi = tc::make_sw128_desc(ka), k_lo = tc::make_sw128_desc(ka + kAtKTileBytes);
-        const uint32_t d_s = tmem_base + (uint32_t)(g * 128);
+        const uint32_t d_s = tmem_base + (uint32_t)(g * kAtTileCols + buf * 64);
 #pragma unroll
         for (int ks = 0; ks < kAtD / 16; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);
@@ -131,44 +140,48 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
           tc::umma_f16(d_s, q_hi + adv, k_lo + adv, idesc_s, 1u);
           tc::umma_f16(d_s, q_hi + adv, k_hi + adv, idesc_s, 1u);
         }
-        tc::umma_commit(&s_full[g]);
+        tc::umma_commit(&s_full[2 * g + buf]);
       };
-      auto issue_pv = [&](int g, int stage) {
-        const uint32_t pa = tc::smem_u32(sm_p + g * 2 * kAtPTileBytes);
+      auto issue_pv = [&](int g, int stage, int buf, bool first) {
         const uint32_t va = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes + 2 * kAtKTileBytes);
-        const uint64_t p_hi = tc::make_sw128_desc(pa), p_lo = tc::make_sw128_desc(pa + kAtPTileBytes);
         const uint64_t v_hi = tc::make_sw128_desc(va), v_lo = tc::make_sw128_desc(va + kAtKTileBytes);
-        const uint32_t d_o = tmem_base + (uint32_t)(g * 128 + 64);
+        const uint32_t d_o = tmem_base + (uint32_t)(g * kAtTileCols + 128);
+        // P(j) overwrote S(j) in place: fp16 pairs, hi in columns [0,32) and lo in [32,64) of the S buffer
+        const uint32_t p_hi = tmem_base + (uint32_t)(g * kAtTileCols + buf * 64), p_lo = p_hi + 32;
 #pragma unroll
         for (int ks = 0; ks < kAtBK / 16; ++ks) {
-          const uint64_t adv_a = (uint64_t)(ks * 32 >> 4);          // 16 keys along K inside P's swizzle atom
+          const uint32_t adv_a = (uint32_t)(ks * 8);                // 16 keys = 8 packed columns
           const uint64_t adv_b = (uint64_t)(ks * 16 * 128 >> 4);    // 16 key rows of 128 B in the V tile
-          tc::umma_f16(d_o, p_lo + adv_a, v_hi + adv_b, idesc_o, ks > 0);
-          tc::umma_f16(d_o, p_hi + adv_a, v_lo + adv_b, idesc_o, 1u);
-          tc::umma_f16(d_o, p_hi + adv_a, v_hi + adv_b, idesc_o, 1u);
+          tc::umma_f16_ts(d_o, p_lo + adv_a, v_hi + adv_b, idesc_o, (first && ks == 0) ? 0u : 1u);
+          tc::umma_f16_ts(d_o, p_hi + adv_a, v_lo + adv_b, idesc_o, 1u);
+          tc::umma_f16_ts(d_o, p_hi + adv_a, v_hi + adv_b, idesc_o, 1u);
         }
-        tc::umma_commit(&o_full[g]);
+        tc::umma_commit(&pv_done[g]);
+      };
+      // K/V of key block b sit in ring stage b % kAtStages; that stage's kv_full completes for the (b / kAtStages)-th time
+      auto wait_kv = [&](int blk) {
+        tc::mbar_wait(&kv_full[blk % kAtStages], (uint32_t)((blk / kAtStages) & 1));
+        tc::tc_fence_after();
       };
       tc::mbar_wait(q_full, 0);
-      tc::mbar_wait(&kv_full[0], 0);
-      tc::tc_fence_after();
-      for (int g = 0; g < kAtTiles; ++g) issue_s(g, 0);
-      int stage = 0;
-      uint32_t phase = 0;  // phase of kv_full[stage] for block j
+      wait_kv(0);
+      for (int g = 0; g < kAtTiles; ++g) issue_s(g, 0, 0);
+      if (nkb > 1) {
+        wait_kv(1);
+        for (int g = 0; g < kAtTiles; ++g) issue_s(g, 1 % kAtStages, 1);
+      }
       for (int j = 0; j < nkb; ++j) {
-        const int nstage = (stage + 1 == kAtStages) ? 0 : stage + 1;
-        const uint32_t nphase = (stage + 1 == kAtStages) ? (phase ^ 1) : phase;
-        const bool more = (j + 1 < nkb);
-        if (more) { tc::mbar_wait(&kv_full[nstage], nphase); tc::tc_fence_after(); }
+        const int stage = j % kAtStages;
         for (int g = 0; g < kAtTiles; ++g) {
-          tc::mbar_wait(&p_full[g], (uint32_t)(j & 1));
+          tc::mbar_wait(&p_full[g], (uint32_t)(j & 1));   // P(j) written, S buffer j & 1 consumed, O rescaled if needed
           tc::tc_fence_after();
-          issue_pv(g, stage);
-          if (more) issue_s(g, nstage);
+          issue_pv(g, stage, j & 1, j == 0);
+          if (j + 2 < nkb) {
+            if (g == 0) wait_kv(j + 2);
+            issue_s(g, (j + 2) % kAtStages, j & 1);
+          }
         }
         tc::umma_commit(&kv_empty[stage]);
-        stage = nstage;
-        phase = nphase;
       }
     }
   } else {
@@ -176,24 +189,20 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     const int g = (warp - 2) >> 2;       // query tile of this warpgroup
     const int quarter = warp & 3;        // TMEM lane quarter this warp may access (warp id % 4)
     const int r = quarter * 32 + lane;   // row inside the tile
-    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * 128);
-    uint8_t* p_hi_tile = sm_p + (g * 2 + 0) * kAtPTileBytes;
-    uint8_t* p_lo_tile = sm_p + (g * 2 + 1) * kAtPTileBytes;
-    float o[kAtD];
-#pragma unroll
-    for (int d = 0; d < kAtD; ++d) o[d] = 0.f;
+    const uint32_t t_row = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(g * kAtTileCols);
+    const uint32_t t_o = t_row + 128;
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkb; ++j) {
       const int valid = min(kAtBK, p.nk - j * kAtBK);
-      tc::mbar_wait(&s_full[g], (uint32_t)(j & 1));
+      tc::mbar_wait(&s_full[2 * g + (j & 1)], (uint32_t)((j >> 1) & 1));
       tc::tc_fence_after();
       // the 64 scores of this row stay in registers between the max pass and the exp pass
       uint32_t sc[kAtBK];
       {
         uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[0]);
         uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[32]);
-        tc::tmem_ld_32x32(t_row, s0);
-        tc::tmem_ld_32x32(t_row + 32, s1);
+        tc::tmem_ld_32x32(t_row + (uint32_t)((j & 1) * 64), s0);
+        tc::tmem_ld_32x32(t_row + (uint32_t)((j & 1) * 64 + 32), s1);
         tc::tmem_wait_ld();
       }
       if (valid < kAtBK) {  // warp-uniform: only the last key block of a ragged Nk (e.g. the 77 context tokens)
@@ -212,45 +221,68 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         mx2 = fmaxf(mx2, __uint_as_float(sc[i + 2]));
         mx3 = fmaxf(mx3, __uint_as_float(sc[i + 3]));
       }
-      const float mx = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      const float m_new = fmaxf(m_run, mx * p.scale_log2);
-      const float alpha = ex2_approx(m_run - m_new);  // 0 on the first block (m_run = -inf)
-      // probabilities are carried scaled by 2^12 (<= 4096) so that their fp16 residuals stay normal numbers;
-      // the row sum carries the same factor, which cancels in the final O / l
-      const float bias = 12.0f - m_new;
+      const float m_blk = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * p.scale_log2;
+      // lazy rescale: keep the old reference maximum unless this block exceeds it by more than 2^kAtTau
+      const bool grow = m_blk > m_run + kAtTau;          // always true on the first block (m_run = -inf)
+      const float m_use = grow ? m_blk : m_run;
+      const float alpha = grow ? ex2_approx(m_run - m_blk) : 1.0f;  // 0 on the first block
+      // probabilities are carried scaled by 2^12 so that their fp16 residuals stay normal numbers (<= 2^15 with the
+      // lazy maximum); the row sum carries the same factor, which cancels in the final O / l
+      const float bias = 12.0f - m_use;
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      // probabilities -> fp16 hi / lo -> swizzled smem (A operand of the PV product)
+      // probabilities -> fp16 hi / lo, kept in registers until the P tile is free (sc[] is dead by then)
+      uint4 hv[kAtBK / 8], lv[kAtBK / 8];
 #pragma unroll
       for (int i = 0; i < kAtBK; i += 8) {
         float pv[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[i + u]), p.scale_log2, bias));
         ls0 += pv[0] + pv[4]; ls1 += pv[1] + pv[5]; ls2 += pv[2] + pv[6]; ls3 += pv[3] + pv[7];
-        uint4 hv, lv;
-        tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv, lv);
-        const int chunk = i >> 3;  // 16-byte chunk index inside the 128-byte row
-        const uint32_t off = (uint32_t)r * 128u + (uint32_t)((chunk ^ (r & 7)) << 4);
-        *reinterpret_cast<uint4*>(p_hi_tile + off) = hv;
-        *reinterpret_cast<uint4*>(p_lo_tile + off) = lv;
+        tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv[i >> 3], lv[i >> 3]);
       }
-      const float lsum = (ls0 + ls1) + (ls2 + ls3);
-      l_run = fmaf(l_run, alpha, lsum);
-      m_run = m_new;
-      // make the generic-proxy smem writes visible to the tensor core (async proxy), then signal
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      l_run = fmaf(l_run, alpha, (ls0 + ls1) + (ls2 + ls3));
+      m_run = m_use;
+      if (j > 0) {
+        // PV(j-1) has landed in O.  Waited for on EVERY block although only the rescale needs it: an mbarrier parity
+        // wait is only meaningful one phase behind, and the final wait below relies on having followed every phase
+        // (by now the product has normally completed, the softmax of this block took longer than the MMA)
+        tc::mbar_wait(&pv_done[g], (uint32_t)((j - 1) & 1));
+        tc::tc_fence_after();
+        if (__any_sync(0xffffffffu, grow)) {
+          // rare: raise the reference maximum of O; tcgen05.ld / .st are warp-wide, rows that keep their maximum
+          // multiply by alpha = 1
+#pragma unroll
+          for (int c = 0; c < kAtD; c += 32) {
+            uint32_t a0[32];
+            tc::tmem_ld_32x32(t_o + c, a0);
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) a0[i] = __float_as_uint(__uint_as_float(a0[i]) * alpha);
+            tc::tmem_st_32x32(t_o + c, a0);
+          }
+        }
+      }
+      // P(j) replaces S(j) in its TMEM buffer (this warp's 32 lanes): the A operand of the PV product is read from
+      // tensor memory, so the probabilities never pass through shared memory
+      {
+        const uint32_t t_p = t_row + (uint32_t)((j & 1) * 64);
+        tc::tmem_st_32x32(t_p, *reinterpret_cast<const uint32_t(*)[32]>(&hv[0]));
+        tc::tmem_st_32x32(t_p + 32, *reinterpret_cast<const uint32_t(*)[32]>(&lv[0]));
+        tc::tmem_wait_st();
+      }
       tc::tc_fence_before();
       tc::mbar_arrive(&p_full[g]);
-      // PV of this block
-      tc::mbar_wait(&o_full[g], (uint32_t)(j & 1));
-      tc::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < kAtD; c += 32) {
-        uint32_t a0[32];
-        tc::tmem_ld_32x32(t_row + 64 + c, a0);
-        tc::tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c + i] = fmaf(o[c + i], alpha, __uint_as_float(a0[i]));
-      }
+    }
+    // all PV products accumulated: O / l
+    tc::mbar_wait(&pv_done[g], (uint32_t)((nkb - 1) & 1));
+    tc::tc_fence_after();
+    float o[kAtD];
+    {
+      uint32_t (&o0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[0]);
+      uint32_t (&o1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&o[32]);
+      tc::tmem_ld_32x32(t_o, o0);
+      tc::tmem_ld_32x32(t_o + 32, o1);
+      tc::tmem_wait_ld();
     }
     const int q = q0 + g * kAtBQ + r;
     if (q < p.nq) {
@@ -276,7 +308,7 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 1) tc::tmem_dealloc<256>(tmem_base);
+  if (warp == 1) tc::tmem_dealloc<kAtTmemCols>(tmem_base);
 }
 
 }  // namespace vidseg
