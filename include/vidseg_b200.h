@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);  /* 2: + gemm_split_ex, conv_temporal_split, temporal_attention, layernorm_bias_split */
+int vidseg_abi_version(void);  /* 3: + operand policy (packed8), split_rows; gemm_split_ex gained out_pair16 */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -174,7 +174,25 @@ int vidseg_refine_masks(const float* feats, const int32_t* labels_in,
  * split pre-scaled by a power of two (weights: 2^8) and the GEMM multiplies its accumulator by the exact inverse
  * (acc_scale).  Activations are channels-last ([B, H, W, C] / [B, N, C]).
  * ------------------------------------------------------------------------- */
-/* elementwise split of n fp32 values times `scale` (x 16-byte aligned). */
+/* Operand policy of the tensor-core GEMMs (process-wide; set it before the first forward, weights are converted once).
+ *   0  every operand is an fp16 pair (hi, lo): three kind::f16 MMAs per product, 22 significant bits;
+ *   1  (default) operands whose row length is a multiple of 64 are "packed8": hi = fp16(x) plus, in the memory of `lo`
+ *      (same size), per 64-element block 64 bytes of e5m2((x - hi) * 16) followed by 64 bytes of e4m3(x); weights,
+ *      which already carry 2^8, use e5m2(w - hi) and e4m3(w / 16).  The two correction products are 2^-11 of the
+ *      result and need ~4 significant bits, so they run as kind::f8f6f4 MMAs at twice the fp16 rate: a product costs
+ *      2 fp16-MMA units instead of 3 at 2^-14.5 relative precision (1.6e-5 rms per GEMM against fp64; the bar of the
+ *      path is 1e-3 on the stashed features).  Attention q / k / v, the K-means filter and operands with other row
+ *      lengths stay fp16 pairs.  Every kernel that produces an operand follows the same rule, so callers only ever
+ *      pass the (hi, lo) pointer pair around. */
+int vidseg_set_operand_mode(int mode);
+int vidseg_get_operand_mode(void);
+
+/* fp32 [rows, cols] times `scale` -> operand in the policy's format for rows of `cols` elements; is_weight selects the
+ * weight scales of the packed8 format (scale is then the 2^8 weight pre-scale). */
+int vidseg_split_rows(const float* x, void* hi, void* lo, long long rows, int cols, float scale, int is_weight,
+                      void* stream);
+
+/* elementwise split of n fp32 values times `scale` into an fp16 PAIR, whatever the policy (x 16-byte aligned). */
 int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, float scale, void* stream);
 
 /* out[M,N] = A[M,K] . W[N,K]^T (+ bias[N]) (+ residual[M,N]).  Replaces the nn.Linear call sites
@@ -194,12 +212,14 @@ int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, cons
  *   blend, blend_alpha [M / rows_per_alpha]: out = a * blend + (1 - a) * out -- AlphaBlender
  *     (sgm/modules/diffusionmodules/util.py:368-391) as used by SpatialVideoTransformer.time_mixer
  *     (video_attention.py:472-476).
- * Order: acc * acc_scale + bias + row_bias + residual, then the blend.  NULL disables a term. */
+ * Order: acc * acc_scale + bias + row_bias + residual, then the blend.  NULL disables a term.
+ * out_pair16 != 0 forces the split output into the fp16-pair format whatever the operand policy says: the q / k / v
+ * projections, whose consumer is vidseg_attention_split. */
 int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                          const float* bias, const float* residual, const float* row_bias,
                          long long rows_per_bias, const float* blend, const float* blend_alpha,
                          long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
-                         int m, int n, int k, float acc_scale, void* stream);
+                         int out_pair16, int m, int n, int k, float acc_scale, void* stream);
 
 /* nn.Conv2d as an implicit GEMM (no im2col: the taps are shifted TMA boxes, zero padding is the TMA out-of-bounds
  * fill).  Replaces the 3x3 / 1x1 convolutions of ResBlock (openaimodel.py:267-315), Downsample (:202-209, stride 2),

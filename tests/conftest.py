@@ -25,3 +25,12 @@ def cuda():
     if not torch.cuda.is_available():
         pytest.fail("this test is marked gpu and needs a CUDA device")
     return torch.device("cuda", 0)
+
+
+@pytest.fixture(params=[0, 1], ids=["pair16", "packed8"])
+def operand_mode(request, lib):
+    """Runs a test under both operand policies of the tensor-core GEMMs (include/vidseg_b200.h,
+    vidseg_set_operand_mode): 0 = fp16 pairs everywhere (3 MMAs per product), 1 = fp16 + fp8 corrections (default)."""
+    lib.vidseg_set_operand_mode(request.param)
+    yield request.param
+    lib.vidseg_set_operand_mode(1)

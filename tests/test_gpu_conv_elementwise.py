@@ -18,7 +18,7 @@ def relerr(got, want):
     (3, 6, 10, 64, 64, 3, 2, ""), (2, 16, 16, 192, 64, 1, 1, "r"), (2, 16, 16, 4, 320, 3, 1, ""),
     (2, 16, 16, 64, 4, 3, 1, ""), (28, 8, 8, 256, 256, 3, 1, "c"), (1, 96, 96, 64, 160, 3, 1, ""),
 ])
-def test_conv2d_matches_fp64(cuda, b, h, w, cin, cout, k, stride, extras):
+def test_conv2d_matches_fp64(cuda, operand_mode, b, h, w, cin, cout, k, stride, extras):
     from vidseg_diffusion_b200 import kernels as K
     g = torch.Generator(device="cpu").manual_seed(b * 1000 + h * 10 + cin + cout + k + stride)
     conv = nn.Conv2d(cin, cout, k, stride=stride, padding=k // 2).to(cuda)
@@ -36,11 +36,11 @@ def test_conv2d_matches_fp64(cuda, b, h, w, cin, cout, k, stride, extras):
     got = K.conv2d(K.image_split(x), conv, chan_bias=cb, residual=res)
     assert got.shape == want.shape
     err = relerr(got, want)
-    assert err < 1e-5, f"conv rel err {err:.3e}"
+    assert err < (1e-4 if (operand_mode == 1 and cin % 64 == 0) else 1e-5), f"conv rel err {err:.3e}"
 
 
 @pytest.mark.parametrize("rows,c", [(1, 320), (1000, 640), (4097, 1280), (77, 64), (5, 2048)])
-def test_layernorm_split(cuda, rows, c):
+def test_layernorm_split(cuda, operand_mode, rows, c):
     from vidseg_diffusion_b200 import kernels as K
     g = torch.Generator(device="cpu").manual_seed(rows + c)
     ln = nn.LayerNorm(c).to(cuda)
@@ -49,20 +49,20 @@ def test_layernorm_split(cuda, rows, c):
         ln.bias.copy_(0.1 * torch.randn(c, generator=g))
     x = (torch.randn(rows, c, generator=g) * 3 + 1).to(cuda)
     want = F.layer_norm(x.double(), (c,), ln.weight.double(), ln.bias.double(), ln.eps)
-    assert relerr(K.layer_norm_split(x, ln).float(), want) < 3e-6
+    assert relerr(K.layer_norm_split(x, ln).float(), want) < (3e-6 if operand_mode == 0 else 6e-5)
 
 
-def test_geglu_split(cuda):
+def test_geglu_split(cuda, operand_mode):
     from vidseg_diffusion_b200 import kernels as K
     x = torch.randn(300, 2 * 1280, generator=torch.Generator().manual_seed(3)).to(cuda) * 2
     val, gate = x.double().chunk(2, dim=-1)
-    assert relerr(K.geglu_split(x).float(), val * F.gelu(gate)) < 3e-6
+    assert relerr(K.geglu_split(x).float(), val * F.gelu(gate)) < (3e-6 if operand_mode == 0 else 6e-5)
 
 
 @pytest.mark.parametrize("b,h,w,c1,c2,silu,eps", [(2, 16, 16, 320, 0, True, 1e-5), (3, 8, 8, 1280, 640, True, 1e-5),
                                                     (1, 64, 64, 320, 320, True, 1e-5), (2, 4, 4, 1280, 1280, True, 1e-5),
                                                     (2, 32, 32, 640, 0, False, 1e-6), (2, 5, 7, 64, 0, True, 1e-5)])
-def test_groupnorm_split_with_concat(cuda, b, h, w, c1, c2, silu, eps):
+def test_groupnorm_split_with_concat(cuda, operand_mode, b, h, w, c1, c2, silu, eps):
     from vidseg_diffusion_b200 import kernels as K
     g = torch.Generator(device="cpu").manual_seed(b + h + c1 + c2)
     c = c1 + c2
@@ -78,16 +78,17 @@ def test_groupnorm_split_with_concat(cuda, b, h, w, c1, c2, silu, eps):
     if silu:
         want = F.silu(want)
     out, raw, first = K.group_norm_split(src, gn, silu=silu, want_raw=True)
-    assert relerr(out.float().permute(0, 3, 1, 2), want) < 4e-6
-    assert relerr(raw.float().permute(0, 3, 1, 2), full.double()) < 2e-6
+    loose = operand_mode == 1
+    assert relerr(out.float().permute(0, 3, 1, 2), want) < (6e-5 if loose else 4e-6)
+    assert relerr(raw.float().permute(0, 3, 1, 2), full.double()) < (6e-5 if loose else 2e-6)
     assert torch.equal(first.permute(0, 3, 1, 2), xa)
     again, _, _ = K.group_norm_split(src, gn, silu=silu)
     assert torch.equal(again.hi, out.hi) and torch.equal(again.lo, out.lo)  # deterministic
 
 
-def test_upsample2x_split(cuda):
+def test_upsample2x_split(cuda, operand_mode):
     from vidseg_diffusion_b200 import kernels as K
     x = torch.randn(2, 64, 5, 7, generator=torch.Generator().manual_seed(1)).to(cuda)
     want = F.interpolate(x.double(), scale_factor=2, mode="nearest")
     got = K.upsample_nearest2x_split(x).float().permute(0, 3, 1, 2)
-    assert got.shape == want.shape and relerr(got, want) < 2e-6
+    assert got.shape == want.shape and relerr(got, want) < (2e-6 if operand_mode == 0 else 6e-5)

@@ -7,6 +7,8 @@ sys.path.insert(0, ROOT)
 from vidseg_diffusion_b200.linear import gemm_split, split, attention_split, Split
 from vidseg_diffusion_b200 import kernels as K
 
+from vidseg_diffusion_b200 import _lib
+_lib.load().vidseg_set_operand_mode(int(os.environ.get("MODE", "1")))
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 res = {}
@@ -23,12 +25,12 @@ def ev(fn, it=3, warm=1):
 which = sys.argv[1:] or ["attn", "gemm", "conv"]
 if "attn" in which:
     for (B, H, N, Nk) in [(28, 5, 4096, 4096), (28, 10, 1024, 1024), (28, 5, 4096, 77)]:
-        q = split(torch.randn(B, N, H * 64, device=dev)); k = split(torch.randn(B, Nk, H * 64, device=dev)); v = split(torch.randn(B, Nk, H * 64, device=dev))
+        q = split(torch.randn(B, N, H * 64, device=dev), pair16=True); k = split(torch.randn(B, Nk, H * 64, device=dev), pair16=True); v = split(torch.randn(B, Nk, H * 64, device=dev), pair16=True)
         ms = ev(lambda: attention_split(q, k, v, H, 0.125))
         res[f"attn_B{B}_H{H}_N{N}_Nk{Nk}"] = {"ms": ms, "alg_TFLOPs": 4.0 * B * H * N * Nk * 64 / ms / 1e9}
 if "gemm" in which:
     for (m, n, kk) in [(28 * 4096, 2560, 320), (28 * 4096, 320, 1280), (28 * 1024, 5120, 640), (28 * 4096, 320, 320)]:
-        a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0)
+        a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0, is_weight=True)
         ms = ev(lambda: gemm_split(a, w))
         res[f"gemm_{m}x{n}x{kk}"] = {"ms": ms, "alg_TFLOPs": 2.0 * m * n * kk / ms / 1e9}
 if "conv" in which:

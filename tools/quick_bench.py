@@ -37,7 +37,7 @@ res["refine_ms"] = ev_time(lambda: refine_masks(db[1], lab, F, h, w), warm=1, it
 try:
     from vidseg_diffusion_b200.linear import gemm_split, split
     for (m, n, kk) in [(28 * 4096, 320, 320), (28 * 4096, 2560, 320), (28 * 4096, 320, 1280), (28 * 1024, 640, 640), (28 * 1024, 5120, 640), (28 * 256, 1280, 1280), (28 * 256, 10240, 1280)]:
-        a = split(torch.randn(m, kk, device=dev)); wt = split(torch.randn(n, kk, device=dev) / kk ** 0.5)
+        a = split(torch.randn(m, kk, device=dev)); wt = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0, is_weight=True)
         ms = ev_time(lambda: gemm_split(a, wt), it=10)
         res[f"gemm_{m}x{n}x{kk}_ms"] = ms
         res[f"gemm_{m}x{n}x{kk}_useful_TFLOPs"] = 2.0 * m * n * kk / ms / 1e9

@@ -55,6 +55,7 @@ struct AttnParams {
   float* out_f32;    // [B, Nq, heads*64] or null
   __half* out_hi;    // split output or null
   __half* out_lo;
+  int out_packed8;   // format of the split output (it feeds the to_out GEMM)
 };
 
 __global__ void __launch_bounds__(kAtThreads, 1)
@@ -296,13 +297,10 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
           *reinterpret_cast<float4*>(p.out_f32 + off + d) = make_float4(o[d], o[d + 1], o[d + 2], o[d + 3]);
       }
       if (p.out_hi) {
+        const size_t row = ((size_t)b * p.nq + q) * ((size_t)p.heads * kAtD);
 #pragma unroll
-        for (int d = 0; d < kAtD; d += 8) {
-          uint4 hv, lv;
-          tc::split8_f16(o[d], o[d + 1], o[d + 2], o[d + 3], o[d + 4], o[d + 5], o[d + 6], o[d + 7], hv, lv);
-          *reinterpret_cast<uint4*>(p.out_hi + off + d) = hv;
-          *reinterpret_cast<uint4*>(p.out_lo + off + d) = lv;
-        }
+        for (int d = 0; d < kAtD; d += 8)
+          tc::store_split8(p.out_hi + row, p.out_lo + row, head * kAtD + d, &o[d], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
       }
     }
   }
@@ -338,7 +336,8 @@ VS_API int vidseg_attention_split(const void* q_hi, const void* q_lo, const void
     attr_err = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
   });
   VS_CHECK_CUDA(attr_err);
-  AttnParams p{batch, heads, nq, nk, scale * 1.4426950408889634f, out_f32, (__half*)out_hi, (__half*)out_lo};
+  AttnParams p{batch, heads, nq, nk, scale * 1.4426950408889634f, out_f32, (__half*)out_hi, (__half*)out_lo,
+               operand_packed8((long long)heads * kAtD) ? 1 : 0};
   dim3 grid((nq + kAtBQ * kAtTiles - 1) / (kAtBQ * kAtTiles), heads, batch);
   VS_LAUNCH_W(4.0 * batch * heads * (double)nq * nk * kAtD, attn_split_kernel, grid, kAtThreads, kAtSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
   VS_POST_LAUNCH();

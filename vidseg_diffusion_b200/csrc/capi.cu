@@ -3,11 +3,13 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace vidseg {
 thread_local char g_last_error[512] = "";
 std::atomic<long long> g_launch_count{0};
 std::atomic<int> g_profile_on{0};
+std::atomic<int> g_operand_mode{1};
 
 namespace {
 struct ProfRecord { cudaEvent_t start, stop; int family; double work; };
@@ -73,8 +75,15 @@ VS_API int vidseg_profile_read(int family, double* ms_total, long long* launches
   return 0;
 }
 
+VS_API int vidseg_set_operand_mode(int mode) {
+  VS_REQUIRE(mode == 0 || mode == 1, "operand mode must be 0 (fp16 pairs) or 1 (fp16 + fp8 corrections)");
+  vidseg::g_operand_mode.store(mode);
+  return 0;
+}
+VS_API int vidseg_get_operand_mode(void) { return vidseg::g_operand_mode.load(); }
+
 VS_API const char* vidseg_last_error(void) { return vidseg::g_last_error; }
-VS_API int vidseg_abi_version(void) { return 2; }
+VS_API int vidseg_abi_version(void) { return 3; }
 VS_API long long vidseg_launch_count(void) { return vidseg::g_launch_count.load(); }
 VS_API int vidseg_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

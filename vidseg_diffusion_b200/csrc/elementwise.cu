@@ -26,7 +26,7 @@ constexpr int kLnMaxQuads = 16;  // C <= 2048
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ row_bias, long long rows_per_bias,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                       __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c) {
+                       __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c, int packed8) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -60,19 +60,17 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ro
     }
   }
   const float rstd = rsqrtf(warp_sum(s2) / (float)c + eps);
-  uint2* hr = reinterpret_cast<uint2*>(hi + row * c);
-  uint2* lr = reinterpret_cast<uint2*>(lo + row * c);
+  __half* hr = hi + row * c;
+  __half* lr = lo + row * c;
 #pragma unroll
   for (int i = 0; i < kLnMaxQuads; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
       const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
-      uint2 h, l;
-      tc::split4_f16((v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y,
-                     (v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w, h, l);
-      hr[q] = h;
-      lr[q] = l;
+      tc::store_split4(hr, lr, q * 4, (v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y,
+                       (v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w, packed8 != 0,
+                       tc::kAct8Sx, tc::kAct8Sl);
     }
   }
 }
@@ -82,7 +80,7 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ro
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 geglu_split_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half* __restrict__ lo, long long rows,
-                   int d) {
+                   int d, int packed8) {
   const int dq = d >> 2;
   const long long total = rows * dq;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -92,11 +90,8 @@ geglu_split_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half*
     const float4* hr = reinterpret_cast<const float4*>(h + row * 2 * d);
     const float4 val = ld_stream_f4(hr + q);
     const float4 gate = ld_stream_f4(hr + dq + q);
-    uint2 a, b;
-    tc::split4_f16(val.x * gelu_erf_f(gate.x), val.y * gelu_erf_f(gate.y), val.z * gelu_erf_f(gate.z),
-                   val.w * gelu_erf_f(gate.w), a, b);
-    reinterpret_cast<uint2*>(hi + row * d)[q] = a;
-    reinterpret_cast<uint2*>(lo + row * d)[q] = b;
+    tc::store_split4(hi + row * d, lo + row * d, q * 4, val.x * gelu_erf_f(gate.x), val.y * gelu_erf_f(gate.y),
+                     val.z * gelu_erf_f(gate.z), val.w * gelu_erf_f(gate.w), packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
   }
 }
 
@@ -161,7 +156,7 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
                        const double* __restrict__ partial, const float* __restrict__ gamma,
                        const float* __restrict__ beta, float eps, int silu, __half* __restrict__ out_hi,
                        __half* __restrict__ out_lo, __half* __restrict__ raw_hi, __half* __restrict__ raw_lo,
-                       int pix_per_block, int kGnChunks) {
+                       int pix_per_block, int kGnChunks, int packed8) {
   __shared__ float s_mean[kGnMaxGroups], s_rstd[kGnMaxGroups];
   const int c = c1 + c2;
   const int nq = c >> 2;
@@ -198,15 +193,9 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
     float y2 = (v.z - s_mean[g2]) * s_rstd[g2] * g.z + bt.z;
     float y3 = (v.w - s_mean[g3]) * s_rstd[g3] * g.w + bt.w;
     if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
-    uint2 h, l;
-    tc::split4_f16(y0, y1, y2, y3, h, l);
-    reinterpret_cast<uint2*>(out_hi + pix * c)[q] = h;
-    reinterpret_cast<uint2*>(out_lo + pix * c)[q] = l;
-    if (raw_hi) {
-      tc::split4_f16(v.x, v.y, v.z, v.w, h, l);
-      reinterpret_cast<uint2*>(raw_hi + pix * c)[q] = h;
-      reinterpret_cast<uint2*>(raw_lo + pix * c)[q] = l;
-    }
+    tc::store_split4(out_hi + pix * c, out_lo + pix * c, ch, y0, y1, y2, y3, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+    if (raw_hi)
+      tc::store_split4(raw_hi + pix * c, raw_lo + pix * c, ch, v.x, v.y, v.z, v.w, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
   }
 }
 
@@ -215,7 +204,7 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __half* __restrict__ lo, int batch,
-                        int h, int w, int c) {
+                        int h, int w, int c, int packed8) {
   const int nq = c >> 2;
   const long long total = (long long)batch * h * w * nq;
   const long long stride = (long long)gridDim.x * blockDim.x;
@@ -226,15 +215,12 @@ upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __
     const int yh = (int)((pix / w) % h);
     const int b = (int)(pix / ((long long)w * h));
     const float4 v = ld_stream_f4(reinterpret_cast<const float4*>(x + pix * c) + q);
-    uint2 a, bb;
-    tc::split4_f16(v.x, v.y, v.z, v.w, a, bb);
 #pragma unroll
     for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
         const long long op = ((long long)b * 2 * h + 2 * yh + dy) * (2 * w) + 2 * xw + dx;
-        reinterpret_cast<uint2*>(hi + op * c)[q] = a;
-        reinterpret_cast<uint2*>(lo + op * c)[q] = bb;
+        tc::store_split4(hi + op * c, lo + op * c, q * 4, v.x, v.y, v.z, v.w, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
       }
   }
 }
@@ -275,7 +261,7 @@ static int layernorm_entry(const float* x, const float* row_bias, long long rows
   const long long grid = (rows + warps - 1) / warps;
   VS_REQUIRE(grid <= 0x7fffffffLL, "too many rows");
   VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel, (int)grid, warps * 32, 0, stream, x, row_bias, rows_per_bias, gamma, beta, eps,
-              (__half*)out_hi, (__half*)out_lo, rows, channels);
+              (__half*)out_hi, (__half*)out_lo, rows, channels, operand_packed8(channels) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -285,7 +271,7 @@ VS_API int vidseg_geglu_split(const float* h, void* out_hi, void* out_lo, long l
   VS_REQUIRE(rows >= 0 && d >= 4 && d % 4 == 0, "D must be a multiple of 4");
   if (rows == 0) return 0;
   VS_LAUNCH_W(12.0 * rows * d, geglu_split_kernel, grid_for(rows * (d / 4), 256), 256, 0, stream, h, (__half*)out_hi,
-              (__half*)out_lo, rows, d);
+              (__half*)out_lo, rows, d, operand_packed8(d) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -326,7 +312,7 @@ VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int 
   const int blocks = (hw + pix_per_block - 1) / pix_per_block;
   VS_LAUNCH_W(bytes * (raw_hi ? 3.0 : 2.0), groupnorm_apply_kernel, dim3(blocks, batch), kGnThreads, 0, stream, x1, c1, x2,
               c2, hw, groups, partial, gamma, beta, eps, silu, (__half*)out_hi, (__half*)out_lo, (__half*)raw_hi,
-              (__half*)raw_lo, pix_per_block, chunks);
+              (__half*)raw_lo, pix_per_block, chunks, operand_packed8(c) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -338,7 +324,7 @@ VS_API int vidseg_upsample2x_split(const float* x, void* out_hi, void* out_lo, i
   if (batch == 0) return 0;
   const long long items = (long long)batch * h * w * (c / 4);
   VS_LAUNCH_W(4.0 * batch * h * w * c * 5.0, upsample2x_split_kernel, grid_for(items, 256), 256, 0, stream, x,
-              (__half*)out_hi, (__half*)out_lo, batch, h, w, c);
+              (__half*)out_hi, (__half*)out_lo, batch, h, w, c, operand_packed8(c) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }

@@ -98,6 +98,22 @@ __global__ void __launch_bounds__(256) split_f16_kernel(const float* __restrict_
   }
 }
 
+// row-aware form: x [rows, cols] -> operand in the format the library policy gives rows of `cols` channels
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, __half* __restrict__ hi,
+                                                         __half* __restrict__ lo, long long rows, int cols, float scale,
+                                                         int packed8, float sx, float sl) {
+  const int nq = cols >> 2;
+  const long long total = rows * nq;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const long long row = i / nq;
+    const int q = (int)(i - row * nq);
+    const float4 v = reinterpret_cast<const float4*>(x + row * cols)[q];
+    tc::store_split4(hi + row * cols, lo + row * cols, q * 4, v.x * scale, v.y * scale, v.z * scale, v.w * scale,
+                     packed8 != 0, sx, sl);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // split GEMM / implicit-GEMM convolution
 //
@@ -131,6 +147,8 @@ struct GemmParams {
   int wo, ho, nb;           // output pixel grid; M = nb * ho * wo
   int tiles_w, tiles_h, tiles_b;
   int c_off[kMaxTaps], w_off[kMaxTaps], p_idx[kMaxTaps], h_off[kMaxTaps];
+  int in_packed8;           // operands in the packed8 format (tc_common.cuh): 4 fp16 + 4 fp8 MMAs per k-block instead of 12
+  int out_packed8;          // format of the split output (out_hi / out_lo)
   float acc_scale;          // exact power-of-two inverse of the operand pre-scaling (weights carry 2^8)
   const float* bias;        // [N] or null
   const float* chan_bias;   // [M / cb_div, N] or null: bias per group of cb_div consecutive output rows (the ResBlock
@@ -232,13 +250,30 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           const uint64_t a_lo = tc::make_sw128_desc(sa + kTileABytes);
           const uint64_t b_hi = tc::make_sw128_desc(sa + 2 * kTileABytes);
           const uint64_t b_lo = tc::make_sw128_desc(sa + 2 * kTileABytes + Cfg::kTileBBytes);
+          if (p.in_packed8) {
+            // the a_lo / b_lo tiles hold [lo8 | x8] rows: corrections as fp8 MMAs (K = 32 each), small terms first
+            constexpr uint32_t idesc_lx = tc::make_idesc_f8(kGemmBM, BN, 1, 0);  // A e5m2 residual x B e4m3 value
+            constexpr uint32_t idesc_xl = tc::make_idesc_f8(kGemmBM, BN, 0, 1);  // A e4m3 value    x B e5m2 residual
 #pragma unroll
-          for (int ks = 0; ks < kGemmBK / 16; ++ks) {
-            const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 elements = 32 bytes along K inside the swizzle atom
-            // small terms first, so that they are not absorbed one by one into a large partial sum
-            tc::umma_f16(d_acc, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-            tc::umma_f16(d_acc, a_hi + adv, b_lo + adv, idesc, 1u);
-            tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+            for (int h = 0; h < 2; ++h) {
+              const uint64_t adv = (uint64_t)(h * 32 >> 4), xoff = (uint64_t)(64 >> 4);
+              tc::umma_f8(d_acc, a_lo + adv, b_lo + xoff + adv, idesc_lx, (kb > 0 || h > 0) ? 1u : 0u);
+              tc::umma_f8(d_acc, a_lo + xoff + adv, b_lo + adv, idesc_xl, 1u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+              tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int ks = 0; ks < kGemmBK / 16; ++ks) {
+              const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 elements = 32 bytes along K inside the swizzle atom
+              // small terms first, so that they are not absorbed one by one into a large partial sum
+              tc::umma_f16(d_acc, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              tc::umma_f16(d_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+              tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+            }
           }
           tc::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
           if (kb == k_blocks - 1) tc::umma_commit(&tmem_full_bar[acc]);
@@ -321,14 +356,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               if (j < ncols) *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
           }
           if (p.out_hi) {
+            __half* hrow = p.out_hi + pix * p.n;
+            __half* lrow = p.out_lo + pix * p.n;
 #pragma unroll
             for (int j = 0; j < 32; j += 8)
-              if (j < ncols) {
-                uint4 hv, lv;
-                tc::split8_f16(v[j], v[j + 1], v[j + 2], v[j + 3], v[j + 4], v[j + 5], v[j + 6], v[j + 7], hv, lv);
-                *reinterpret_cast<uint4*>(p.out_hi + off + j) = hv;
-                *reinterpret_cast<uint4*>(p.out_lo + off + j) = lv;
-              }
+              if (j < ncols) tc::store_split8(hrow, lrow, col0 + j, &v[j], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
           }
         }
       }
@@ -382,6 +414,8 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   p.tiles_h = (p.ho + p.bh - 1) / p.bh;
   p.tiles_b = (p.nb + p.bb - 1) / p.bb;
   p.kc_per_tap = (p.cin + kGemmBK - 1) / kGemmBK;
+  if (p.in_packed8 < 0) p.in_packed8 = operand_packed8(p.cin) ? 1 : 0;       // library policy unless the caller fixed it
+  if (p.out_packed8 < 0) p.out_packed8 = operand_packed8(p.n) ? 1 : 0;
   if (p.cb_div <= 0) p.cb_div = (long long)p.ho * p.wo;  // default: one bias row per sample
   if (p.ba_div <= 0) p.ba_div = 1;
   const uint32_t box[5] = {(uint32_t)kGemmBK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
@@ -404,6 +438,8 @@ int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const v
   p.wo = m; p.ho = 1; p.nb = 1;
   p.acc_scale = acc_scale;
   p.out_f32 = out_f32;
+  p.in_packed8 = 0;   // the K-means filter keeps the fp16 pair (its error band is derived for it)
+  p.out_packed8 = 0;
   const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
   const uint64_t row = (uint64_t)k * 2;
   const uint64_t astrides[4] = {row, row * m, row * m, row * m};
@@ -428,12 +464,27 @@ VS_API int vidseg_split_f16(const float* x, void* hi, void* lo, long long n, flo
   return 0;
 }
 
+VS_API int vidseg_split_rows(const float* x, void* hi, void* lo, long long rows, int cols, float scale, int is_weight,
+                             void* stream) {
+  VS_REQUIRE(rows >= 0 && cols >= 1, "bad shape");
+  if (rows == 0) return 0;
+  VS_REQUIRE(x && hi && lo, "null pointer");
+  if (cols % 4 != 0 || (uintptr_t)x % 16 != 0) return vidseg_split_f16(x, hi, lo, rows * cols, scale, stream);
+  const int packed8 = operand_packed8(cols) ? 1 : 0;
+  const long long items = rows * (cols / 4);
+  int grid = (int)std::min<long long>((items + 255) / 256, (long long)kNumSMs * 8);
+  VS_LAUNCH_W(8.0 * rows * cols, split_rows_kernel, grid, 256, 0, stream, x, (__half*)hi, (__half*)lo, rows, cols, scale,
+              packed8, is_weight ? tc::kWgt8Sx : tc::kAct8Sx, is_weight ? tc::kWgt8Sl : tc::kAct8Sl);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
 #undef VS_FAMILY
 #define VS_FAMILY vidseg::kFamGemm
 static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                       const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
                       const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
-                      int m, int n, int k, float acc_scale, void* stream) {
+                      int out_pair16, int m, int n, int k, float acc_scale, void* stream) {
   VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null operand pointer");
   VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
@@ -452,6 +503,8 @@ static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, cons
   p.chan_bias = row_bias; p.cb_div = rows_per_bias;
   p.blend = blend; p.blend_alpha = blend_alpha; p.ba_div = rows_per_alpha;
   p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
+  p.in_packed8 = -1;
+  p.out_packed8 = out_pair16 ? 0 : -1;
   const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
   const uint64_t row = (uint64_t)k * 2;
   const uint64_t astrides[4] = {row, row * m, row * m, row * m};
@@ -461,16 +514,16 @@ static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, cons
 VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                              const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
                              float acc_scale, void* stream) {
-  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, out_f32, out_hi, out_lo, m, n,
-                    k, acc_scale, stream);
+  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, out_f32, out_hi, out_lo, 0, m,
+                    n, k, acc_scale, stream);
 }
 
 VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                                 const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
                                 const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi,
-                                void* out_lo, int m, int n, int k, float acc_scale, void* stream) {
+                                void* out_lo, int out_pair16, int m, int n, int k, float acc_scale, void* stream) {
   return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, row_bias, rows_per_bias, blend, blend_alpha, rows_per_alpha,
-                    out_f32, out_hi, out_lo, m, n, k, acc_scale, stream);
+                    out_f32, out_hi, out_lo, out_pair16, m, n, k, acc_scale, stream);
 }
 
 #undef VS_FAMILY
@@ -496,6 +549,7 @@ VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w
   p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
   p.nb = batch;
   p.acc_scale = acc_scale;
+  p.in_packed8 = -1; p.out_packed8 = -1;
   uint64_t adims[5], astrides[4];
   const uint64_t px = (uint64_t)cin * 2;  // bytes per pixel
   if (stride == 1) {
@@ -550,6 +604,7 @@ VS_API int vidseg_conv_temporal_split(const void* x_hi, const void* x_lo, const 
   p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
   p.nb = videos; p.ho = frames; p.wo = hw;
   p.acc_scale = acc_scale;
+  p.in_packed8 = -1; p.out_packed8 = -1;
   const uint64_t px = (uint64_t)cin * 2;
   const uint64_t adims[5] = {(uint64_t)cin, (uint64_t)hw, 1, (uint64_t)frames, (uint64_t)videos};
   const uint64_t astrides[4] = {px, px * hw, px * hw, px * hw * frames};

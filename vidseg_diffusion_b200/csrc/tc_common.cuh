@@ -4,8 +4,10 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 
 namespace vidseg {
 namespace tc {
@@ -207,7 +209,89 @@ __device__ __forceinline__ void split4_f16(float v0, float v1, float v2, float v
   split2_f16(v2, v3, hi.y, lo.y);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Operand formats of the tensor-core GEMMs.
+//   pair16  : x ~= hi + lo, two fp16 tensors -> three kind::f16 MMAs per product (lo.hi + hi.lo + hi.hi), 22 bits.
+//   packed8 : hi = fp16(x) plus an fp8 side tensor of the SAME size as lo: every 64-element block of a row is 128
+//             bytes = [lo8: e5m2((x - hi) * sl), 64 B | x8: e4m3(x * sx), 64 B].  The two correction products
+//             (x - hi).w and x.(w - w_hi) only need ~4 significant bits each (they are 2^-11 of the result), so they
+//             run as kind::f8f6f4 MMAs at twice the fp16 rate: one product costs 1 + 1/2 + 1/2 = 2 fp16-MMA units
+//             instead of 3, at 2^-14.5 relative precision per product (measured 1.6e-5 rms per GEMM against fp64; the
+//             parity bar of the path is 1e-3).  Scales: activations (sx, sl) = (1, 16), weights -- already carrying
+//             2^8 -- (1/16, 1), so that lo8_a.x8_w and x8_a.lo8_w both land on the 2^8 scale of hi_a.hi_w and all
+//             three accumulate in ONE fp32 TMEM accumulator.  A 64-element block is one 128-byte swizzle row, i.e.
+//             the fp8 tensor moves through the very same TMA maps as the fp16 lo tensor did.
+// Needs the row length (channels) to be a multiple of 64; other operands stay pair16.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr float kAct8Sx = 1.0f, kAct8Sl = 16.0f;
+constexpr float kWgt8Sx = 0.0625f, kWgt8Sl = 1.0f;
+
+__device__ __forceinline__ uint32_t pack4_fp8(float a, float b, float c, float d, __nv_fp8_interpretation_t kind) {
+  const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, kind);   // a in the low byte
+  const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, kind);
+  return lo | (hi << 16);
+}
+// four consecutive elements c..c+3 (c % 4 == 0) of one operand row
+__device__ __forceinline__ void store_split4(__half* hi_row, __half* lo_row, int c, float v0, float v1, float v2,
+                                             float v3, bool packed8, float sx, float sl) {
+  const __half2 h01 = __floats2half2_rn(v0, v1), h23 = __floats2half2_rn(v2, v3);
+  const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+  *reinterpret_cast<uint2*>(hi_row + c) = make_uint2(h2_bits(h01), h2_bits(h23));
+  const float r0 = v0 - f01.x, r1 = v1 - f01.y, r2 = v2 - f23.x, r3 = v3 - f23.y;
+  if (!packed8) {
+    *reinterpret_cast<uint2*>(lo_row + c) = make_uint2(h2_bits(__floats2half2_rn(r0, r1)), h2_bits(__floats2half2_rn(r2, r3)));
+  } else {
+    uint8_t* aux = reinterpret_cast<uint8_t*>(lo_row) + ((c >> 6) << 7) + (c & 63);
+    *reinterpret_cast<uint32_t*>(aux) = pack4_fp8(r0 * sl, r1 * sl, r2 * sl, r3 * sl, __NV_E5M2);
+    *reinterpret_cast<uint32_t*>(aux + 64) = pack4_fp8(v0 * sx, v1 * sx, v2 * sx, v3 * sx, __NV_E4M3);
+  }
+}
+// eight consecutive elements (c % 8 == 0)
+__device__ __forceinline__ void store_split8(__half* hi_row, __half* lo_row, int c, const float* v, bool packed8, float sx,
+                                             float sl) {
+  if (!packed8) {
+    uint4 hv, lv;
+    split8_f16(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], hv, lv);
+    *reinterpret_cast<uint4*>(hi_row + c) = hv;
+    *reinterpret_cast<uint4*>(lo_row + c) = lv;
+  } else {
+    uint4 hv;
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; i += 2) {
+      const __half2 h = __floats2half2_rn(v[i], v[i + 1]);
+      const float2 f = __half22float2(h);
+      (&hv.x)[i >> 1] = h2_bits(h);
+      r[i] = (v[i] - f.x) * sl;
+      r[i + 1] = (v[i + 1] - f.y) * sl;
+    }
+    *reinterpret_cast<uint4*>(hi_row + c) = hv;
+    uint8_t* aux = reinterpret_cast<uint8_t*>(lo_row) + ((c >> 6) << 7) + (c & 63);
+    *reinterpret_cast<uint2*>(aux) = make_uint2(pack4_fp8(r[0], r[1], r[2], r[3], __NV_E5M2), pack4_fp8(r[4], r[5], r[6], r[7], __NV_E5M2));
+    *reinterpret_cast<uint2*>(aux + 64) = make_uint2(pack4_fp8(v[0] * sx, v[1] * sx, v[2] * sx, v[3] * sx, __NV_E4M3),
+                                                     pack4_fp8(v[4] * sx, v[5] * sx, v[6] * sx, v[7] * sx, __NV_E4M3));
+  }
+}
+
+// Instruction descriptor for kind::f8f6f4 (same bit layout as make_idesc_f16; a/b_format: 0 = E4M3, 1 = E5M2), fp32 accumulate
+__host__ __device__ constexpr uint32_t make_idesc_f8(int m, int n, int a_e5m2, int b_e5m2) {
+  return (1u << 4) | ((uint32_t)a_e5m2 << 7) | ((uint32_t)b_e5m2 << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem], 8-bit operands, K = 32 per instruction
+__device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 }  // namespace tc
+
+// library-wide operand policy (vidseg_set_operand_mode): 0 = pair16 everywhere, 1 = packed8 wherever the channel count allows
+extern std::atomic<int> g_operand_mode;
+inline bool operand_packed8(long long channels) { return g_operand_mode.load(std::memory_order_relaxed) != 0 && channels % 64 == 0; }
 
 // host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
 int encode_tmap_2d_f16(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t outer_stride_bytes,

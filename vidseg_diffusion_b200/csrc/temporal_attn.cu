@@ -23,7 +23,7 @@ template <int kMaxT>
 __global__ void __launch_bounds__(kTaWarps * 32)
 temporal_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
                      float* __restrict__ out_f32, __half* __restrict__ out_hi, __half* __restrict__ out_lo,
-                     int videos, int frames, int sites, int heads, float scale) {
+                     int videos, int frames, int sites, int heads, float scale, int packed8) {
   extern __shared__ float sm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long seq = (long long)blockIdx.x * kTaWarps + warp;
@@ -96,10 +96,13 @@ temporal_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, c
       const size_t off = row0 + (size_t)i * frame_stride + 2 * lane;
       if (out_f32) *reinterpret_cast<float2*>(out_f32 + off) = make_float2(ox, oy);
       if (out_hi) {
-        uint32_t h, l;
-        tc::split2_f16(ox, oy, h, l);
-        *reinterpret_cast<uint32_t*>(out_hi + off) = h;
-        *reinterpret_cast<uint32_t*>(out_lo + off) = l;
+        // a lane pair shares one 4-element group: even lanes store (the packed8 format is written 4 elements at a time)
+        const float px = __shfl_down_sync(0xffffffffu, ox, 1), py = __shfl_down_sync(0xffffffffu, oy, 1);
+        if ((lane & 1) == 0) {
+          const size_t rowoff = row0 - (size_t)head * kTaD + (size_t)i * frame_stride;   // start of the token's row
+          tc::store_split4(out_hi + rowoff, out_lo + rowoff, head * kTaD + 2 * lane, ox, oy, px, py, packed8 != 0,
+                           tc::kAct8Sx, tc::kAct8Sl);
+        }
       }
     }
   }
@@ -121,7 +124,8 @@ static int launch_temporal(const float* q, const float* k, const float* v, float
   VS_CHECK_CUDA(attr_err);
   const double bytes = 16.0 * (double)videos * frames * sites * heads * kTaD;  // q, k, v fp32 in; hi | lo fp16 out
   VS_LAUNCH_W(bytes, temporal_attn_kernel<kMaxT>, (int)blocks, kTaWarps * 32, smem, stream, q, k, v, out_f32,
-              (__half*)out_hi, (__half*)out_lo, videos, frames, sites, heads, scale);
+              (__half*)out_hi, (__half*)out_lo, videos, frames, sites, heads, scale,
+              operand_packed8((long long)heads * kTaD) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }

@@ -12,14 +12,14 @@ import weakref
 import torch
 
 from . import _lib
-from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, split
+from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, packed8, split
 
 _WEIGHT_CACHE = {}
 _WORKSPACES = {}
 
 
 def _cached(param, tag, make):
-    key = (id(param), tag)
+    key = (id(param), tag, _lib.load().vidseg_get_operand_mode())
     hit = _WEIGHT_CACHE.get(key)
     stamp = (param.data_ptr(), param._version, param.device)
     if hit is not None and hit[0] == stamp and hit[1]() is param:
@@ -39,7 +39,7 @@ def _f32(param, tag="f32"):
 
 def weight_split(param):
     """[N, K] nn.Linear weight -> cached Split."""
-    return _cached(param, "lin", lambda w: split(w.float().contiguous(), WEIGHT_SCALE))
+    return _cached(param, "lin", lambda w: split(w.float().contiguous(), WEIGHT_SCALE, is_weight=True))
 
 
 def conv_weight_split(param, cin_pad=None):
@@ -48,7 +48,9 @@ def conv_weight_split(param, cin_pad=None):
         w = w.float().permute(0, 2, 3, 1)  # [Cout, kh, kw, Cin]
         if cin_pad is not None and cin_pad != w.shape[-1]:
             w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
-        return split(w.reshape(w.shape[0], -1).contiguous(), WEIGHT_SCALE)
+        if packed8(w.shape[-1]):   # same policy as the activation it meets: decided by the channels of one tap
+            return split(w.reshape(-1, w.shape[-1]).contiguous(), WEIGHT_SCALE, is_weight=True).reshape(w.shape[0], -1)
+        return split(w.reshape(w.shape[0], -1).contiguous(), WEIGHT_SCALE, is_weight=True, pair16=True)
     return _cached(param, f"conv{cin_pad}", make)
 
 
@@ -155,7 +157,12 @@ def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blen
     if bt != videos * frames or cin != conv.in_channels:
         raise _lib.VidsegError("conv_temporal: shape mismatch")
     cout = conv.out_channels
-    ws = _cached(conv.weight, "conv_t", lambda t: split(t.float()[:, :, :, 0, 0].permute(0, 2, 1).reshape(cout, 3 * cin).contiguous(), WEIGHT_SCALE))
+    def make_t(t):
+        w = t.float()[:, :, :, 0, 0].permute(0, 2, 1).contiguous()   # [Cout, 3, Cin], tap-major
+        if packed8(cin):
+            return split(w.reshape(-1, cin), WEIGHT_SCALE, is_weight=True).reshape(cout, 3 * cin)
+        return split(w.reshape(cout, 3 * cin), WEIGHT_SCALE, is_weight=True, pair16=True)
+    ws = _cached(conv.weight, "conv_t", make_t)
     out = torch.empty((bt, h, w, cout), dtype=torch.float32, device=xs.hi.device)
     res = None if residual is None else nhwc(residual, "residual")
     bl = None if blend is None else nhwc(blend, "blend")
@@ -204,6 +211,7 @@ def temporal_attention(q, k, v, videos, frames, heads, scale):
 # normalisation / gating / resampling kernels (all emit the split operand of the next GEMM)
 # ------------------------------------------------------------------------------------------------
 def _empty_split(shape, device):
+    """Output buffers of a producer kernel; the kernel fills them in the policy's format for rows of shape[-1]."""
     return Split(torch.empty(shape, dtype=torch.float16, device=device), torch.empty(shape, dtype=torch.float16, device=device))
 
 

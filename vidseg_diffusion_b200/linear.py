@@ -5,48 +5,77 @@ import torch
 from . import _lib
 
 
-class Split:
-    """An fp32 tensor carried as two fp16 tensors: x * scale ~= hi + lo (scale is a power of two, 1 for activations)."""
-    __slots__ = ("hi", "lo", "scale")
+def packed8(channels):
+    """The library's operand policy (include/vidseg_b200.h, vidseg_set_operand_mode): rows of ``channels`` elements are
+    carried as fp16 + fp8 corrections when the mode is on and the row length is a multiple of 64."""
+    return _lib.load().vidseg_get_operand_mode() != 0 and channels % 64 == 0
 
-    def __init__(self, hi, lo, scale=1.0):
+
+class Split:
+    """A tensor-core operand: an fp32 tensor x carried as hi = fp16(x * scale) plus a same-sized side tensor ``lo``:
+    either lo = fp16(x * scale - hi) (``fmt == "pair16"``) or, per 64-element block of a row, 64 bytes of
+    e5m2((x * scale - hi) * sl) followed by 64 bytes of e4m3(x * scale * sx) (``fmt == "packed8"``).  ``scale`` is a
+    power of two (1 for activations, 2^8 for weights).  The kernels pick the format from the library policy and the row
+    length; this object only records it so that ``float()`` can decode either."""
+    __slots__ = ("hi", "lo", "scale", "fmt", "sl")
+
+    def __init__(self, hi, lo, scale=1.0, fmt=None, sl=16.0):
         self.hi = hi
         self.lo = lo
         self.scale = scale
+        self.fmt = fmt if fmt is not None else ("packed8" if packed8(hi.shape[-1]) else "pair16")
+        self.sl = sl
 
     @property
     def shape(self):
         return self.hi.shape
 
     def reshape(self, *shape):
-        return Split(self.hi.reshape(*shape), self.lo.reshape(*shape), self.scale)
+        out = Split(self.hi.reshape(*shape), self.lo.reshape(*shape), self.scale, self.fmt, self.sl)
+        if self.fmt == "packed8" and out.hi.shape[-1] % 64:
+            raise _lib.VidsegError("Split.reshape: a packed8 operand needs rows that are multiples of 64 elements")
+        return out
 
     def float(self):
-        return (self.hi.float() + self.lo.float()) / self.scale
+        """Decode to fp32 (tests / debugging; the e4m3 copy of x is redundant here)."""
+        if self.fmt == "pair16":
+            return (self.hi.float() + self.lo.float()) / self.scale
+        c = self.hi.shape[-1]
+        aux = self.lo.contiguous().view(torch.uint8).reshape(*self.hi.shape[:-1], c // 64, 128)
+        lo8 = aux[..., :64].contiguous().view(torch.float8_e5m2).float().reshape(self.hi.shape)
+        return (self.hi.float() + lo8 / self.sl) / self.scale
 
     def __getitem__(self, idx):
-        return Split(self.hi[idx].contiguous(), self.lo[idx].contiguous(), self.scale)
+        return Split(self.hi[idx].contiguous(), self.lo[idx].contiguous(), self.scale, self.fmt, self.sl)
 
 
 WEIGHT_SCALE = 256.0  # tc::kWeightScale
 
 
-def split(x, scale=1.0):
-    """fp32 CUDA tensor -> Split of x * scale (one streaming kernel)."""
+def split(x, scale=1.0, is_weight=False, pair16=False):
+    """fp32 CUDA tensor [.., C] -> Split of x * scale (one streaming kernel).  ``pair16`` forces the fp16-pair format
+    (attention operands); otherwise the library policy decides from C.  ``is_weight`` selects the weight scales."""
     x = _lib.require_cuda_tensor(x, torch.float32, "x")
     hi = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lo = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     lib = _lib.load()
+    cols = x.shape[-1] if x.dim() else 1
     with torch.cuda.device(x.device):
-        _lib.check(lib.vidseg_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), float(scale), _lib.stream_ptr()), "split_f16")
-    return Split(hi, lo, float(scale))
+        if pair16 or x.numel() == 0:
+            _lib.check(lib.vidseg_split_f16(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel(), float(scale), _lib.stream_ptr()), "split_f16")
+            return Split(hi, lo, float(scale), "pair16")
+        _lib.check(lib.vidseg_split_rows(x.data_ptr(), hi.data_ptr(), lo.data_ptr(), x.numel() // cols, cols, float(scale),
+                                         1 if is_weight else 0, _lib.stream_ptr()), "split_rows")
+    return Split(hi, lo, float(scale), None, 1.0 if is_weight else 16.0)
 
 
 def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, row_bias=None, rows_per_bias=1,
-               blend=None, blend_alpha=None, rows_per_alpha=1):
+               blend=None, blend_alpha=None, rows_per_alpha=1, split_pair16=False):
     """out = a @ w.T (+ bias) (+ row_bias[row // rows_per_bias]) (+ residual), then optionally
     out = alpha * blend + (1 - alpha) * out with alpha = blend_alpha[row // rows_per_alpha].
-    a: Split [.., K], w: Split [N, K] (nn.Linear layout).  Returns (out_f32 or None, Split or None)."""
+    a: Split [.., K], w: Split [N, K] (nn.Linear layout), both in the format the policy gives rows of K elements.
+    ``split_pair16``: the split output feeds the attention kernel (fp16 pair) instead of another GEMM.
+    Returns (out_f32 or None, Split or None)."""
     k = a.hi.shape[-1]
     lead = a.hi.shape[:-1]
     m = a.hi.numel() // k
@@ -57,6 +86,9 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, 
         _lib.require_cuda_tensor(t, torch.float16, name)
     for t, name in ((a.lo, "a.lo"), (w.lo, "w.lo")):
         _lib.require_cuda_tensor(t, torch.float16, name)
+    want_fmt = "packed8" if packed8(k) else "pair16"
+    if a.fmt != want_fmt or w.fmt != want_fmt:
+        raise _lib.VidsegError(f"gemm_split: operands are {a.fmt} / {w.fmt}, the policy expects {want_fmt} for K={k}")
     dev = a.hi.device
     out = torch.empty((*lead, n), dtype=torch.float32, device=dev) if want_f32 else None
     oh = torch.empty((*lead, n), dtype=torch.float16, device=dev) if want_split else None
@@ -81,7 +113,7 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, 
     lib = _lib.load()
     ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(dev):
-        if row_bias is None and blend is None:
+        if row_bias is None and blend is None and not split_pair16:
             _lib.check(lib.vidseg_gemm_split(
                 a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
                 ptr(out), ptr(oh), ptr(ol), m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split")
@@ -89,8 +121,9 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, 
             _lib.check(lib.vidseg_gemm_split_ex(
                 a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
                 ptr(row_bias), int(rows_per_bias), ptr(blend), ptr(blend_alpha), int(rows_per_alpha),
-                ptr(out), ptr(oh), ptr(ol), m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split_ex")
-    return out, (Split(oh, ol) if want_split else None)
+                ptr(out), ptr(oh), ptr(ol), 1 if split_pair16 else 0, m, n, k, 1.0 / (a.scale * w.scale),
+                _lib.stream_ptr()), "gemm_split_ex")
+    return out, (Split(oh, ol, 1.0, "pair16" if split_pair16 else None) if want_split else None)
 
 
 def attention_split(q, k, v, heads, scale=None, want_f32=False, want_split=True):
@@ -104,6 +137,8 @@ def attention_split(q, k, v, heads, scale=None, want_f32=False, want_split=True)
         _lib.require_cuda_tensor(t, torch.float16, name)
     for t, name in ((q.lo, "q.lo"), (k.lo, "k.lo"), (v.lo, "v.lo")):
         _lib.require_cuda_tensor(t, torch.float16, name)
+    if q.fmt != "pair16" or k.fmt != "pair16" or v.fmt != "pair16":
+        raise _lib.VidsegError("attention_split: q / k / v must be fp16-pair operands (split(..., pair16=True))")
     dev = q.hi.device
     out = torch.empty((b, nq, c), dtype=torch.float32, device=dev) if want_f32 else None
     oh = torch.empty((b, nq, c), dtype=torch.float16, device=dev) if want_split else None

@@ -107,18 +107,19 @@ class CrossAttention(nn.Module):
         """xs: Split [B, N, C] (already normalised); context: Split [B, L, Cctx] or None.
         Returns to_out(attention) (+ residual) as fp32 [B, N, C]."""
         cs = xs if context is None else context
+        # q / k / v feed the attention kernel, which takes fp16-pair operands whatever the GEMM operand policy is
         if injected_q is not None:
-            q, qs = injected_q, K.split(injected_q.float().contiguous())
+            q, qs = injected_q, K.split(injected_q.float().contiguous(), pair16=True)
         else:
-            q, qs = K.linear(xs, self.to_q.weight, want_f32=True, want_split=True)
+            q, qs = K.linear(xs, self.to_q.weight, want_f32=True, want_split=True, split_pair16=True)
         if injected_k is not None:
-            k, ks = injected_k, K.split(injected_k.float().contiguous())
+            k, ks = injected_k, K.split(injected_k.float().contiguous(), pair16=True)
         else:
-            k, ks = K.linear(cs, self.to_k.weight, want_f32=True, want_split=True)
+            k, ks = K.linear(cs, self.to_k.weight, want_f32=True, want_split=True, split_pair16=True)
         if injected_v is not None:
-            vs = K.split(injected_v.float().contiguous())
+            vs = K.split(injected_v.float().contiguous(), pair16=True)
         else:
-            _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True)
+            _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True, split_pair16=True)
         self.q = q
         self.k = k
         _, os_ = K.attention(qs, ks, vs, self.heads, self.scale)
