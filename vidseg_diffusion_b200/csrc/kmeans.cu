@@ -121,24 +121,24 @@ __global__ void __launch_bounds__(32) km_colstats_kernel(const float* __restrict
   const float* p = x + col;
   float s = 0.f;
   int i = 0;
-  for (; i + 8 <= n; i += 8) {
-    float v[8];
+  for (; i + 32 <= n; i += 32) {
+    float v[32];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(i + u) * d];
+    for (int u = 0; u < 32; ++u) v[u] = p[(size_t)(i + u) * d];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s = __fadd_rn(s, v[u]);
+    for (int u = 0; u < 32; ++u) s = __fadd_rn(s, v[u]);
   }
   for (; i < n; ++i) s = __fadd_rn(s, p[(size_t)i * d]);
   const float m = (float)((double)s / (double)n);
   mean[col] = m;
   float s2 = 0.f;
   i = 0;
-  for (; i + 8 <= n; i += 8) {
-    float v[8];
+  for (; i + 32 <= n; i += 32) {
+    float v[32];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = p[(size_t)(i + u) * d];
+    for (int u = 0; u < 32; ++u) v[u] = p[(size_t)(i + u) * d];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
+    for (int u = 0; u < 32; ++u) {
       const float t = __fsub_rn(v[u], m);
       s2 = __fadd_rn(s2, __fmul_rn(t, t));
     }
@@ -202,14 +202,20 @@ __global__ void __launch_bounds__(256) km_center_kernel(const float* __restrict_
 // distances of every point to the T candidates of each run, in float64 as
 // _euclidean_distances_upcast (-2 x.y + ||y||^2 + ||x||^2), rounded to fp32, clamped at 0,
 // min-ed with the current closest distances; per-warp float64 partial potentials.
+// Register-tiled: a warp works on kPotRows rows at a time so that every candidate value read from shared memory feeds
+// kPotRows FMAs (the first version issued one shared load per FMA and ran at 110 M warp instructions per launch);
+// the candidate count is a template parameter so that no predicated-off work is issued.  Per (row, candidate) the
+// lane partial sums run over ascending c and are combined by the same butterfly as before: results are unchanged.
+constexpr int kPotRows = 4;
+template <int T>
 __global__ void __launch_bounds__(kPotWarps * 32)
-km_kpp_dist_kernel(const float* __restrict__ xc, const double* __restrict__ xx, int n, int d, int t_count,
+km_kpp_dist_kernel(const float* __restrict__ xc, const double* __restrict__ xx, int n, int d,
                    const int* __restrict__ cand, const float* __restrict__ closest, int use_min,
                    float* __restrict__ newdist, double* __restrict__ potpart, int t_stride) {
-  extern __shared__ double cs[];  // [t_count][d]
+  extern __shared__ double cs[];  // [T][d]
   const int r = blockIdx.y;
   const int* my_cand = cand + r * kMaxTrials;
-  for (int e = threadIdx.x; e < t_count * d; e += blockDim.x) {
+  for (int e = threadIdx.x; e < T * d; e += blockDim.x) {
     const int t = e / d, c = e - t * d;
     cs[e] = (double)xc[(size_t)my_cand[t] * d + c];
   }
@@ -218,40 +224,69 @@ km_kpp_dist_kernel(const float* __restrict__ xc, const double* __restrict__ xx, 
   const int warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * kPotWarps + warp;
   double cand_xx = 0.0;
-  if (lane < t_count) cand_xx = xx[my_cand[lane]];
+  if (lane < T) cand_xx = xx[my_cand[lane]];
   double potacc = 0.0;
-  for (int row = gwarp; row < n; row += kPotParts) {
-    const float* xr = xc + (size_t)row * d;
-    double acc[kMaxTrials];
+  // rows gwarp, gwarp + kPotParts, ... as before (the per-warp potential partials keep their composition); four at a time
+  for (int row0 = gwarp; row0 < n; row0 += kPotParts * kPotRows) {
+    double acc[kPotRows][T];
 #pragma unroll
-    for (int t = 0; t < kMaxTrials; ++t) acc[t] = 0.0;
-    for (int c = lane; c < d; c += 32) {
-      const double xv = (double)xr[c];
+    for (int q = 0; q < kPotRows; ++q)
 #pragma unroll
-      for (int t = 0; t < kMaxTrials; ++t)
-        if (t < t_count) acc[t] = fma(xv, cs[t * d + c], acc[t]);
+      for (int t = 0; t < T; ++t) acc[q][t] = 0.0;
+    const float* xr[kPotRows];
+#pragma unroll
+    for (int q = 0; q < kPotRows; ++q) {
+      const int row = row0 + q * kPotParts;
+      xr[q] = xc + (size_t)(row < n ? row : row0) * d;   // out-of-range rows recompute row0 and are discarded
     }
-    double mine = 0.0;
+    for (int c = lane; c < d; c += 32) {
+      double xv[kPotRows];
 #pragma unroll
-    for (int t = 0; t < kMaxTrials; ++t) {
-      if (t < t_count) {
-        const double s = warp_sum(acc[t]);
-        if (lane == t) mine = s;
+      for (int q = 0; q < kPotRows; ++q) xv[q] = (double)xr[q][c];
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const double cv = cs[t * d + c];
+#pragma unroll
+        for (int q = 0; q < kPotRows; ++q) acc[q][t] = fma(xv[q], cv, acc[q][t]);
       }
     }
-    if (lane < t_count) {
-      double dd = -2.0 * mine;
-      dd += cand_xx;
-      dd += xx[row];
-      float f = (float)dd;
-      f = fmaxf(f, 0.f);
-      const size_t rn = (size_t)r * n + row;
-      if (use_min) f = fminf(closest[rn], f);
-      newdist[((size_t)r * t_stride + lane) * n + row] = f;
-      potacc += (double)f;
+#pragma unroll
+    for (int q = 0; q < kPotRows; ++q) {
+      const int row = row0 + q * kPotParts;
+      double mine = 0.0;
+#pragma unroll
+      for (int t = 0; t < T; ++t) {
+        const double s = warp_sum(acc[q][t]);
+        if (lane == t) mine = s;
+      }
+      if (lane < T && row < n) {
+        double dd = -2.0 * mine;
+        dd += cand_xx;
+        dd += xx[row];
+        float f = (float)dd;
+        f = fmaxf(f, 0.f);
+        const size_t rn = (size_t)r * n + row;
+        if (use_min) f = fminf(closest[rn], f);
+        newdist[((size_t)r * t_stride + lane) * n + row] = f;
+        potacc += (double)f;
+      }
     }
   }
-  if (lane < t_count) potpart[((size_t)r * t_stride + lane) * kPotParts + gwarp] = potacc;
+  if (lane < T) potpart[((size_t)r * t_stride + lane) * kPotParts + gwarp] = potacc;
+}
+
+typedef void (*KppDistFn)(const float*, const double*, int, int, const int*, const float*, int, float*, double*, int);
+static KppDistFn kpp_dist_fn(int t) {
+  switch (t) {
+    case 1: return km_kpp_dist_kernel<1>;
+    case 2: return km_kpp_dist_kernel<2>;
+    case 3: return km_kpp_dist_kernel<3>;
+    case 4: return km_kpp_dist_kernel<4>;
+    case 5: return km_kpp_dist_kernel<5>;
+    case 6: return km_kpp_dist_kernel<6>;
+    case 7: return km_kpp_dist_kernel<7>;
+    default: return km_kpp_dist_kernel<8>;
+  }
 }
 
 // one block per run: pick the best candidate of step c (np.argmin of the potentials), commit it
@@ -531,9 +566,9 @@ km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* _
   *lp = best_j;
 }
 
-// exact float64 evaluation of the candidates of every ambiguous pair, identical to km_assign_kernel:
-// acc = fma(x[c], centre[c], acc) over ascending c, score cn_j - 2 acc, lowest index wins ties.
-// One warp per pair, lane = candidate centre (k <= 32 per pass).
+// float64 evaluation of the candidates of every ambiguous pair: score cn_j - 2 x.c_j with the dot product accumulated
+// in float64 (lane-strided partial sums + butterfly; km_assign_kernel uses one sequential chain -- the two agree to
+// ~1e-16 relative, far below any gap the fp32 data can produce), lowest index wins ties.  One warp per pair.
 __global__ void __launch_bounds__(256)
 km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float* __restrict__ centers,
                          const double* __restrict__ cnorm, const double* __restrict__ xx, const float* __restrict__ sdot,
@@ -560,24 +595,36 @@ km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float*
     double bs = 1e300;
     int bj = 0x7fffffff;
     for (int j0 = 0; j0 < k; j0 += 32) {
-      const int j = j0 + lane;
-      double es = 1e300;
-      if (j < k) {
-        const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
-        if (sc <= best + (best_tau + band * sqrt(cn[j])) * xn) {
-          const float* cr = centers + ((size_t)r * k + j) * d;
-          double acc = 0.0;
-          for (int c = 0; c < d; ++c) acc = fma((double)xr[c], (double)cr[c], acc);
-          es = cn[j] - 2.0 * acc;
-        }
+      // lanes = candidate centres: which of them fall inside the filter's error band of the best score
+      const int jl = j0 + lane;
+      bool need = false;
+      if (jl < k) {
+        const double sc = cn[jl] - 2.0 * ((double)sr[jl] * inv);
+        need = sc <= best + (best_tau + band * sqrt(cn[jl])) * xn;
       }
-      if (es < bs || (es == bs && j < bj)) { bs = es; bj = j; }
-    }
+      unsigned mask = __ballot_sync(0xffffffffu, need);
+      // every candidate in the band: float64 dot product with the 32 lanes striding over the channels (the whole
+      // warp works on one 640-long chain instead of one lane per chain), lowest index wins ties
+      while (mask) {
+        const int j = j0 + __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float* cr = centers + ((size_t)r * k + j) * d;
+        double acc = 0.0;
+        for (int c0 = lane; c0 < d; c0 += 8 * 32) {
+          float xa[8], ca[8];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double so = __shfl_xor_sync(0xffffffffu, bs, o);
-      const int jo = __shfl_xor_sync(0xffffffffu, bj, o);
-      if (so < bs || (so == bs && jo < bj)) { bs = so; bj = jo; }
+          for (int u = 0; u < 8; ++u) {
+            const int c = c0 + 32 * u;
+            xa[u] = (c < d) ? xr[c] : 0.f;
+            ca[u] = (c < d) ? cr[c] : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) acc = fma((double)xa[u], (double)ca[u], acc);
+        }
+        acc = warp_sum(acc);
+        const double es = cn[j] - 2.0 * acc;
+        if (es < bs) { bs = es; bj = j; }   // ascending j: the first minimum is kept
+      }
     }
     if (lane == 0) {
       int* lp = labels + (size_t)r * labels_stride + row;
@@ -590,13 +637,18 @@ km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float*
 // ------------------------------------------------------------------------------------------
 // Lloyd M-step, part 1: per (run, row slab, 128-column tile) float64 cluster sums in shared memory.
 // ------------------------------------------------------------------------------------------
+template <int RPB>   // runs per block: the X tile is read once for RPB runs (the kernel is bound by re-reading X from L2)
 __global__ void __launch_bounds__(kColTile)
-km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin, int row_end,
+km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int runs, int row_begin, int row_end,
                   const int* __restrict__ labels, const int* __restrict__ flags, double* __restrict__ part,
                   int* __restrict__ partcnt) {
-  extern __shared__ double acc[];  // [k][kColTile]
-  const int r = blockIdx.z;
-  if (flags[r * 4 + 0]) return;
+  extern __shared__ double acc[];  // [RPB][k][kColTile]
+  const int rb = blockIdx.z * RPB;
+  bool live[RPB];
+  bool any = false;
+#pragma unroll
+  for (int q = 0; q < RPB; ++q) { live[q] = (rb + q < runs) && !flags[(rb + q) * 4 + 0]; any |= live[q]; }
+  if (!any) return;
   const int slab = blockIdx.x, tile = blockIdx.y;
   const int tid = threadIdx.x;
   const int col = tile * kColTile + tid;
@@ -604,29 +656,51 @@ km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int row_begi
   const int per = (rows + kSlabs - 1) / kSlabs;
   const int r0 = row_begin + slab * per;
   const int r1 = min(row_end, r0 + per);
-  for (int j = 0; j < k; ++j) acc[j * kColTile + tid] = 0.0;
-  const int* lab = labels + (size_t)r * n;
+  for (int j = 0; j < RPB * k; ++j) acc[j * kColTile + tid] = 0.0;
+  const int* lab[RPB];
+#pragma unroll
+  for (int q = 0; q < RPB; ++q) lab[q] = labels + (size_t)(live[q] ? rb + q : rb) * n;
   if (col < d) {
     int i = r0;
     // 16 rows in flight per thread: the loop is bound by L2 latency, not by the shared-memory adds
     for (; i + 16 <= r1; i += 16) {
-      int l[16];
+      int l[RPB][16];
       float v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) { l[u] = lab[i + u]; v[u] = x[(size_t)(i + u) * d + col]; }
+      for (int u = 0; u < 16; ++u) v[u] = x[(size_t)(i + u) * d + col];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) acc[l[u] * kColTile + tid] += (double)v[u];
+      for (int q = 0; q < RPB; ++q)
+#pragma unroll
+        for (int u = 0; u < 16; ++u) l[q][u] = lab[q][i + u];
+#pragma unroll
+      for (int q = 0; q < RPB; ++q)
+        if (live[q]) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) acc[(q * k + l[q][u]) * kColTile + tid] += (double)v[u];
+        }
     }
-    for (; i < r1; ++i) acc[lab[i] * kColTile + tid] += (double)x[(size_t)i * d + col];
-    double* out = part + (((size_t)r * kSlabs + slab) * k) * d + col;
-    for (int j = 0; j < k; ++j) out[(size_t)j * d] = acc[j * kColTile + tid];
+    for (; i < r1; ++i) {
+      const double v = (double)x[(size_t)i * d + col];
+#pragma unroll
+      for (int q = 0; q < RPB; ++q)
+        if (live[q]) acc[(q * k + lab[q][i]) * kColTile + tid] += v;
+    }
+#pragma unroll
+    for (int q = 0; q < RPB; ++q)
+      if (live[q]) {
+        double* out = part + (((size_t)(rb + q) * kSlabs + slab) * k) * d + col;
+        for (int j = 0; j < k; ++j) out[(size_t)j * d] = acc[(q * k + j) * kColTile + tid];
+      }
   }
   if (tile == 0) {
-    for (int j = tid; j < k; j += kColTile) {
-      int cnt = 0;
-      for (int i = r0; i < r1; ++i) cnt += (lab[i] == j);
-      partcnt[((size_t)r * kSlabs + slab) * k + j] = cnt;
-    }
+#pragma unroll
+    for (int q = 0; q < RPB; ++q)
+      if (live[q])
+        for (int j = tid; j < k; j += kColTile) {
+          int cnt = 0;
+          for (int i = r0; i < r1; ++i) cnt += (lab[q][i] == j);
+          partcnt[((size_t)(rb + q) * kSlabs + slab) * k + j] = cnt;
+        }
   }
 }
 
@@ -640,8 +714,12 @@ km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcn
   if (flags[r * 4 + 0]) return;
   double* o = partial + ((size_t)r * k + j) * (d + 1);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    double v[kSlabs];
+#pragma unroll
+    for (int sl = 0; sl < kSlabs; ++sl) v[sl] = part[(((size_t)r * kSlabs + sl) * k + j) * d + c];  // all in flight
     double s = 0.0;
-    for (int sl = 0; sl < kSlabs; ++sl) s += part[(((size_t)r * kSlabs + sl) * k + j) * d + c];
+#pragma unroll
+    for (int sl = 0; sl < kSlabs; ++sl) s += v[sl];   // fixed order
     o[c] = s;
   }
   if (threadIdx.x == 0) {
@@ -757,20 +835,31 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
   // _average_centers + _center_shift
   double ss = 0.0, nn = 0.0;
   const bool has = cnt[j] > 0.0;
-  for (int c = lane; c < d; c += 32) {
-    float nv;
-    if (has) {
-      nv = (float)(pr[(size_t)j * (d + 1) + c] / cnt[j]);
-    } else {
-      // centers[j] = centers[argmax_weight]: averaged already if argmax < j, raw sum otherwise
-      const double raw = pr[(size_t)am * (d + 1) + c];
-      nv = (am < j && cnt[am] > 0.0) ? (float)(raw / cnt[am]) : (float)raw;
+  // centers[j] = centers[argmax_weight] for an empty cluster: averaged already if argmax < j, raw sum otherwise
+  const int src = has ? j : am;
+  const double div = has ? cnt[j] : ((am < j && cnt[am] > 0.0) ? cnt[am] : 1.0);
+  const double* prow = pr + (size_t)src * (d + 1);
+  float* crow = cr + (size_t)j * d;
+  for (int c0 = lane; c0 < d; c0 += 8 * 32) {   // 8 independent loads in flight; accumulation order unchanged
+    double raw[8];
+    float ov[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 32 * u;
+      raw[u] = (c < d) ? prow[c] : 0.0;
+      ov[u] = (c < d) ? crow[c] : 0.f;
     }
-    const float ov = cr[(size_t)j * d + c];
-    const double df = (double)nv - (double)ov;
-    ss = fma(df, df, ss);
-    nn = fma((double)nv, (double)nv, nn);
-    cr[(size_t)j * d + c] = nv;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 32 * u;
+      if (c < d) {
+        const float nv = (div == 1.0 && !has) ? (float)raw[u] : (float)(raw[u] / div);
+        const double df = (double)nv - (double)ov[u];
+        ss = fma(df, df, ss);
+        nn = fma((double)nv, (double)nv, nn);
+        crow[c] = nv;
+      }
+    }
   }
   ss = warp_sum(ss);
   nn = warp_sum(nn);
@@ -990,13 +1079,13 @@ VS_API int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand, void
   VS_CHECK_CUDA(cudaMemcpy2DAsync(at<int>(ws, L.cand), kMaxTrials * 4, first_idx, 4, 4, L.r, cudaMemcpyDeviceToDevice, st));
   const size_t smem = (size_t)L.t * L.d * 8;
   VS_REQUIRE(smem <= 200 * 1024, "n_trials * d too large for the seeding kernel");
-  if (smem > 48 * 1024)
-    VS_CHECK_CUDA(cudaFuncSetAttribute(km_kpp_dist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(kPotBlocks, L.r);
   for (int c = 0; c < L.k; ++c) {
     const int tc = (c == 0) ? 1 : L.t;
-    VS_LAUNCH(km_kpp_dist_kernel, grid, kPotWarps * 32, (size_t)tc * L.d * 8, st, at<float>(ws, L.xc), at<double>(ws, L.xx),
-              L.n, L.d, tc, at<int>(ws, L.cand), at<float>(ws, L.closest), c > 0 ? 1 : 0, at<float>(ws, L.newdist),
+    KppDistFn fn = kpp_dist_fn(tc);
+    if (smem > 48 * 1024) VS_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VS_LAUNCH(fn, grid, kPotWarps * 32, (size_t)tc * L.d * 8, st, at<float>(ws, L.xc), at<double>(ws, L.xx), L.n, L.d,
+              at<int>(ws, L.cand), at<float>(ws, L.closest), c > 0 ? 1 : 0, at<float>(ws, L.newdist),
               at<double>(ws, L.potpart), L.t);
     VS_POST_LAUNCH();
     VS_LAUNCH(km_kpp_select_scan_kernel, L.r, 1024, 0, st, at<float>(ws, L.xc), L.n, L.d, L.k, L.t, L.t, c, tc,
@@ -1026,13 +1115,22 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
   if (changed == nullptr) changed = at<int>(ws, L.changed);
-  const size_t smem = (size_t)L.k * kColTile * 8;
-  VS_REQUIRE(smem <= 200 * 1024, "k too large for the M-step kernel");
-  if (smem > 48 * 1024)
-    VS_CHECK_CUDA(cudaFuncSetAttribute(km_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, L.r);
-  VS_LAUNCH(km_partial_kernel, grid, kColTile, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin, row_end,
-            at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
+  const size_t smem1 = (size_t)L.k * kColTile * 8;
+  VS_REQUIRE(smem1 <= 200 * 1024, "k too large for the M-step kernel");
+  if (false && 2 * smem1 <= 96 * 1024) {   // two runs per pass over X: measured slower (83 vs 72 us) -- the adds bound it
+    const size_t smem = 2 * smem1;
+    static cudaError_t attr2 = cudaFuncSetAttribute(km_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+    VS_CHECK_CUDA(attr2);
+    dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, (L.r + 1) / 2);
+    VS_LAUNCH(km_partial_kernel<2>, grid, kColTile, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, L.r, row_begin, row_end,
+              at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
+  } else {
+    static cudaError_t attr1 = cudaFuncSetAttribute(km_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    VS_CHECK_CUDA(attr1);
+    dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, L.r);
+    VS_LAUNCH(km_partial_kernel<1>, grid, kColTile, smem1, stream, at<float>(ws, L.xc), L.n, L.d, L.k, L.r, row_begin, row_end,
+              at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
+  }
   VS_POST_LAUNCH();
   VS_LAUNCH(km_reduce_kernel, dim3(L.k, L.r), 256, 0, stream, at<double>(ws, L.part), at<int>(ws, L.partcnt), L.d, L.k,
             at<int>(ws, L.flags), partial, at<int>(ws, L.changed), changed);
