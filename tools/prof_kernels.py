@@ -33,6 +33,16 @@ if "gemm" in which:
         a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0, is_weight=True)
         ms = ev(lambda: gemm_split(a, w))
         res[f"gemm_{m}x{n}x{kk}"] = {"ms": ms, "alg_TFLOPs": 2.0 * m * n * kk / ms / 1e9}
+if "gemmres" in which:   # the memory-bound projection shape of the first UNet level, with residual (to_out / proj_out)
+    m, n, kk = 28 * 4096, 320, 320
+    a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0, is_weight=True)
+    res_t = torch.randn(m, n, device=dev); bias = torch.randn(n, device=dev)
+    big = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    def run():
+        big.zero_()   # flush L2
+        return gemm_split(a, w, bias, res_t)
+    ms = ev(run, it=3) - ev(lambda: big.zero_(), it=3)
+    res["gemmres_114688x320x320_fr"] = {"ms": ms, "GBs": (m * kk * 4 + 2 * m * n * 4) / ms / 1e6}
 if "conv" in which:
     for (B, H, C, Co) in [(28, 64, 320, 320), (28, 32, 640, 640), (28, 64, 640, 320)]:
         conv = torch.nn.Conv2d(C, Co, 3, padding=1).to(dev)

@@ -163,8 +163,9 @@ struct GemmParams {
   __half* out_lo;
 };
 
+constexpr int kGemmThreads = 256;   // TMA warp, MMA warp, TMEM-alloc warp, spare, 4 epilogue warps (8 measured no faster)
 template <int BN>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                   const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
                   const __grid_constant__ GemmParams p) {
@@ -193,7 +194,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], 128); }
+    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kGemmThreads - 128); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr);
@@ -284,7 +285,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;  // TMEM lanes [32*ew, 32*ew+32)
+    // epilogue warps: a TMEM lane quarter (warp id % 4) may be shared by two warps that split the tile's columns
+    // (kGemmThreads = 384); with four warps each one walks all columns
+    const int ew = (warp - 4) & 3;     // TMEM lanes [32*ew, 32*ew+32)
+    const int chalf = (warp - 4) >> 2; // which half of the 32-column chunks
+    constexpr int kChunks = (BN + 31) / 32, kChunks0 = (kGemmThreads > 256) ? (kChunks + 1) / 2 : kChunks;
+    const int c_begin = chalf ? kChunks0 * 32 : 0, c_end = chalf ? BN : kChunks0 * 32;
     const int r = ew * 32 + lane;  // row of the tile = pixel of the patch
     const int pw = r % p.bw, ph = (r / p.bw) % p.bh, pb = r / (p.bw * p.bh);
     int acc = 0;
@@ -299,15 +305,37 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       const size_t pix = ((size_t)b * p.ho + h) * p.wo + w;
       const size_t cb_row = p.chan_bias ? (size_t)((long long)pix / p.cb_div) : 0;
       const float blend_a = (p.blend && row_ok) ? __ldg(p.blend_alpha + (long long)pix / p.ba_div) : 0.f;
+      // The residual (and blend) rows of this tile come from HBM: start them towards L2 now, while the MMAs of the tile
+      // are still running, and keep the loads of chunk c+1 in flight while chunk c is processed (measured before: the
+      // epilogue of the K=320 projections sat on these loads, 29 % of DRAM bandwidth)
+      const int tile_cols = min(c_end, p.n - n0);
+      if (row_ok) {
+        if (p.residual)
+          for (int j = c_begin; j < tile_cols; j += 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + pix * p.n + n0 + j));
+        if (p.blend)
+          for (int j = c_begin; j < tile_cols; j += 32)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.blend + pix * p.n + n0 + j));
+      }
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
+      float4 res_cur[8], res_nxt[8];
+      auto load_res = [&](float4 (&dst)[8], int c0) {
+        const int nc = min(32, p.n - c0);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = (p.residual && row_ok && 4 * j < nc) ? *reinterpret_cast<const float4*>(p.residual + pix * p.n + c0 + 4 * j)
+                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      load_res(res_cur, n0 + c_begin);
 #pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
+      for (int c = c_begin; c < c_end; c += 32) {
         const int col0 = n0 + c;
         if (col0 >= p.n) break;  // warp-uniform
         uint32_t rr[32];
         tc::tmem_ld_32x32(t_acc + c, rr);
+        if (c + 32 < c_end && col0 + 32 < p.n) load_res(res_nxt, col0 + 32);
         tc::tmem_wait_ld();
         if (row_ok) {
           float v[32];
@@ -334,11 +362,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           }
           if (p.residual) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) {
-                const float4 q = *reinterpret_cast<const float4*>(p.residual + off + j);
-                v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
-              }
+            for (int j = 0; j < 32; j += 4) {
+              const float4 q = res_cur[j >> 2];   // zero beyond ncols
+              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            }
           }
           if (p.blend) {
             const float a = blend_a, na = 1.0f - a;
@@ -363,6 +390,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               if (j < ncols) tc::store_split8(hrow, lrow, col0 + j, &v[j], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) res_cur[j] = res_nxt[j];
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&tmem_empty_bar[acc]);
@@ -401,7 +430,7 @@ static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
   VS_CHECK_CUDA(attr_err);
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b, n_tiles = (p.n + BN - 1) / BN;
   const int grid = std::min(m_tiles * n_tiles, kNumSMs);
-  VS_LAUNCH_FW(family, flops, gemm_split_kernel<BN>, grid, 256, Cfg::kSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
+  VS_LAUNCH_FW(family, flops, gemm_split_kernel<BN>, grid, kGemmThreads, Cfg::kSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
   VS_POST_LAUNCH();
   return 0;
 }
