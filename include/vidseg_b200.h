@@ -205,6 +205,14 @@ int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, cons
                       const float* bias, const float* residual, float* out_f32,
                       void* out_hi, void* out_lo, int m, int n, int k, float acc_scale, void* stream);
 
+/* GEGLU.proj + gate in one kernel (sgm/modules/attention.py:89-96: x, gate = proj(x).chunk(2, -1); x * gelu(gate)).
+ *   w_*: [2*D, K] weight whose rows were permuted so that every 64-row group is 32 value rows followed by the 32 gate
+ *        rows of the same output features: row 64*j + i = proj.weight[32*j + i], row 64*j + 32 + i = proj.weight[D + 32*j + i];
+ *   bias [2*D] permuted the same way (or NULL); out_*: operand [M, D] in the policy's format.
+ * The fp32 [M, 2*D] intermediate is never written (1.17 GB per first-level FeedForward at config 2). */
+int vidseg_gemm_geglu_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                            void* out_hi, void* out_lo, int m, int d, int k, float acc_scale, void* stream);
+
 /* vidseg_gemm_split with the epilogue terms of the SVD temporal layers:
  *   row_bias [M / rows_per_bias, N]: one bias row per group of rows_per_bias consecutive output rows -- the
  *     frame-position embedding 'x_mix = x + emb' (sgm/modules/video_attention.py:417-427, 452-453; group = the

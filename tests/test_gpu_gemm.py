@@ -63,3 +63,26 @@ def test_packed8_operand_layout(cuda, lib, is_weight):
     want_x = (xs * sx).to(torch.float8_e4m3fn).view(torch.uint8).reshape(37, 3, 64)
     assert torch.equal(aux[..., :64], want_lo) and torch.equal(aux[..., 64:], want_x)
     assert ((s.float() - x).abs() <= 2.0 ** -13 * x.abs() + 1e-6).all()
+
+
+@pytest.mark.parametrize("m,d,k", [(300, 1280, 320), (1000, 256, 64), (129, 32, 96), (4096, 2560, 640)])
+def test_fused_geglu_projection(cuda, operand_mode, m, d, k):
+    """GEGLU.proj + value * gelu(gate) in one kernel (weight rows permuted into 32 value | 32 gate groups) against
+    the float64 definition (attention.py:89-96)."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from vidseg_diffusion_b200 import kernels as K
+    from vidseg_diffusion_b200.linear import split
+    g = torch.Generator(device="cpu").manual_seed(m + d + k)
+    proj = nn.Linear(k, 2 * d).to(cuda)
+    with torch.no_grad():
+        proj.weight.copy_(torch.randn(2 * d, k, generator=g) / k ** 0.5)
+        proj.bias.copy_(torch.randn(2 * d, generator=g))
+    x = torch.randn(m, k, generator=g).to(cuda)
+    val, gate = (x.double() @ proj.weight.double().T + proj.bias.double()).chunk(2, dim=-1)
+    want = val * F.gelu(gate)
+    got = K.linear_geglu(split(x), proj)
+    assert got.hi.shape == (m, d)
+    err = (got.float().double() - want).abs().max().item() / want.abs().max().item()
+    packed_in = operand_mode == 1 and k % 64 == 0
+    assert err < (2e-4 if (packed_in or got.fmt == "packed8") else 1e-5), f"rel err {err:.3e} ({got.fmt})"

@@ -147,6 +147,7 @@ struct GemmParams {
   int wo, ho, nb;           // output pixel grid; M = nb * ho * wo
   int tiles_w, tiles_h, tiles_b;
   int c_off[kMaxTaps], w_off[kMaxTaps], p_idx[kMaxTaps], h_off[kMaxTaps];
+  int geglu;                // fused GEGLU epilogue: columns come in 64-wide groups [32 value | 32 gate], out[.., N/2] = value * gelu(gate)
   int in_packed8;           // operands in the packed8 format (tc_common.cuh): 4 fp16 + 4 fp8 MMAs per k-block instead of 12
   int out_packed8;          // format of the split output (out_hi / out_lo)
   float acc_scale;          // exact power-of-two inverse of the operand pre-scaling (weights carry 2^8)
@@ -320,6 +321,48 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
+      if (p.geglu) {
+        // FeedForward's GEGLU (attention.py:89-96) fused into the projection GEMM: the weight rows were permuted on the
+        // host so that each 64-column group holds 32 value columns followed by their 32 gate columns; the fp32
+        // [M, 2D] intermediate (the largest tensor of the UNet) is never written.
+        const int dn = p.n >> 1;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          const int col0 = n0 + c;
+          if (col0 >= p.n) break;  // warp-uniform
+          uint32_t rv[32], rg[32];
+          tc::tmem_ld_32x32(t_acc + c, rv);
+          tc::tmem_ld_32x32(t_acc + c + 32, rg);
+          tc::tmem_wait_ld();
+          if (row_ok) {
+            float o[32];
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+              if (p.bias) {
+                bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                bg = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
+              }
+              const float vb[4] = {bv.x, bv.y, bv.z, bv.w}, gb[4] = {bg.x, bg.y, bg.z, bg.w};
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const float val = fmaf(__uint_as_float(rv[j + u]), p.acc_scale, vb[u]);
+                const float gate = fmaf(__uint_as_float(rg[j + u]), p.acc_scale, gb[u]);
+                o[j + u] = val * (0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f)));
+              }
+            }
+            __half* hrow = p.out_hi + pix * dn;
+            __half* lrow = p.out_lo + pix * dn;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8)
+              tc::store_split8(hrow, lrow, (col0 >> 1) + j, &o[j], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       float4 res_cur[8], res_nxt[8];
       auto load_res = [&](float4 (&dst)[8], int c0) {
         const int nc = min(32, p.n - c0);
@@ -444,7 +487,7 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   p.tiles_b = (p.nb + p.bb - 1) / p.bb;
   p.kc_per_tap = (p.cin + kGemmBK - 1) / kGemmBK;
   if (p.in_packed8 < 0) p.in_packed8 = operand_packed8(p.cin) ? 1 : 0;       // library policy unless the caller fixed it
-  if (p.out_packed8 < 0) p.out_packed8 = operand_packed8(p.n) ? 1 : 0;
+  if (p.out_packed8 < 0) p.out_packed8 = operand_packed8(p.geglu ? p.n / 2 : p.n) ? 1 : 0;
   if (p.cb_div <= 0) p.cb_div = (long long)p.ho * p.wo;  // default: one bias row per sample
   if (p.ba_div <= 0) p.ba_div = 1;
   const uint32_t box[5] = {(uint32_t)kGemmBK, (uint32_t)p.bw, 1u, (uint32_t)p.bh, (uint32_t)p.bb};
@@ -452,8 +495,8 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
   if (int e = encode_tmap_16bit(&ta_lo, a_lo, 5, adims, astrides, box)) return e;
   const double flops = 2.0 * (double)p.nb * p.ho * p.wo * (double)p.n * (double)p.k;
-  if (p.n % 256 == 0) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
-  if (p.n % 160 == 0) return launch_gemm<160>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  if (p.n % 256 == 0 || (p.geglu && p.n > 128)) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  if (p.n % 160 == 0 && !p.geglu) return launch_gemm<160>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
   return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
 }
 
@@ -545,6 +588,25 @@ VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_h
                              float acc_scale, void* stream) {
   return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, out_f32, out_hi, out_lo, 0, m,
                     n, k, acc_scale, stream);
+}
+
+VS_API int vidseg_gemm_geglu_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                   void* out_hi, void* out_lo, int m, int d, int k, float acc_scale, void* stream) {
+  VS_REQUIRE(a_hi && a_lo && w_hi && w_lo && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(m >= 0 && d >= 32 && d % 32 == 0 && k >= 8 && k % 8 == 0, "D must be a multiple of 32, K of 8");
+  if (m == 0) return 0;
+  GemmParams p{};
+  p.n = 2 * d; p.k = k; p.taps = 1; p.cin = k;
+  p.wo = m; p.ho = 1; p.nb = 1;
+  p.acc_scale = acc_scale;
+  p.bias = bias;
+  p.geglu = 1;
+  p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
+  p.in_packed8 = -1; p.out_packed8 = -1;
+  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
+  const uint64_t row = (uint64_t)k * 2;
+  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
+  return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, kFamGemm, stream);
 }
 
 VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,

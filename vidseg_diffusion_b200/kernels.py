@@ -109,6 +109,35 @@ def linear(xs, weight, bias=None, residual=None, want_f32=True, want_split=False
     return gemm_split(xs, weight_split(weight), b, residual, want_f32=want_f32, want_split=want_split, **epilogue)
 
 
+def _geglu_perm(d, device):
+    """Row order of the fused GEGLU projection: 64-row groups of 32 value rows + the 32 gate rows of the same features."""
+    j = torch.arange(d // 32, device=device)[:, None] * 32 + torch.arange(32, device=device)[None, :]   # [d/32, 32]
+    return torch.cat([j, j + d], dim=1).reshape(-1)
+
+
+def linear_geglu(xs, proj):
+    """GEGLU.proj followed by value * gelu(gate) (attention.py:89-96) as ONE GEMM whose epilogue applies the gate.
+    xs: Split [.., K]; proj: nn.Linear(K, 2*D).  Returns the Split operand [.., D] of FeedForward.net[2]."""
+    k = xs.hi.shape[-1]
+    d = proj.out_features // 2
+    if d % 32 or proj.in_features != k:
+        raise _lib.VidsegError(f"linear_geglu: unsupported shape K={k} D={d}")
+    ws = _cached(proj.weight, "geglu", lambda w: split(w.float()[_geglu_perm(d, w.device)].contiguous(), WEIGHT_SCALE, is_weight=True))
+    bias = None if proj.bias is None else _cached(proj.bias, "geglu_b", lambda b: b.float()[_geglu_perm(d, b.device)].contiguous())
+    want = "packed8" if packed8(k) else "pair16"
+    if xs.fmt != want or ws.fmt != want:
+        raise _lib.VidsegError(f"linear_geglu: operands are {xs.fmt} / {ws.fmt}, the policy expects {want} for K={k}")
+    m = xs.hi.numel() // k
+    out = _empty_split((*xs.hi.shape[:-1], d), xs.hi.device)
+    lib = _lib.load()
+    with torch.cuda.device(xs.hi.device):
+        _lib.check(lib.vidseg_gemm_geglu_split(xs.hi.data_ptr(), xs.lo.data_ptr(), ws.hi.data_ptr(), ws.lo.data_ptr(),
+                                               bias.data_ptr() if bias is not None else None, out.hi.data_ptr(),
+                                               out.lo.data_ptr(), m, d, k, 1.0 / (xs.scale * ws.scale), _lib.stream_ptr()),
+                   "gemm_geglu_split")
+    return out
+
+
 def attention(qs, ks, vs, heads, scale):
     return attention_split(qs, ks, vs, heads, scale, want_f32=False, want_split=True)
 

@@ -31,6 +31,8 @@ class GEGLU(nn.Module):
         self.proj = nn.Linear(dim_in, dim_out * 2)
 
     def forward_split(self, xs):
+        if (self.proj.out_features // 2) % 32 == 0:
+            return K.linear_geglu(xs, self.proj)      # gate applied in the GEMM epilogue, no fp32 [.., 2D] intermediate
         h, _ = K.linear(xs, self.proj.weight, self.proj.bias, want_f32=True)
         return K.geglu_split(h)
 
