@@ -166,6 +166,25 @@ int vidseg_refine_masks(const float* feats, const int32_t* labels_in,
                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------- *
+ * match_gt_mask mode
+ *
+ * Replaces scripts/sampling/feature_extraction.py:589-594 (every K-means label of frame 0 takes the most frequent
+ * ground-truth label of its cells; ties -> smallest label) and :606-612
+ * (sklearn KNeighborsClassifier(n_neighbors=4).fit(ref_feature_map, ref_mask).predict(tokens): brute force,
+ * float64 squared distances, neighbours ordered by (distance, index), uniform vote, smallest label on ties).
+ *   fake_labels, gt_labels: int32 [n]; gt values must lie in [0, 1024); err_flag int32 (device): 1 = out of range.
+ *   ref fp32 [n_ref, D], ref_labels int32 [n_ref], query fp32 [n_query, D]; D % 8 == 0; k <= 8.
+ *   err_flag: 2 = more than 64 references tie inside the filter band of the k-th neighbour (duplicated rows).
+ * vidseg_knn_predict reads one scalar back (max reference norm) and therefore synchronises the stream once.
+ * ------------------------------------------------------------------------- */
+int vidseg_majority_map(const int32_t* fake_labels, const int32_t* gt_labels, int n, int num_fake,
+                        int32_t* ref_labels, int32_t* err_flag, void* stream);
+size_t vidseg_knn_workspace_bytes(int n_ref, int n_query, int d);
+int vidseg_knn_predict(const float* ref, const int32_t* ref_labels, int n_ref, const float* query, int n_query, int d,
+                       int k, int32_t* labels_out, int32_t* err_flag, void* workspace, size_t workspace_bytes,
+                       void* stream);
+
+/* ------------------------------------------------------------------------- *
  * A1-A8  UNet forward on the tcgen05 tensor cores
  *
  * Split operands: an fp32 tensor x is carried as hi = fp16(x) and lo = fp16(x - hi), x ~= hi + lo (22 significant

@@ -42,6 +42,10 @@ SIGNATURES = {
     "vidseg_kmeans_fit_predict": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidseg_kmeans_release": (c_int, [c_void_p]),
+    "vidseg_majority_map": (c_int, [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "vidseg_knn_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "vidseg_knn_predict": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                   c_size_t, c_void_p]),
     "vidseg_split_f16": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_void_p]),
     "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_gemm_split_ex": (c_int, [c_void_p] * 7 + [c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,

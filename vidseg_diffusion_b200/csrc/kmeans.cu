@@ -1024,6 +1024,193 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
   return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------
+// match_gt_mask mode: majority map and brute-force 4-NN label propagation
+//   scripts/sampling/feature_extraction.py:589-594 (every K-means label takes the most frequent ground-truth label
+//   of its cells) and :606-612 (KNeighborsClassifier(n_neighbors=4).fit(ref).predict(all tokens)).
+// The k-NN search is the K-means E-step design again: one pair16 tcgen05 GEMM gives the approximate scores
+// ||r||^2 - 2 q.r of a chunk of queries against every reference point; per query one warp finds the k-th smallest
+// score, collects every reference whose score lies inside the filter's error band of it, re-evaluates those few in
+// float64 and keeps the k nearest by (distance, index) -- what sklearn's float64 brute force returns.
+// ------------------------------------------------------------------------------------------
+constexpr int kGtRange = 1024;   // ground-truth labels must lie in [0, kGtRange)
+__global__ void __launch_bounds__(1024)
+mg_majority_kernel(const int* __restrict__ fake, const int* __restrict__ gt, int n, int num_fake, int* __restrict__ ref,
+                   int* __restrict__ err) {
+  __shared__ int hist[kGtRange];
+  __shared__ int s_best;
+  for (int f = 0; f < num_fake; ++f) {
+    for (int i = threadIdx.x; i < kGtRange; i += blockDim.x) hist[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+      if (fake[i] == f) {
+        const int g = gt[i];
+        if (g < 0 || g >= kGtRange) atomicExch(err, 1); else atomicAdd(&hist[g], 1);
+      }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int best = -1, bc = 0;
+      for (int g = 0; g < kGtRange; ++g) if (hist[g] > bc) { bc = hist[g]; best = g; }   // first maximum: smallest label
+      s_best = best;
+    }
+    __syncthreads();
+    if (s_best >= 0)
+      for (int i = threadIdx.x; i < n; i += blockDim.x) if (fake[i] == f) ref[i] = s_best;
+    __syncthreads();
+  }
+}
+
+// float64 squared norms of fp32 rows + running |max| (operand scale); one warp per row
+__global__ void __launch_bounds__(256)
+knn_norm_kernel(const float* __restrict__ x, int n, int d, double* __restrict__ nrm, unsigned* __restrict__ absmax) {
+  const int lane = threadIdx.x & 31;
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (row >= n) return;
+  const float* xr = x + (size_t)row * d;
+  double s = 0.0;
+  float m = 0.f;
+  for (int c = lane; c < d; c += 32) { const float v = xr[c]; s = fma((double)v, (double)v, s); m = fmaxf(m, fabsf(v)); }
+  s = warp_sum(s);
+  m = warp_max(m);
+  if (lane == 0) { nrm[row] = s; atomicMax(absmax, __float_as_uint(m)); }
+}
+
+constexpr int kKnnMaxK = 8;
+constexpr int kKnnMaxCand = 64;
+constexpr int kKnnWarps = 8;
+__global__ void __launch_bounds__(kKnnWarps * 32)
+knn_select_kernel(const float* __restrict__ q, const float* __restrict__ ref, const int* __restrict__ ref_labels, int nq,
+                  int nr, int d, int k, const float* __restrict__ sdot, int ld, const double* __restrict__ rnorm,
+                  const double* __restrict__ qnorm, const unsigned* __restrict__ absmax, double band, double rn_max_sqrt,
+                  int* __restrict__ out, int* __restrict__ err) {
+  __shared__ int s_cand[kKnnWarps][kKnnMaxCand];
+  __shared__ double s_dist[kKnnWarps][kKnnMaxCand];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row = blockIdx.x * kKnnWarps + warp;
+  if (row >= nq) return;
+  const float sc_op = km_operand_scale(absmax[0]);
+  const double inv = 1.0 / ((double)sc_op * (double)sc_op);
+  const float* sr = sdot + (size_t)row * ld;
+  // pass 1: the k smallest approximate scores (lane-local sorted lists, then k rounds of warp minimum)
+  double loc[kKnnMaxK];
+#pragma unroll
+  for (int t = 0; t < kKnnMaxK; ++t) loc[t] = 1e300;
+  for (int j = lane; j < nr; j += 32) {
+    double v = rnorm[j] - 2.0 * ((double)sr[j] * inv);
+#pragma unroll
+    for (int t = 0; t < kKnnMaxK; ++t)
+      if (t < k && v < loc[t]) { const double tmp = loc[t]; loc[t] = v; v = tmp; }
+  }
+  double vk = 1e300;
+  for (int round = 0; round < k; ++round) {
+    double m = loc[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmin(m, __shfl_xor_sync(0xffffffffu, m, o));
+    vk = m;
+    // the lane holding it pops its head (lowest lane on ties)
+    const unsigned who = __ballot_sync(0xffffffffu, loc[0] == m);
+    if (lane == __ffs(who) - 1) {
+#pragma unroll
+      for (int t = 0; t + 1 < kKnnMaxK; ++t) loc[t] = loc[t + 1];
+      loc[kKnnMaxK - 1] = 1e300;
+    }
+  }
+  // pass 2: every reference inside the error band of the k-th score (ascending index order)
+  const double thresh = vk + 2.0 * band * sqrt(qnorm[row]) * rn_max_sqrt;
+  int count = 0;
+  for (int j0 = 0; j0 < nr; j0 += 32) {
+    const int j = j0 + lane;
+    const bool in = (j < nr) && (rnorm[j] - 2.0 * ((double)sr[j] * inv) <= thresh);
+    const unsigned mask = __ballot_sync(0xffffffffu, in);
+    if (in) {
+      const int pos = count + __popc(mask & ((1u << lane) - 1));
+      if (pos < kKnnMaxCand) s_cand[warp][pos] = j;
+    }
+    count += __popc(mask);
+  }
+  if (count > kKnnMaxCand) { if (lane == 0) atomicExch(err, 2); count = kKnnMaxCand; }
+  __syncwarp();
+  // exact float64 distances of the candidates (minus the constant ||q||^2), warp-cooperative dot products
+  const float* qr = q + (size_t)row * d;
+  for (int e = 0; e < count; ++e) {
+    const int j = s_cand[warp][e];
+    const float* rr = ref + (size_t)j * d;
+    double acc = 0.0;
+    for (int c0 = lane; c0 < d; c0 += 8 * 32) {
+      float xa[8], ca[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = c0 + 32 * u;
+        xa[u] = (c < d) ? qr[c] : 0.f;
+        ca[u] = (c < d) ? rr[c] : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) acc = fma((double)xa[u], (double)ca[u], acc);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) s_dist[warp][e] = rnorm[j] - 2.0 * acc;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    // k nearest by (distance, index); candidates are in ascending index order, so a strict '<' keeps the lower index
+    int lab[kKnnMaxK];
+    for (int t = 0; t < k; ++t) {
+      int bi = -1;
+      double bd = 1e300;
+      for (int e = 0; e < count; ++e)
+        if (s_cand[warp][e] >= 0 && s_dist[warp][e] < bd) { bd = s_dist[warp][e]; bi = e; }
+      lab[t] = (bi >= 0) ? ref_labels[s_cand[warp][bi]] : 0x7fffffff;
+      if (bi >= 0) s_cand[warp][bi] = -1;
+    }
+    // scipy.stats.mode: most frequent label, smallest on ties
+    int best = 0x7fffffff, bc = 0;
+    for (int t = 0; t < k; ++t) {
+      int c = 0;
+      for (int u = 0; u < k; ++u) c += (lab[u] == lab[t]);
+      if (c > bc || (c == bc && lab[t] < best)) { bc = c; best = lab[t]; }
+    }
+    out[row] = best;
+  }
+}
+
+__global__ void knn_max_kernel(const double* __restrict__ v, int n, double* __restrict__ out) {
+  double m = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, v[i]);
+  m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 16)); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 8));
+  m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 4)); m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 2));
+  m = fmax(m, __shfl_xor_sync(0xffffffffu, m, 1));
+  __shared__ double sm[32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t = fmax(t, sm[w]);
+    out[0] = t;
+  }
+}
+
+constexpr int kKnnChunk = 4096;   // queries per filter GEMM
+struct KnnLayout { size_t rn, qn, absmax, err, rmax, rs_hi, rs_lo, qs_hi, qs_lo, sdot, total; int nr_pad; };
+static KnnLayout knn_layout(int nr, int nq, int d) {
+  KnnLayout L{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off = align_up(off + bytes, 256); return o; };
+  L.nr_pad = (nr + 7) / 8 * 8;
+  const int qc = nq < kKnnChunk ? nq : kKnnChunk;
+  L.rn = take((size_t)nr * 8);
+  L.qn = take((size_t)nq * 8);
+  L.absmax = take(16);
+  L.err = take(16);
+  L.rmax = take(16);
+  L.rs_hi = take((size_t)L.nr_pad * d * 2);
+  L.rs_lo = take((size_t)L.nr_pad * d * 2);
+  L.qs_hi = take((size_t)qc * d * 2);
+  L.qs_lo = take((size_t)qc * d * 2);
+  L.sdot = take((size_t)qc * L.nr_pad * 4);
+  L.total = off;
+  return L;
+}
 }  // namespace vidseg
 
 using namespace vidseg;
@@ -1320,5 +1507,70 @@ VS_API int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_
 VS_API int vidseg_kmeans_release(void* workspace) {
   std::lock_guard<std::mutex> lk(g_km_mu);
   g_km_registry.erase(workspace);
+  return 0;
+}
+
+
+// ------------------------------------------------------------------------------------------
+// match_gt_mask entry points
+// ------------------------------------------------------------------------------------------
+VS_API int vidseg_majority_map(const int32_t* fake_labels, const int32_t* gt_labels, int n, int num_fake,
+                               int32_t* ref_labels, int32_t* err_flag, void* stream) {
+  VS_REQUIRE(fake_labels && gt_labels && ref_labels && err_flag, "null pointer");
+  VS_REQUIRE(n >= 0 && num_fake >= 1, "bad shape");
+  if (n == 0) return 0;
+  VS_CHECK_CUDA(cudaMemsetAsync(err_flag, 0, 4, (cudaStream_t)stream));
+  VS_LAUNCH(mg_majority_kernel, 1, 1024, 0, stream, fake_labels, gt_labels, n, num_fake, ref_labels, err_flag);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API size_t vidseg_knn_workspace_bytes(int n_ref, int n_query, int d) {
+  if (n_ref <= 0 || n_query <= 0 || d <= 0) return 0;
+  return knn_layout(n_ref, n_query, d).total;
+}
+
+VS_API int vidseg_knn_predict(const float* ref, const int32_t* ref_labels, int n_ref, const float* query, int n_query, int d,
+                              int k, int32_t* labels_out, int32_t* err_flag, void* workspace, size_t workspace_bytes,
+                              void* stream) {
+  VS_REQUIRE(ref && ref_labels && query && labels_out && err_flag && workspace, "null pointer");
+  VS_REQUIRE(n_ref >= 1 && n_query >= 0 && d >= 8 && d % 8 == 0, "need D % 8 == 0");
+  VS_REQUIRE(k >= 1 && k <= kKnnMaxK && k <= n_ref, "k must be 1..8 and <= n_ref");
+  if (n_query == 0) return 0;
+  const KnnLayout L = knn_layout(n_ref, n_query, d);
+  if (workspace_bytes < L.total)
+    return set_error(VIDSEG_E_WORKSPACE, "%s: need %lld bytes, got %lld", "k-NN workspace", (long long)L.total, (long long)workspace_bytes);
+  void* ws = workspace;
+  cudaStream_t st = (cudaStream_t)stream;
+  VS_CHECK_CUDA(cudaMemsetAsync(at<unsigned>(ws, L.absmax), 0, 16, st));
+  VS_CHECK_CUDA(cudaMemsetAsync(err_flag, 0, 4, st));
+  VS_LAUNCH(knn_norm_kernel, (n_ref * 32 + 255) / 256, 256, 0, st, ref, n_ref, d, at<double>(ws, L.rn), at<unsigned>(ws, L.absmax));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(knn_norm_kernel, (n_query * 32 + 255) / 256, 256, 0, st, query, n_query, d, at<double>(ws, L.qn), at<unsigned>(ws, L.absmax));
+  VS_POST_LAUNCH();
+  VS_LAUNCH(knn_max_kernel, 1, 1024, 0, st, at<double>(ws, L.rn), n_ref, at<double>(ws, L.rmax));
+  VS_POST_LAUNCH();
+  const size_t r_valid = (size_t)n_ref * d, r_total = (size_t)L.nr_pad * d;
+  VS_LAUNCH(km_split_scaled_kernel, (int)std::min<size_t>((r_total + 255) / 256, (size_t)kNumSMs * 16), 256, 0, st, ref, r_valid,
+            r_total, at<unsigned>(ws, L.absmax), at<__half>(ws, L.rs_hi), at<__half>(ws, L.rs_lo));
+  VS_POST_LAUNCH();
+  double rmax = 0.0;   // the band needs max ||r||: a scalar read-back (this mode runs once per window, not per step)
+  VS_CHECK_CUDA(cudaMemcpyAsync(&rmax, at<double>(ws, L.rmax), 8, cudaMemcpyDeviceToHost, st));
+  VS_CHECK_CUDA(cudaStreamSynchronize(st));
+  const double band = 2.0 * ((double)d * 0x1p-22 + 0x1p-20);
+  for (int q0 = 0; q0 < n_query; q0 += kKnnChunk) {
+    const int qc = std::min(kKnnChunk, n_query - q0);
+    const size_t q_total = (size_t)qc * d;
+    VS_LAUNCH(km_split_scaled_kernel, (int)std::min<size_t>((q_total + 255) / 256, (size_t)kNumSMs * 16), 256, 0, st,
+              query + (size_t)q0 * d, q_total, q_total, at<unsigned>(ws, L.absmax), at<__half>(ws, L.qs_hi), at<__half>(ws, L.qs_lo));
+    VS_POST_LAUNCH();
+    if (int e = gemm_split_run(at<__half>(ws, L.qs_hi), at<__half>(ws, L.qs_lo), at<__half>(ws, L.rs_hi), at<__half>(ws, L.rs_lo),
+                               at<float>(ws, L.sdot), qc, L.nr_pad, d, 1.0f, kFamKMeans, stream))
+      return e;
+    VS_LAUNCH(knn_select_kernel, (qc + kKnnWarps - 1) / kKnnWarps, kKnnWarps * 32, 0, st, query + (size_t)q0 * d, ref, ref_labels,
+              qc, n_ref, d, k, at<float>(ws, L.sdot), L.nr_pad, at<double>(ws, L.rn), at<double>(ws, L.qn) + q0,
+              at<unsigned>(ws, L.absmax), band, sqrt(rmax), labels_out + q0, err_flag);
+    VS_POST_LAUNCH();
+  }
   return 0;
 }

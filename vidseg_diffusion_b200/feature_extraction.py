@@ -174,8 +174,6 @@ def feature_extraction_main(mode, num_clusters, t_start, block_name, experiment_
     feature_types = [item for item in feature_types.split(",") if item]
     if mode not in ("kmeans_masks", "correct_low_res_mask", "match_gt_mask"):
         raise ValueError(f"mode {mode} not supported")
-    if mode == "match_gt_mask":
-        raise NotImplementedError("match_gt_mask is the next row of the hot-path scope table (SURVEY.md section 8f)")
     out_root = os.path.join(exp_path_root, experiment_name, mode)
     os.makedirs(out_root, exist_ok=True)
     block_str = "_".join(block_name) if isinstance(block_name, list) else block_name
@@ -199,6 +197,13 @@ def feature_extraction_main(mode, num_clusters, t_start, block_name, experiment_
                     blocks, t, out_path, num_frames=num_frames, num_clusters=num_clusters,
                     feature_height=feature_height, feature_width=feature_width, attn_type=attn_type,
                     frame_name_list=frame_name_list, write_pngs=write_pngs)
+            elif mode == "match_gt_mask":
+                from .match_gt import match_gt_mask
+                unique_labels, ref_mask, ref_feature_map = match_gt_mask(
+                    blocks, gt_mask_path=gt_mask_path, feature_height=feature_height, feature_width=feature_width,
+                    output_folder=out_path, num_masks=num_clusters, selected_timestep=t, frame_name_list=frame_name_list,
+                    ref_mask=ref_mask, ref_feature_map=ref_feature_map, ref_unique_labels=ref_unique_labels,
+                    use_gt_mask=use_gt_mask, num_frames=num_frames, write_pngs=write_pngs)
             else:  # correct_low_res_mask
                 if len(blocks) != 1:
                     # the reference would average the blocks here too (:739-745)
