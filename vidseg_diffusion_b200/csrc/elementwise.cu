@@ -23,6 +23,9 @@ __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f +
 // ---------------------------------------------------------------------------------------------
 constexpr int kLnMaxQuads = 16;  // C <= 2048
 
+// Q = float4 per lane (C <= 128 * Q): the row lives in 4*Q registers, so the common C = 320 / 640 instantiations keep
+// enough warps resident to cover the HBM latency (the single 16-quad version ran at 1.2 TB/s)
+template <int Q>
 __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ row_bias, long long rows_per_bias,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -35,10 +38,10 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ro
   // optional bias shared by groups of rows_per_bias consecutive rows, added BEFORE the normalisation: the
   // frame-position embedding / single-token cross-attention output of the temporal layers
   const float4* br = row_bias ? reinterpret_cast<const float4*>(row_bias + (row / rows_per_bias) * c) : nullptr;
-  float4 v[kLnMaxQuads];
+  float4 v[Q];
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
+  for (int i = 0; i < Q; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) {
       v[i] = ld_stream_f4(xr + q);
@@ -52,7 +55,7 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ro
   const float mean = warp_sum(s) / (float)c;
   float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
+  for (int i = 0; i < Q; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) {
       const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
@@ -63,7 +66,7 @@ layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ ro
   __half* hr = hi + row * c;
   __half* lr = lo + row * c;
 #pragma unroll
-  for (int i = 0; i < kLnMaxQuads; ++i) {
+  for (int i = 0; i < Q; ++i) {
     const int q = lane + 32 * i;
     if (q < nq) {
       const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
@@ -176,26 +179,37 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
     s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
   }
   __syncthreads();
+  // per-channel affine form in shared memory: y = v * scale[c] + shift[c] with scale = rstd_g * gamma, shift = beta -
+  // mean_g * scale (one FMA per element and no per-element group lookup; the first version spent four integer
+  // divisions per quad on it)
+  extern __shared__ float s_aff[];   // [c] scale, [c] shift
   const int cpg = c / groups;
+  for (int ch = threadIdx.x; ch < c; ch += kGnThreads) {
+    const int g = ch / cpg;
+    const float sc = s_rstd[g] * __ldg(gamma + ch);
+    s_aff[ch] = sc;
+    s_aff[c + ch] = __ldg(beta + ch) - s_mean[g] * sc;
+  }
+  __syncthreads();
   const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
-  const long long total = (long long)(p1 - p0) * nq;
-  for (long long i = threadIdx.x; i < total; i += kGnThreads) {
-    const int pp = p0 + (int)(i / nq);
-    const int q = (int)(i % nq);
+  const int total = (p1 - p0) * nq;
+  // (pixel, quad) of this thread advance incrementally: no division in the loop
+  int pp = p0 + threadIdx.x / nq, q = threadIdx.x % nq;
+  const int dp = kGnThreads / nq, dq = kGnThreads % nq;
+  for (int i = threadIdx.x; i < total; i += kGnThreads) {
     const int ch = q * 4;
     const long long pix = (long long)b * hw + pp;
     const float4 v = gn_load(x1, c1, x2, c2, pix, ch);
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
-    const int g0 = ch / cpg, g1 = (ch + 1) / cpg, g2 = (ch + 2) / cpg, g3 = (ch + 3) / cpg;
-    float y0 = (v.x - s_mean[g0]) * s_rstd[g0] * g.x + bt.x;
-    float y1 = (v.y - s_mean[g1]) * s_rstd[g1] * g.y + bt.y;
-    float y2 = (v.z - s_mean[g2]) * s_rstd[g2] * g.z + bt.z;
-    float y3 = (v.w - s_mean[g3]) * s_rstd[g3] * g.w + bt.w;
+    const float4 sc = *reinterpret_cast<const float4*>(s_aff + ch);
+    const float4 sh = *reinterpret_cast<const float4*>(s_aff + c + ch);
+    float y0 = fmaf(v.x, sc.x, sh.x), y1 = fmaf(v.y, sc.y, sh.y), y2 = fmaf(v.z, sc.z, sh.z), y3 = fmaf(v.w, sc.w, sh.w);
     if (silu) { y0 = silu_f(y0); y1 = silu_f(y1); y2 = silu_f(y2); y3 = silu_f(y3); }
     tc::store_split4(out_hi + pix * c, out_lo + pix * c, ch, y0, y1, y2, y3, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
     if (raw_hi)
       tc::store_split4(raw_hi + pix * c, raw_lo + pix * c, ch, v.x, v.y, v.z, v.w, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+    pp += dp;
+    q += dq;
+    if (q >= nq) { q -= nq; ++pp; }
   }
 }
 
@@ -260,8 +274,17 @@ static int layernorm_entry(const float* x, const float* row_bias, long long rows
   const int warps = 8;
   const long long grid = (rows + warps - 1) / warps;
   VS_REQUIRE(grid <= 0x7fffffffLL, "too many rows");
-  VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel, (int)grid, warps * 32, 0, stream, x, row_bias, rows_per_bias, gamma, beta, eps,
-              (__half*)out_hi, (__half*)out_lo, rows, channels, operand_packed8(channels) ? 1 : 0);
+  const int quads = (channels / 4 + 31) / 32;
+  const int p8 = operand_packed8(channels) ? 1 : 0;
+#define VS_LN_LAUNCH(QQ)                                                                                                  \
+  VS_LAUNCH_W(8.0 * rows * channels, layernorm_split_kernel<QQ>, (int)grid, warps * 32, 0, stream, x, row_bias, rows_per_bias, \
+              gamma, beta, eps, (__half*)out_hi, (__half*)out_lo, rows, channels, p8)
+  if (quads <= 1) VS_LN_LAUNCH(1);
+  else if (quads <= 3) VS_LN_LAUNCH(3);
+  else if (quads <= 5) VS_LN_LAUNCH(5);
+  else if (quads <= 10) VS_LN_LAUNCH(10);
+  else VS_LN_LAUNCH(16);
+#undef VS_LN_LAUNCH
   VS_POST_LAUNCH();
   return 0;
 }
@@ -310,7 +333,8 @@ VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int 
   int pix_per_block = (16384 + nq - 1) / nq;
   if (pix_per_block > hw) pix_per_block = hw;
   const int blocks = (hw + pix_per_block - 1) / pix_per_block;
-  VS_LAUNCH_W(bytes * (raw_hi ? 3.0 : 2.0), groupnorm_apply_kernel, dim3(blocks, batch), kGnThreads, 0, stream, x1, c1, x2,
+  VS_REQUIRE((size_t)c * 8 <= 48 * 1024, "C too large for the group-norm apply kernel");
+  VS_LAUNCH_W(bytes * (raw_hi ? 3.0 : 2.0), groupnorm_apply_kernel, dim3(blocks, batch), kGnThreads, (size_t)c * 8, stream, x1, c1, x2,
               c2, hw, groups, partial, gamma, beta, eps, silu, (__half*)out_hi, (__half*)out_lo, (__half*)raw_hi,
               (__half*)raw_lo, pix_per_block, chunks, operand_packed8(c) ? 1 : 0);
   VS_POST_LAUNCH();
