@@ -16,6 +16,7 @@
 // (tcgen05.ld 32x32b -> registers -> bias/residual -> fp32 and/or fp16 hi/lo stores).  3-stage smem
 // ring (mbarrier full/empty), 2-stage TMEM accumulator ring (tmem_full/tmem_empty) so the epilogue of
 // tile i overlaps the MMAs of tile i+1.
+#include <cstdlib>
 #include <mutex>
 
 #define VS_FAMILY vidseg::kFamGemm
@@ -165,7 +166,11 @@ struct GemmParams {
 };
 
 constexpr int kGemmThreads = 256;   // TMA warp, MMA warp, TMEM-alloc warp, spare, 4 epilogue warps (8 measured no faster)
-template <int BN>
+// CL = 2: two CTAs of a thread-block cluster work on two adjacent M tiles of the SAME N tile; each loads half of the
+// weight (B) tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per k-block drops
+// from A + B to A + B/2 (the packed8 GEMMs are bound by that traffic, not by the MMA pipe: ncu 69 % tensor-active).
+// A stage may only be refilled when BOTH CTAs have consumed it: the MMA issuer's commit arrives on both empty barriers.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                   const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
@@ -184,8 +189,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
   const int n_tiles = (p.n + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
   const int k_blocks = p.taps * p.kc_per_tap;
+  // work items: (group of CL adjacent M tiles, N tile); CTA `crank` of the cluster takes M tile CL * group + crank
+  // (beyond the last M tile the TMA out-of-bounds fill and the epilogue's row check make the CTA a no-op that still
+  // keeps the pair's barriers in step)
+  const int crank = (CL > 1) ? (int)tc::cluster_ctarank() : 0;
+  const int num_tiles = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const int first_item = blockIdx.x / CL, item_stride = gridDim.x / CL;
+  auto m_tile_of = [&](int item) { return (item / n_tiles) * CL + crank; };
 
   if (warp == 0 && lane == 0) {
     tc::prefetch_tmap(&tmap_a_hi);
@@ -194,13 +205,14 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     tc::prefetch_tmap(&tmap_b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], CL); }
     for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kGemmThreads - 128); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr);
   tc::tc_fence_before();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
 
@@ -209,8 +221,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int mt = tile / n_tiles;
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+        const int mt = m_tile_of(tile);
         const int n0 = (tile % n_tiles) * BN;
         const int w0 = (mt % p.tiles_w) * p.bw;
         const int h0 = ((mt / p.tiles_w) % p.tiles_h) * p.bh;
@@ -225,8 +237,16 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
             const int kb0 = tap * p.cin + kc * kGemmBK;
             tc::tma_load_5d(st, &tmap_a_hi, &full_bar[stage], ca, cw, cp, ch, b0);
             tc::tma_load_5d(st + kTileABytes, &tmap_a_lo, &full_bar[stage], ca, cw, cp, ch, b0);
-            tc::tma_load_2d(st + 2 * kTileABytes, &tmap_b_hi, &full_bar[stage], kb0, n0);
-            tc::tma_load_2d(st + 2 * kTileABytes + Cfg::kTileBBytes, &tmap_b_lo, &full_bar[stage], kb0, n0);
+            if (CL > 1) {   // this CTA's half of the B rows, delivered to both CTAs of the pair
+              constexpr int kHalfRows = BN / 2, kHalfBytes = Cfg::kTileBBytes / 2;
+              tc::tma_load_2d_mc(st + 2 * kTileABytes + crank * kHalfBytes, &tmap_b_hi, &full_bar[stage], kb0,
+                                 n0 + crank * kHalfRows, (uint16_t)0x3);
+              tc::tma_load_2d_mc(st + 2 * kTileABytes + Cfg::kTileBBytes + crank * kHalfBytes, &tmap_b_lo, &full_bar[stage],
+                                 kb0, n0 + crank * kHalfRows, (uint16_t)0x3);
+            } else {
+              tc::tma_load_2d(st + 2 * kTileABytes, &tmap_b_hi, &full_bar[stage], kb0, n0);
+              tc::tma_load_2d(st + 2 * kTileABytes + Cfg::kTileBBytes, &tmap_b_lo, &full_bar[stage], kb0, n0);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -240,7 +260,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
         tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_acc = tmem_base + (uint32_t)(acc * Cfg::kAccStride);
@@ -277,7 +297,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
-          tc::umma_commit(&empty_bar[stage]);  // frees the smem stage once these MMAs have read it
+          // frees the smem stage once these MMAs have read it (in both CTAs of a pair: either may overwrite it)
+          if (CL > 1) tc::umma_commit_mc(&empty_bar[stage], (uint16_t)0x3); else tc::umma_commit(&empty_bar[stage]);
           if (kb == k_blocks - 1) tc::umma_commit(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -296,8 +317,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     const int pw = r % p.bw, ph = (r / p.bw) % p.bh, pb = r / (p.bw * p.bh);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int mt = tile / n_tiles;
+    for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+      const int mt = m_tile_of(tile);
       const int n0 = (tile % n_tiles) * BN;
       const int w = (mt % p.tiles_w) * p.bw + pw;
       const int h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + ph;
@@ -443,6 +464,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (CL > 1) tc::cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 2) tc::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
 }
 
@@ -458,24 +480,62 @@ static void pick_patch(int wo, int ho, int nb, int* bw_out, int* bh_out, int* bb
     }
 }
 
-template <int BN>
-static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const void* w_hi, const void* w_lo,
-                       const GemmParams& p, double flops, int family, void* stream) {
+template <int BN, int CL>
+static int launch_gemm_cl(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const void* w_hi, const void* w_lo,
+                          const GemmParams& p, double flops, int family, void* stream) {
   using Cfg = GemmCfg<BN>;
   CUtensorMap tb_hi, tb_lo;
-  if (int e = encode_tmap_2d_f16(&tb_hi, w_hi, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN)) return e;
-  if (int e = encode_tmap_2d_f16(&tb_lo, w_lo, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN)) return e;
+  if (int e = encode_tmap_2d_f16(&tb_hi, w_hi, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN / CL)) return e;
+  if (int e = encode_tmap_2d_f16(&tb_lo, w_lo, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN / CL)) return e;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_split_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(gemm_split_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   VS_CHECK_CUDA(attr_err);
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b, n_tiles = (p.n + BN - 1) / BN;
-  const int grid = std::min(m_tiles * n_tiles, kNumSMs);
-  VS_LAUNCH_FW(family, flops, gemm_split_kernel<BN>, grid, kGemmThreads, Cfg::kSmemBytes, stream, ta_hi, ta_lo, tb_hi, tb_lo, p);
+  const int items = ((m_tiles + CL - 1) / CL) * n_tiles;
+  const int grid = std::min(items, kNumSMs / CL) * CL;
+  const bool prof = g_profile_on.load(std::memory_order_relaxed) != 0;
+  if (prof) profile_before(family, flops, (cudaStream_t)stream);
+  if (CL == 1) {
+    gemm_split_kernel<BN, CL><<<grid, kGemmThreads, Cfg::kSmemBytes, (cudaStream_t)stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, CL>, ta_hi, ta_lo, tb_hi, tb_lo, p));
+  }
+  if (prof) profile_after((cudaStream_t)stream);
+  g_launch_count.fetch_add(1, std::memory_order_relaxed);
   VS_POST_LAUNCH();
   return 0;
+}
+
+// Measured on B200 (tools/prof_kernels.py, packed8): the 2-CTA multicast form is correct but only 0-3 % faster (3x3 conv
+// 562 vs 556, [28672,5120,640] 455 vs 442 algorithmic TFLOP/s) -- the packed8 GEMMs are bound by the bytes that must be
+// in flight INTO shared memory per k-block (72-96 KB every ~0.34 us against ~1 us of TMA latency with 216 KB of smem),
+// which multicast does not reduce.  It therefore stays opt-in (VIDSEG_GEMM_CLUSTER=1); the cure is the 2-SM MMA
+// (cta_group::2, half of B per SM), a next-round item.
+static bool use_cluster(const GemmParams& p, int bn) {
+  static const int env = [] { const char* e = getenv("VIDSEG_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
+  if (!env) return false;
+  const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b, n_tiles = (p.n + bn - 1) / bn;
+  return m_tiles >= 2 && (long long)m_tiles * n_tiles >= 2LL * kNumSMs;
+}
+
+template <int BN>
+static int launch_gemm(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const void* w_hi, const void* w_lo,
+                       const GemmParams& p, double flops, int family, void* stream) {
+  if (use_cluster(p, BN)) return launch_gemm_cl<BN, 2>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  return launch_gemm_cl<BN, 1>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
 }
 
 // shared host path of the Linear and convolution entry points
