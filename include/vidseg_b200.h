@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);  /* 3: + operand policy (packed8), split_rows; gemm_split_ex gained out_pair16 */
+int vidseg_abi_version(void);  /* 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -239,14 +239,16 @@ int vidseg_gemm_geglu_split(const void* a_hi, const void* a_lo, const void* w_hi
  *   blend, blend_alpha [M / rows_per_alpha]: out = a * blend + (1 - a) * out -- AlphaBlender
  *     (sgm/modules/diffusionmodules/util.py:368-391) as used by SpatialVideoTransformer.time_mixer
  *     (video_attention.py:472-476).
- * Order: acc * acc_scale + bias + row_bias + residual, then the blend.  NULL disables a term.
+ *   row_scalar [M]: one value per output row added to all of its columns -- the mask modulation
+ *     'attn_out[i + num_masks] += lambda * mask[:, None]' of sgm/modules/attention.py:646-663, 697-719, 730-752.
+ * Order: acc * acc_scale + bias + row_bias + row_scalar + residual, then the blend.  NULL disables a term.
  * out_pair16 != 0 forces the split output into the fp16-pair format whatever the operand policy says: the q / k / v
  * projections, whose consumer is vidseg_attention_split. */
 int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo,
                          const float* bias, const float* residual, const float* row_bias,
                          long long rows_per_bias, const float* blend, const float* blend_alpha,
-                         long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
-                         int out_pair16, int m, int n, int k, float acc_scale, void* stream);
+                         long long rows_per_alpha, const float* row_scalar, float* out_f32, void* out_hi,
+                         void* out_lo, int out_pair16, int m, int n, int k, float acc_scale, void* stream);
 
 /* nn.Conv2d as an implicit GEMM (no im2col: the taps are shifted TMA boxes, zero padding is the TMA out-of-bounds
  * fill).  Replaces the 3x3 / 1x1 convolutions of ResBlock (openaimodel.py:267-315), Downsample (:202-209, stride 2),

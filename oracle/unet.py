@@ -173,8 +173,27 @@ def _attention(sd, p, x, context, heads, stash, tag, kind):
     return F.linear(o, sd[p + ".to_out.0.weight"], sd[p + ".to_out.0.bias"])
 
 
-def _transformer(sd, p, x, context, heads, stash, tag):
-    """SpatialTransformer.forward (attention.py:889-927) with one BasicTransformerBlock (:609-759)."""
+def _modulation(mod, batch, tokens):
+    """attention.py:646-663 / :697-719 / :730-752: per-(sample, token) additive term [B, N, 1] or None."""
+    if mod is None:
+        return None
+    masks = mod["feature_masks"]
+    nm = len(masks)
+    add = torch.zeros(batch, tokens, 1)
+    for i, mask in enumerate(masks):
+        if i in mod["block_frames"] and i in mod["layer_frames"] and i in mod["timestep_frames"]:
+            lam = mod["lambda_start"] if mod["schedule"] == "constant" else \
+                mod["lambda_start"] + (mod["lambda_end"] - mod["lambda_start"]) * i / mod["num_frames"]
+            add[i + nm] += lam * torch.as_tensor(mask, dtype=torch.float32).reshape(-1, 1)
+            if mod["uc"]:
+                add[i] += lam * torch.as_tensor(mask, dtype=torch.float32).reshape(-1, 1)
+    return add
+
+
+def _transformer(sd, p, x, context, heads, stash, tag, mod=None):
+    """SpatialTransformer.forward (attention.py:889-927) with one BasicTransformerBlock (:609-759).  ``mod``: the mask
+    modulation of this block (dict with feature_masks, block_frames, layer_frames, timestep_frames, lambda_start,
+    lambda_end, schedule, num_frames, uc, attn_types) or None."""
     b, c, h, w = x.shape
     x_in = x
     x = F.group_norm(x, 32, sd[p + ".norm.weight"], sd[p + ".norm.bias"], eps=1e-6)
@@ -182,11 +201,13 @@ def _transformer(sd, p, x, context, heads, stash, tag):
     x = F.linear(x, sd[p + ".proj_in.weight"], sd[p + ".proj_in.bias"])
     tb = p + ".transformer_blocks.0"
     ln = lambda t, n: F.layer_norm(t, (c,), sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"], eps=1e-5)
-    x = x + _attention(sd, tb + ".attn1", ln(x, "norm1"), None, heads, stash, tag, "self")
-    x = x + _attention(sd, tb + ".attn2", ln(x, "norm2"), context, heads, stash, tag, "cross")
+    add = _modulation(mod, x.shape[0], x.shape[1])
+    site = lambda kind: add if (add is not None and kind in mod["attn_types"]) else 0.0
+    x = x + (_attention(sd, tb + ".attn1", ln(x, "norm1"), None, heads, stash, tag, "self") + site("self_attn"))
+    x = x + (_attention(sd, tb + ".attn2", ln(x, "norm2"), context, heads, stash, tag, "cross") + site("cross_attn"))
     hgate = F.linear(ln(x, "norm3"), sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
     val, gate = hgate.chunk(2, dim=-1)
-    x = x + F.linear(val * F.gelu(gate), sd[tb + ".ff.net.2.weight"], sd[tb + ".ff.net.2.bias"])
+    x = x + (F.linear(val * F.gelu(gate), sd[tb + ".ff.net.2.weight"], sd[tb + ".ff.net.2.bias"]) + site("ff_out"))
     x = F.linear(x, sd[p + ".proj_out.weight"], sd[p + ".proj_out.bias"])
     return x.reshape(b, h, w, c).permute(0, 3, 1, 2) + x_in
 
@@ -204,7 +225,7 @@ def _resblock(sd, p, x, emb):
     return x + h
 
 
-def _run_block(sd, prefix, layers, h, emb, context, stash, tag):
+def _run_block(sd, prefix, layers, h, emb, context, stash, tag, mod=None):
     for j, (kind, cin, cout) in enumerate(layers):
         p = f"{prefix}.{j}"
         if kind == "conv":
@@ -212,7 +233,7 @@ def _run_block(sd, prefix, layers, h, emb, context, stash, tag):
         elif kind == "res":
             h = _resblock(sd, p, h, emb)
         elif kind == "attn":
-            h = _transformer(sd, p, h, context, cout, stash, tag)
+            h = _transformer(sd, p, h, context, cout, stash, tag, mod)
         elif kind == "down":
             h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
         elif kind == "up":
@@ -222,7 +243,7 @@ def _run_block(sd, prefix, layers, h, emb, context, stash, tag):
 
 
 @torch.no_grad()
-def unet_forward(sd, cfg, x, timesteps, context, stash=None):
+def unet_forward(sd, cfg, x, timesteps, context, stash=None, modulate_params=None):
     """UNetModel.forward (openaimodel.py:831-954), inference path without modulation/injection.
 
     sd: {key: fp32 CPU tensor}; x [B, Cin, H, W]; timesteps [B]; context [B, L, Cctx].
@@ -241,6 +262,17 @@ def unet_forward(sd, cfg, x, timesteps, context, stash=None):
     h = _run_block(sd, "middle_block", middle, h, emb, context, stash, "middle_block")
     for i, layers in enumerate(outputs):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, stash, f"output_block_{i}")
+        mod = None
+        mp = modulate_params
+        if mp is not None and i in mp["modulate_block_idx"] and len(layers) > 1 and layers[1][0] == "attn" \
+                and "spatial" in mp["modulate_layer_type"]:
+            # openaimodel.py:907-916 (block frames) and attention.py:906-913 (layer frames)
+            every = list(range(mp["num_frames"]))
+            mod = dict(feature_masks=mp["feature_masks"], block_frames=mp["modulate_block_frames"].get(i, every),
+                       layer_frames=mp["modulate_layer_frames"].get("spatial", every),
+                       timestep_frames=mp["modulate_timestep_frames_group"], lambda_start=mp["modulate_lambda_start"],
+                       lambda_end=mp["modulate_lambda_end"], schedule=mp["modulate_schedule"], num_frames=mp["num_frames"],
+                       uc=mp["modulate_uc"], attn_types=mp["modulate_attn_type"])
+        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, stash, f"output_block_{i}", mod)
     h = F.silu(F.group_norm(h, 32, sd["out.0.weight"], sd["out.0.bias"], eps=1e-5))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)

@@ -21,7 +21,7 @@ sys.path.insert(0, os.path.join(HERE, ".."))
 
 from oracle import unet as ounet  # noqa: E402
 from oracle.ref_import import import_reference  # noqa: E402
-from synth import synthetic_unet_inputs, synthetic_unet_weights  # noqa: E402
+from synth import synthetic_modulate_params, synthetic_unet_inputs, synthetic_unet_weights  # noqa: E402
 
 # (name, cfg, seed, F, latent_hw, context_len, (token stride, channel stride) for the stored q)
 CASES = [
@@ -62,6 +62,22 @@ def main():
         print(name, "oracle vs reference:", {k: f"{v:.2e}" for k, v in errs.items()},
               "| out absmax", float(out_ref.abs().max()), "q7 absmax", float(q_ref[7].abs().max()))
         assert max(errs.values()) < 2e-5, errs
+        extra = {}
+        if name == "tiny":
+            # the same step with mask modulation switched on (is_modulate_step=True, attention.py:646-752,
+            # openaimodel.py:907-916): reference output + stashed q of block 8, and the oracle must agree
+            mp = synthetic_modulate_params(seed, F, (hw // 2) ** 2)
+            mp_t = dict(mp, feature_masks=[torch.from_numpy(m) for m in mp["feature_masks"]])
+            with torch.no_grad():
+                out_mod = model(x, timesteps=t, context=ctx, is_modulate_step=True, modulate_params=mp_t)
+            q8_mod = model.output_blocks[8][1].transformer_blocks[0].attn1.q
+            st2 = {}
+            out_mod_or = ounet.unet_forward(sd, cfg, x, t, ctx, st2, modulate_params=mp)
+            e1, e2 = relerr(out_mod_or, out_mod), relerr(st2[("output_block_8", "spatial_self_attn_q")], q8_mod)
+            print("tiny + modulation: oracle vs reference", f"{e1:.2e} {e2:.2e}", "| changed output by",
+                  f"{relerr(out_mod, out_ref):.2e}")
+            assert max(e1, e2) < 2e-5 and relerr(out_mod, out_ref) > 1e-2
+            extra = dict(out_mod=out_mod.numpy(), q8_mod=q8_mod.numpy())
         ts, cs = stride
         keys = np.array(sorted(shapes))
         np.savez_compressed(
@@ -69,7 +85,7 @@ def main():
             out=out_ref.numpy(), q6=q_ref[6][:, ::ts, ::cs].numpy(), q7=q_ref[7][:, ::ts, ::cs].numpy(),
             q8=q_ref[8][:, ::ts, ::cs].numpy(), q_stride=np.array(stride), keys=keys,
             shapes=np.array([",".join(map(str, shapes[k])) for k in keys]),
-            meta=np.array([seed, F, hw, L]))
+            meta=np.array([seed, F, hw, L]), **extra)
 
 
 if __name__ == "__main__":

@@ -113,3 +113,16 @@ def synthetic_video_unet_inputs(seed, num_frames, latent_hw, in_channels, contex
     context = np.concatenate([np.zeros_like(ctx), ctx], 0)
     t = np.full((2 * num_frames,), c_noise, dtype=np.float32)
     return x, t, context, np.concatenate([y, y], 0)
+
+
+def synthetic_modulate_params(seed, num_frames, tokens):
+    """A mask-modulation request as svd_single_video_inference.py:438-500 builds it (values seeded): one feature mask per
+    frame at the resolution of output blocks 6-8, modulation of the cross-attention and feed-forward outputs of blocks
+    7 and 8 with a linear lambda schedule, frame subsets per block / layer / timestep, unconditional half included."""
+    r = np.random.RandomState(seed)
+    masks = [(r.rand(tokens) > 0.6).astype(np.float32) for _ in range(num_frames)]
+    return dict(modulate_block_idx=[7, 8], modulate_block_frames={8: list(range(0, num_frames, 2))},
+                modulate_layer_type=["spatial"], modulate_layer_frames={},
+                modulate_attn_type=["cross_attn", "ff_out"], feature_masks=masks,
+                modulate_timestep_frames_group=list(range(num_frames)), modulate_lambda_start=3.0,
+                modulate_lambda_end=1.0, modulate_schedule="linear", num_frames=num_frames, modulate_uc=True)

@@ -104,3 +104,23 @@ def test_cuda_graph_replay_matches_eager_launches(cuda):
         got, out_g = graphed.segment(x, t, ctx, 2, seed=seed)
         assert torch.equal(out_g, out_e) and torch.equal(got, want)
     assert graphed.graph_replays == 2 and graphed.graph_kernel_launches > 0
+
+
+def test_unet_mask_modulation_matches_reference_golden(cuda, operand_mode):
+    """UNetModel(is_modulate_step=True): the per-(sample, token) modulation terms ride in the epilogue of the GEMMs that
+    produce attn2_out / ff_out of the selected output blocks; against the reference run (golden) and the oracle."""
+    from synth import synthetic_modulate_params
+    cfg = ounet.TINY_CONFIG
+    g = np.load(os.path.join(GOLDEN, "unet_tiny.npz"))
+    seed, F, hw, L = (int(v) for v in g["meta"])
+    model, sd = build(cfg, seed, cuda)
+    x, t, ctx = synthetic_unet_inputs(seed, F, hw, cfg["in_channels"], L, cfg["context_dim"])
+    mp = synthetic_modulate_params(seed, F, (hw // 2) ** 2)
+    mp_dev = dict(mp, feature_masks=[torch.from_numpy(m).to(cuda) for m in mp["feature_masks"]])
+    out = model(torch.from_numpy(x).to(cuda), timesteps=torch.from_numpy(t).to(cuda), context=torch.from_numpy(ctx).to(cuda),
+                is_modulate_step=True, modulate_params=mp_dev)
+    q8 = model.output_blocks[8][1].transformer_blocks[0].attn1.q
+    tol = EXPECTED if operand_mode == 0 else EXPECTED_PACKED8
+    assert relerr(out, g["out_mod"]) < tol and relerr(q8, g["q8_mod"]) < tol
+    out_plain = model(torch.from_numpy(x).to(cuda), timesteps=torch.from_numpy(t).to(cuda), context=torch.from_numpy(ctx).to(cuda))
+    assert relerr(out_plain, g["out"]) < tol and relerr(out, g["out"]) > 1e-2

@@ -54,8 +54,8 @@ def test_unet_rejects_cpu_tensors_and_unbuilt_rows():
         model = UNetModel(use_linear_in_transformer=True, **cfg)
     with pytest.raises(_lib.VidsegError):
         model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=torch.zeros(2, 7, 96))
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=None, is_modulate_step=True)
+    with pytest.raises(NotImplementedError):      # feature injection reads .pt dumps: a next row
+        model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=None, is_injected_step=True)
     with pytest.raises(NotImplementedError):
         UNetModel(use_linear_in_transformer=False, **cfg)
 
@@ -109,3 +109,19 @@ def test_video_unet_rejects_cpu_tensors_and_unbuilt_rows():
         model(torch.zeros(4, 8, 16, 16), **args)
     with pytest.raises(NotImplementedError):
         model(torch.zeros(4, 8, 16, 16), is_modulate_step=True, **args)
+
+
+def test_oracle_mask_modulation_matches_reference_golden():
+    """is_modulate_step=True (attention.py:646-752, openaimodel.py:907-916): the restatement against the reference run."""
+    from synth import synthetic_modulate_params, synthetic_unet_inputs, synthetic_unet_weights
+    cfg = ounet.TINY_CONFIG
+    g = np.load(os.path.join(GOLDEN, "unet_tiny.npz"))
+    seed, F, hw, L = (int(v) for v in g["meta"])
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ounet.param_shapes(cfg), seed).items()}
+    x, t, ctx = (torch.from_numpy(a) for a in synthetic_unet_inputs(seed, F, hw, cfg["in_channels"], L, cfg["context_dim"]))
+    stash = {}
+    out = ounet.unet_forward(sd, cfg, x, t, ctx, stash, modulate_params=synthetic_modulate_params(seed, F, (hw // 2) ** 2))
+    rel = lambda a, b: float(np.abs(a - b).max() / np.abs(b).max())
+    assert rel(out.numpy(), g["out_mod"]) < 2e-5
+    assert rel(stash[("output_block_8", "spatial_self_attn_q")].numpy(), g["q8_mod"]) < 2e-5
+    assert rel(g["out_mod"], g["out"]) > 1e-2      # the modulation is not a no-op

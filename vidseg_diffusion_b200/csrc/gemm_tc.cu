@@ -157,6 +157,7 @@ struct GemmParams {
                             // time embedding per sample; per-frame / per-video vectors of the temporal layers)
   long long cb_div;
   const float* residual;    // [M, N] or null
+  const float* row_scalar;  // [M] or null: one value per output row added to all of its columns (mask modulation)
   const float* blend;       // [M, N] or null: out = a * blend + (1 - a) * out, a = blend_alpha[row / ba_div] (AlphaBlender)
   const float* blend_alpha;
   long long ba_div;
@@ -327,6 +328,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       const size_t pix = ((size_t)b * p.ho + h) * p.wo + w;
       const size_t cb_row = p.chan_bias ? (size_t)((long long)pix / p.cb_div) : 0;
       const float blend_a = (p.blend && row_ok) ? __ldg(p.blend_alpha + (long long)pix / p.ba_div) : 0.f;
+      const float row_add = (p.row_scalar && row_ok) ? __ldg(p.row_scalar + pix) : 0.f;
       // The residual (and blend) rows of this tile come from HBM: start them towards L2 now, while the MMAs of the tile
       // are still running, and keep the loads of chunk c+1 in flight while chunk c is processed (measured before: the
       // epilogue of the K=320 projections sat on these loads, 29 % of DRAM bandwidth)
@@ -423,6 +425,10 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
                 const float4 bb4 = __ldg(reinterpret_cast<const float4*>(cb + j));
                 v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
               }
+          }
+          if (p.row_scalar) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += row_add;
           }
           if (p.residual) {
 #pragma unroll
@@ -615,8 +621,8 @@ VS_API int vidseg_split_rows(const float* x, void* hi, void* lo, long long rows,
 #define VS_FAMILY vidseg::kFamGemm
 static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                       const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
-                      const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi, void* out_lo,
-                      int out_pair16, int m, int n, int k, float acc_scale, void* stream) {
+                      const float* blend_alpha, long long rows_per_alpha, const float* row_scalar, float* out_f32,
+                      void* out_hi, void* out_lo, int out_pair16, int m, int n, int k, float acc_scale, void* stream) {
   VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null operand pointer");
   VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
@@ -634,6 +640,7 @@ static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, cons
   p.bias = bias; p.residual = residual; p.out_f32 = out_f32;
   p.chan_bias = row_bias; p.cb_div = rows_per_bias;
   p.blend = blend; p.blend_alpha = blend_alpha; p.ba_div = rows_per_alpha;
+  p.row_scalar = row_scalar;
   p.out_hi = (__half*)out_hi; p.out_lo = (__half*)out_lo;
   p.in_packed8 = -1;
   p.out_packed8 = out_pair16 ? 0 : -1;
@@ -646,8 +653,8 @@ static int gemm_entry(const void* a_hi, const void* a_lo, const void* w_hi, cons
 VS_API int vidseg_gemm_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                              const float* residual, float* out_f32, void* out_hi, void* out_lo, int m, int n, int k,
                              float acc_scale, void* stream) {
-  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, out_f32, out_hi, out_lo, 0, m,
-                    n, k, acc_scale, stream);
+  return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, nullptr, 1, nullptr, nullptr, 1, nullptr, out_f32, out_hi, out_lo,
+                    0, m, n, k, acc_scale, stream);
 }
 
 VS_API int vidseg_gemm_geglu_split(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -671,10 +678,11 @@ VS_API int vidseg_gemm_geglu_split(const void* a_hi, const void* a_lo, const voi
 
 VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, const float* bias,
                                 const float* residual, const float* row_bias, long long rows_per_bias, const float* blend,
-                                const float* blend_alpha, long long rows_per_alpha, float* out_f32, void* out_hi,
-                                void* out_lo, int out_pair16, int m, int n, int k, float acc_scale, void* stream) {
+                                const float* blend_alpha, long long rows_per_alpha, const float* row_scalar,
+                                float* out_f32, void* out_hi, void* out_lo, int out_pair16, int m, int n, int k,
+                                float acc_scale, void* stream) {
   return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, row_bias, rows_per_bias, blend, blend_alpha, rows_per_alpha,
-                    out_f32, out_hi, out_lo, out_pair16, m, n, k, acc_scale, stream);
+                    row_scalar, out_f32, out_hi, out_lo, out_pair16, m, n, k, acc_scale, stream);
 }
 
 #undef VS_FAMILY

@@ -70,9 +70,10 @@ def split(x, scale=1.0, is_weight=False, pair16=False):
 
 
 def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, row_bias=None, rows_per_bias=1,
-               blend=None, blend_alpha=None, rows_per_alpha=1, split_pair16=False):
+               blend=None, blend_alpha=None, rows_per_alpha=1, split_pair16=False, row_scalar=None):
     """out = a @ w.T (+ bias) (+ row_bias[row // rows_per_bias]) (+ residual), then optionally
-    out = alpha * blend + (1 - alpha) * out with alpha = blend_alpha[row // rows_per_alpha].
+    out = alpha * blend + (1 - alpha) * out with alpha = blend_alpha[row // rows_per_alpha].  ``row_scalar`` [M]: one value
+    per output row added to all of its columns (mask modulation).
     a: Split [.., K], w: Split [N, K] (nn.Linear layout), both in the format the policy gives rows of K elements.
     ``split_pair16``: the split output feeds the attention kernel (fp16 pair) instead of another GEMM.
     Returns (out_f32 or None, Split or None)."""
@@ -110,17 +111,21 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, 
         _lib.require_cuda_tensor(blend_alpha, torch.float32, "blend_alpha")
         if blend.numel() != m * n or rows_per_alpha < 1 or blend_alpha.numel() != -(-m // rows_per_alpha):
             raise _lib.VidsegError("gemm_split: blend / blend_alpha shape mismatch")
+    if row_scalar is not None:
+        _lib.require_cuda_tensor(row_scalar, torch.float32, "row_scalar")
+        if row_scalar.numel() != m:
+            raise _lib.VidsegError(f"gemm_split: row_scalar must have one entry per output row ({m})")
     lib = _lib.load()
     ptr = lambda t: t.data_ptr() if t is not None else None
     with torch.cuda.device(dev):
-        if row_bias is None and blend is None and not split_pair16:
+        if row_bias is None and blend is None and row_scalar is None and not split_pair16:
             _lib.check(lib.vidseg_gemm_split(
                 a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
                 ptr(out), ptr(oh), ptr(ol), m, n, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split")
         else:
             _lib.check(lib.vidseg_gemm_split_ex(
                 a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), ptr(bias), ptr(residual),
-                ptr(row_bias), int(rows_per_bias), ptr(blend), ptr(blend_alpha), int(rows_per_alpha),
+                ptr(row_bias), int(rows_per_bias), ptr(blend), ptr(blend_alpha), int(rows_per_alpha), ptr(row_scalar),
                 ptr(out), ptr(oh), ptr(ol), 1 if split_pair16 else 0, m, n, k, 1.0 / (a.scale * w.scale),
                 _lib.stream_ptr()), "gemm_split_ex")
     return out, (Split(oh, ol, 1.0, "pair16" if split_pair16 else None) if want_split else None)

@@ -19,6 +19,37 @@ from ... import kernels as K
 from ...linear import Split, split as _split
 
 
+def get_modulate_lambda(modulate_lambda_start, modulate_lambda_end, modulate_schedule, total_steps, current_step):
+    """reference sgm/modules/diffusionmodules/util.py:382-391."""
+    assert modulate_schedule in ["constant", "linear"]
+    if modulate_schedule == "constant":
+        return modulate_lambda_start
+    return modulate_lambda_start + (modulate_lambda_end - modulate_lambda_start) * current_step / total_steps
+
+
+def modulation_rows(modulate_params, batch, tokens, device):
+    """The mask modulation of one attention / feed-forward output (reference attention.py:646-663, 697-719, 730-752):
+    ``out[i + num_masks] += lambda_i * mask_i[:, None]`` (and ``out[i]`` with modulate_uc) for every frame i selected by
+    the block / layer / timestep frame groups.  Returned as one value per output row, fp32 [batch * tokens]; it is
+    added in the epilogue of the GEMM that produces the output."""
+    masks = modulate_params["feature_masks"]
+    num_masks = len(masks)
+    rows = torch.zeros(batch, tokens, dtype=torch.float32, device=device)
+    for i, mask in enumerate(masks):
+        if i in modulate_params["modulate_block_frames_group"] and i in modulate_params["modulate_layer_frames_group"] \
+                and i in modulate_params["modulate_timestep_frames_group"]:
+            lam = get_modulate_lambda(modulate_params["modulate_lambda_start"], modulate_params["modulate_lambda_end"],
+                                      modulate_params["modulate_schedule"], total_steps=modulate_params["num_frames"],
+                                      current_step=i)
+            m = torch.as_tensor(mask).to(device=device, dtype=torch.float32).reshape(-1)
+            if m.numel() != tokens:
+                raise _lib.VidsegError(f"modulation mask {i} has {m.numel()} cells, the layer has {tokens} tokens")
+            rows[i + num_masks] += lam * m
+            if modulate_params["modulate_uc"]:
+                rows[i] += lam * m
+    return rows.reshape(-1)
+
+
 def _unsupported(name):
     raise NotImplementedError(f"{name}: not on the B200 hot path (SURVEY.md section 8f, next rows)")
 
@@ -105,7 +136,8 @@ class CrossAttention(nn.Module):
         out, _ = K.linear(vs, lin.weight, lin.bias, want_f32=True)
         return out.reshape(out.shape[0], out.shape[-1])
 
-    def forward_split(self, xs, context=None, residual=None, injected_q=None, injected_k=None, injected_v=None):
+    def forward_split(self, xs, context=None, residual=None, injected_q=None, injected_k=None, injected_v=None,
+                      row_scalar=None):
         """xs: Split [B, N, C] (already normalised); context: Split [B, L, Cctx] or None.
         Returns to_out(attention) (+ residual) as fp32 [B, N, C]."""
         cs = xs if context is None else context
@@ -126,7 +158,7 @@ class CrossAttention(nn.Module):
         self.k = k
         _, os_ = K.attention(qs, ks, vs, self.heads, self.scale)
         lin = self.to_out[0]
-        out, _ = K.linear(os_, lin.weight, lin.bias, residual=residual, want_f32=True)
+        out, _ = K.linear(os_, lin.weight, lin.bias, residual=residual, want_f32=True, row_scalar=row_scalar)
         return out
 
     def forward(self, x, context=None, mask=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
@@ -167,8 +199,6 @@ class BasicTransformerBlock(nn.Module):
 
     def _forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
                  is_modulate_step=False, is_injected_step=False, modulate_params=None):
-        if is_modulate_step:
-            _unsupported("BasicTransformerBlock(is_modulate_step=True)")
         if additional_tokens is not None or n_times_crossframe_attn_in_self:
             _unsupported("BasicTransformerBlock(additional_tokens / n_times_crossframe_attn_in_self)")
         inj = {"self": [None] * 3, "cross": [None] * 3}
@@ -181,17 +211,27 @@ class BasicTransformerBlock(nn.Module):
         if context is not None and not isinstance(context, Split):
             context = K.split(context.float().contiguous())
         x = x.float().contiguous()
+        # mask modulation (reference :646-663, :697-719, :730-752): one added value per (sample, token), identical for the
+        # three sites, applied in the epilogue of the GEMM that produces attn1_out / attn2_out / ff_out
+        mod = {"self_attn": None, "cross_attn": None, "ff_out": None}
+        if is_modulate_step:
+            rows = modulation_rows(modulate_params, x.shape[0], x.shape[1], x.device)
+            for kind in mod:
+                if kind in modulate_params["modulate_attn_type"]:
+                    mod[kind] = rows
         ctx1 = context if self.disable_self_attn else None
-        x = self.attn1.forward_split(K.layer_norm_split(x, self.norm1), ctx1, x, *inj["self"])
+        x = self.attn1.forward_split(K.layer_norm_split(x, self.norm1), ctx1, x, *inj["self"], row_scalar=mod["self_attn"])
         self.attn1_out = None  # the reference keeps attn1_out / attn2_out / ff_out for modulation only
-        if context is not None and context.hi.shape[1] == 1 and not any(v is not None for v in inj["cross"]):
+        if context is not None and context.hi.shape[1] == 1 and not any(v is not None for v in inj["cross"]) \
+                and not is_modulate_step:
             # one context token: attn2's output is one vector per sample, carried as a row bias of norm3 / ff
             n = x.shape[1]
             a = self.attn2.forward_single_token(K.layer_norm_split(x, self.norm2), context)
             return self.ff.forward_split(K.layer_norm_split(x, self.norm3, row_bias=a, rows_per_bias=n), x,
                                          row_bias=a, rows_per_bias=n)
-        x = self.attn2.forward_split(K.layer_norm_split(x, self.norm2), context, x, *inj["cross"])
-        x = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x)
+        x = self.attn2.forward_split(K.layer_norm_split(x, self.norm2), context, x, *inj["cross"], row_scalar=mod["cross_attn"])
+        ff_kw = {"row_scalar": mod["ff_out"]} if mod["ff_out"] is not None else {}
+        x = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x, **ff_kw)
         return x
 
 
@@ -221,8 +261,6 @@ class SpatialTransformer(nn.Module):
         self.use_linear = use_linear
 
     def forward(self, x, context=None, is_modulate_step=False, is_injected_step=False, modulate_params=None):
-        if is_modulate_step:
-            _unsupported("SpatialTransformer(is_modulate_step=True)")
         if not isinstance(context, (list, tuple)):
             context = [context]
         context = [c if (c is None or isinstance(c, Split)) else K.split(c.float().contiguous()) for c in context]
@@ -234,7 +272,15 @@ class SpatialTransformer(nn.Module):
         t, _ = K.linear(xs.reshape(b, h * w, c), self.proj_in.weight, self.proj_in.bias, want_f32=True)
         for i, block in enumerate(self.transformer_blocks):
             ctx = context[0] if (i > 0 and len(context) == 1) else context[i]
-            t = block(t, context=ctx, is_injected_step=is_injected_step, modulate_params=modulate_params)
+            mod_spatial = False
+            if is_modulate_step and "spatial" in modulate_params["modulate_layer_type"]:   # reference :906-913
+                mod_spatial = True
+                if "spatial" in modulate_params["modulate_layer_frames"].keys():
+                    modulate_params["modulate_layer_frames_group"] = modulate_params["modulate_layer_frames"]["spatial"]
+                else:
+                    modulate_params["modulate_layer_frames_group"] = list(range(modulate_params["num_frames"]))
+            t = block(t, context=ctx, is_modulate_step=mod_spatial, is_injected_step=is_injected_step,
+                      modulate_params=modulate_params)
         # proj_out + residual x_in, still in token layout; the result is handed on as b c h w (channels_last view)
         out, _ = K.linear(K.split(t), self.proj_out.weight, self.proj_out.bias, residual=x_tok, want_f32=True)
         return K.as_nchw(out.reshape(b, h, w, c))

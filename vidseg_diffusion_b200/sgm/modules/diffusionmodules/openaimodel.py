@@ -233,7 +233,8 @@ class UNetModel(nn.Module):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional"
         if is_modulate_step:
-            _unsupported("UNetModel(is_modulate_step=True)")
+            assert modulate_params is not None
+            modulate_block_idx = modulate_params["modulate_block_idx"]
         if is_injected_step:
             _unsupported("UNetModel(is_injected_step=True) (feature injection from .pt dumps)")
         if not x.is_cuda:
@@ -250,9 +251,17 @@ class UNetModel(nn.Module):
             h = module(h, emb, context=context)
             hs.append(h)
         h = self.middle_block(h, emb, context)
-        for module in self.output_blocks:
+        for i, module in enumerate(self.output_blocks):
             h = K.concat_channels(h, hs.pop())
-            h = module(h, emb, context=context)
+            # mask modulation happens in the transformer layers of the selected output blocks only (reference :907-916)
+            mod_block = False
+            if is_modulate_step and i in modulate_block_idx and len(module) > 1 and "SpatialTransformer" in str(type(module[1])):
+                mod_block = True
+                if i in modulate_params["modulate_block_frames"].keys():
+                    modulate_params["modulate_block_frames_group"] = modulate_params["modulate_block_frames"][i]
+                else:
+                    modulate_params["modulate_block_frames_group"] = list(range(modulate_params["num_frames"]))
+            h = module(h, emb, context=context, is_modulate_step=mod_block, modulate_params=modulate_params)
         hs_out, _, _ = K.group_norm_split(h, self.out[0], silu=True)
         h = K.conv2d(hs_out, self.out[2])
         return h.contiguous().to(in_dtype)
