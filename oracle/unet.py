@@ -156,11 +156,17 @@ def timestep_embedding(timesteps, dim, max_period=10000):
     return emb
 
 
-def _attention(sd, p, x, context, heads, stash, tag, kind):
-    """attention.py:286-364.  x [B, N, C]; context [B, L, Cctx] or None (self-attention)."""
+def _attention(sd, p, x, context, heads, stash, tag, kind, injected=None):
+    """attention.py:286-364.  x [B, N, C]; context [B, L, Cctx] or None (self-attention).  ``injected``: {key: tensor};
+    a key containing ``spatial_{kind}_attn_q`` / ``_k`` replaces the projection (:305-315; v is never injected here)."""
     ctx = x if context is None else context
     q = F.linear(x, sd[p + ".to_q.weight"])
     k = F.linear(ctx, sd[p + ".to_k.weight"])
+    for key, val in (injected or {}).items():
+        if f"spatial_{kind}_attn_q" in key:
+            q = val
+        elif f"spatial_{kind}_attn_k" in key:
+            k = val
     v = F.linear(ctx, sd[p + ".to_v.weight"])
     if stash is not None:
         stash[(tag, f"spatial_{kind}_attn_q")] = q
@@ -190,7 +196,7 @@ def _modulation(mod, batch, tokens):
     return add
 
 
-def _transformer(sd, p, x, context, heads, stash, tag, mod=None):
+def _transformer(sd, p, x, context, heads, stash, tag, mod=None, injected=None):
     """SpatialTransformer.forward (attention.py:889-927) with one BasicTransformerBlock (:609-759).  ``mod``: the mask
     modulation of this block (dict with feature_masks, block_frames, layer_frames, timestep_frames, lambda_start,
     lambda_end, schedule, num_frames, uc, attn_types) or None."""
@@ -203,8 +209,8 @@ def _transformer(sd, p, x, context, heads, stash, tag, mod=None):
     ln = lambda t, n: F.layer_norm(t, (c,), sd[f"{tb}.{n}.weight"], sd[f"{tb}.{n}.bias"], eps=1e-5)
     add = _modulation(mod, x.shape[0], x.shape[1])
     site = lambda kind: add if (add is not None and kind in mod["attn_types"]) else 0.0
-    x = x + (_attention(sd, tb + ".attn1", ln(x, "norm1"), None, heads, stash, tag, "self") + site("self_attn"))
-    x = x + (_attention(sd, tb + ".attn2", ln(x, "norm2"), context, heads, stash, tag, "cross") + site("cross_attn"))
+    x = x + (_attention(sd, tb + ".attn1", ln(x, "norm1"), None, heads, stash, tag, "self", injected) + site("self_attn"))
+    x = x + (_attention(sd, tb + ".attn2", ln(x, "norm2"), context, heads, stash, tag, "cross", injected) + site("cross_attn"))
     hgate = F.linear(ln(x, "norm3"), sd[tb + ".ff.net.0.proj.weight"], sd[tb + ".ff.net.0.proj.bias"])
     val, gate = hgate.chunk(2, dim=-1)
     x = x + (F.linear(val * F.gelu(gate), sd[tb + ".ff.net.2.weight"], sd[tb + ".ff.net.2.bias"]) + site("ff_out"))
@@ -225,7 +231,7 @@ def _resblock(sd, p, x, emb):
     return x + h
 
 
-def _run_block(sd, prefix, layers, h, emb, context, stash, tag, mod=None):
+def _run_block(sd, prefix, layers, h, emb, context, stash, tag, mod=None, injected=None):
     for j, (kind, cin, cout) in enumerate(layers):
         p = f"{prefix}.{j}"
         if kind == "conv":
@@ -233,7 +239,7 @@ def _run_block(sd, prefix, layers, h, emb, context, stash, tag, mod=None):
         elif kind == "res":
             h = _resblock(sd, p, h, emb)
         elif kind == "attn":
-            h = _transformer(sd, p, h, context, cout, stash, tag, mod)
+            h = _transformer(sd, p, h, context, cout, stash, tag, mod, injected)
         elif kind == "down":
             h = F.conv2d(h, sd[p + ".op.weight"], sd[p + ".op.bias"], stride=2, padding=1)
         elif kind == "up":
@@ -243,7 +249,7 @@ def _run_block(sd, prefix, layers, h, emb, context, stash, tag, mod=None):
 
 
 @torch.no_grad()
-def unet_forward(sd, cfg, x, timesteps, context, stash=None, modulate_params=None):
+def unet_forward(sd, cfg, x, timesteps, context, stash=None, modulate_params=None, injection=None):
     """UNetModel.forward (openaimodel.py:831-954), inference path without modulation/injection.
 
     sd: {key: fp32 CPU tensor}; x [B, Cin, H, W]; timesteps [B]; context [B, L, Cctx].
@@ -256,8 +262,17 @@ def unet_forward(sd, cfg, x, timesteps, context, stash=None, modulate_params=Non
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     hs = []
     h = x.float()
+    def inj(kind, i, layers):
+        """openaimodel.py:880-893, 918-935: {key: tensor} of the features stashed for this block, or None.
+        ``injection``: dict(block_types, input_block_indices, output_block_indices, feature_types, timestep, features)."""
+        if injection is None or kind not in injection["block_types"] or i not in injection[f"{kind}_block_indices"] \
+                or len(layers) < 2 or layers[1][0] != "attn":
+            return None
+        keys = [f"{kind}_block_{i}_{ft}_time_{injection['timestep']}" for ft in injection["feature_types"]]
+        return {k: injection["features"][k] for k in keys if k in injection["features"]}
+
     for i, layers in enumerate(inputs):
-        h = _run_block(sd, f"input_blocks.{i}", layers, h, emb, context, stash, f"input_block_{i}")
+        h = _run_block(sd, f"input_blocks.{i}", layers, h, emb, context, stash, f"input_block_{i}", None, inj("input", i, layers))
         hs.append(h)
     h = _run_block(sd, "middle_block", middle, h, emb, context, stash, "middle_block")
     for i, layers in enumerate(outputs):
@@ -273,6 +288,7 @@ def unet_forward(sd, cfg, x, timesteps, context, stash=None, modulate_params=Non
                        timestep_frames=mp["modulate_timestep_frames_group"], lambda_start=mp["modulate_lambda_start"],
                        lambda_end=mp["modulate_lambda_end"], schedule=mp["modulate_schedule"], num_frames=mp["num_frames"],
                        uc=mp["modulate_uc"], attn_types=mp["modulate_attn_type"])
-        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, stash, f"output_block_{i}", mod)
+        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, stash, f"output_block_{i}", mod,
+                       inj("output", i, layers))
     h = F.silu(F.group_norm(h, 32, sd["out.0.weight"], sd["out.0.bias"], eps=1e-5))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)

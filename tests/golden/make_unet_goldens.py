@@ -78,6 +78,41 @@ def main():
                   f"{relerr(out_mod, out_ref):.2e}")
             assert max(e1, e2) < 2e-5 and relerr(out_mod, out_ref) > 1e-2
             extra = dict(out_mod=out_mod.numpy(), q8_mod=q8_mod.numpy())
+            # feature injection (is_injected_step=True, openaimodel.py:880-893 / 918-935, sgm/util.py:277-296): the q / k
+            # stashed by the pass above are written as .pt files in the reference's feature_maps layout
+            # (svd_single_video_inference.py:113-130) and injected into a SECOND pass on a different latent
+            import tempfile
+            with tempfile.TemporaryDirectory() as root:
+                fm = os.path.join(root, "src", "feature_maps")
+                os.makedirs(fm)
+                with torch.no_grad():
+                    model(x, timesteps=t, context=ctx)
+                for kind, blocks in (("input", (4, 5)), ("output", (7, 8))):
+                    for i in blocks:
+                        tb = getattr(model, f"{kind}_blocks")[i][1].transformer_blocks[0]
+                        torch.save(tb.attn1.q.clone(), os.path.join(fm, f"{kind}_block_{i}_spatial_self_attn_q_time_24.pt"))
+                        torch.save(tb.attn1.k.clone(), os.path.join(fm, f"{kind}_block_{i}_spatial_self_attn_k_time_24.pt"))
+                x2 = torch.from_numpy(synthetic_unet_inputs(seed + 50, F, hw, cfg["in_channels"], L, cfg["context_dim"])[0])
+                inj = dict(injected_block_types=["input", "output"], input_block_indices=[4, 5], output_block_indices=[7, 8],
+                           feature_folder=root, exp_name="src", timestep=24,
+                           injected_feature_types=["spatial_self_attn_q", "spatial_self_attn_k"])
+                with torch.no_grad():
+                    out_inj = model(x2, timesteps=t, context=ctx, is_injected_step=True, modulate_params=dict(inj))
+                    out_plain2 = model(x2, timesteps=t, context=ctx)
+                st1 = {}
+                ounet.unet_forward(sd, cfg, x, t, ctx, st1)
+                feats = {}
+                for kind, blocks in (("input", (4, 5)), ("output", (7, 8))):
+                    for i in blocks:
+                        for n in ("q", "k"):
+                            feats[f"{kind}_block_{i}_spatial_self_attn_{n}_time_24"] = st1[(f"{kind}_block_{i}", f"spatial_self_attn_{n}")]
+                out_inj_or = ounet.unet_forward(sd, cfg, x2, t, ctx, None, injection=dict(
+                    block_types=["input", "output"], input_block_indices=[4, 5], output_block_indices=[7, 8],
+                    feature_types=["spatial_self_attn_q", "spatial_self_attn_k"], timestep=24, features=feats))
+                e3 = relerr(out_inj_or, out_inj)
+                print("tiny + injection: oracle vs reference", f"{e3:.2e}", "| changed output by", f"{relerr(out_inj, out_plain2):.2e}")
+                assert e3 < 2e-5 and relerr(out_inj, out_plain2) > 1e-3
+                extra.update(out_inj=out_inj.numpy())
         ts, cs = stride
         keys = np.array(sorted(shapes))
         np.savez_compressed(

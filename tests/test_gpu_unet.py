@@ -124,3 +124,37 @@ def test_unet_mask_modulation_matches_reference_golden(cuda, operand_mode):
     assert relerr(out, g["out_mod"]) < tol and relerr(q8, g["q8_mod"]) < tol
     out_plain = model(torch.from_numpy(x).to(cuda), timesteps=torch.from_numpy(t).to(cuda), context=torch.from_numpy(ctx).to(cuda))
     assert relerr(out_plain, g["out"]) < tol and relerr(out, g["out"]) > 1e-2
+
+
+def test_unet_feature_injection_matches_reference_golden(cuda, tmp_path):
+    """UNetModel(is_injected_step=True): q / k of a first pass are injected into the self-attention of input blocks 4, 5
+    and output blocks 7, 8 of a second pass on another latent -- once from the tensors still in HBM, once through the
+    reference's .pt files (sgm/util.py:277-296); both must match the reference run (golden)."""
+    cfg = ounet.TINY_CONFIG
+    g = np.load(os.path.join(GOLDEN, "unet_tiny.npz"))
+    seed, F, hw, L = (int(v) for v in g["meta"])
+    model, _ = build(cfg, seed, cuda)
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    x, t, ctx = synthetic_unet_inputs(seed, F, hw, cfg["in_channels"], L, cfg["context_dim"])
+    x2 = synthetic_unet_inputs(seed + 50, F, hw, cfg["in_channels"], L, cfg["context_dim"])[0]
+    model(dev(x), timesteps=dev(t), context=dev(ctx))
+    feats = {}
+    fm = tmp_path / "src" / "feature_maps"
+    fm.mkdir(parents=True)
+    for kind, blocks in (("input", (4, 5)), ("output", (7, 8))):
+        for i in blocks:
+            tb = getattr(model, f"{kind}_blocks")[i][1].transformer_blocks[0]
+            for n in ("q", "k"):
+                key = f"{kind}_block_{i}_spatial_self_attn_{n}_time_24"
+                feats[key] = getattr(tb.attn1, n).clone()
+                torch.save(feats[key].cpu(), str(fm / (key + ".pt")))
+    mp = dict(injected_block_types=["input", "output"], input_block_indices=[4, 5], output_block_indices=[7, 8], timestep=24,
+              injected_feature_types=["spatial_self_attn_q", "spatial_self_attn_k"])
+    out_mem = model(dev(x2), timesteps=dev(t), context=dev(ctx), is_injected_step=True, modulate_params=dict(mp, features=feats))
+    out_pt = model(dev(x2), timesteps=dev(t), context=dev(ctx), is_injected_step=True,
+                   modulate_params=dict(mp, feature_folder=str(tmp_path), exp_name="src"))
+    assert torch.equal(out_mem, out_pt)
+    assert relerr(out_mem, g["out_inj"]) < EXPECTED_PACKED8
+    with pytest.raises(ValueError):     # the reference's error when a requested block has no stored features
+        model(dev(x2), timesteps=dev(t), context=dev(ctx), is_injected_step=True,
+              modulate_params=dict(mp, features={}, output_block_indices=[6]))

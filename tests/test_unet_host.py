@@ -54,8 +54,6 @@ def test_unet_rejects_cpu_tensors_and_unbuilt_rows():
         model = UNetModel(use_linear_in_transformer=True, **cfg)
     with pytest.raises(_lib.VidsegError):
         model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=torch.zeros(2, 7, 96))
-    with pytest.raises(NotImplementedError):      # feature injection reads .pt dumps: a next row
-        model(torch.zeros(2, 4, 16, 16), timesteps=torch.zeros(2), context=None, is_injected_step=True)
     with pytest.raises(NotImplementedError):
         UNetModel(use_linear_in_transformer=False, **cfg)
 

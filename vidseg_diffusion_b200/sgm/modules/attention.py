@@ -110,6 +110,9 @@ class CrossAttention(nn.Module):
         self.to_v = nn.Linear(context_dim, inner_dim, bias=False)
         self.to_out = nn.Sequential(nn.Linear(inner_dim, query_dim), nn.Dropout(dropout))
         self.backend = backend
+        # the reference's SDPA class ignores injected_v (attention.py:316), its xformers class uses it (:435-444);
+        # BasicTransformerBlock sets this from attn_mode
+        self.inject_v = False
         self._stash = {"q": None, "k": None}
 
     # the Q/K "hook" (reference :330-331): plain attributes there; here the temporal layers keep their activations in
@@ -150,7 +153,7 @@ class CrossAttention(nn.Module):
             k, ks = injected_k, K.split(injected_k.float().contiguous(), pair16=True)
         else:
             k, ks = K.linear(cs, self.to_k.weight, want_f32=True, want_split=True, split_pair16=True)
-        if injected_v is not None:
+        if injected_v is not None and self.inject_v:
             vs = K.split(injected_v.float().contiguous(), pair16=True)
         else:
             _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True, split_pair16=True)
@@ -187,6 +190,7 @@ class BasicTransformerBlock(nn.Module):
         self.ff = FeedForward(dim, dropout=dropout, glu=gated_ff)
         self.attn2 = attn_cls(query_dim=dim, context_dim=context_dim, heads=n_heads, dim_head=d_head,
                               dropout=dropout, backend=sdp_backend)
+        self.attn1.inject_v = self.attn2.inject_v = (attn_mode == "softmax-xformers")
         self.norm1 = nn.LayerNorm(dim)
         self.norm2 = nn.LayerNorm(dim)
         self.norm3 = nn.LayerNorm(dim)

@@ -12,6 +12,7 @@ import torch.nn as nn
 from .... import _lib
 from .... import kernels as K
 from ..attention import SpatialTransformer, _unsupported
+from ...util import load_target_features
 from .util import normalization, timestep_embedding, zero_module
 
 
@@ -235,8 +236,6 @@ class UNetModel(nn.Module):
         if is_modulate_step:
             assert modulate_params is not None
             modulate_block_idx = modulate_params["modulate_block_idx"]
-        if is_injected_step:
-            _unsupported("UNetModel(is_injected_step=True) (feature injection from .pt dumps)")
         if not x.is_cuda:
             raise _lib.VidsegError("UNetModel.forward: expected CUDA tensors (the hot path has no CPU fallback)")
         in_dtype = x.dtype
@@ -245,10 +244,21 @@ class UNetModel(nn.Module):
         emb = K.dense(K.dense(emb, self.time_embed[0]), self.time_embed[2], act_silu_in=True)
         if context is not None:
             context = K.split(context.float().contiguous())  # split once, shared by the 16 cross-attention layers
+        def injected_features(kind, i, module):
+            """reference :880-893 / :918-935: the q / k tensors stashed by another pass for block i, or None."""
+            if not (is_injected_step and kind in modulate_params["injected_block_types"] and len(module) > 1
+                    and "SpatialTransformer" in str(type(module[1])) and i in modulate_params[f"{kind}_block_indices"]):
+                return False
+            modulate_params["injected_features_group"] = load_target_features(
+                modulate_params.get("feature_folder"), modulate_params.get("exp_name"), modulate_params["timestep"], kind,
+                modulate_params["injected_feature_types"], i, x.device, features=modulate_params.get("features"))
+            return len(modulate_params["injected_features_group"]) > 0
+
         hs = []
         h = x
-        for module in self.input_blocks:
-            h = module(h, emb, context=context)
+        for i, module in enumerate(self.input_blocks):
+            h = module(h, emb, context=context, is_injected_step=injected_features("input", i, module),
+                       modulate_params=modulate_params)
             hs.append(h)
         h = self.middle_block(h, emb, context)
         for i, module in enumerate(self.output_blocks):
@@ -261,7 +271,8 @@ class UNetModel(nn.Module):
                     modulate_params["modulate_block_frames_group"] = modulate_params["modulate_block_frames"][i]
                 else:
                     modulate_params["modulate_block_frames_group"] = list(range(modulate_params["num_frames"]))
-            h = module(h, emb, context=context, is_modulate_step=mod_block, modulate_params=modulate_params)
+            h = module(h, emb, context=context, is_modulate_step=mod_block,
+                       is_injected_step=injected_features("output", i, module), modulate_params=modulate_params)
         hs_out, _, _ = K.group_norm_split(h, self.out[0], silu=True)
         h = K.conv2d(hs_out, self.out[2])
         return h.contiguous().to(in_dtype)
