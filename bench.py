@@ -31,6 +31,8 @@ WORKLOADS = {
                 desc="configs[1] plus --is_refine_mask"),
     "c3": dict(cfg="svd", frames=14, latent=64, ctx_len=1, num_masks=20, aggre=True, refine=True,
                desc="SVD VideoUNet 1 step + aggregate(out 8,7,6) + KMeans(20, n_init=10) + mask refinement, 14 frames 512x512 (BASELINE configs[2])"),
+    "c5": dict(cfg="svd", frames=28, latent=96, ctx_len=1, num_masks=50, aggre=True, refine=True,
+               desc="SVD VideoUNet, 28 frames 768x768, num_masks=50, refinement: ONE clip of BASELINE configs[4] on one GPU (size check)"),
     "c1": dict(cfg="sd21", frames=4, latent=32, ctx_len=77, num_masks=5, aggre=False, refine=False,
                desc="SD-2.1, 4 frames 256x256, num_masks=5 (BASELINE configs[0])"),
     "tiny": dict(cfg="tiny", frames=2, latent=16, ctx_len=7, num_masks=3, aggre=True, refine=True,
@@ -39,7 +41,7 @@ WORKLOADS = {
                   desc="toy-width VideoUNet, plumbing check only"),
 }
 # algorithmic FLOPs of one UNet step (FlopCounterMode over the reference modules)
-UNET_TFLOP = {"c2": 22.519, "c2r": 22.519, "c1": 1.449, "c3": 35.542}
+UNET_TFLOP = {"c2": 22.519, "c2r": 22.519, "c1": 1.449, "c3": 35.542, "c5": 179.076}
 
 
 def read_peaks():
