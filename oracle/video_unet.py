@@ -132,12 +132,19 @@ def _video_resblock(sd, p, x, emb, T, indicator):
     return out.permute(0, 2, 1, 3, 4).reshape(bt, c, h, w)
 
 
-def _temporal_attention(sd, p, x, context, heads, stash, tag, kind):
+def _temporal_attention(sd, p, x, context, heads, stash, tag, kind, injected=None):
     """CrossAttention.forward on the '(b s) t c' layout; stash under the reference's dump names
-    ``temporal_{self|cross}_attn_{q|k}`` (svd_single_video_inference.py:121-125)."""
+    ``temporal_{self|cross}_attn_{q|k}`` (svd_single_video_inference.py:121-125).  ``injected``: {key: tensor}, a key
+    containing ``temporal_{kind}_attn_q`` / ``_k`` replaces the projection (video_attention.py:167-176; the SDPA class
+    never injects v)."""
     ctx = x if context is None else context
     q = F.linear(x, sd[p + ".to_q.weight"])
     k = F.linear(ctx, sd[p + ".to_k.weight"])
+    for key, val in (injected or {}).items():
+        if f"temporal_{kind}_attn_q" in key:
+            q = val
+        elif f"temporal_{kind}_attn_k" in key:
+            k = val
     v = F.linear(ctx, sd[p + ".to_v.weight"])
     if stash is not None:
         stash[(tag, f"temporal_{kind}_attn_q")] = q
@@ -156,7 +163,24 @@ def _geglu_ff(sd, p, x):
     return F.linear(val * F.gelu(gate), sd[p + ".net.2.weight"], sd[p + ".net.2.bias"])
 
 
-def _video_transformer(sd, p, x, context, heads, T, indicator, stash, tag):
+def _temporal_modulation(mod, bs, T):
+    """video_attention.py:197-216: out[half_hw:, i] += lambda_i * mask_i[:, None] on the '(b s) t c' layout -> [bs, T, 1]."""
+    if mod is None:
+        return None
+    half = bs // 2
+    add = torch.zeros(bs, T, 1)
+    for i, mask in enumerate(mod["feature_masks"]):
+        if i in mod["block_frames"] and i in mod["layer_frames"] and i in mod["timestep_frames"]:
+            lam = mod["lambda_start"] if mod["schedule"] == "constant" else \
+                mod["lambda_start"] + (mod["lambda_end"] - mod["lambda_start"]) * i / mod["num_frames"]
+            m = torch.as_tensor(mask, dtype=torch.float32).reshape(-1, 1)
+            add[half:, i] += lam * m
+            if mod["uc"]:
+                add[:half, i] += lam * m
+    return add
+
+
+def _video_transformer(sd, p, x, context, heads, T, indicator, stash, tag, mod_spatial=None, mod_temporal=None, injected=None):
     """SpatialVideoTransformer.forward (video_attention.py:378-489), depth 1, use_linear, use_spatial_context."""
     bt, c, h, w = x.shape
     b, s = bt // T, h * w
@@ -171,16 +195,22 @@ def _video_transformer(sd, p, x, context, heads, T, indicator, stash, tag):
     # spatial block (attention.py:609-759)
     tb = p + ".transformer_blocks.0"
     ln = lambda t, pre, n: F.layer_norm(t, (c,), sd[f"{pre}.{n}.weight"], sd[f"{pre}.{n}.bias"], eps=1e-5)
-    x = x + ou._attention(sd, tb + ".attn1", ln(x, tb, "norm1"), None, heads, stash, tag, "self")
-    x = x + ou._attention(sd, tb + ".attn2", ln(x, tb, "norm2"), context, heads, stash, tag, "cross")
-    x = x + _geglu_ff(sd, tb + ".ff", ln(x, tb, "norm3"))
+    add_s = ou._modulation(mod_spatial, bt, s)
+    site_s = lambda kind: add_s if (add_s is not None and kind in mod_spatial["attn_types"]) else 0.0
+    x = x + (ou._attention(sd, tb + ".attn1", ln(x, tb, "norm1"), None, heads, stash, tag, "self", injected) + site_s("self_attn"))
+    x = x + (ou._attention(sd, tb + ".attn2", ln(x, tb, "norm2"), context, heads, stash, tag, "cross", injected) + site_s("cross_attn"))
+    x = x + (_geglu_ff(sd, tb + ".ff", ln(x, tb, "norm3")) + site_s("ff_out"))
     # temporal block (video_attention.py:145-285)
     ts = p + ".time_stack.0"
     xm = (x + emb).reshape(b, T, s, c).permute(0, 2, 1, 3).reshape(b * s, T, c)  # '(b t) s c -> (b s) t c'
     xm = _geglu_ff(sd, ts + ".ff_in", ln(xm, ts, "norm_in")) + xm
-    xm = _temporal_attention(sd, ts + ".attn1", ln(xm, ts, "norm1"), None, heads, stash, tag, "self") + xm
-    xm = _temporal_attention(sd, ts + ".attn2", ln(xm, ts, "norm2"), time_context, heads, stash, tag, "cross") + xm
-    xm = xm + _geglu_ff(sd, ts + ".ff", ln(xm, ts, "norm3"))
+    add_t = _temporal_modulation(mod_temporal, b * s, T)
+    site_t = lambda kind: add_t if (add_t is not None and kind in mod_temporal["attn_types"]) else 0.0
+    xm = (_temporal_attention(sd, ts + ".attn1", ln(xm, ts, "norm1"), None, heads, stash, tag, "self", injected)
+          + site_t("self_attn")) + xm
+    xm = (_temporal_attention(sd, ts + ".attn2", ln(xm, ts, "norm2"), time_context, heads, stash, tag, "cross")
+          + site_t("cross_attn")) + xm
+    xm = xm + (_geglu_ff(sd, ts + ".ff", ln(xm, ts, "norm3")) + site_t("ff_out"))
     xm = xm.reshape(b, s, T, c).permute(0, 2, 1, 3).reshape(bt, s, c)
     alpha = _alpha(sd, p + ".time_mixer.mix_factor", indicator).reshape(bt, 1, 1)  # 'b t -> (b t) 1 1'
     x = alpha * x + (1.0 - alpha) * xm
@@ -188,13 +218,13 @@ def _video_transformer(sd, p, x, context, heads, T, indicator, stash, tag):
     return x.reshape(bt, h, w, c).permute(0, 3, 1, 2) + x_in
 
 
-def _run_block(sd, prefix, layers, h, emb, context, T, indicator, stash, tag):
+def _run_block(sd, prefix, layers, h, emb, context, T, indicator, stash, tag, mods=(None, None), injected=None):
     for j, (kind, cin, cout) in enumerate(layers):
         p = f"{prefix}.{j}"
         if kind == "res":
             h = _video_resblock(sd, p, h, emb, T, indicator)
         elif kind == "attn":
-            h = _video_transformer(sd, p, h, context, cout, T, indicator, stash, tag)
+            h = _video_transformer(sd, p, h, context, cout, T, indicator, stash, tag, mods[0], mods[1], injected)
         else:
             h = _plain_layer(sd, p, kind, h)
     return h
@@ -212,7 +242,8 @@ def _plain_layer(sd, p, kind, h):
 
 
 @torch.no_grad()
-def video_unet_forward(sd, cfg, x, timesteps, context, y, num_video_frames, image_only_indicator=None, stash=None):
+def video_unet_forward(sd, cfg, x, timesteps, context, y, num_video_frames, image_only_indicator=None, stash=None,
+                       modulate_params=None, injection=None):
     """VideoUNet.forward (video_model.py:451-566), inference path without modulation / injection.
 
     x [B=(b t), Cin, H, W]; timesteps [B]; context [B, L, Cctx]; y [B, adm]; image_only_indicator [b, t] (zeros).
@@ -226,14 +257,42 @@ def video_unet_forward(sd, cfg, x, timesteps, context, y, num_video_frames, imag
     emb = F.linear(F.silu(emb), sd["time_embed.2.weight"], sd["time_embed.2.bias"])
     lab = F.linear(y.float(), sd["label_emb.0.0.weight"], sd["label_emb.0.0.bias"])
     emb = emb + F.linear(F.silu(lab), sd["label_emb.0.2.weight"], sd["label_emb.0.2.bias"])
+    def inj(kind, i, layers):
+        """video_model.py:480-497, 532-550 (same convention as oracle/unet.py)."""
+        if injection is None or kind not in injection["block_types"] or i not in injection[f"{kind}_block_indices"] \
+                or len(layers) < 2 or layers[1][0] != "attn":
+            return None
+        keys = [f"{kind}_block_{i}_{ft}_time_{injection['timestep']}" for ft in injection["feature_types"]]
+        return {k: injection["features"][k] for k in keys if k in injection["features"]}
+
+    def mods(i, layers):
+        """video_model.py:523-530 (block frames) + video_attention.py:437-463 (layer frames per layer type)."""
+        mp = modulate_params
+        if mp is None or i not in mp["modulate_block_idx"] or len(layers) < 2 or layers[1][0] != "attn":
+            return (None, None)
+        every = list(range(mp["num_frames"]))
+        out = []
+        for kind in ("spatial", "temporal"):
+            if kind not in mp["modulate_layer_type"]:
+                out.append(None)
+                continue
+            out.append(dict(feature_masks=mp["feature_masks"], block_frames=mp["modulate_block_frames"].get(i, every),
+                            layer_frames=mp["modulate_layer_frames"].get(kind, every),
+                            timestep_frames=mp["modulate_timestep_frames_group"], lambda_start=mp["modulate_lambda_start"],
+                            lambda_end=mp["modulate_lambda_end"], schedule=mp["modulate_schedule"],
+                            num_frames=mp["num_frames"], uc=mp["modulate_uc"], attn_types=mp["modulate_attn_type"]))
+        return tuple(out)
+
     hs = []
     h = x.float()
     for i, layers in enumerate(inputs):
-        h = _run_block(sd, f"input_blocks.{i}", layers, h, emb, context, T, ind, stash, f"input_block_{i}")
+        h = _run_block(sd, f"input_blocks.{i}", layers, h, emb, context, T, ind, stash, f"input_block_{i}",
+                       injected=inj("input", i, layers))
         hs.append(h)
     h = _run_block(sd, "middle_block", middle, h, emb, context, T, ind, stash, "middle_block")
     for i, layers in enumerate(outputs):
         h = torch.cat([h, hs.pop()], dim=1)
-        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, T, ind, stash, f"output_block_{i}")
+        h = _run_block(sd, f"output_blocks.{i}", layers, h, emb, context, T, ind, stash, f"output_block_{i}",
+                       mods(i, layers), inj("output", i, layers))
     h = F.silu(F.group_norm(h, 32, sd["out.0.weight"], sd["out.0.bias"], eps=1e-5))
     return F.conv2d(h, sd["out.2.weight"], sd["out.2.bias"], padding=1)

@@ -22,7 +22,7 @@ sys.path.insert(0, os.path.join(HERE, ".."))
 
 from oracle import video_unet as ov  # noqa: E402
 from oracle.ref_import import import_reference  # noqa: E402
-from synth import synthetic_unet_weights, synthetic_video_unet_inputs  # noqa: E402
+from synth import synthetic_modulate_params, synthetic_unet_weights, synthetic_video_unet_inputs  # noqa: E402
 
 # (name, cfg, seed, F, latent_hw, (token stride, channel stride) for the stored q)
 CASES = [
@@ -74,6 +74,52 @@ def main():
         print(name, "oracle vs reference:", {k: f"{v:.2e}" for k, v in errs.items()},
               "| out absmax", float(out_ref.abs().max()), "tq7 shape", tuple(tq_ref.shape))
         assert max(errs.values()) < 2e-5, errs
+        extra = {}
+        if name == "video_tiny":
+            # mask modulation of the spatial AND temporal layers (video_attention.py:197-278, 437-463; video_model.py:523-530)
+            mp = dict(synthetic_modulate_params(seed, F, (hw // 2) ** 2), modulate_layer_type=["spatial", "temporal"],
+                      modulate_attn_type=["self_attn", "cross_attn", "ff_out"], modulate_layer_frames={"temporal": [0, 2]})
+            mp_t = dict(mp, feature_masks=[torch.from_numpy(m) for m in mp["feature_masks"]])
+            with torch.no_grad():
+                out_mod = model(x, timesteps=t, context=ctx, y=y, num_video_frames=F, image_only_indicator=ind,
+                                is_modulate_step=True, modulate_params=mp_t)
+            out_mod_or = ov.video_unet_forward(sd, cfg, x, t, ctx, y, F, ind, None, modulate_params=mp)
+            e1 = relerr(out_mod_or, out_mod)
+            print("video_tiny + modulation: oracle vs reference", f"{e1:.2e}", "| changed output by", f"{relerr(out_mod, out_ref):.2e}")
+            assert e1 < 2e-5 and relerr(out_mod, out_ref) > 1e-2
+            # feature injection into the spatial and temporal self-attention of input block 5 / output block 7 through the
+            # reference's .pt files (video_model.py:480-497, 532-550; sgm/util.py:277-296), second pass on another latent
+            import tempfile
+            with tempfile.TemporaryDirectory() as root:
+                fm = os.path.join(root, "src", "feature_maps")
+                os.makedirs(fm)
+                with torch.no_grad():
+                    model(x, timesteps=t, context=ctx, y=y, num_video_frames=F, image_only_indicator=ind)
+                types = ["spatial_self_attn_q", "spatial_self_attn_k", "temporal_self_attn_q", "temporal_self_attn_k"]
+                for kind, i in (("input", 5), ("output", 7)):
+                    layer = getattr(model, f"{kind}_blocks")[i][1]
+                    for ft in types:
+                        blk = layer.transformer_blocks[0] if ft.startswith("spatial") else layer.time_stack[0]
+                        torch.save(getattr(blk.attn1, ft[-1]).clone(), os.path.join(fm, f"{kind}_block_{i}_{ft}_time_24.pt"))
+                x2 = torch.from_numpy(synthetic_video_unet_inputs(seed + 50, F, hw, cfg["in_channels"], cfg["context_dim"],
+                                                                  cfg["adm_in_channels"])[0])
+                inj = dict(injected_block_types=["input", "output"], input_block_indices=[5], output_block_indices=[7],
+                           feature_folder=root, exp_name="src", timestep=24, injected_feature_types=types)
+                with torch.no_grad():
+                    out_inj = model(x2, timesteps=t, context=ctx, y=y, num_video_frames=F, image_only_indicator=ind,
+                                    is_injected_step=True, modulate_params=dict(inj))
+                    out_plain2 = model(x2, timesteps=t, context=ctx, y=y, num_video_frames=F, image_only_indicator=ind)
+                st1 = {}
+                ov.video_unet_forward(sd, cfg, x, t, ctx, y, F, ind, st1)
+                feats = {f"{kind}_block_{i}_{ft}_time_24": st1[(f"{kind}_block_{i}", ft)]
+                         for kind, i in (("input", 5), ("output", 7)) for ft in types}
+                out_inj_or = ov.video_unet_forward(sd, cfg, x2, t, ctx, y, F, ind, None, injection=dict(
+                    block_types=["input", "output"], input_block_indices=[5], output_block_indices=[7], feature_types=types,
+                    timestep=24, features=feats))
+                e2 = relerr(out_inj_or, out_inj)
+                print("video_tiny + injection: oracle vs reference", f"{e2:.2e}", "| changed output by", f"{relerr(out_inj, out_plain2):.2e}")
+                assert e2 < 2e-5 and relerr(out_inj, out_plain2) > 1e-3
+            extra = dict(out_mod=out_mod.numpy(), out_inj=out_inj.numpy())
         ts, cs = stride
         keys = np.array(sorted(shapes))
         np.savez_compressed(
@@ -81,7 +127,7 @@ def main():
             out=out_ref.numpy(), q6=q_ref[6][:, ::ts, ::cs].numpy(), q7=q_ref[7][:, ::ts, ::cs].numpy(),
             q8=q_ref[8][:, ::ts, ::cs].numpy(), tq7=tq_ref[::ts, :, ::cs].numpy(), tk2_7=tk2_ref[::ts, :, ::cs].numpy(),
             q_stride=np.array(stride), keys=keys, shapes=np.array([",".join(map(str, shapes[k])) for k in keys]),
-            meta=np.array([seed, F, hw]))
+            meta=np.array([seed, F, hw]), **extra)
 
 
 if __name__ == "__main__":

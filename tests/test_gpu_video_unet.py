@@ -112,3 +112,36 @@ def test_video_image_only_indicator_switches_the_temporal_branch_off(cuda):
     want = ov.video_unet_forward(sd, cfg, torch.from_numpy(x), torch.from_numpy(t), torch.from_numpy(ctx),
                                  torch.from_numpy(y), F, ind)
     assert relerr(out, want) < 5e-4
+
+
+def test_video_unet_modulation_and_injection_match_reference_golden(cuda, operand_mode, tmp_path):
+    """VideoUNet(is_modulate_step=True) with spatial AND temporal layer modulation, and VideoUNet(is_injected_step=True)
+    with spatial and temporal q / k injected from tensors still in HBM, against the reference runs (golden)."""
+    from synth import synthetic_modulate_params
+    cfg = ov.TINY_VIDEO_CONFIG
+    g = np.load(os.path.join(GOLDEN, "unet_video_tiny.npz"))
+    seed, F, hw = (int(v) for v in g["meta"])
+    model, _ = build(cfg, seed, cuda)
+    dev = lambda a: torch.from_numpy(a).to(cuda)
+    x, t, ctx, y = synthetic_video_unet_inputs(seed, F, hw, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"])
+    kw = dict(timesteps=dev(t), context=dev(ctx), y=dev(y), num_video_frames=F, image_only_indicator=torch.zeros(2, F, device=cuda))
+    tol = EXPECTED if operand_mode == 0 else 5e-4
+    mp = dict(synthetic_modulate_params(seed, F, (hw // 2) ** 2), modulate_layer_type=["spatial", "temporal"],
+              modulate_attn_type=["self_attn", "cross_attn", "ff_out"], modulate_layer_frames={"temporal": [0, 2]})
+    mp["feature_masks"] = [torch.from_numpy(m).to(cuda) for m in mp["feature_masks"]]
+    out_mod = model(dev(x), is_modulate_step=True, modulate_params=mp, **kw)
+    assert relerr(out_mod, g["out_mod"]) < tol
+    # injection: first pass stashes, second pass on another latent takes q / k of input block 5 and output block 7
+    model(dev(x), **kw)
+    types = ["spatial_self_attn_q", "spatial_self_attn_k", "temporal_self_attn_q", "temporal_self_attn_k"]
+    feats = {}
+    for kind, i in (("input", 5), ("output", 7)):
+        layer = getattr(model, f"{kind}_blocks")[i][1]
+        for ft in types:
+            blk = layer.transformer_blocks[0] if ft.startswith("spatial") else layer.time_stack[0]
+            feats[f"{kind}_block_{i}_{ft}_time_24"] = getattr(blk.attn1, ft[-1]).clone()
+    x2 = synthetic_video_unet_inputs(seed + 50, F, hw, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"])[0]
+    inj = dict(injected_block_types=["input", "output"], input_block_indices=[5], output_block_indices=[7], timestep=24,
+               injected_feature_types=types, features=feats)
+    out_inj = model(dev(x2), is_injected_step=True, modulate_params=inj, **kw)
+    assert relerr(out_inj, g["out_inj"]) < tol

@@ -105,8 +105,6 @@ def test_video_unet_rejects_cpu_tensors_and_unbuilt_rows():
     args = dict(timesteps=torch.zeros(4), context=torch.zeros(4, 1, 96), y=torch.zeros(4, 48), num_video_frames=2)
     with pytest.raises(_lib.VidsegError):
         model(torch.zeros(4, 8, 16, 16), **args)
-    with pytest.raises(NotImplementedError):
-        model(torch.zeros(4, 8, 16, 16), is_modulate_step=True, **args)
 
 
 def test_oracle_mask_modulation_matches_reference_golden():

@@ -13,6 +13,7 @@ from .... import kernels as K
 from ..attention import _unsupported
 from ..video_attention import SpatialVideoTransformer
 from .openaimodel import Downsample, ResBlock, TimestepEmbedSequential, Upsample
+from ...util import load_target_features
 from .util import AlphaBlender, normalization, timestep_embedding, zero_module
 
 
@@ -142,9 +143,8 @@ class VideoUNet(nn.Module):
         assert (y is not None) == (self.num_classes is not None), \
             "must specify y if and only if the model is class-conditional -> no, relax this TODO"
         if is_modulate_step:
-            _unsupported("VideoUNet(is_modulate_step=True)")
-        if is_injected_step:
-            _unsupported("VideoUNet(is_injected_step=True) (feature injection from .pt dumps)")
+            assert modulate_params is not None
+            modulate_block_idx = modulate_params["modulate_block_idx"]
         if not x.is_cuda:
             raise _lib.VidsegError("VideoUNet.forward: expected CUDA tensors (the hot path has no CPU fallback)")
         if num_video_frames is None or x.shape[0] % num_video_frames:
@@ -162,15 +162,33 @@ class VideoUNet(nn.Module):
         context = K.split(context.float().contiguous())  # split once, shared by all cross-attention layers
         kw = dict(context=context, image_only_indicator=image_only_indicator, time_context=time_context,
                   num_video_frames=num_video_frames)
+        def injected_features(kind, i, module):
+            """reference :480-497 / :532-550: the q / k (/ v) tensors stashed by another pass for block i, or False."""
+            if not (is_injected_step and kind in modulate_params["injected_block_types"] and len(module) > 1
+                    and "SpatialVideoTransformer" in str(type(module[1])) and i in modulate_params[f"{kind}_block_indices"]):
+                return False
+            modulate_params["injected_features_group"] = load_target_features(
+                modulate_params.get("feature_folder"), modulate_params.get("exp_name"), modulate_params["timestep"], kind,
+                modulate_params["injected_feature_types"], i, x.device, features=modulate_params.get("features"))
+            return len(modulate_params["injected_features_group"]) > 0
+
         hs = []
         h = x
-        for module in self.input_blocks:
-            h = module(h, emb, **kw)
+        for i, module in enumerate(self.input_blocks):
+            h = module(h, emb, is_injected_step=injected_features("input", i, module), modulate_params=modulate_params, **kw)
             hs.append(h)
         h = self.middle_block(h, emb, **kw)
-        for module in self.output_blocks:
+        for i, module in enumerate(self.output_blocks):
             h = K.concat_channels(h, hs.pop())
-            h = module(h, emb, **kw)
+            mod_block = False   # reference :523-530
+            if is_modulate_step and i in modulate_block_idx and len(module) > 1 and "SpatialVideoTransformer" in str(type(module[1])):
+                mod_block = True
+                if i in modulate_params["modulate_block_frames"].keys():
+                    modulate_params["modulate_block_frames_group"] = modulate_params["modulate_block_frames"][i]
+                else:
+                    modulate_params["modulate_block_frames_group"] = list(range(modulate_params["num_frames"]))
+            h = module(h, emb, is_modulate_step=mod_block, is_injected_step=injected_features("output", i, module),
+                       modulate_params=modulate_params, **kw)
         hs_out, _, _ = K.group_norm_split(h, self.out[0], silu=True)
         h = K.conv2d(hs_out, self.out[2])
         return h.contiguous().to(in_dtype)

@@ -17,8 +17,15 @@ import torch.nn as nn
 from ... import _lib
 from ... import kernels as K
 from ...linear import Split
-from .attention import CrossAttention, FeedForward, SpatialTransformer, _unsupported
+from .attention import CrossAttention, FeedForward, SpatialTransformer, _unsupported, modulation_rows
 from .diffusionmodules.util import AlphaBlender, timestep_embedding
+
+
+def _to_frame_major(t, videos, frames):
+    """the reference's '(b s) t c' tensor (an injected feature dump) -> frame-major [(b t), s, c]."""
+    bs, T, c = t.shape
+    s = bs // videos
+    return t.reshape(videos, s, frames, c).permute(0, 2, 1, 3).reshape(videos * frames, s, c).float().contiguous()
 
 
 def _to_site_major(t, videos, frames):
@@ -51,6 +58,7 @@ class VideoTransformerBlock(nn.Module):
         self.timesteps = timesteps
         self.disable_self_attn = disable_self_attn
         self.attn1 = attn_cls(query_dim=inner_dim, heads=n_heads, dim_head=d_head, dropout=dropout)
+        self.attn1.inject_v = (attn_mode == "softmax-xformers")   # the SDPA class ignores injected_v (attention.py:316)
         self.ff = FeedForward(inner_dim, dim_out=dim, dropout=dropout, glu=gated_ff)
         if disable_temporal_crossattention:
             self.attn2 = None
@@ -77,15 +85,13 @@ class VideoTransformerBlock(nn.Module):
                 context = context[:: x.shape[1]]
             context = K.split(context.float().contiguous())
         return self.forward_frames(x.float().contiguous(), context, timesteps, is_modulate_step=is_modulate_step,
-                                   is_injected_step=is_injected_step)
+                                   is_injected_step=is_injected_step, modulate_params=modulate_params)
 
     def forward_frames(self, x, context, timesteps, frame_bias=None, blend=None, blend_alpha=None, want_split=False,
-                       is_modulate_step=False, is_injected_step=False):
+                       is_modulate_step=False, is_injected_step=False, modulate_params=None):
         """x: fp32 [(b t), s, c]; frame_bias [(b t), c] is added to x first (x_mix = x + emb, reference :452-453);
         context: Split [b, 1, D], the time context of every clip; blend / blend_alpha [(b t)]: the AlphaBlender mix
         with the spatial branch applied to the result.  Returns fp32 [(b t), s, c] (and its Split with want_split)."""
-        if is_modulate_step or is_injected_step:
-            _unsupported("VideoTransformerBlock(is_modulate_step / is_injected_step)")
         bt, s, c = x.shape
         T = timesteps
         videos = bt // T
@@ -99,17 +105,32 @@ class VideoTransformerBlock(nn.Module):
             h = x + frame_bias[:, None, :]
         else:
             h = x
+        # mask modulation (reference :197-216, :233-254, :260-278): 'out[half_hw:, i] += lambda_i * mask_i[:, None]' on the
+        # '(b s) t c' layout is row (T + i) * S + s of the frame-major layout -- the same per-row term as in the spatial
+        # blocks, added in the epilogue of the GEMM that produces attn1_out / attn2_out / ff_out
+        mod = {"self_attn": None, "cross_attn": None, "ff_out": None}
+        if is_modulate_step:
+            rows = modulation_rows(modulate_params, bt, s, x.device)
+            for kind in mod:
+                if kind in modulate_params["modulate_attn_type"]:
+                    mod[kind] = rows
+        inj = {}
+        if is_injected_step:   # reference :167-176: lookup by substring of the dict key, tensors in '(b s) t c'
+            for key, val in modulate_params["injected_features_group"].items():
+                for name in "qkv":
+                    if f"temporal_self_attn_{name}" in key:
+                        inj[name] = _to_frame_major(val, videos, T)
         # attn1: self-attention over the frames of every site
         hs = K.layer_norm_split(h, self.norm1)
         a1 = self.attn1
-        q, _ = K.linear(hs, a1.to_q.weight, want_f32=True)
-        k, _ = K.linear(hs, a1.to_k.weight, want_f32=True)
-        v, _ = K.linear(hs, a1.to_v.weight, want_f32=True)
+        q = inj["q"] if "q" in inj else K.linear(hs, a1.to_q.weight, want_f32=True)[0]
+        k = inj["k"] if "k" in inj else K.linear(hs, a1.to_k.weight, want_f32=True)[0]
+        v = inj["v"] if ("v" in inj and a1.inject_v) else K.linear(hs, a1.to_v.weight, want_f32=True)[0]
         a1.q = lambda: _to_site_major(q, videos, T)
         a1.k = lambda: _to_site_major(k, videos, T)
         o = K.temporal_attention(q, k, v, videos, T, a1.heads, a1.scale)
         lin = a1.to_out[0]
-        h, _ = K.linear(o, lin.weight, lin.bias, residual=h, want_f32=True)
+        h, _ = K.linear(o, lin.weight, lin.bias, residual=h, want_f32=True, row_scalar=mod["self_attn"])
         # attn2: cross-attention to the clip's time context
         cb = {}
         if self.attn2 is not None:
@@ -123,8 +144,15 @@ class VideoTransformerBlock(nn.Module):
             a2.k = lambda: k2.repeat_interleave(s, dim=0)     # [(b s), 1, c]: the repeated time context's keys
             lin2 = a2.to_out[0]
             av, _ = K.linear(v2, lin2.weight, lin2.bias, want_f32=True)   # one vector per clip (softmax over 1 key = 1)
-            cb = dict(row_bias=av.reshape(videos, c), rows_per_bias=T * s)
+            if mod["cross_attn"] is not None:
+                # modulated attn2_out is no longer one vector per clip: materialise x = x + attn2_out (rare path)
+                h = (h.view(videos, T * s, c) + av.reshape(videos, 1, c)).view(bt, s, c) + mod["cross_attn"].view(bt, s, 1)
+                h = h.contiguous()
+            else:
+                cb = dict(row_bias=av.reshape(videos, c), rows_per_bias=T * s)
         ep = dict(blend=blend, blend_alpha=blend_alpha, rows_per_alpha=s) if blend is not None else {}
+        if mod["ff_out"] is not None:
+            ep["row_scalar"] = mod["ff_out"]
         # x = x + attn2_out;  x = x + ff(norm3(x))   [is_res]
         return self.ff.forward_split(K.layer_norm_split(h, self.norm3, **cb), h, want_split=want_split, **cb, **ep)
 
@@ -162,8 +190,6 @@ class SpatialVideoTransformer(SpatialTransformer):
 
     def forward(self, x, context=None, time_context=None, timesteps=None, image_only_indicator=None,
                 is_modulate_step=False, is_injected_step=False, modulate_params=None):
-        if is_modulate_step or is_injected_step:
-            _unsupported("SpatialVideoTransformer(is_modulate_step / is_injected_step)")
         bt, c, h, w = x.shape
         T = timesteps
         videos = bt // T
@@ -189,11 +215,22 @@ class SpatialVideoTransformer(SpatialTransformer):
         alpha = self.time_mixer.frame_alpha(image_only_indicator, videos, T)
         ts = None
         n = len(self.transformer_blocks)
+        def layer_mod(kind):   # reference :437-445 / :455-463: which frames this layer type modulates
+            if not (is_modulate_step and kind in modulate_params["modulate_layer_type"]):
+                return False
+            if kind in modulate_params["modulate_layer_frames"].keys():
+                modulate_params["modulate_layer_frames_group"] = modulate_params["modulate_layer_frames"][kind]
+            else:
+                modulate_params["modulate_layer_frames_group"] = list(range(modulate_params["num_frames"]))
+            return True
+
         for i, (block, mix_block) in enumerate(zip(self.transformer_blocks, self.time_stack)):
-            t = block(t, context=spatial_context)
+            t = block(t, context=spatial_context, is_modulate_step=layer_mod("spatial"), is_injected_step=is_injected_step,
+                      modulate_params=modulate_params)
             # x_mix = x + emb -> temporal block -> alpha * x + (1 - alpha) * x_mix, the last two fused in its output GEMM
             res = mix_block.forward_frames(t, time_ctx, T, frame_bias=emb, blend=t, blend_alpha=alpha,
-                                           want_split=(i == n - 1))
+                                           want_split=(i == n - 1), is_modulate_step=layer_mod("temporal"),
+                                           is_injected_step=is_injected_step, modulate_params=modulate_params)
             t, ts = res if i == n - 1 else (res, None)
         out, _ = K.linear(ts, self.proj_out.weight, self.proj_out.bias, residual=x_tok, want_f32=True)
         out = K.as_nchw(out.reshape(bt, h, w, c))
