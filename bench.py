@@ -385,8 +385,8 @@ def run_b200(args, wl, cfg):
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     nf = max(1, min(args.ref_frames, F))
-    if args.no_cpu_baseline:
-        t_cpu, sample = float("nan"), "skipped (--no-cpu-baseline)"
+    if args.no_cpu_baseline or world > 1:   # the CPU leg is timed at N=1 only (rank 0)
+        t_cpu, sample = float("nan"), "skipped (--no-cpu-baseline)" if args.no_cpu_baseline else "timed at N=1 only"
     else:
         t_cpu = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], nf, seed)
         sample = (f"{nf} of {F} frames, one pass (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32 + "

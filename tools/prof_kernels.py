@@ -44,7 +44,7 @@ if "gemmres" in which:   # the memory-bound projection shape of the first UNet l
     ms = ev(run, it=3) - ev(lambda: big.zero_(), it=3)
     res["gemmres_114688x320x320_fr"] = {"ms": ms, "GBs": (m * kk * 4 + 2 * m * n * 4) / ms / 1e6}
 if "conv" in which:
-    for (B, H, C, Co) in [(28, 64, 320, 320), (28, 32, 640, 640), (28, 64, 640, 320)]:
+    for (B, H, C, Co) in [(28, 64, 320, 320), (28, 32, 640, 640), (28, 64, 640, 320), (28, 8, 1280, 1280), (28, 8, 2560, 1280), (28, 16, 1280, 1280)]:
         conv = torch.nn.Conv2d(C, Co, 3, padding=1).to(dev)
         x = split(torch.randn(B, H, H, C, device=dev))
         ms = ev(lambda: K.conv2d(x, conv))

@@ -561,7 +561,13 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
   if (int e = encode_tmap_16bit(&ta_lo, a_lo, 5, adims, astrides, box)) return e;
   const double flops = 2.0 * (double)p.nb * p.ho * p.wo * (double)p.n * (double)p.k;
-  if (p.n % 256 == 0 || (p.geglu && p.n > 128)) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  // small grids (the 8x8 / 16x16 levels of the UNet): 128-wide N tiles double the number of CTAs when 256-wide ones would
+  // leave SMs idle
+  const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  const bool underfilled = p.n % 128 == 0 && p.n > 128 && m_tiles * ((p.n + 255) / 256) < (3 * kNumSMs) / 4;
+  if (!underfilled && (p.n % 256 == 0 || (p.geglu && p.n > 128)))
+    return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  if (underfilled) return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
   if (p.n % 160 == 0 && !p.geglu) return launch_gemm<160>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
   return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
 }
