@@ -8,8 +8,8 @@
 //
 // One CTA = 256 queries of one (batch, head): two 128-row query tiles, each owned by a softmax
 // warpgroup (128 threads = 128 TMEM lanes).  Per 64-key block and tile:
-//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x64x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator), issued TWO
-//              blocks ahead into a double-buffered S region of TMEM, so a softmax group never waits for its scores
+//   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x128x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator) for a block of
+//              128 keys; S(j+1) of a tile is issued right behind PV(j) of the same tile, the other tile's softmax runs meanwhile
 //   softmax  : tcgen05.ld S, row max / exp2 / row sum in registers, P -> fp16 hi/lo into swizzled smem
 //   MMA warp : O += P V    (12 x tcgen05.mma 128x64x16, V is the MN-major B operand); O stays in TMEM across the whole
 //              key loop, so the softmax group does not wait for this product either
@@ -27,18 +27,18 @@ namespace vidseg {
 
 constexpr int kAtBQ = 128;        // queries per tile
 constexpr int kAtTiles = 2;       // query tiles per CTA
-constexpr int kAtBK = 64;         // keys per block
+constexpr int kAtBK = 128;        // keys per block (128-wide S tiles: the 64-wide ones were bound by operand fetch, 6 KB of smem per 32 math cycles)
 constexpr int kAtD = 64;          // head dim
-constexpr int kAtStages = 4;      // K/V ring depth: the refill of a stage (TMA latency ~1 us) overlaps several key blocks of work
+constexpr int kAtStages = 2;      // K/V ring depth (64 KB per stage)
 constexpr int kAtQTileBytes = kAtBQ * kAtD * 2;  // 16 KB (one of hi / lo)
-constexpr int kAtKTileBytes = kAtBK * kAtD * 2;  // 8 KB
+constexpr int kAtKTileBytes = kAtBK * kAtD * 2;  // 16 KB
 constexpr int kAtPTileBytes = kAtBQ * kAtBK * 2; // 16 KB
 constexpr int kAtSmemQ = kAtTiles * 2 * kAtQTileBytes;          // 64 KB
-constexpr int kAtSmemKV = kAtStages * 4 * kAtKTileBytes;        // 64 KB
+constexpr int kAtSmemKV = kAtStages * 4 * kAtKTileBytes;        // 128 KB
 constexpr int kAtSmemP = 0;                                     // P lives in TMEM
 constexpr int kAtSmemBytes = kAtSmemQ + kAtSmemKV + kAtSmemP + 1024 + 256;
 constexpr int kAtThreads = 64 + kAtTiles * 128;
-constexpr int kAtTmemCols = 512;       // per tile: S buffer 0 | S buffer 1 | O, 64 columns each
+constexpr int kAtTmemCols = 512;       // per tile: S (128 columns; P overwrites it in place) | O (64 columns)
 constexpr int kAtTileCols = 192;
 constexpr float kAtTau = 3.0f;         // lazy-rescale threshold (log2 units): p <= 2^(12+3) stays inside fp16  // producer warp, MMA warp, 2 softmax warpgroups
 
@@ -128,12 +128,12 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     if (lane == 0) {
       constexpr uint32_t idesc_s = tc::make_idesc_f16(kAtBQ, kAtBK, 0, 0);   // Q (K-major) x K (K-major)
       constexpr uint32_t idesc_o = tc::make_idesc_f16(kAtBQ, kAtD, 0, 1);    // P (K-major) x V (MN-major)
-      auto issue_s = [&](int g, int stage, int buf) {
+      auto issue_s = [&](int g, int stage) {
         const uint32_t qa = tc::smem_u32(sm_q + g * 2 * kAtQTileBytes);
         const uint32_t ka = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes);
         const uint64_t q_hi = tc::make_sw128_desc(qa), q_lo = tc::make_sw128_desc(qa + kAtQTileBytes);
         const uint64_t k_hi = tc::make_sw128_desc(ka), k_lo = tc::make_sw128_desc(ka + kAtKTileBytes);
-        const uint32_t d_s = tmem_base + (uint32_t)(g * kAtTileCols + buf * 64);
+        const uint32_t d_s = tmem_base + (uint32_t)(g * kAtTileCols);
 #pragma unroll
         for (int ks = 0; ks < kAtD / 16; ++ks) {
           const uint64_t adv = (uint64_t)(ks * 32 >> 4);
@@ -141,21 +141,22 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
           tc::umma_f16(d_s, q_hi + adv, k_lo + adv, idesc_s, 1u);
           tc::umma_f16(d_s, q_hi + adv, k_hi + adv, idesc_s, 1u);
         }
-        tc::umma_commit(&s_full[2 * g + buf]);
+        tc::umma_commit(&s_full[g]);
       };
-      auto issue_pv = [&](int g, int stage, int buf, bool first) {
+      auto issue_pv = [&](int g, int stage, bool first) {
         const uint32_t va = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes + 2 * kAtKTileBytes);
         const uint64_t v_hi = tc::make_sw128_desc(va), v_lo = tc::make_sw128_desc(va + kAtKTileBytes);
         const uint32_t d_o = tmem_base + (uint32_t)(g * kAtTileCols + 128);
-        // P(j) overwrote S(j) in place: fp16 pairs, hi in columns [0,32) and lo in [32,64) of the S buffer
-        const uint32_t p_hi = tmem_base + (uint32_t)(g * kAtTileCols + buf * 64), p_lo = p_hi + 32;
+        // P(j) overwrote S(j) in place, 64 keys at a time: the fp16 pairs of keys [64h, 64h+64) sit in the 64 columns that
+        // held their scores -- hi in the first 32, lo in the last 32, two keys per column
+        const uint32_t p_base = tmem_base + (uint32_t)(g * kAtTileCols);
 #pragma unroll
         for (int ks = 0; ks < kAtBK / 16; ++ks) {
-          const uint32_t adv_a = (uint32_t)(ks * 8);                // 16 keys = 8 packed columns
+          const uint32_t p_hi = p_base + (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8), p_lo = p_hi + 32;
           const uint64_t adv_b = (uint64_t)(ks * 16 * 128 >> 4);    // 16 key rows of 128 B in the V tile
-          tc::umma_f16_ts(d_o, p_lo + adv_a, v_hi + adv_b, idesc_o, (first && ks == 0) ? 0u : 1u);
-          tc::umma_f16_ts(d_o, p_hi + adv_a, v_lo + adv_b, idesc_o, 1u);
-          tc::umma_f16_ts(d_o, p_hi + adv_a, v_hi + adv_b, idesc_o, 1u);
+          tc::umma_f16_ts(d_o, p_lo, v_hi + adv_b, idesc_o, (first && ks == 0) ? 0u : 1u);
+          tc::umma_f16_ts(d_o, p_hi, v_lo + adv_b, idesc_o, 1u);
+          tc::umma_f16_ts(d_o, p_hi, v_hi + adv_b, idesc_o, 1u);
         }
         tc::umma_commit(&pv_done[g]);
       };
@@ -166,20 +167,16 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       };
       tc::mbar_wait(q_full, 0);
       wait_kv(0);
-      for (int g = 0; g < kAtTiles; ++g) issue_s(g, 0, 0);
-      if (nkb > 1) {
-        wait_kv(1);
-        for (int g = 0; g < kAtTiles; ++g) issue_s(g, 1 % kAtStages, 1);
-      }
+      for (int g = 0; g < kAtTiles; ++g) issue_s(g, 0);
       for (int j = 0; j < nkb; ++j) {
         const int stage = j % kAtStages;
         for (int g = 0; g < kAtTiles; ++g) {
-          tc::mbar_wait(&p_full[g], (uint32_t)(j & 1));   // P(j) written, S buffer j & 1 consumed, O rescaled if needed
+          tc::mbar_wait(&p_full[g], (uint32_t)(j & 1));   // P(j) written over S(j), O rescaled if needed
           tc::tc_fence_after();
-          issue_pv(g, stage, j & 1, j == 0);
-          if (j + 2 < nkb) {
-            if (g == 0) wait_kv(j + 2);
-            issue_s(g, (j + 2) % kAtStages, j & 1);
+          issue_pv(g, stage, j == 0);
+          if (j + 1 < nkb) {   // S(j+1) of this tile goes into the region PV(j) has just read (same pipe, in order)
+            if (g == 0) wait_kv(j + 1);
+            issue_s(g, (j + 1) % kAtStages);
           }
         }
         tc::umma_commit(&kv_empty[stage]);
@@ -195,24 +192,20 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
     float m_run = -INFINITY, l_run = 0.f;
     for (int j = 0; j < nkb; ++j) {
       const int valid = min(kAtBK, p.nk - j * kAtBK);
-      tc::mbar_wait(&s_full[2 * g + (j & 1)], (uint32_t)((j >> 1) & 1));
+      tc::mbar_wait(&s_full[g], (uint32_t)(j & 1));
       tc::tc_fence_after();
-      // the 64 scores of this row stay in registers between the max pass and the exp pass
+      // the 128 scores of this row stay in registers between the max pass and the exp pass
       uint32_t sc[kAtBK];
-      {
-        uint32_t (&s0)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[0]);
-        uint32_t (&s1)[32] = *reinterpret_cast<uint32_t(*)[32]>(&sc[32]);
-        tc::tmem_ld_32x32(t_row + (uint32_t)((j & 1) * 64), s0);
-        tc::tmem_ld_32x32(t_row + (uint32_t)((j & 1) * 64 + 32), s1);
-        tc::tmem_wait_ld();
-      }
+#pragma unroll
+      for (int c = 0; c < kAtBK; c += 32) tc::tmem_ld_32x32(t_row + c, *reinterpret_cast<uint32_t(*)[32]>(&sc[c]));
+      tc::tmem_wait_ld();
       if (valid < kAtBK) {  // warp-uniform: only the last key block of a ragged Nk (e.g. the 77 context tokens)
 #pragma unroll
         for (int i = 0; i < kAtBK; ++i)
           if (i >= valid) sc[i] = 0xff800000u;  // -inf: exp2 -> 0, max unaffected
       }
       // four independent chains for the row maximum and the row sum (one thread owns the whole row, so a single
-      // chain would serialise 64 dependent operations at the ALU latency)
+      // chain would serialise dependent operations at the ALU latency)
       float mx0 = __uint_as_float(sc[0]), mx1 = __uint_as_float(sc[1]), mx2 = __uint_as_float(sc[2]),
             mx3 = __uint_as_float(sc[3]);
 #pragma unroll
@@ -227,26 +220,9 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
       const bool grow = m_blk > m_run + kAtTau;          // always true on the first block (m_run = -inf)
       const float m_use = grow ? m_blk : m_run;
       const float alpha = grow ? ex2_approx(m_run - m_blk) : 1.0f;  // 0 on the first block
-      // probabilities are carried scaled by 2^12 so that their fp16 residuals stay normal numbers (<= 2^15 with the
-      // lazy maximum); the row sum carries the same factor, which cancels in the final O / l
-      const float bias = 12.0f - m_use;
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      // probabilities -> fp16 hi / lo, kept in registers until the P tile is free (sc[] is dead by then)
-      uint4 hv[kAtBK / 8], lv[kAtBK / 8];
-#pragma unroll
-      for (int i = 0; i < kAtBK; i += 8) {
-        float pv[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[i + u]), p.scale_log2, bias));
-        ls0 += pv[0] + pv[4]; ls1 += pv[1] + pv[5]; ls2 += pv[2] + pv[6]; ls3 += pv[3] + pv[7];
-        tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv[i >> 3], lv[i >> 3]);
-      }
-      l_run = fmaf(l_run, alpha, (ls0 + ls1) + (ls2 + ls3));
-      m_run = m_use;
       if (j > 0) {
-        // PV(j-1) has landed in O.  Waited for on EVERY block although only the rescale needs it: an mbarrier parity
-        // wait is only meaningful one phase behind, and the final wait below relies on having followed every phase
-        // (by now the product has normally completed, the softmax of this block took longer than the MMA)
+        // PV(j-1) has landed in O (it preceded S(j) in the tensor pipe, so this wait returns at once; it is still made
+        // on EVERY block because an mbarrier parity wait is only meaningful one phase behind)
         tc::mbar_wait(&pv_done[g], (uint32_t)((j - 1) & 1));
         tc::tc_fence_after();
         if (__any_sync(0xffffffffu, grow)) {
@@ -263,14 +239,30 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
           }
         }
       }
-      // P(j) replaces S(j) in its TMEM buffer (this warp's 32 lanes): the A operand of the PV product is read from
-      // tensor memory, so the probabilities never pass through shared memory
-      {
-        const uint32_t t_p = t_row + (uint32_t)((j & 1) * 64);
-        tc::tmem_st_32x32(t_p, *reinterpret_cast<const uint32_t(*)[32]>(&hv[0]));
-        tc::tmem_st_32x32(t_p + 32, *reinterpret_cast<const uint32_t(*)[32]>(&lv[0]));
-        tc::tmem_wait_st();
+      // probabilities are carried scaled by 2^12 so that their fp16 residuals stay normal numbers (<= 2^15 with the
+      // lazy maximum); the row sum carries the same factor, which cancels in the final O / l.  P replaces S in place,
+      // 32 keys at a time: hi pairs -> 16 columns, lo pairs -> 16 columns of the 64 columns that held the scores of
+      // their 64-key half (the A operand of the PV product is read from tensor memory)
+      const float bias = 12.0f - m_use;
+      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
+#pragma unroll
+      for (int c = 0; c < kAtBK; c += 32) {
+        uint4 hv[4], lv[4];
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          float pv[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[c + i + u]), p.scale_log2, bias));
+          ls0 += pv[0] + pv[4]; ls1 += pv[1] + pv[5]; ls2 += pv[2] + pv[6]; ls3 += pv[3] + pv[7];
+          tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv[i >> 3], lv[i >> 3]);
+        }
+        const uint32_t t_p = t_row + (uint32_t)((c >> 6) * 64 + ((c >> 5) & 1) * 16);
+        tc::tmem_st_32x16(t_p, *reinterpret_cast<const uint32_t(*)[16]>(&hv[0]));
+        tc::tmem_st_32x16(t_p + 32, *reinterpret_cast<const uint32_t(*)[16]>(&lv[0]));
       }
+      tc::tmem_wait_st();
+      l_run = fmaf(l_run, alpha, (ls0 + ls1) + (ls2 + ls3));
+      m_run = m_use;
       tc::tc_fence_before();
       tc::mbar_arrive(&p_full[g]);
     }
