@@ -158,3 +158,20 @@ def test_unet_feature_injection_matches_reference_golden(cuda, tmp_path):
     with pytest.raises(ValueError):     # the reference's error when a requested block has no stored features
         model(dev(x2), timesteps=dev(t), context=dev(ctx), is_injected_step=True,
               modulate_params=dict(mp, features={}, output_block_indices=[6]))
+
+
+def test_segment_many_equals_segment_clip_by_clip(cuda):
+    """ClipSegmenter.segment_many (two-stream software pipeline over a stream of clips) returns exactly the label maps of
+    segment() called clip by clip."""
+    from vidseg_diffusion_b200.pipeline import ClipSegmenter
+    cfg = ounet.TINY_CONFIG
+    model, _ = build(cfg, 5, cuda)
+    clips = []
+    for seed in (5, 6, 7):
+        clips.append(tuple(torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(seed, 2, 16, cfg["in_channels"], 7, cfg["context_dim"])))
+    one = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True)
+    want = [one.segment(x, t, c, 2, seed=1)[0].cpu() for x, t, c in clips]
+    for graph in (False, True):
+        seg = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, use_cuda_graph=graph)
+        got = list(seg.segment_many(clips, 2, seed=1, to_host=True))
+        assert len(got) == 3 and all(torch.equal(g, w) for g, w in zip(got, want))

@@ -104,8 +104,8 @@ class ClipSegmenter:
         self.last = {"kmeans": km, "features": x}
         return labels
 
-    def refine(self, labels, num_frames, feature_height, feature_width):
-        fm = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0]
+    def refine(self, labels, num_frames, feature_height, feature_width, features=None):
+        fm = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0] if features is None else features
         refined, traj, keep = refine_masks(fm, labels, num_frames, feature_height, feature_width)
         self.last.update(trajectories=traj, keep=keep)
         return refined
@@ -135,3 +135,58 @@ class ClipSegmenter:
         unet_kwargs = {k: (v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v) for k, v in unet_kwargs.items()}
         labels, _ = self.segment(x, t, c, num_frames, seed, **unet_kwargs)
         return labels.cpu()
+
+    @torch.no_grad()
+    def segment_many(self, clips, num_frames, seed=None, to_host=True):
+        """A stream of clips, software-pipelined: while the clustering (K-means polls its convergence flags from the host,
+        many small latency-bound launches) and the refinement of clip i run on a second CUDA stream, the UNet stage of
+        clip i+1 -- one CUDA-graph launch -- already runs on the first.  Results are identical to ``segment`` /
+        ``segment_host`` clip by clip; only the schedule changes.
+
+        ``clips``: iterable of ``(x, timesteps, context)`` or ``(x, timesteps, context, unet_kwargs)``; host tensors
+        (pinned) are copied to the device inside.  Yields one label map per clip, in order (CPU int32 if ``to_host``)."""
+        dev = next(self.model.parameters()).device
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=dev, priority=-1)   # the small K-means kernels go first when SMs free up
+        side = self._side_stream
+        main = torch.cuda.current_stream(dev)
+        to_dev = lambda v: v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v
+
+        def finish(pending):
+            feats, fm7, ready, fh, fw = pending
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                labels = self.cluster(num_frames, fh, fw, seed, features=feats)
+                if self.is_refine_mask:
+                    labels = self.refine(labels, num_frames, fh, fw, features=fm7)
+                out = labels.cpu() if to_host else labels
+                done = torch.cuda.Event()
+                done.record(side)
+            if not to_host:
+                main.wait_event(done)
+            return out
+
+        pending = None
+        for clip in clips:
+            x, t, c = (to_dev(v) for v in clip[:3])
+            kw = {k: to_dev(v) for k, v in (clip[3] if len(clip) > 3 else {}).items()}
+            if self.use_cuda_graph:
+                _, feats = self._graphed_unet_features(x, t, c, num_frames, kw)
+            else:
+                self.unet_step(x, t, c, **kw)
+                feats = self._features(num_frames)
+            # the graph's buffers (and the modules' stash) are overwritten by the next clip: snapshot what the second
+            # stream will read
+            feats = feats.clone()
+            feats.record_stream(side)
+            fm7 = None
+            if self.is_refine_mask:
+                fm7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0].clone()
+                fm7.record_stream(side)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (feats, fm7, ready, x.shape[-2] // 2, x.shape[-1] // 2)
+        if pending is not None:
+            yield finish(pending)
