@@ -62,6 +62,16 @@ int vidseg_aggregate_normalize(const float* const* blocks_host, int n_blocks,
  * ------------------------------------------------------------------------- */
 size_t vidseg_kmeans_workspace_bytes(int n, int d, int k, int n_init, int n_trials);
 
+/* Variant of the Lloyd M-step (sklearn/cluster/_k_means_lloyd.pyx:_update_chunk_dense, the centers_new sums).  Process
+ * wide; read when a workspace is sized and prepared, so set it before vidseg_kmeans_workspace_bytes.
+ *   1  (default; VIDSEG_KMEANS_MSTEP=0 in the environment selects 0) the sums of all runs are one int8 tensor-core
+ *      product: rows carried as 48-bit fixed point in six signed base-256 digit planes, labels as a 0/1 matrix,
+ *      tcgen05.mma.kind::i8 accumulating in int32 -- exact integer arithmetic, independent of tiling and order;
+ *   0  float64 accumulation in shared memory in a fixed slab order.
+ * Both produce the same `partial` [R, K, D+1] float64 array up to the last bit of float64 rounding. */
+int vidseg_set_kmeans_mstep(int mode);
+int vidseg_get_kmeans_mstep(void);
+
 /* mean-centre (sequential fp32 column sums, as numpy's X.mean(axis=0)),
  * tolerance mean(var(X,0))*tol_rel, float64 squared row norms; registers the
  * problem shape with the workspace (host side) and resets the per-run state. */

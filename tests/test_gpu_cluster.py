@@ -144,3 +144,67 @@ def test_feature_extraction_main_layout(cuda, tmp_path):
     assert np.array_equal(ref_mask, g["ref_mask"])
     ctree = sorted(os.path.relpath(os.path.join(d, f), tmp_path) for d, _, fs in os.walk(mask_folder + "_corrected") for f in fs)
     assert ctree == list(g["corrected_tree"])
+
+
+@pytest.mark.parametrize("n,d,k,rows", [(1500, 72, 7, (0, 1500)), (4096, 640, 20, (0, 4096)), (1500, 72, 7, (300, 1111)),
+                                        (14336, 640, 20, (0, 14336))])
+def test_mstep_tensor_core_sums_match_float64_sums(cuda, n, d, k, rows):
+    """The int8 tensor-core M-step (exact fixed-point sums) against the float64 shared-memory M-step on the same
+    labels: counts identical, sums equal to float64 rounding, and against a numpy float64 sum of the centred rows."""
+    from vidseg_diffusion_b200 import _lib
+    from vidseg_diffusion_b200.distributed import CudaLloydBackend
+    from vidseg_diffusion_b200.kmeans import draw_kmeanspp_randoms
+    lib = _lib.load()
+    r = np.random.RandomState(n + d + k)
+    scale = np.exp(r.uniform(-6, 1, size=d)).astype(np.float32)        # columns of very different magnitude
+    X = torch.from_numpy((r.standard_normal((n, d)).astype(np.float32) * scale + 0.3).astype(np.float32)).to(cuda)
+    np.random.seed(5)
+    first, rand = draw_kmeanspp_randoms(n, k, 10)
+    out = {}
+    keep = lib.vidseg_get_kmeans_mstep()
+    try:
+        for mode in (0, 1):
+            _lib.check(lib.vidseg_set_kmeans_mstep(mode), "set_kmeans_mstep")
+            be = CudaLloydBackend(k, 10, 300, 1e-4)
+            be.prepare(X)
+            be.seed(first, rand)
+            be.assign(0, n)
+            partial, _ = be.partial(*rows)
+            out[mode] = partial.cpu().numpy()
+            be.assign(0, n)   # labels unchanged; exercises a second pass over the same buffers
+            again, _ = be.partial(*rows)
+            assert np.array_equal(again.cpu().numpy(), out[mode])
+            be.release()
+    finally:
+        lib.vidseg_set_kmeans_mstep(keep)
+    assert np.array_equal(out[0][..., d], out[1][..., d])
+    assert out[1][..., d].sum() == 10 * (rows[1] - rows[0])
+    ref_mag = np.abs(out[0][..., :d]).max(axis=(0, 1), keepdims=True) + 1e-30
+    # fixed point: every element is rounded to 2^-46 of the largest centred magnitude (most are exact); the float64
+    # chain rounds at 2^-53 of its running sum
+    xc = X.double().cpu().numpy()
+    xmax = float(np.abs(xc - xc.mean(0, keepdims=True)).max())
+    err = np.abs(out[0][..., :d] - out[1][..., :d])
+    assert float(err.max()) <= (rows[1] - rows[0]) * xmax * 2.0 ** -46, float(err.max())
+    assert float((err / ref_mag).max()) < 1e-6
+
+
+def test_kmeans_fit_identical_under_both_msteps(cuda):
+    from vidseg_diffusion_b200 import _lib
+    from vidseg_diffusion_b200.kmeans import KMeans
+    lib = _lib.load()
+    r = np.random.RandomState(3)
+    X = torch.from_numpy(r.standard_normal((3000, 64)).astype(np.float32)).to(cuda)   # no structure: many iterations
+    res = {}
+    keep = lib.vidseg_get_kmeans_mstep()
+    try:
+        for mode in (0, 1):
+            _lib.check(lib.vidseg_set_kmeans_mstep(mode), "set_kmeans_mstep")
+            np.random.seed(2)
+            km = KMeans(n_clusters=9, n_init=10)
+            res[mode] = (km.fit_predict(X).cpu().numpy(), km.cluster_centers_.cpu().numpy(), km.n_iter_)
+    finally:
+        lib.vidseg_set_kmeans_mstep(keep)
+    assert np.array_equal(res[0][0], res[1][0])
+    assert res[0][2] == res[1][2]
+    assert np.allclose(res[0][1], res[1][1], atol=1e-6)

@@ -53,6 +53,8 @@ SIGNATURES = {
     "vidseg_gemm_geglu_split": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_set_operand_mode": (c_int, [c_int]),
     "vidseg_get_operand_mode": (c_int, []),
+    "vidseg_set_kmeans_mstep": (c_int, [c_int]),
+    "vidseg_get_kmeans_mstep": (c_int, []),
     "vidseg_split_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_int, c_void_p]),
     "vidseg_conv_temporal_split": (c_int, [c_void_p] * 12 + [c_int] * 5 + [c_float, c_void_p]),
     "vidseg_temporal_attention": (c_int, [c_void_p] * 6 + [c_int] * 4 + [c_float, c_void_p]),

@@ -17,6 +17,7 @@
 //   * HBM-bound streaming: per Lloyd iteration X (N*D*4 bytes) is read once by the E-step and once
 //     by the M-step; at the clip sizes of BASELINE.json X is L2-resident (36.7 MB < 126 MB).
 #include <mutex>
+#include <atomic>
 #include <unordered_map>
 #include <vector>
 
@@ -33,6 +34,14 @@ constexpr int kPotParts = kPotBlocks * kPotWarps;
 constexpr int kSlabs = 32;           // row slabs of the M-step partial sums
 constexpr int kColTile = 128;        // columns per M-step block
 constexpr int kScanChunk = 4096;
+constexpr int kMqPlanes = 6;         // signed base-256 digits of the 48-bit fixed-point rows
+constexpr int kMqFracBits = 35;      // q = rint(x * s * 2^35) with |x s| < 2^11  ->  |q| < 2^46
+constexpr int kMqStages = 6;         // 32 KB per stage: one-hot tile + digit tile
+constexpr int kMqSplit = 2;          // CTAs sharing one output tile's reduction range
+constexpr int kMqBK = 128;           // rows (reduction index) per stage: 128 int8 = one 128-byte swizzle row
+constexpr int kMqThreads = 192;      // TMA warp, MMA warp, 4 epilogue warps
+constexpr int kOhRows = 16;          // points per thread in the one-hot kernel (one 16-byte store per cluster)
+constexpr int kOhThreads = 128;
 
 struct KmLayout {
   int n, d, k, r, t;
@@ -40,10 +49,27 @@ struct KmLayout {
   int max_iter;
   size_t xc, mean, var, xx, closest, newdist, potpart, cand, pot, centers, cnorm, center_idx, labels, part, partcnt,
       partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, xs_hi, xs_lo, cs_hi, cs_lo, sdot,
-      absmax, amb_list, upd_cnt, upd_argmax, upd_shift, upd_ticket, total;
+      absmax, amb_list, upd_cnt, upd_argmax, upd_shift, upd_ticket, mq_planes, mq_onehot, mq_cnt, mq_part, total;
   int rk_pad;   // R*K rounded up to a multiple of 8 (row length of the tensor-core score matrix)
   int use_tc;   // E-step on the tensor cores (needs D % 8 == 0)
+  int use_mq;   // M-step sums as an exact int8 tensor-core product (fixed-point digit planes x one-hot labels)
+  int n_pad;    // rows rounded up to the 128-row reduction block of that product
+  int mq_blocks;  // one-hot blocks per run (count partials)
+  CUtensorMap tm_onehot, tm_planes;
 };
+
+// M-step variant: 1 = exact int8 tensor-core sums (default), 0 = float64 shared-memory sums (km_partial_kernel).
+// vidseg_set_kmeans_mstep() or VIDSEG_KMEANS_MSTEP=0/1; read when a workspace is sized / prepared.
+static std::atomic<int> g_km_mstep{-1};
+static int km_mstep_mode() {
+  int m = g_km_mstep.load(std::memory_order_relaxed);
+  if (m < 0) {
+    const char* e = getenv("VIDSEG_KMEANS_MSTEP");
+    m = (e && e[0] == '0') ? 0 : 1;
+    g_km_mstep.store(m, std::memory_order_relaxed);
+  }
+  return m;
+}
 
 static KmLayout km_layout(int n, int d, int k, int r, int t) {
   KmLayout L{};
@@ -88,6 +114,15 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
     L.cs_lo = take((size_t)L.rk_pad * d * 2);
     L.sdot = take((size_t)n * L.rk_pad * 4);
     L.amb_list = take((size_t)n * r * 8);
+  }
+  L.n_pad = (n + kMqBK - 1) / kMqBK * kMqBK;
+  L.mq_blocks = (L.n_pad / kOhRows + kOhThreads - 1) / kOhThreads;
+  L.use_mq = (L.use_tc && km_mstep_mode() != 0 && n <= (1 << 17) && d % 4 == 0) ? 1 : 0;
+  if (L.use_mq) {
+    L.mq_planes = take((size_t)kMqPlanes * d * L.n_pad);
+    L.mq_onehot = take((size_t)r * k * L.n_pad);
+    L.mq_cnt = take((size_t)r * L.mq_blocks * k * 4);
+    L.mq_part = take((size_t)kMqSplit * kMqPlanes * r * k * d * 4);
   }
   L.total = off;
   return L;
@@ -148,6 +183,68 @@ __global__ void __launch_bounds__(32) km_colstats_kernel(const float* __restrict
     s2 = __fadd_rn(s2, __fmul_rn(t, t));
   }
   var[col] = (float)((double)s2 / (double)n);
+}
+
+// Same arithmetic (one sequential fp32 chain per column, rows in order), fed through an 8-deep cp.async ring so that
+// ~500 rows of the 32-column strip are in flight instead of 32: the chain of adds, not the load latency, sets the time.
+constexpr int kCsRows = 64, kCsStages = 8, kCsThreads = 256;
+__global__ void __launch_bounds__(kCsThreads) km_colstats_ring_kernel(const float* __restrict__ x, int n, int d,
+                                                                      float* __restrict__ mean, float* __restrict__ var) {
+  extern __shared__ __align__(16) float ring[];   // [stage][row][32]
+  const int c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = (n + kCsRows - 1) / kCsRows;
+  const int cols = min(32, d - c0);               // multiple of 4
+  auto issue = [&](int chunk) {
+    if (chunk < n_chunks) {
+      float* dst = ring + (size_t)(chunk % kCsStages) * kCsRows * 32;
+      for (int e = threadIdx.x; e < kCsRows * 8; e += kCsThreads) {
+        const int row = e >> 3, seg = e & 7;
+        const int gi = chunk * kCsRows + row;
+        if (gi < n && seg * 4 < cols) {
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + row * 32 + seg * 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + (size_t)gi * d + c0 + seg * 4) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  float m = 0.f;
+  for (int pass = 0; pass < 2; ++pass) {
+    float s = 0.f;
+    for (int c = 0; c < kCsStages - 1; ++c) issue(c);
+    for (int chunk = 0; chunk < n_chunks; ++chunk) {
+      asm volatile("cp.async.wait_group %0;" ::"n"(kCsStages - 2) : "memory");
+      __syncthreads();                        // chunk landed for everyone; the slot of chunk-1 is free again
+      issue(chunk + kCsStages - 1);
+      if (warp == 0) {
+        const float* src = ring + (size_t)(chunk % kCsStages) * kCsRows * 32 + lane;
+        const int rows = min(kCsRows, n - chunk * kCsRows);
+        if (rows == kCsRows) {
+          float v[kCsRows];
+#pragma unroll
+          for (int u = 0; u < kCsRows; ++u) v[u] = src[u * 32];
+          if (pass == 0) {
+#pragma unroll
+            for (int u = 0; u < kCsRows; ++u) s = __fadd_rn(s, v[u]);
+          } else {
+#pragma unroll
+            for (int u = 0; u < kCsRows; ++u) { const float t = __fsub_rn(v[u], m); s = __fadd_rn(s, __fmul_rn(t, t)); }
+          }
+        } else {
+          for (int u = 0; u < rows; ++u) {
+            const float v = src[u * 32];
+            if (pass == 0) s = __fadd_rn(s, v);
+            else { const float t = __fsub_rn(v, m); s = __fadd_rn(s, __fmul_rn(t, t)); }
+          }
+        }
+      }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    if (pass == 0) m = (float)((double)s / (double)n);   // only warp 0's value is used
+    else if (warp == 0 && lane < cols) { mean[c0 + lane] = m; var[c0 + lane] = (float)((double)s / (double)n); }
+  }
 }
 
 // tol = mean(var) * tol_rel (sklearn/_kmeans.py:285-294); also resets the per-run state.
@@ -304,14 +401,26 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
   __shared__ double s_vals[kMaxTrials];
   __shared__ int s_cnt[kMaxTrials];
   __shared__ int s_best;
-  __shared__ float s_run;
+  __shared__ float s_run[2];   // running sum entering chunk i lives in slot i & 1
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
-  if (tid < prev_t) {
-    const double* pp = potpart + ((size_t)r * t_stride + tid) * kPotParts;
-    double s = 0.0;
-    for (int i = 0; i < kPotParts; ++i) s += pp[i];
-    s_pot[tid] = (float)s;
+  // potentials: the kPotParts partials of every candidate are fetched by the whole block (one thread walking 512
+  // dependent global loads cost 40 us), then added in the same fixed order as before
+  {
+    double* stage = reinterpret_cast<double*>(buf);   // kScanChunk floats = 2048 doubles >= 4 * kPotParts
+    static_assert(kScanChunk * 4 >= 4 * kPotParts * 8, "staging buffer too small");
+    for (int t0 = 0; t0 < prev_t; t0 += 4) {
+      const int tn = min(4, prev_t - t0);
+      for (int e = tid; e < tn * kPotParts; e += blockDim.x)
+        stage[e] = potpart[((size_t)r * t_stride + t0 + e / kPotParts) * kPotParts + (e % kPotParts)];
+      __syncthreads();
+      if (tid < tn) {
+        double s = 0.0;
+        for (int i = 0; i < kPotParts; ++i) s += stage[tid * kPotParts + i];
+        s_pot[t0 + tid] = (float)s;
+      }
+      __syncthreads();
+    }
   }
   if (tid < kMaxTrials) s_cnt[tid] = 0;
   __syncthreads();
@@ -322,7 +431,7 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
     s_best = best;
     pot[r] = s_pot[best];
     center_idx[r * k + c] = cand[r * kMaxTrials + best];
-    s_run = 0.f;
+    s_run[0] = 0.f;
   }
   __syncthreads();
   const int best = s_best;
@@ -334,9 +443,14 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
   __syncthreads();  // cand[] of this step fully consumed before it is overwritten below
   const float* src = newdist + ((size_t)r * t_stride + best) * n;
   float* dst = closest + (size_t)r * n;
-  int cnt[kMaxTrials];
-#pragma unroll
-  for (int t = 0; t < kMaxTrials; ++t) cnt[t] = 0;
+  // searchsorted(cumsum, v) = index of the first running sum >= v (the sums are non-decreasing).  One thread walks the
+  // chain -- 4 cycles per dependent fp32 add is the floor -- and records the running sum only at 16-element group ends;
+  // the crossing group of every v is then found in parallel and replayed from its recorded start value (same adds in
+  // the same order: the same floats as np.cumsum).
+  constexpr int kGrp = 16;
+  __shared__ float bound[kScanChunk / kGrp];
+  __shared__ int s_found[kMaxTrials];
+  if (tid < kMaxTrials) s_found[tid] = 0;
   for (int base = 0; base < n; base += kScanChunk) {
     const int len = min(kScanChunk, n - base);
     for (int j = tid; j < len; j += blockDim.x) {
@@ -346,38 +460,60 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
     }
     __syncthreads();
     if (!more) { __syncthreads(); continue; }
+    const int ngroups = (len + kGrp - 1) / kGrp;
+    const int slot = (base / kScanChunk) & 1;
+    const float run_in = s_run[slot];
     if (tid == 0) {
-      float run = s_run;
+      float run = run_in;
       int j = 0;
-      for (; j + 8 <= len; j += 8) {
-        float v[8];
+      float v[kGrp], w[kGrp];
+      if (len >= kGrp) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = buf[j + u];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { run = __fadd_rn(run, v[u]); buf[j + u] = run; }
+        for (int u = 0; u < kGrp; u += 4) *reinterpret_cast<float4*>(&v[u]) = *reinterpret_cast<const float4*>(&buf[u]);
       }
-      for (; j < len; ++j) { run = __fadd_rn(run, buf[j]); buf[j] = run; }
-      s_run = run;
+      for (; j + kGrp <= len; j += kGrp) {
+        const bool nxt = (j + 2 * kGrp <= len);
+        if (nxt) {   // next group's loads are issued before this group's adds
+#pragma unroll
+          for (int u = 0; u < kGrp; u += 4)
+            *reinterpret_cast<float4*>(&w[u]) = *reinterpret_cast<const float4*>(&buf[j + kGrp + u]);
+        }
+#pragma unroll
+        for (int u = 0; u < kGrp; ++u) run = __fadd_rn(run, v[u]);
+        bound[j / kGrp] = run;
+#pragma unroll
+        for (int u = 0; u < kGrp; ++u) v[u] = w[u];
+      }
+      if (j < len) {
+        for (; j < len; ++j) run = __fadd_rn(run, buf[j]);
+        bound[ngroups - 1] = run;
+      }
+      s_run[slot ^ 1] = run;
     }
     __syncthreads();
-    for (int j = tid; j < len; j += blockDim.x) {
-      const double v = (double)buf[j];
-#pragma unroll
-      for (int t = 0; t < kMaxTrials; ++t)
-        if (t < t_count) cnt[t] += (v < s_vals[t]) ? 1 : 0;
+    // warp t looks for the crossing group of value t
+    const int wid = tid >> 5, lane = tid & 31;
+    if (wid < t_count && !s_found[wid]) {
+      const double v = s_vals[wid];
+      int below = 0;
+      for (int g = lane; g < ngroups; g += 32) below += ((double)bound[g] < v) ? 1 : 0;
+      below = warp_sum(below);
+      if (below < ngroups && lane == 0) {
+        float run = (below == 0) ? run_in : bound[below - 1];
+        const int j0 = below * kGrp, j1 = min(len, j0 + kGrp);
+        int idx = j0;
+        for (int j = j0; j < j1; ++j) {
+          run = __fadd_rn(run, buf[j]);
+          if ((double)run < v) ++idx; else break;
+        }
+        s_cnt[wid] = base + idx;
+        s_found[wid] = 1;
+      }
     }
     __syncthreads();
   }
   if (!more) return;
-#pragma unroll
-  for (int t = 0; t < kMaxTrials; ++t) {
-    if (t < t_count) {
-      const int s = warp_sum(cnt[t]);
-      if ((tid & 31) == 0 && s) atomicAdd(&s_cnt[t], s);
-    }
-  }
-  __syncthreads();
-  if (tid < t_count) cand[r * kMaxTrials + tid] = min(s_cnt[tid], n - 1);  // np.clip(.., None, n-1)
+  if (tid < t_count) cand[r * kMaxTrials + tid] = s_found[tid] ? min(s_cnt[tid], n - 1) : n - 1;  // np.clip(.., None, n-1)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -701,6 +837,219 @@ km_partial_kernel(const float* __restrict__ x, int n, int d, int k, int runs, in
           for (int i = r0; i < r1; ++i) cnt += (lab[q][i] == j);
           partcnt[((size_t)(rb + q) * kSlabs + slab) * k + j] = cnt;
         }
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------
+// Lloyd M-step on the tensor cores, exact by construction.
+//
+// The cluster sums of all runs are ONE product  sums[r*K + j][c] = sum_i onehot[r*K + j][i] * x[i][c]  with a 0/1
+// left operand.  Floating-point tensor-core accumulation would make the result depend on the (unspecified) order of
+// the adds; integers do not.  Each centred value is therefore carried as a 48-bit fixed-point number
+// q = rint(x * s * 2^35) (s = the power-of-two operand scale of the E-step, |x s| < 2^11), written once per fit as six
+// SIGNED base-256 digit planes [6][D][N_pad] int8 (row index contiguous: the reduction dimension of the MMA).  Per
+// iteration the labels become an int8 one-hot matrix [R*K][N_pad] and tcgen05.mma.kind::i8 accumulates
+// digit-plane x one-hot in int32 (|sum| <= N * 128 < 2^31; N <= 2^17 keeps the 48-bit total inside int64): every product and every add is exact, so
+// sum_p 256^p * acc_p is THE integer sum of the q_i, independent of tiling and order.  Values with magnitude below
+// 2^-22 of the data's maximum lose bits below 2^-47 of that maximum in the conversion (the float64 chain of
+// km_partial_kernel rounds at 2^-53 of the running sum); everything else is exact, which the float64 chain is not.
+// Cost per iteration at N = 14336, D = 640, R*K = 200: 22 G int8 MACs on the tensor cores instead of 9 M float64
+// read-modify-writes per SM in shared memory.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+km_quantize_kernel(const float* __restrict__ x, int n, int n_pad, int d, const unsigned* __restrict__ absmax,
+                   int8_t* __restrict__ planes) {
+  __shared__ __align__(16) int8_t dig[kMqPlanes][32][kMqBK + 4];   // [plane][column][row]
+  const int i0 = blockIdx.x * kMqBK, c0 = blockIdx.y * 32;
+  const double scale = (double)km_operand_scale(absmax[0]) * (double)(1ll << kMqFracBits);
+  for (int e = threadIdx.x; e < kMqBK * 32; e += blockDim.x) {
+    const int i = e >> 5, c = e & 31;
+    long long q = 0;
+    if (i0 + i < n && c0 + c < d) q = __double2ll_rn((double)x[(size_t)(i0 + i) * d + c0 + c] * scale);
+#pragma unroll
+    for (int p = 0; p < kMqPlanes; ++p) {
+      const int dgt = (int)((q + 128) & 255) - 128;   // balanced digit in [-128, 127]
+      q = (q - dgt) >> 8;
+      dig[p][c][i] = (int8_t)dgt;
+    }
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < kMqPlanes * 32 * (kMqBK / 4); e += blockDim.x) {
+    const int iw = e & 31, c = (e >> 5) & 31, p = e >> 10;
+    if (c0 + c < d)
+      *reinterpret_cast<uint32_t*>(planes + ((size_t)p * d + c0 + c) * n_pad + i0 + iw * 4) =
+          *reinterpret_cast<const uint32_t*>(&dig[p][c][iw * 4]);
+  }
+}
+
+// labels -> one-hot rows (every byte of an active run's rows is rewritten, so no clearing pass) + per-block counts
+__global__ void __launch_bounds__(kOhThreads)
+km_onehot_kernel(const int* __restrict__ labels, int n, int n_pad, int k, int row_begin, int row_end,
+                 const int* __restrict__ flags, int8_t* __restrict__ onehot, int* __restrict__ cntpart) {
+  extern __shared__ int hist[];  // [k]
+  const int r = blockIdx.y;
+  if (flags[r * 4 + 0]) return;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) hist[j] = 0;
+  __syncthreads();
+  const int i0 = (blockIdx.x * kOhThreads + threadIdx.x) * kOhRows;
+  if (i0 < n_pad) {
+    int lab[kOhRows];
+    const int* lr = labels + (size_t)r * n;
+#pragma unroll
+    for (int u = 0; u < kOhRows; ++u) {
+      const int i = i0 + u;
+      lab[u] = (i >= row_begin && i < row_end) ? lr[i] : -1;
+      if (lab[u] >= 0) atomicAdd(&hist[lab[u]], 1);
+    }
+    int8_t* orow = onehot + (size_t)r * k * n_pad + i0;
+    for (int j = 0; j < k; ++j) {
+      uint32_t w[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        w[q] = (lab[4 * q] == j ? 1u : 0u) | (lab[4 * q + 1] == j ? 0x100u : 0u) | (lab[4 * q + 2] == j ? 0x10000u : 0u) |
+               (lab[4 * q + 3] == j ? 0x1000000u : 0u);
+      *reinterpret_cast<uint4*>(orow + (size_t)j * n_pad) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  __syncthreads();
+  for (int j = threadIdx.x; j < k; j += blockDim.x) cntpart[((size_t)r * gridDim.x + blockIdx.x) * k + j] = hist[j];
+}
+
+struct MqParams {
+  int kb_lo, kb_hi, kb_per_split, m_tiles, n_tiles, rk, d, k, runs;
+  int* out;          // [split][plane][rk][d] int32
+  const int* flags;
+};
+
+__global__ void __launch_bounds__(kMqThreads, 1)
+km_mstep_mma_kernel(const __grid_constant__ CUtensorMap tm_onehot, const __grid_constant__ CUtensorMap tm_planes,
+                    const MqParams p) {
+  extern __shared__ __align__(1024) uint8_t mq_smem_raw[];
+  constexpr int kTile = 128 * kMqBK;              // bytes of one operand tile (128 rows x 128 int8)
+  constexpr int kStageBytes = 2 * kTile;
+  int item = blockIdx.x;
+  const int nt = item % p.n_tiles; item /= p.n_tiles;
+  const int mt = item % p.m_tiles; item /= p.m_tiles;
+  const int pl = item % kMqPlanes;
+  const int sp = item / kMqPlanes;
+  const int m0 = mt * 128, n0 = nt * 128;
+  {  // a tile whose runs have all converged has nothing to add (uniform: decided before any barrier exists)
+    const int r_lo = m0 / p.k, r_hi = min(p.runs - 1, (m0 + 127) / p.k);
+    bool live = false;
+    for (int r = r_lo; r <= r_hi; ++r) live |= (p.flags[r * 4 + 0] == 0);
+    if (!live) return;
+  }
+  const int kb0 = p.kb_lo + sp * p.kb_per_split, kb1 = min(p.kb_hi, kb0 + p.kb_per_split);
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)mq_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kMqStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kMqStages;
+  uint64_t* acc_bar = empty_bar + kMqStages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    tc::prefetch_tmap(&tm_onehot);
+    tc::prefetch_tmap(&tm_planes);
+    for (int s = 0; s < kMqStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(acc_bar, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == 1) tc::tmem_alloc<128>(tmem_ptr);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        tc::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * kStageBytes;
+        tc::mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+        // the maps are declared over 16-bit elements: 64 of them per 128-byte row of int8
+        tc::tma_load_2d(st, &tm_onehot, &full_bar[stage], kb * (kMqBK / 2), m0);
+        tc::tma_load_3d(st + kTile, &tm_planes, &full_bar[stage], kb * (kMqBK / 2), n0, pl);
+        if (++stage == kMqStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_i8(128, 128);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        tc::mbar_wait(&full_bar[stage], phase);
+        tc::tc_fence_after();
+        const uint32_t sa = tc::smem_u32(smem + stage * kStageBytes);
+        const uint64_t a = tc::make_sw128_desc(sa), b = tc::make_sw128_desc(sa + kTile);
+#pragma unroll
+        for (int ks = 0; ks < kMqBK / 32; ++ks) {
+          const uint64_t adv = (uint64_t)(ks * 32 >> 4);
+          tc::umma_i8(tmem_base, a + adv, b + adv, idesc, (kb > kb0 || ks > 0) ? 1u : 0u);
+        }
+        tc::umma_commit(&empty_bar[stage]);
+        if (++stage == kMqStages) { stage = 0; phase ^= 1; }
+      }
+      tc::umma_commit(acc_bar);
+    }
+  } else {
+    // epilogue: warp w reads TMEM lanes 32*(w%4) .. +31 (its hardware quadrant); lane = one output row
+    const int quad = warp & 3;
+    const int row = m0 + quad * 32 + lane;
+    tc::mbar_wait(acc_bar, 0);
+    tc::tc_fence_after();
+    int* orow = p.out + (((size_t)sp * kMqPlanes + pl) * p.rk + row) * p.d + n0;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      uint32_t v[32];
+      tc::tmem_ld_32x32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(cc * 32), v);
+      tc::tmem_wait_ld();
+      if (row < p.rk) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int c = n0 + cc * 32 + q * 4;
+          if (c < p.d)   // d % 4 == 0
+            *reinterpret_cast<int4*>(orow + cc * 32 + q * 4) =
+                make_int4((int)v[4 * q], (int)v[4 * q + 1], (int)v[4 * q + 2], (int)v[4 * q + 3]);
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<128>(tmem_base);
+}
+
+// sum over splits and digit planes (exact in int64), back to float64, plus the counts -> partial [R, K, D+1]
+__global__ void __launch_bounds__(256)
+km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cntpart, int cnt_blocks, int d, int k,
+                        int rk, const int* __restrict__ flags, const unsigned* __restrict__ absmax,
+                        double* __restrict__ partial, const int* __restrict__ changed_ws, int* __restrict__ changed_out) {
+  const int r = blockIdx.y, j = blockIdx.x;
+  if (j == 0 && threadIdx.x == 0 && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+  if (flags[r * 4 + 0]) return;
+  const double inv = 1.0 / ((double)km_operand_scale(absmax[0]) * (double)(1ll << kMqFracBits));
+  double* o = partial + ((size_t)r * k + j) * (d + 1);
+  const size_t row = (size_t)r * k + j;
+  for (int c = threadIdx.x; c < d; c += blockDim.x) {
+    int v[kMqSplit * kMqPlanes];
+#pragma unroll
+    for (int e = 0; e < kMqSplit * kMqPlanes; ++e) v[e] = part[((size_t)e * rk + row) * d + c];   // all in flight
+    long long tot = 0;
+#pragma unroll
+    for (int p = kMqPlanes - 1; p >= 0; --p) {
+      long long dsum = 0;
+#pragma unroll
+      for (int s = 0; s < kMqSplit; ++s) dsum += v[s * kMqPlanes + p];
+      tot = tot * 256 + dsum;
+    }
+    o[c] = (double)tot * inv;   // |tot| < 2^24 * 2^46: the conversion may round once at 2^-53 relative
+  }
+  if (threadIdx.x == 0) {
+    long long cnt = 0;
+    for (int b = 0; b < cnt_blocks; ++b) cnt += cntpart[((size_t)r * cnt_blocks + b) * k + j];
+    o[d] = (double)cnt;
   }
 }
 
@@ -1215,6 +1564,13 @@ static KnnLayout knn_layout(int nr, int nq, int d) {
 
 using namespace vidseg;
 
+VS_API int vidseg_set_kmeans_mstep(int mode) {
+  VS_REQUIRE(mode == 0 || mode == 1, "mode must be 0 (float64 sums) or 1 (int8 tensor-core sums)");
+  g_km_mstep.store(mode, std::memory_order_relaxed);
+  return 0;
+}
+VS_API int vidseg_get_kmeans_mstep(void) { return km_mstep_mode(); }
+
 VS_API size_t vidseg_kmeans_workspace_bytes(int n, int d, int k, int n_init, int n_trials) {
   if (n <= 0 || d <= 0 || k <= 0 || n_init <= 0 || n_trials <= 0 || n_trials > kMaxTrials) return 0;
   return km_layout(n, d, k, n_init, n_trials).total;
@@ -1231,12 +1587,29 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
   L.max_iter = max_iter;
   if (workspace_bytes < L.total)
     return set_error(VIDSEG_E_WORKSPACE, "%s: need %lld bytes, got %lld", "k-means workspace", (long long)L.total, (long long)workspace_bytes);
+  void* ws = workspace;
+  if (L.use_mq) {
+    // int8 tiles described as 16-bit elements (two per element): 64 per 128-byte swizzle row
+    const uint64_t d_oh[2] = {(uint64_t)L.n_pad / 2, (uint64_t)n_init * k}, s_oh[1] = {(uint64_t)L.n_pad};
+    const uint32_t b_oh[2] = {kMqBK / 2, 128};
+    if (int e = encode_tmap_16bit(&L.tm_onehot, at<int8_t>(ws, L.mq_onehot), 2, d_oh, s_oh, b_oh)) return e;
+    const uint64_t d_pl[3] = {(uint64_t)L.n_pad / 2, (uint64_t)d, (uint64_t)kMqPlanes};
+    const uint64_t s_pl[2] = {(uint64_t)L.n_pad, (uint64_t)d * L.n_pad};
+    const uint32_t b_pl[3] = {kMqBK / 2, 128, 1};
+    if (int e = encode_tmap_16bit(&L.tm_planes, at<int8_t>(ws, L.mq_planes), 3, d_pl, s_pl, b_pl)) return e;
+  }
   {
     std::lock_guard<std::mutex> lk(g_km_mu);
     g_km_registry[workspace] = L;
   }
-  void* ws = workspace;
-  VS_LAUNCH(km_colstats_kernel, (d + 31) / 32, 32, 0, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
+  if (d % 4 == 0 && ((uintptr_t)x % 16) == 0) {
+    constexpr int kCsSmem = kCsStages * kCsRows * 32 * 4;
+    static cudaError_t attr_cs = cudaFuncSetAttribute(km_colstats_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmem);
+    VS_CHECK_CUDA(attr_cs);
+    VS_LAUNCH(km_colstats_ring_kernel, (d + 31) / 32, kCsThreads, kCsSmem, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
+  } else {
+    VS_LAUNCH(km_colstats_kernel, (d + 31) / 32, 32, 0, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
+  }
   VS_POST_LAUNCH();
   VS_LAUNCH(km_tol_reset_kernel, 1, 256, 0, stream, at<float>(ws, L.var), d, tol_rel, at<float>(ws, L.tol),
             at<unsigned>(ws, L.absmax), at<int>(ws, L.flags), at<int>(ws, L.changed), n_init);
@@ -1246,6 +1619,11 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
   VS_POST_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.labels), 0xFF, (size_t)n_init * n * 4, (cudaStream_t)stream));
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.upd_ticket), 0, (size_t)n_init * 4, (cudaStream_t)stream));
+  if (L.use_mq) {
+    VS_LAUNCH(km_quantize_kernel, dim3(L.n_pad / kMqBK, (d + 31) / 32), 256, 0, stream, at<float>(ws, L.xc), n, L.n_pad, d,
+              at<unsigned>(ws, L.absmax), at<int8_t>(ws, L.mq_planes));
+    VS_POST_LAUNCH();
+  }
   if (L.use_tc) {
     const size_t tot = (size_t)n * d;
     VS_LAUNCH(km_split_scaled_kernel, (int)std::min<size_t>((tot + 255) / 256, (size_t)kNumSMs * 16), 256, 0, stream,
@@ -1302,6 +1680,39 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
   if (changed == nullptr) changed = at<int>(ws, L.changed);
+  if (L.use_mq) {
+    VS_LAUNCH(km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
+              L.k, row_begin, row_end, at<int>(ws, L.flags), at<int8_t>(ws, L.mq_onehot), at<int>(ws, L.mq_cnt));
+    VS_POST_LAUNCH();
+    MqParams mp{};
+    mp.kb_lo = row_begin / kMqBK;
+    mp.kb_hi = (row_end + kMqBK - 1) / kMqBK;
+    mp.kb_per_split = (mp.kb_hi - mp.kb_lo + kMqSplit - 1) / kMqSplit;
+    mp.rk = L.r * L.k;
+    mp.d = L.d;
+    mp.k = L.k;
+    mp.runs = L.r;
+    mp.m_tiles = (mp.rk + 127) / 128;
+    mp.n_tiles = (L.d + 127) / 128;
+    mp.out = at<int>(ws, L.mq_part);
+    mp.flags = at<int>(ws, L.flags);
+    constexpr size_t kMqSmem = (size_t)kMqStages * 2 * 128 * kMqBK + 1024 + 256;
+    static cudaError_t attr_mq = cudaFuncSetAttribute(km_mstep_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMqSmem);
+    VS_CHECK_CUDA(attr_mq);
+    if (mp.kb_hi > mp.kb_lo) {
+      const double macs = (double)mp.m_tiles * 128 * mp.n_tiles * 128 * kMqPlanes * (double)(mp.kb_hi - mp.kb_lo) * kMqBK;
+      VS_LAUNCH_W(2.0 * macs, km_mstep_mma_kernel, mp.m_tiles * mp.n_tiles * kMqPlanes * kMqSplit, kMqThreads, kMqSmem, stream,
+                  L.tm_onehot, L.tm_planes, mp);
+      VS_POST_LAUNCH();
+    } else {
+      VS_CHECK_CUDA(cudaMemsetAsync(mp.out, 0, (size_t)kMqSplit * kMqPlanes * mp.rk * L.d * 4, (cudaStream_t)stream));
+    }
+    VS_LAUNCH(km_mstep_combine_kernel, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
+              L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
+              changed);
+    VS_POST_LAUNCH();
+    return 0;
+  }
   const size_t smem1 = (size_t)L.k * kColTile * 8;
   VS_REQUIRE(smem1 <= 200 * 1024, "k too large for the M-step kernel");
   if (false && 2 * smem1 <= 96 * 1024) {   // two runs per pass over X: measured slower (83 vs 72 us) -- the adds bound it

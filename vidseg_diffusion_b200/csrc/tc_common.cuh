@@ -322,6 +322,20 @@ __device__ __forceinline__ void umma_f8(uint32_t tmem_d, uint64_t desc_a, uint64
       : "memory");
 }
 
+// Instruction descriptor for kind::i8: signed 8-bit operands (a/b_format = 1), 32-bit integer accumulation (c_format = 2)
+__host__ __device__ constexpr uint32_t make_idesc_i8(int m, int n) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem], int8 operands, int32 accumulators, K = 32 per instruction
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 }  // namespace tc
 
 // library-wide operand policy (vidseg_set_operand_mode): 0 = pair16 everywhere, 1 = packed8 wherever the channel count allows
