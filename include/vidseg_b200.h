@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);  /* 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
+int vidseg_abi_version(void);  /* 5: + sampler_step, set/get_kmeans_mstep; 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -193,6 +193,23 @@ size_t vidseg_knn_workspace_bytes(int n_ref, int n_query, int d);
 int vidseg_knn_predict(const float* ref, const int32_t* ref_labels, int n_ref, const float* query, int n_query, int d,
                        int k, int32_t* labels_out, int32_t* err_flag, void* workspace, size_t workspace_bytes,
                        void* stream);
+
+/* -------------------------------------------------------------------------
+ * R7  Sampler step
+ * One Euler step of the EDM sampler on the latent, fused: replaces the elementwise chain between two UNet calls of
+ * EDMSampler.sampler_step (sgm/modules/diffusionmodules/sampling.py:102-132: Denoiser.forward's
+ * net * c_out + input * c_skip, denoiser.py:41-48; the guider's x_u + scale * (x_c - x_u), guiders.py:28-31, 81-90;
+ * to_d, sampling_utils.py:34-35; euler_step, sampling.py:92-93) and the latent blending of
+ * EulerEDMSampler.__call__ (sampling.py:229-250: x * mask + ori_xt * (1 - mask), mask upsampled nearest-neighbour).
+ * Same IEEE fp32 operations in the same order as the reference's eager chain: bit-identical given the same network output.
+ *   x [B,C,H,W]; net [G*B,C,H,W] (G = 2 when guided: unconditional half first); c_skip, c_out [G*B]; scale [B]
+ *   (guided only); sigma_hat, sigma_next [B]; mask [B, mask_h, mask_w] fp32 or fp64 (mask_is_f64: the blend then runs
+ *   in float64 and is rounded once, as torch's type promotion does) with ori_xt [B,C,H,W], or both null; out [B,C,H,W].
+ * ------------------------------------------------------------------------- */
+int vidseg_sampler_step(const float* x, const float* net, const float* c_skip, const float* c_out, const float* scale,
+                        const float* sigma_hat, const float* sigma_next, const void* mask, int mask_is_f64,
+                        const float* ori_xt, float* out, int batch, int channels, int height, int width, int mask_h,
+                        int mask_w, int guided, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * A1-A8  UNet forward on the tcgen05 tensor cores

@@ -1,0 +1,120 @@
+"""Pin oracle/sampler.py to the UNMODIFIED reference sampler and write the sampler goldens.
+
+Run in the authoring container only (needs /root/reference):
+    python tests/golden/make_sampler_goldens.py
+The reference ``EulerEDMSampler`` + ``DiscreteDenoiser(EpsScaling)`` + ``VanillaCFG`` (configs/inference/sd_2_1.yaml:7-16,
+63-79) drive the reference ``UNetModel`` (tiny width, seeded synthetic weights) wrapped in the reference
+``OpenAIWrapper``, fp32 on the CPU, exactly as scripts/sampling/svd_single_video_inference.py:146-160, 322-330 does:
+  run A  plain: 6-step schedule, t_start = 2 (steps 2..5); the img_callback writes the stashed q / k of output blocks 7
+         and 8 and x_t as ``.pt`` files in the reference's feature_maps layout (svd_single_video_inference.py:113-130);
+  run B  mask modulation at steps 3 and 4, feature injection from step 3 on, latent blending on steps 3..4, reading those files.
+What is stored comes from the REFERENCE runs.  The oracle loop (oracle/sampler.py) with the same reference UNet as its
+network must reproduce both runs bit for bit.
+"""
+import os
+import sys
+import tempfile
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+sys.path.insert(0, os.path.join(HERE, ".."))
+
+from oracle import sampler as osamp  # noqa: E402
+from oracle import unet as ounet  # noqa: E402
+from oracle.ref_import import import_reference  # noqa: E402
+from synth import synthetic_modulate_params, synthetic_unet_inputs, synthetic_unet_weights  # noqa: E402
+
+SEED, F, HW, L, STEPS, T_START = 3, 2, 16, 7, 6, 2
+BLOCKS = (7, 8)
+
+
+def sampler_modulate_params(seed, frames, tokens, **extra):
+    """The request svd_single_video_inference.py:438-500 builds for one modulated run (values seeded)."""
+    mp = synthetic_modulate_params(seed, frames, tokens)
+    mp.update(modulate_timestep=[3, 4], modulate_timestep_frames={}, is_injected_features=True, modulate_lambda_start=60.0,
+              modulate_lambda_end=25.0,
+              injected_block_types=["output"], output_block_indices=list(BLOCKS), input_block_indices=[],
+              injected_feature_types=["spatial_self_attn_q", "spatial_self_attn_k"], latent_mask_start=3, latent_mask_end=4)
+    mp.update(extra)
+    return mp
+
+
+def main():
+    om = import_reference("sgm.modules.diffusionmodules.openaimodel")
+    rs = import_reference("sgm.modules.diffusionmodules.sampling")
+    rd = import_reference("sgm.modules.diffusionmodules.denoiser")
+    rw = import_reference("sgm.modules.diffusionmodules.wrappers")
+    cfg = ounet.TINY_CONFIG
+    model = om.UNetModel(use_checkpoint=False, use_linear_in_transformer=True, transformer_depth=1, **cfg).eval()
+    shapes = ounet.param_shapes(cfg)
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(shapes, SEED).items()}
+    model.load_state_dict(sd, strict=True)
+    net = rw.OpenAIWrapper(model)
+    ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    den = rd.DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                              num_idx=1000, discretization_config=ddpm)
+    smp = rs.EulerEDMSampler(discretization_config=ddpm, num_steps=STEPS, device="cpu", s_churn=0.0, s_tmin=0.0, s_tmax=999.0,
+                             s_noise=1.0, guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                                                         "params": {"scale": 5.0}})
+    x, _, ctx = synthetic_unet_inputs(SEED, F, HW, cfg["in_channels"], L, cfg["context_dim"])
+    latent = torch.from_numpy(x)[:F].contiguous()   # the synthetic UNet batch is already CFG-doubled: one half here
+    ctx = torch.from_numpy(ctx)[:F].contiguous()
+    c, uc = {"crossattn": ctx}, {"crossattn": torch.zeros_like(ctx) + 0.05 * ctx.flip(0)}
+
+    def denoiser(inp, sigma, cc, **kw):
+        return den(net, inp, sigma, cc, **kw)
+
+    with tempfile.TemporaryDirectory() as root, torch.no_grad():
+        fm = os.path.join(root, "src", "feature_maps")
+        os.makedirs(fm)
+        per_step = {}
+
+        def save_cb(xt, i):   # svd_single_video_inference.py:110-130
+            for b in BLOCKS:
+                tb = model.output_blocks[b][1].transformer_blocks[0]
+                torch.save(tb.attn1.q.clone(), os.path.join(fm, f"output_block_{b}_spatial_self_attn_q_time_{i}.pt"))
+                torch.save(tb.attn1.k.clone(), os.path.join(fm, f"output_block_{b}_spatial_self_attn_k_time_{i}.pt"))
+            torch.save(xt.clone(), os.path.join(fm, f"xt_time_{i}.pt"))
+            per_step[i] = xt.clone()
+
+        out_a = smp(denoiser, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=T_START)
+        mp = sampler_modulate_params(SEED, F, (HW // 2) ** 2, feature_folder=root, exp_name="src")
+        mp_t = dict(mp, feature_masks=[torch.from_numpy(m) for m in mp["feature_masks"]])
+        out_b = smp(denoiser, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=mp_t, t_start=T_START,
+                    is_latent_blending=True, feature_height=HW // 2, feature_width=HW // 2)
+        # float64 masks (what the reference script builds: numpy / 255.0): the blend is promoted to float64
+        mp_64 = dict(mp, feature_masks=[torch.from_numpy(m.astype(np.float64) * 0.75) for m in mp["feature_masks"]])
+        out_b64 = smp(denoiser, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=mp_64, t_start=T_START,
+                      is_latent_blending=True, feature_height=HW // 2, feature_width=HW // 2)
+
+        # ---- the oracle loop on the same network must agree bit for bit
+        def network(x_in, c_noise, cond, **flags):
+            return net(x_in, c_noise, cond, **flags)
+
+        sig = osamp.legacy_ddpm_sigmas(STEPS)
+        assert torch.equal(sig, smp.discretization(STEPS, device="cpu"))
+        quant = osamp.make_discrete_quantizer(1000)
+        o_a = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.eps_scaling, 5.0, quant, t_start=T_START)
+        xt_store = {f"xt_time_{i}": v for i, v in per_step.items()}
+        o_b = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.eps_scaling, 5.0, quant, t_start=T_START,
+                                     is_modulate=True, modulate_params=dict(mp_t), is_latent_blending=True,
+                                     feature_height=HW // 2, feature_width=HW // 2, xt_store=xt_store)
+        o_b64 = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.eps_scaling, 5.0, quant, t_start=T_START,
+                                       is_modulate=True, modulate_params=dict(mp_64), is_latent_blending=True,
+                                       feature_height=HW // 2, feature_width=HW // 2, xt_store=xt_store)
+        assert torch.equal(o_a, out_a) and torch.equal(o_b, out_b) and torch.equal(o_b64, out_b64)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        print("oracle == reference on runs A, B, B64; modulation+injection+blending changed the result by",
+              f"{rel(out_b, out_a):.2e}; float64 masks by {rel(out_b64, out_b):.2e}; |x| max {float(out_a.abs().max()):.3f}")
+        assert rel(out_b, out_a) > 1e-2
+    np.savez_compressed(os.path.join(HERE, "sampler_tiny.npz"), latent=latent.numpy(), ctx=ctx.numpy(),
+                        uctx=uc["crossattn"].numpy(), out_a=out_a.numpy(), out_b=out_b.numpy(), out_b64=out_b64.numpy(),
+                        steps_a=np.stack([per_step[i].numpy() for i in sorted(per_step)]), sigmas=sig.numpy(),
+                        meta=np.array([SEED, F, HW, L, STEPS, T_START]))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,110 @@
+"""Sampler row without a GPU: the oracle loop with the oracle UNet against the goldens the
+reference sampler produced (tests/golden/make_sampler_goldens.py), and the host mirror's schedules / configuration."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sampler as osamp
+from oracle import unet as ounet
+from synth import synthetic_unet_weights
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sampler_tiny.npz")
+BLOCKS = (7, 8)
+
+
+def modulate_params_for(seed, frames, tokens, **extra):
+    from golden.make_sampler_goldens import sampler_modulate_params
+    return sampler_modulate_params(seed, frames, tokens, **extra)
+
+
+def relerr(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return float((a - b).abs().max() / b.abs().max())
+
+
+def test_oracle_loop_with_oracle_unet_matches_reference_goldens():
+    g = np.load(GOLDEN)
+    seed, F, hw, L, steps, t_start = (int(v) for v in g["meta"])
+    cfg = ounet.TINY_CONFIG
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ounet.param_shapes(cfg), seed).items()}
+    latent, ctx, uctx = (torch.from_numpy(g[k]) for k in ("latent", "ctx", "uctx"))
+    c, uc = {"crossattn": ctx}, {"crossattn": uctx}
+    store = {}
+    last = {}
+
+    def network(x_in, c_noise, cond, is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        inj = None
+        if is_injected_step:
+            mp = modulate_params
+            inj = dict(block_types=mp["injected_block_types"], input_block_indices=mp["input_block_indices"],
+                       output_block_indices=mp["output_block_indices"], feature_types=mp["injected_feature_types"],
+                       timestep=mp["timestep"], features=store)
+        last.clear()
+        return ounet.unet_forward(sd, cfg, x_in, c_noise, cond["crossattn"], last,
+                                  modulate_params=modulate_params if is_modulate_step else None, injection=inj)
+
+    def save_cb(xt, i):
+        for b in BLOCKS:
+            for n in ("q", "k"):
+                store[f"output_block_{b}_spatial_self_attn_{n}_time_{i}"] = last[(f"output_block_{b}", f"spatial_self_attn_{n}")].clone()
+        store[f"xt_time_{i}"] = xt.clone()
+
+    sig = osamp.legacy_ddpm_sigmas(steps)
+    assert np.array_equal(sig.numpy(), g["sigmas"])
+    quant = osamp.make_discrete_quantizer(1000)
+    out_a = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.eps_scaling, 5.0, quant, t_start=t_start,
+                                   img_callback=save_cb)
+    assert relerr(out_a, g["out_a"]) < 2e-5
+    for n, i in enumerate(range(t_start, steps)):
+        assert relerr(store[f"xt_time_{i}"], g["steps_a"][n]) < 2e-5
+    mp = modulate_params_for(seed, F, (hw // 2) ** 2)
+    for key, masks in (("out_b", [torch.from_numpy(m) for m in mp["feature_masks"]]),
+                       ("out_b64", [torch.from_numpy(m.astype(np.float64) * 0.75) for m in mp["feature_masks"]])):
+        out = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.eps_scaling, 5.0, quant, t_start=t_start,
+                                     is_modulate=True, modulate_params=dict(mp, feature_masks=masks), is_latent_blending=True,
+                                     feature_height=hw // 2, feature_width=hw // 2, xt_store=store)
+        assert relerr(out, g[key]) < 5e-5, key
+        assert relerr(out, g["out_a"]) > 1e-2
+
+
+def test_host_mirror_builds_from_the_reference_config_and_matches_the_schedules():
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    smp = instantiate_from_config({   # configs/inference/sd_2_1.yaml:63-79
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"discretization_config": ddpm, "num_steps": 6, "s_churn": 0, "s_tmin": 0, "s_tmax": 999, "s_noise": 1,
+                   "device": "cpu",
+                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 5}}}})
+    assert type(smp).__module__.startswith("vidseg_diffusion_b200.")
+    g = np.load(GOLDEN)
+    assert np.array_equal(smp.discretization(6, device="cpu").numpy(), g["sigmas"])
+    den = instantiate_from_config({   # sd_2_1.yaml:7-16
+        "target": "sgm.modules.diffusionmodules.denoiser.DiscreteDenoiser",
+        "params": {"num_idx": 1000, "discretization_config": ddpm,
+                   "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}}})
+    assert torch.equal(den.sigmas, osamp.legacy_ddpm_sigmas(1000, append_zero=False, flip=True))
+    s = torch.tensor([14.0, 0.7, 0.03])
+    assert torch.equal(den.possibly_quantize_sigma(s), osamp.make_discrete_quantizer(1000)[0](s))
+    # SVD: EDM schedule with sigma_max 700, linear guidance over the frames (configs/inference/svd.yaml)
+    edm = instantiate_from_config({"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                                   "params": {"sigma_max": 700.0}})
+    assert torch.equal(edm(25), osamp.edm_sigmas(25, sigma_max=700.0))
+    lin = instantiate_from_config({"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                                   "params": {"max_scale": 2.5, "min_scale": 1.0, "num_frames": 14}})
+    sc = lin.sample_scales(28, "cpu")
+    assert sc.shape == (28,) and torch.equal(sc[:14], torch.linspace(1.0, 2.5, 14)) and torch.equal(sc[14:], sc[:14])
+    x = torch.randn(56, 4, 3, 3)
+    want = lin(x, None)
+    x_u, x_c = x.chunk(2)
+    assert torch.equal(want, x_u + sc[:, None, None, None] * (x_c - x_u))
+
+
+def test_sampler_step_fails_loudly_without_cuda():
+    from vidseg_diffusion_b200 import _lib
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.sampling import fused_step
+    x = torch.zeros(2, 4, 8, 8)
+    one = torch.ones(2)
+    with pytest.raises(_lib.VidsegError):
+        fused_step(x, x, one, one, None, one, one)

@@ -53,6 +53,7 @@ SIGNATURES = {
     "vidseg_gemm_geglu_split": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_set_operand_mode": (c_int, [c_int]),
     "vidseg_get_operand_mode": (c_int, []),
+    "vidseg_sampler_step": (c_int, [c_void_p] * 8 + [c_int, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "vidseg_set_kmeans_mstep": (c_int, [c_int]),
     "vidseg_get_kmeans_mstep": (c_int, []),
     "vidseg_split_rows": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_float, c_int, c_void_p]),

@@ -28,7 +28,8 @@
 namespace vidseg {
 
 constexpr int kMaxTrials = 8;
-constexpr int kPotBlocks = 64;       // row blocks per run in the seeding distance kernel
+constexpr int kPotBlocks = 148;      // row blocks of the seeding distance kernels (one per SM)
+constexpr int kInertiaBlocks = 64;   // row blocks per run of the inertia kernel
 constexpr int kPotWarps = 8;         // warps per block there
 constexpr int kPotParts = kPotBlocks * kPotWarps;
 constexpr int kSlabs = 32;           // row slabs of the M-step partial sums
@@ -95,7 +96,7 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
   L.changed = take((size_t)r * 4);
   L.flags = take((size_t)r * 4 * 4);  // done, strict, n_iter, reserved
   L.tol = take(16);
-  L.inertia_part = take((size_t)r * kPotBlocks * 8);
+  L.inertia_part = take((size_t)r * kInertiaBlocks * 8);
   L.inertia = take((size_t)r * 8);
   L.same = take((size_t)r * r * 4);
   L.rand = take((size_t)r * (k > 1 ? k - 1 : 1) * t * 8);
@@ -186,23 +187,24 @@ __global__ void __launch_bounds__(32) km_colstats_kernel(const float* __restrict
 }
 
 // Same arithmetic (one sequential fp32 chain per column, rows in order), fed through an 8-deep cp.async ring so that
-// ~500 rows of the 32-column strip are in flight instead of 32: the chain of adds, not the load latency, sets the time.
-constexpr int kCsRows = 64, kCsStages = 8, kCsThreads = 256;
+// ~900 rows of an 8-column strip (80 blocks at D = 640) are in flight instead of 32: the chain of adds, not the load latency, sets the time.
+constexpr int kCsCols = 8, kCsRows = 128, kCsStages = 8, kCsThreads = 256;
 __global__ void __launch_bounds__(kCsThreads) km_colstats_ring_kernel(const float* __restrict__ x, int n, int d,
                                                                       float* __restrict__ mean, float* __restrict__ var) {
-  extern __shared__ __align__(16) float ring[];   // [stage][row][32]
-  const int c0 = blockIdx.x * 32;
+  extern __shared__ __align__(16) float ring[];   // [stage][row][kCsCols]
+  const int c0 = blockIdx.x * kCsCols;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int n_chunks = (n + kCsRows - 1) / kCsRows;
-  const int cols = min(32, d - c0);               // multiple of 4
+  const int cols = min(kCsCols, d - c0);          // multiple of 4
+  constexpr int kSegs = kCsCols / 4;
   auto issue = [&](int chunk) {
     if (chunk < n_chunks) {
-      float* dst = ring + (size_t)(chunk % kCsStages) * kCsRows * 32;
-      for (int e = threadIdx.x; e < kCsRows * 8; e += kCsThreads) {
-        const int row = e >> 3, seg = e & 7;
+      float* dst = ring + (size_t)(chunk % kCsStages) * kCsRows * kCsCols;
+      for (int e = threadIdx.x; e < kCsRows * kSegs; e += kCsThreads) {
+        const int row = e / kSegs, seg = e % kSegs;
         const int gi = chunk * kCsRows + row;
         if (gi < n && seg * 4 < cols) {
-          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + row * 32 + seg * 4);
+          const unsigned sa = (unsigned)__cvta_generic_to_shared(dst + row * kCsCols + seg * 4);
           asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(x + (size_t)gi * d + c0 + seg * 4) : "memory");
         }
       }
@@ -217,13 +219,13 @@ __global__ void __launch_bounds__(kCsThreads) km_colstats_ring_kernel(const floa
       asm volatile("cp.async.wait_group %0;" ::"n"(kCsStages - 2) : "memory");
       __syncthreads();                        // chunk landed for everyone; the slot of chunk-1 is free again
       issue(chunk + kCsStages - 1);
-      if (warp == 0) {
-        const float* src = ring + (size_t)(chunk % kCsStages) * kCsRows * 32 + lane;
+      if (warp == 0 && lane < kCsCols) {
+        const float* src = ring + (size_t)(chunk % kCsStages) * kCsRows * kCsCols + lane;
         const int rows = min(kCsRows, n - chunk * kCsRows);
         if (rows == kCsRows) {
           float v[kCsRows];
 #pragma unroll
-          for (int u = 0; u < kCsRows; ++u) v[u] = src[u * 32];
+          for (int u = 0; u < kCsRows; ++u) v[u] = src[u * kCsCols];
           if (pass == 0) {
 #pragma unroll
             for (int u = 0; u < kCsRows; ++u) s = __fadd_rn(s, v[u]);
@@ -233,7 +235,7 @@ __global__ void __launch_bounds__(kCsThreads) km_colstats_ring_kernel(const floa
           }
         } else {
           for (int u = 0; u < rows; ++u) {
-            const float v = src[u * 32];
+            const float v = src[u * kCsCols];
             if (pass == 0) s = __fadd_rn(s, v);
             else { const float t = __fsub_rn(v, m); s = __fadd_rn(s, __fmul_rn(t, t)); }
           }
@@ -265,7 +267,7 @@ __global__ void km_tol_reset_kernel(const float* __restrict__ var, int d, float 
   }
   for (int i = threadIdx.x; i < r * 4; i += blockDim.x) flags[i] = 0;
   for (int i = threadIdx.x; i < r; i += blockDim.x) changed[i] = 0;
-  if (threadIdx.x == 0) absmax[0] = 0u;
+  if (threadIdx.x == 0) { absmax[0] = 0u; absmax[1] = 0u; absmax[2] = 0u; }   // |x| max, ambiguity count, its ticket
 }
 
 // xc = x - mean (fp32), xx = float64 squared norm of the centred fp32 row.  Warp per row.
@@ -372,6 +374,140 @@ km_kpp_dist_kernel(const float* __restrict__ xc, const double* __restrict__ xx, 
   if (lane < T) potpart[((size_t)r * t_stride + lane) * kPotParts + gwarp] = potacc;
 }
 
+// The same distances for ALL runs from one pass over X: the kernel above re-reads X once per run (R x 36.7 MB from L2
+// per seeding step, which is what bounded it).  Here the candidates of every run sit in shared memory as doubles
+// ([R][T][d], 205 KB at R = 10, T = 4, d = 640), a warp keeps four rows of X in registers as doubles and walks the
+// runs; per (row, candidate) the lane chains and the butterfly are those of the per-run kernel, so the distances are
+// bit-identical to it.
+// Sum NV values across the warp with the halving butterfly: after the step with lane mask o a lane keeps only the half
+// of the values selected by its bit o, so 16 values cost 15 exchanges instead of 80.  Every value is still combined
+// pairwise over lane masks 16, 8, 4, 2, 1 in that order -- the adds (and so the bits) of warp_sum(double).
+// Result: value index (lane >> 1) for NV = 16, lane for NV = 32.
+template <int NV>
+__device__ __forceinline__ double warp_sum_halving(double (&v)[NV], int lane) {
+  static_assert(NV == 16 || NV == 32, "16 or 32 values");
+  double cur[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) cur[i] = v[i];
+  int o = 16;
+#pragma unroll
+  for (int cnt = NV / 2; cnt >= 1; cnt >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < cnt; ++i) {
+      const double lo = cur[i], hi = cur[i + cnt];
+      const double send = up ? lo : hi, keep = up ? hi : lo;
+      cur[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+    }
+    o >>= 1;
+  }
+  if (NV == 16) cur[0] += __shfl_xor_sync(0xffffffffu, cur[0], 1);
+  return cur[0];
+}
+
+template <int T, int CH>   // CH = 32-column chunks held in registers per row (d <= 32 * CH)
+__global__ void __launch_bounds__(kPotWarps * 32, 1)
+km_kpp_dist_all_kernel(const float* __restrict__ xc, const double* __restrict__ xx, int n, int d, int runs,
+                       const int* __restrict__ cand, const float* __restrict__ closest, int use_min,
+                       float* __restrict__ newdist, double* __restrict__ potpart, int t_stride) {
+  constexpr int NV = (kPotRows * T <= 16) ? 16 : 32;   // (row, candidate) pairs reduced together
+  extern __shared__ double cs[];  // [runs][T][d], then candidate norms [runs][T], then potentials [warps][runs][NV]
+  double* cxx = cs + (size_t)runs * T * d;
+  double* pot_sm = cxx + runs * T;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int rt = warp; rt < runs * T; rt += kPotWarps) {   // a warp per candidate row: all its loads in flight at once
+    const int src = cand[(rt / T) * kMaxTrials + (rt % T)];
+    const float* xr = xc + (size_t)src * d;
+    float tmp[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) tmp[i] = (lane + 32 * i < d) ? xr[lane + 32 * i] : 0.f;
+#pragma unroll
+    for (int i = 0; i < CH; ++i)
+      if (lane + 32 * i < d) cs[(size_t)rt * d + lane + 32 * i] = (double)tmp[i];
+    if (lane == 0) cxx[rt] = xx[src];
+  }
+  for (int e = threadIdx.x; e < kPotWarps * runs * NV; e += blockDim.x) pot_sm[e] = 0.0;
+  __syncthreads();
+  const int gwarp = blockIdx.x * kPotWarps + warp;
+  double* my_pot = pot_sm + (size_t)warp * runs * NV;
+  const int kk = (NV == 16) ? (lane >> 1) : lane;        // the pair this lane finalises
+  const int my_q = kk / T, my_t = kk - my_q * T;
+  const bool owner = (NV == 32 || (lane & 1) == 0) && kk < kPotRows * T;
+  for (int row0 = gwarp; row0 < n; row0 += kPotParts * kPotRows) {
+    double xv[kPotRows][CH];
+#pragma unroll
+    for (int q = 0; q < kPotRows; ++q) {
+      const int row = row0 + q * kPotParts;
+      const float* xr = xc + (size_t)(row < n ? row : row0) * d;   // out-of-range rows recompute row0 and are discarded
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int c = lane + 32 * i;
+        xv[q][i] = (c < d) ? (double)xr[c] : 0.0;
+      }
+    }
+    const int my_row = row0 + my_q * kPotParts;
+    const bool live = owner && my_row < n;
+    const double my_xx = live ? xx[my_row] : 0.0;
+    for (int r = 0; r < runs; ++r) {
+      double acc[NV];
+#pragma unroll
+      for (int e = 0; e < NV; ++e) acc[e] = 0.0;
+      const double* cr = cs + (size_t)r * T * d;
+#pragma unroll
+      for (int i = 0; i < CH; ++i) {
+        const int c = lane + 32 * i;
+        if (32 * i < d) {                       // uniform
+          const int cc = min(c, d - 1);         // a lane past the row end multiplies by its zero x value
+#pragma unroll
+          for (int t = 0; t < T; ++t) {
+            const double cv = cr[t * d + cc];
+#pragma unroll
+            for (int q = 0; q < kPotRows; ++q) acc[q * T + t] = fma(xv[q][i], cv, acc[q * T + t]);
+          }
+        }
+      }
+      const double mine = warp_sum_halving<NV>(acc, lane);
+      if (live) {
+        double dd = -2.0 * mine;
+        dd += cxx[r * T + my_t];
+        dd += my_xx;
+        float f = (float)dd;
+        f = fmaxf(f, 0.f);
+        if (use_min) f = fminf(closest[(size_t)r * n + my_row], f);
+        newdist[((size_t)r * t_stride + my_t) * n + my_row] = f;
+        my_pot[r * NV + kk] += (double)f;
+      }
+    }
+  }
+  __syncwarp();
+  for (int e = lane; e < runs * T; e += 32) {
+    const int r = e / T, t = e - r * T;
+    double tot = 0.0;
+#pragma unroll
+    for (int q = 0; q < kPotRows; ++q) tot += my_pot[r * NV + q * T + t];   // fixed order
+    potpart[((size_t)r * t_stride + t) * kPotParts + gwarp] = tot;
+  }
+}
+
+typedef void (*KppDistAllFn)(const float*, const double*, int, int, int, const int*, const float*, int, float*, double*, int);
+template <int CH>
+static KppDistAllFn kpp_dist_all_fn_ch(int t) {
+  switch (t) {
+    case 1: return km_kpp_dist_all_kernel<1, CH>;
+    case 2: return km_kpp_dist_all_kernel<2, CH>;
+    case 3: return km_kpp_dist_all_kernel<3, CH>;
+    case 4: return km_kpp_dist_all_kernel<4, CH>;
+    case 5: return km_kpp_dist_all_kernel<5, CH>;
+    case 6: return km_kpp_dist_all_kernel<6, CH>;
+    default: return nullptr;
+  }
+}
+static KppDistAllFn kpp_dist_all_fn(int t, int d) {
+  if (d <= 128) return kpp_dist_all_fn_ch<4>(t);
+  if (d <= 640) return kpp_dist_all_fn_ch<20>(t);
+  return nullptr;
+}
+
 typedef void (*KppDistFn)(const float*, const double*, int, int, const int*, const float*, int, float*, double*, int);
 static KppDistFn kpp_dist_fn(int t) {
   switch (t) {
@@ -396,7 +532,7 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
                           int prev_t, const double* __restrict__ potpart, const float* __restrict__ newdist,
                           float* __restrict__ closest, int* __restrict__ cand, float* __restrict__ pot,
                           float* __restrict__ centers, int* __restrict__ center_idx, const double* __restrict__ rand) {
-  __shared__ float buf[kScanChunk];
+  __shared__ __align__(16) float buf[kScanChunk];
   __shared__ float s_pot[kMaxTrials];
   __shared__ double s_vals[kMaxTrials];
   __shared__ int s_cnt[kMaxTrials];
@@ -404,23 +540,15 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
   __shared__ float s_run[2];   // running sum entering chunk i lives in slot i & 1
   const int r = blockIdx.x;
   const int tid = threadIdx.x;
-  // potentials: the kPotParts partials of every candidate are fetched by the whole block (one thread walking 512
-  // dependent global loads cost 40 us), then added in the same fixed order as before
-  {
-    double* stage = reinterpret_cast<double*>(buf);   // kScanChunk floats = 2048 doubles >= 4 * kPotParts
-    static_assert(kScanChunk * 4 >= 4 * kPotParts * 8, "staging buffer too small");
-    for (int t0 = 0; t0 < prev_t; t0 += 4) {
-      const int tn = min(4, prev_t - t0);
-      for (int e = tid; e < tn * kPotParts; e += blockDim.x)
-        stage[e] = potpart[((size_t)r * t_stride + t0 + e / kPotParts) * kPotParts + (e % kPotParts)];
-      __syncthreads();
-      if (tid < tn) {
-        double s = 0.0;
-        for (int i = 0; i < kPotParts; ++i) s += stage[tid * kPotParts + i];
-        s_pot[t0 + tid] = (float)s;
-      }
-      __syncthreads();
-    }
+  // potentials: warp t adds the kPotParts partials of candidate t -- lane-strided chains, then the fixed butterfly
+  // (one thread walking the partials was 512 dependent global loads, 40 us)
+  if ((tid >> 5) < prev_t) {
+    const int t = tid >> 5;
+    const double* pp = potpart + ((size_t)r * t_stride + t) * kPotParts;
+    double sacc = 0.0;
+    for (int i = tid & 31; i < kPotParts; i += 32) sacc += pp[i];
+    sacc = warp_sum(sacc);
+    if ((tid & 31) == 0) s_pot[t] = (float)sacc;
   }
   if (tid < kMaxTrials) s_cnt[tid] = 0;
   __syncthreads();
@@ -466,23 +594,34 @@ km_kpp_select_scan_kernel(const float* __restrict__ xc, int n, int d, int k, int
     if (tid == 0) {
       float run = run_in;
       int j = 0;
+      // two groups per trip, no branch around the loads: group j+16 is fetched before the adds of group j and
+      // group j+32 (clamped to the last full group -- a harmless re-read) before the adds of group j+16
+      const int last_full = (len / kGrp - 1) * kGrp;
       float v[kGrp], w[kGrp];
       if (len >= kGrp) {
 #pragma unroll
         for (int u = 0; u < kGrp; u += 4) *reinterpret_cast<float4*>(&v[u]) = *reinterpret_cast<const float4*>(&buf[u]);
       }
-      for (; j + kGrp <= len; j += kGrp) {
-        const bool nxt = (j + 2 * kGrp <= len);
-        if (nxt) {   // next group's loads are issued before this group's adds
+      for (; j + 2 * kGrp <= len; j += 2 * kGrp) {
 #pragma unroll
-          for (int u = 0; u < kGrp; u += 4)
-            *reinterpret_cast<float4*>(&w[u]) = *reinterpret_cast<const float4*>(&buf[j + kGrp + u]);
-        }
+        for (int u = 0; u < kGrp; u += 4)
+          *reinterpret_cast<float4*>(&w[u]) = *reinterpret_cast<const float4*>(&buf[j + kGrp + u]);
 #pragma unroll
         for (int u = 0; u < kGrp; ++u) run = __fadd_rn(run, v[u]);
         bound[j / kGrp] = run;
+        const int nj = min(j + 2 * kGrp, last_full);
 #pragma unroll
-        for (int u = 0; u < kGrp; ++u) v[u] = w[u];
+        for (int u = 0; u < kGrp; u += 4)
+          *reinterpret_cast<float4*>(&v[u]) = *reinterpret_cast<const float4*>(&buf[nj + u]);
+#pragma unroll
+        for (int u = 0; u < kGrp; ++u) run = __fadd_rn(run, w[u]);
+        bound[j / kGrp + 1] = run;
+      }
+      if (j + kGrp <= len) {   // odd number of full groups: v already holds group j
+#pragma unroll
+        for (int u = 0; u < kGrp; ++u) run = __fadd_rn(run, v[u]);
+        bound[j / kGrp] = run;
+        j += kGrp;
       }
       if (j < len) {
         for (; j < len; ++j) run = __fadd_rn(run, buf[j]);
@@ -709,7 +848,7 @@ __global__ void __launch_bounds__(256)
 km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float* __restrict__ centers,
                          const double* __restrict__ cnorm, const double* __restrict__ xx, const float* __restrict__ sdot,
                          int ld, const unsigned* __restrict__ absmax, int* __restrict__ labels, int labels_stride,
-                         int* __restrict__ changed, int count_changes, double band, const int* __restrict__ amb_count,
+                         int* __restrict__ changed, int count_changes, double band, int* __restrict__ amb_count,
                          const int2* __restrict__ amb_list) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -767,6 +906,13 @@ km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float*
       if (count_changes && *lp != bj) atomicAdd(&changed[r], 1);
       *lp = bj;
     }
+  }
+  // the last block to finish clears the list for the next E-step (every block has read the count by then);
+  // amb_count[1] is the ticket
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&amb_count[1], 1) == (int)gridDim.x - 1) { amb_count[0] = 0; amb_count[1] = 0; }
   }
 }
 
@@ -1171,7 +1317,8 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
                      const int* __restrict__ argmax_all, const int* __restrict__ changed_in,
                      int* __restrict__ changed_ws, float* __restrict__ centers, double* __restrict__ cnorm,
                      int* __restrict__ flags, const float* __restrict__ tol, int max_iter, float* __restrict__ shiftsq,
-                     int* __restrict__ ticket) {
+                     int* __restrict__ ticket, const unsigned* __restrict__ absmax, __half* __restrict__ cs_hi,
+                     __half* __restrict__ cs_lo) {
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * kUpdWarps + (threadIdx.x >> 5);
   if (w >= runs * k) return;
@@ -1189,6 +1336,10 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
   const double div = has ? cnt[j] : ((am < j && cnt[am] > 0.0) ? cnt[am] : 1.0);
   const double* prow = pr + (size_t)src * (d + 1);
   float* crow = cr + (size_t)j * d;
+  // the tensor-core E-step reads the centres as scaled fp16 pairs: written here instead of by a pass of their own
+  const float op_scale = cs_hi ? km_operand_scale(absmax[0]) : 1.f;
+  __half* hrow = cs_hi ? cs_hi + ((size_t)r * k + j) * d : nullptr;
+  __half* lrow = cs_hi ? cs_lo + ((size_t)r * k + j) * d : nullptr;
   for (int c0 = lane; c0 < d; c0 += 8 * 32) {   // 8 independent loads in flight; accumulation order unchanged
     double raw[8];
     float ov[8];
@@ -1207,6 +1358,12 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
         ss = fma(df, df, ss);
         nn = fma((double)nv, (double)nv, nn);
         crow[c] = nv;
+        if (hrow) {
+          __half h, l;
+          tc::split_f16(nv * op_scale, h, l);
+          hrow[c] = h;
+          lrow[c] = l;
+        }
       }
     }
   }
@@ -1255,7 +1412,7 @@ km_inertia_kernel(const float* __restrict__ x, int n, int d, int k, int row_begi
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int gwarp = blockIdx.x * 8 + warp;
   double acc = 0.0;
-  for (int row = row_begin + gwarp; row < row_end; row += kPotBlocks * 8) {
+  for (int row = row_begin + gwarp; row < row_end; row += kInertiaBlocks * 8) {
     const float* xr = x + (size_t)row * d;
     const float* cc = centers + ((size_t)r * k + labels[(size_t)r * n + row]) * d;
     double s = 0.0;
@@ -1267,14 +1424,14 @@ km_inertia_kernel(const float* __restrict__ x, int n, int d, int k, int row_begi
   if (threadIdx.x == 0) {
     double t = 0.0;
     for (int w = 0; w < 8; ++w) t += red[w];
-    part[(size_t)r * kPotBlocks + blockIdx.x] = t;
+    part[(size_t)r * kInertiaBlocks + blockIdx.x] = t;
   }
 }
 __global__ void km_inertia_reduce_kernel(const double* __restrict__ part, double* __restrict__ out) {
   const int r = blockIdx.x;
   if (threadIdx.x == 0) {
     double t = 0.0;
-    for (int b = 0; b < kPotBlocks; ++b) t += part[(size_t)r * kPotBlocks + b];
+    for (int b = 0; b < kInertiaBlocks; ++b) t += part[(size_t)r * kInertiaBlocks + b];
     out[r] = t;
   }
 }
@@ -1345,10 +1502,7 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
     return km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers),
                             at<double>(ws, L.cnorm), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed),
                             at<int>(ws, L.flags), count_changes, only_nonstrict, stream);
-  const size_t c_valid = (size_t)L.r * L.k * L.d, c_total = (size_t)L.rk_pad * L.d;
-  VS_LAUNCH(km_split_scaled_kernel, (int)((c_total + 255) / 256), 256, 0, stream, at<float>(ws, L.centers), c_valid, c_total,
-            at<unsigned>(ws, L.absmax), at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo));
-  VS_POST_LAUNCH();
+  // cs_hi / cs_lo: the centres as scaled fp16 pairs, kept current by vidseg_kmeans_seed and km_update_avg_kernel
   if (int e = gemm_split_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
                              at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo),
                              at<float>(ws, L.sdot) + (size_t)row_begin * L.rk_pad, rows, L.rk_pad, L.d, 1.0f, kFamKMeans, stream))
@@ -1358,8 +1512,7 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
   const double band = 2.0 * ((double)L.d * 0x1p-22 + 0x1p-20);
   const long long total = (long long)rows * L.r;
   int* amb_count = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
-  VS_CHECK_CUDA(cudaMemsetAsync(amb_count, 0, 4, (cudaStream_t)stream));
-  const size_t smem = (size_t)L.r * L.k * 16;
+  const size_t smem = (size_t)L.r * L.k * 16;   // amb_count {count, ticket} is cleared by prepare and by every resolve
   VS_REQUIRE(smem <= 48 * 1024, "n_init * k too large for the tensor-core E-step");
   VS_LAUNCH(km_assign_tc_kernel, (int)((total + 255) / 256), 256, smem, stream, L.k, L.r, row_begin, row_end,
             at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
@@ -1603,10 +1756,10 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
     g_km_registry[workspace] = L;
   }
   if (d % 4 == 0 && ((uintptr_t)x % 16) == 0) {
-    constexpr int kCsSmem = kCsStages * kCsRows * 32 * 4;
+    constexpr int kCsSmem = kCsStages * kCsRows * kCsCols * 4;
     static cudaError_t attr_cs = cudaFuncSetAttribute(km_colstats_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kCsSmem);
     VS_CHECK_CUDA(attr_cs);
-    VS_LAUNCH(km_colstats_ring_kernel, (d + 31) / 32, kCsThreads, kCsSmem, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
+    VS_LAUNCH(km_colstats_ring_kernel, (d + kCsCols - 1) / kCsCols, kCsThreads, kCsSmem, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
   } else {
     VS_LAUNCH(km_colstats_kernel, (d + 31) / 32, 32, 0, stream, x, n, d, at<float>(ws, L.mean), at<float>(ws, L.var));
   }
@@ -1647,6 +1800,21 @@ VS_API int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand, void
   dim3 grid(kPotBlocks, L.r);
   for (int c = 0; c < L.k; ++c) {
     const int tc = (c == 0) ? 1 : L.t;
+    // all runs from one pass over X when their candidates fit in shared memory
+    const size_t smem_all = ((size_t)L.r * tc * L.d + (size_t)L.r * tc + (size_t)kPotWarps * L.r * (kPotRows * tc <= 16 ? 16 : 32)) * 8;
+    KppDistAllFn fa = (smem_all <= 220 * 1024) ? kpp_dist_all_fn(tc, L.d) : nullptr;
+    if (fa) {
+      VS_CHECK_CUDA(cudaFuncSetAttribute(fa, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      VS_LAUNCH(fa, kPotBlocks, kPotWarps * 32, smem_all, st, at<float>(ws, L.xc), at<double>(ws, L.xx), L.n, L.d, L.r,
+                at<int>(ws, L.cand), at<float>(ws, L.closest), c > 0 ? 1 : 0, at<float>(ws, L.newdist),
+                at<double>(ws, L.potpart), L.t);
+      VS_POST_LAUNCH();
+      VS_LAUNCH(km_kpp_select_scan_kernel, L.r, 1024, 0, st, at<float>(ws, L.xc), L.n, L.d, L.k, L.t, L.t, c, tc,
+                at<double>(ws, L.potpart), at<float>(ws, L.newdist), at<float>(ws, L.closest), at<int>(ws, L.cand),
+                at<float>(ws, L.pot), at<float>(ws, L.centers), at<int>(ws, L.center_idx), rand);
+      VS_POST_LAUNCH();
+      continue;
+    }
     KppDistFn fn = kpp_dist_fn(tc);
     if (smem > 48 * 1024) VS_CHECK_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VS_LAUNCH(fn, grid, kPotWarps * 32, (size_t)tc * L.d * 8, st, at<float>(ws, L.xc), at<double>(ws, L.xx), L.n, L.d,
@@ -1661,6 +1829,12 @@ VS_API int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand, void
   VS_LAUNCH(km_cnorm_kernel, (L.r * L.k * 32 + 255) / 256, 256, 0, st, at<float>(ws, L.centers), L.d, L.r * L.k,
             at<double>(ws, L.cnorm));
   VS_POST_LAUNCH();
+  if (L.use_tc) {
+    const size_t c_valid = (size_t)L.r * L.k * L.d, c_total = (size_t)L.rk_pad * L.d;   // padding rows are zero
+    VS_LAUNCH(km_split_scaled_kernel, (int)((c_total + 255) / 256), 256, 0, st, at<float>(ws, L.centers), c_valid, c_total,
+              at<unsigned>(ws, L.absmax), at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo));
+    VS_POST_LAUNCH();
+  }
   return 0;
 }
 
@@ -1750,7 +1924,8 @@ VS_API int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double*
   VS_LAUNCH(km_update_avg_kernel, (L.r * L.k + kUpdWarps - 1) / kUpdWarps, kUpdWarps * 32, 0, stream, L.d, L.k, L.r, partial,
             at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax), changed, at<int>(ws, L.changed), at<float>(ws, L.centers),
             at<double>(ws, L.cnorm), at<int>(ws, L.flags), at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.upd_shift),
-            at<int>(ws, L.upd_ticket));
+            at<int>(ws, L.upd_ticket), at<unsigned>(ws, L.absmax), L.use_tc ? at<__half>(ws, L.cs_hi) : nullptr,
+            L.use_tc ? at<__half>(ws, L.cs_lo) : nullptr);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -1792,7 +1967,7 @@ VS_API int vidseg_kmeans_inertia(void* workspace, size_t workspace_bytes, int ro
   if (inertia_partial == nullptr) inertia_partial = at<double>(ws, L.inertia);
   // rerun the E-step of runs that stopped on tolerance / max_iter (sklearn/_kmeans.py:741-753)
   if (int e = km_assign_runs(ws, L, row_begin, row_end, 0, 1, stream)) return e;
-  VS_LAUNCH(km_inertia_kernel, dim3(kPotBlocks, L.r), 256, 0, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin,
+  VS_LAUNCH(km_inertia_kernel, dim3(kInertiaBlocks, L.r), 256, 0, stream, at<float>(ws, L.xc), L.n, L.d, L.k, row_begin,
             row_end, at<float>(ws, L.centers), at<int>(ws, L.labels), at<double>(ws, L.inertia_part));
   VS_POST_LAUNCH();
   VS_LAUNCH(km_inertia_reduce_kernel, L.r, 32, 0, stream, at<double>(ws, L.inertia_part), inertia_partial);
