@@ -116,5 +116,103 @@ def main():
                         meta=np.array([SEED, F, HW, L, STEPS, T_START]))
 
 
+V_SEED, V_F, V_STEPS, V_T_START = 4, 3, 5, 2
+V_TYPES = ["spatial_self_attn_q", "spatial_self_attn_k", "temporal_self_attn_q", "temporal_self_attn_k"]
+
+
+def video_modulate_params(seed, frames, tokens, **extra):
+    mp = synthetic_modulate_params(seed, frames, tokens)
+    mp.update(modulate_layer_type=["spatial", "temporal"], modulate_attn_type=["self_attn", "cross_attn", "ff_out"],
+              modulate_layer_frames={"temporal": [0, 2]}, modulate_lambda_start=40.0, modulate_lambda_end=15.0,
+              modulate_timestep=[3], modulate_timestep_frames={}, is_injected_features=True,
+              injected_block_types=["output"], output_block_indices=[7], input_block_indices=[],
+              injected_feature_types=list(V_TYPES), latent_mask_start=3, latent_mask_end=3)
+    mp.update(extra)
+    return mp
+
+
+def video_inputs(cfg):
+    """Conditioning of one SVD clip as svd_single_video_inference.py builds it: CLIP image token (crossattn), the
+    conditioning-frame latent (concat), fps / motion / cond_aug embeddings (vector); zeros in the unconditional branch."""
+    from synth import synthetic_video_unet_inputs
+    x, _, ctx, y = synthetic_video_unet_inputs(V_SEED, V_F, HW, cfg["in_channels"], cfg["context_dim"], cfg["adm_in_channels"])
+    half = cfg["in_channels"] // 2
+    latent = torch.from_numpy(x[V_F:, :half]).contiguous()
+    c = {"crossattn": torch.from_numpy(ctx[V_F:]).contiguous(), "concat": torch.from_numpy(x[V_F:, half:]).contiguous(),
+         "vector": torch.from_numpy(y[V_F:]).contiguous()}
+    uc = {"crossattn": torch.zeros_like(c["crossattn"]), "concat": torch.zeros_like(c["concat"]), "vector": c["vector"].clone()}
+    return latent, c, uc
+
+
+def main_video():
+    """SVD flavour (configs/inference/svd.yaml): Denoiser(VScalingWithEDMcNoise), EDM schedule with sigma_max = 700,
+    LinearPredictionGuider over the frames, VideoUNet with its extra inputs (svd_single_video_inference.py:316-330)."""
+    from make_video_unet_goldens import build_reference
+    from oracle import video_unet as ov
+    rs = import_reference("sgm.modules.diffusionmodules.sampling")
+    rd = import_reference("sgm.modules.diffusionmodules.denoiser")
+    rw = import_reference("sgm.modules.diffusionmodules.wrappers")
+    cfg = ov.TINY_VIDEO_CONFIG
+    model = build_reference(cfg)
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ov.param_shapes(cfg), V_SEED).items()}
+    model.load_state_dict(sd, strict=True)
+    net = rw.OpenAIWrapper(model)
+    den = rd.Denoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"})
+    smp = rs.EulerEDMSampler(
+        discretization_config={"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization", "params": {"sigma_max": 700.0}},
+        num_steps=V_STEPS, device="cpu",
+        guider_config={"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                       "params": {"max_scale": 2.5, "min_scale": 1.0, "num_frames": V_F}})
+    latent, c, uc = video_inputs(cfg)
+    extra = dict(image_only_indicator=torch.zeros(2, V_F), num_video_frames=V_F)
+
+    def denoiser(inp, sigma, cc, **kw):
+        return den(net, inp, sigma, cc, **kw, **extra)
+
+    with tempfile.TemporaryDirectory() as root, torch.no_grad():
+        fm = os.path.join(root, "src", "feature_maps")
+        os.makedirs(fm)
+        per_step = {}
+
+        def save_cb(xt, i):
+            layer = model.output_blocks[7][1]
+            for ft in V_TYPES:
+                blk = layer.transformer_blocks[0] if ft.startswith("spatial") else layer.time_stack[0]
+                torch.save(getattr(blk.attn1, ft[-1]).clone(), os.path.join(fm, f"output_block_7_{ft}_time_{i}.pt"))
+            torch.save(xt.clone(), os.path.join(fm, f"xt_time_{i}.pt"))
+            per_step[i] = xt.clone()
+
+        out_a = smp(denoiser, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=V_T_START)
+        mp = video_modulate_params(V_SEED, V_F, (HW // 2) ** 2, feature_folder=root, exp_name="src")
+        mp_t = dict(mp, feature_masks=[torch.from_numpy(m) for m in mp["feature_masks"]])
+        out_b = smp(denoiser, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=mp_t, t_start=V_T_START,
+                    is_latent_blending=True, feature_height=HW // 2, feature_width=HW // 2)
+
+        def network(x_in, c_noise, cond, **flags):
+            return net(x_in, c_noise, cond, **flags, **extra)
+
+        sig = osamp.edm_sigmas(V_STEPS, sigma_max=700.0)
+        assert torch.equal(sig, smp.discretization(V_STEPS, device="cpu"))
+        fs = torch.linspace(1.0, 2.5, V_F)
+        o_a = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.v_scaling_edm_cnoise, None, None,
+                                     t_start=V_T_START, frame_scales=fs)
+        o_b = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.v_scaling_edm_cnoise, None, None,
+                                     t_start=V_T_START, frame_scales=fs, is_modulate=True, modulate_params=dict(mp_t),
+                                     is_latent_blending=True, feature_height=HW // 2, feature_width=HW // 2,
+                                     xt_store={f"xt_time_{i}": v for i, v in per_step.items()})
+        assert torch.equal(o_a, out_a) and torch.equal(o_b, out_b)
+        rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+        print("video: oracle == reference on runs A, B; modulation+injection+blending changed the result by",
+              f"{rel(out_b, out_a):.2e}; |x| max {float(out_a.abs().max()):.3f}")
+        assert rel(out_b, out_a) > 1e-2
+    np.savez_compressed(os.path.join(HERE, "sampler_video_tiny.npz"), out_a=out_a.numpy(), out_b=out_b.numpy(),
+                        steps_a=np.stack([per_step[i].numpy() for i in sorted(per_step)]), sigmas=sig.numpy(),
+                        meta=np.array([V_SEED, V_F, HW, V_STEPS, V_T_START]))
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["sd", "video"]
+    if "sd" in which:
+        main()
+    if "video" in which:
+        main_video()

@@ -120,3 +120,52 @@ def test_euler_edm_sampler_matches_reference_goldens(cuda, operand_mode):
     assert torch.equal(out_a2, out_a)
     print({k: f"{v:.2e}" for k, v in errs.items()})
     assert max(errs.values()) <= TOL, errs
+
+
+def test_euler_edm_sampler_on_the_video_unet_matches_reference_goldens(cuda, operand_mode):
+    """SVD flavour (configs/inference/svd.yaml): Denoiser + VScalingWithEDMcNoise, EDM schedule with sigma_max 700,
+    LinearPredictionGuider, VideoUNet with image_only_indicator / num_video_frames; modulation of spatial and temporal
+    layers, injection of spatial and temporal q / k from HBM, latent blending."""
+    from test_gpu_video_unet import build as build_video
+    from test_sampler_host import VGOLDEN, V_TYPES, video_case
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.wrappers import OpenAIWrapper
+    mk, ov, cfg = video_case()
+    g = np.load(VGOLDEN)
+    seed, F, hw, steps, t_start = (int(v) for v in g["meta"])
+    model, _ = build_video(cfg, seed, cuda)
+    smp = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"num_steps": steps, "device": str(cuda),
+                   "discretization_config": {"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                                             "params": {"sigma_max": 700.0}},
+                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                                     "params": {"max_scale": 2.5, "min_scale": 1.0, "num_frames": F}}}})
+    den = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.denoiser.Denoiser",
+        "params": {"scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"}}}).to(cuda)
+    denoiser = den.bind(OpenAIWrapper(model), image_only_indicator=torch.zeros(2, F, device=cuda), num_video_frames=F)
+    latent, c, uc = mk.video_inputs(cfg)
+    latent = latent.to(cuda)
+    c, uc = ({k: v.to(cuda) for k, v in d.items()} for d in (c, uc))
+    store = {}
+
+    def save_cb(xt, i):
+        layer = model.output_blocks[7][1]
+        for ft in V_TYPES:
+            blk = layer.transformer_blocks[0] if ft.startswith("spatial") else layer.time_stack[0]
+            store[f"output_block_7_{ft}_time_{i}"] = getattr(blk.attn1, ft[-1]).clone()
+        store[f"xt_time_{i}"] = xt.clone()
+
+    out_a = smp(denoiser, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=t_start)
+    errs = {"out_a": relerr(out_a, g["out_a"])}
+    for n, i in enumerate(range(t_start, steps)):
+        errs[f"xt_{i}"] = relerr(store[f"xt_time_{i}"], g["steps_a"][n])
+    mp = mk.video_modulate_params(seed, F, (hw // 2) ** 2, features=store)
+    mp["feature_masks"] = [torch.from_numpy(m).to(cuda) for m in mp["feature_masks"]]
+    out_b = smp(denoiser, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=mp, t_start=t_start,
+                is_latent_blending=True, feature_height=hw // 2, feature_width=hw // 2)
+    errs["out_b"] = relerr(out_b, g["out_b"])
+    assert relerr(out_b, g["out_a"]) > 5e-3
+    print({k: f"{v:.2e}" for k, v in errs.items()})
+    assert max(errs.values()) <= TOL, errs

@@ -108,3 +108,54 @@ def test_sampler_step_fails_loudly_without_cuda():
     one = torch.ones(2)
     with pytest.raises(_lib.VidsegError):
         fused_step(x, x, one, one, None, one, one)
+
+
+VGOLDEN = os.path.join(os.path.dirname(__file__), "golden", "sampler_video_tiny.npz")
+V_TYPES = ["spatial_self_attn_q", "spatial_self_attn_k", "temporal_self_attn_q", "temporal_self_attn_k"]
+
+
+def video_case():
+    from golden import make_sampler_goldens as mk
+    from oracle import video_unet as ov
+    return mk, ov, ov.TINY_VIDEO_CONFIG
+
+
+def test_oracle_loop_with_oracle_video_unet_matches_reference_goldens():
+    """SVD flavour: VScalingWithEDMcNoise, EDM schedule (sigma_max 700), LinearPredictionGuider, VideoUNet inputs."""
+    mk, ov, cfg = video_case()
+    g = np.load(VGOLDEN)
+    seed, F, hw, steps, t_start = (int(v) for v in g["meta"])
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ov.param_shapes(cfg), seed).items()}
+    latent, c, uc = mk.video_inputs(cfg)
+    ind = torch.zeros(2, F)
+    store, last = {}, {}
+
+    def network(x_in, c_noise, cond, is_modulate_step=False, is_injected_step=False, modulate_params=None):
+        inj = None
+        if is_injected_step:
+            mp = modulate_params
+            inj = dict(block_types=mp["injected_block_types"], input_block_indices=mp["input_block_indices"],
+                       output_block_indices=mp["output_block_indices"], feature_types=mp["injected_feature_types"],
+                       timestep=mp["timestep"], features=store)
+        last.clear()
+        x_cat = torch.cat((x_in, cond["concat"]), dim=1)   # OpenAIWrapper (wrappers.py:24-34)
+        return ov.video_unet_forward(sd, cfg, x_cat, c_noise, cond["crossattn"], cond["vector"], F, ind, last,
+                                     modulate_params=modulate_params if is_modulate_step else None, injection=inj)
+
+    def save_cb(xt, i):
+        for ft in V_TYPES:
+            store[f"output_block_7_{ft}_time_{i}"] = last[("output_block_7", ft)].clone()
+        store[f"xt_time_{i}"] = xt.clone()
+
+    sig = osamp.edm_sigmas(steps, sigma_max=700.0)
+    assert np.array_equal(sig.numpy(), g["sigmas"])
+    fs = torch.linspace(1.0, 2.5, F)
+    out_a = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.v_scaling_edm_cnoise, None, None,
+                                   t_start=t_start, frame_scales=fs, img_callback=save_cb)
+    assert relerr(out_a, g["out_a"]) < 5e-5
+    mp = mk.video_modulate_params(seed, F, (hw // 2) ** 2)
+    mp["feature_masks"] = [torch.from_numpy(m) for m in mp["feature_masks"]]
+    out_b = osamp.euler_edm_sample(network, latent.clone(), c, uc, sig, osamp.v_scaling_edm_cnoise, None, None,
+                                   t_start=t_start, frame_scales=fs, is_modulate=True, modulate_params=mp,
+                                   is_latent_blending=True, feature_height=hw // 2, feature_width=hw // 2, xt_store=store)
+    assert relerr(out_b, g["out_b"]) < 5e-5 and relerr(out_b, g["out_a"]) > 1e-2
