@@ -240,7 +240,7 @@ def run_reference(args, wl, cfg):
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -432,12 +432,35 @@ def run_b200(args, wl, cfg):
         "cpu_baseline": {"value": (nf / t_cpu if t_cpu == t_cpu else None), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "clocks": clocks,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def guard_stdout():
+    """stdout carries exactly one JSON line: everything libraries print at the C level (the NCCL version banner, cuDNN /
+    driver notices) or through Python's sys.stdout goes to stderr; ``emit`` writes to the original descriptor."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        sys.stdout.buffer.write(data)
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
