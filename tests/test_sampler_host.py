@@ -159,3 +159,40 @@ def test_oracle_loop_with_oracle_video_unet_matches_reference_goldens():
                                    t_start=t_start, frame_scales=fs, is_modulate=True, modulate_params=mp,
                                    is_latent_blending=True, feature_height=hw // 2, feature_width=hw // 2, xt_store=store)
     assert relerr(out_b, g["out_b"]) < 5e-5 and relerr(out_b, g["out_a"]) > 1e-2
+
+
+@pytest.mark.parametrize("flavour", ["sd", "svd"])
+def test_denoiser_mirror_equals_the_oracle_on_cpu(flavour):
+    """Denoiser.forward / .raw are plain torch around the network (the kernels sit inside the network and the fused
+    step): with a toy network they run on the CPU and must equal oracle.denoise bit for bit, quantisation included."""
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(4, 4, 6, 6, generator=g)
+    sigma = torch.tensor([14.1, 3.3, 0.9, 0.05])
+    seen = {}
+
+    def network(x_in, c_noise, cond, **kw):
+        seen["c_noise"], seen["kw"] = c_noise, kw
+        return torch.tanh(x_in) * cond["w"] + 0.01 * c_noise.float()[:, None, None, None]
+
+    cond = {"w": torch.randn(4, 1, 1, 1, generator=g)}
+    if flavour == "sd":
+        ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+        den = instantiate_from_config({"target": "sgm.modules.diffusionmodules.denoiser.DiscreteDenoiser",
+                                       "params": {"num_idx": 1000, "discretization_config": ddpm, "scaling_config": {
+                                           "target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}}})
+        want = osamp.denoise(network, x, sigma, cond, osamp.eps_scaling, osamp.make_discrete_quantizer(1000))
+    else:
+        den = instantiate_from_config({"target": "sgm.modules.diffusionmodules.denoiser.Denoiser", "params": {
+            "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"}}})
+        want = osamp.denoise(network, x, sigma, cond, osamp.v_scaling_edm_cnoise)
+    got = den(network, x, sigma, cond, is_modulate_step=True)
+    assert torch.equal(got, want)
+    assert seen["kw"]["is_modulate_step"] is True and seen["kw"]["is_injected_step"] is False
+    if flavour == "sd":
+        assert seen["c_noise"].dtype == torch.int64       # the UNet's timestep index
+    bound = den.bind(network)
+    net, c_skip, c_out = bound.raw(x, sigma, cond)
+    assert c_skip.shape == c_out.shape == (4,)
+    assert torch.equal(net * c_out[:, None, None, None] + x * c_skip[:, None, None, None], want)
+    assert torch.equal(bound(x, sigma, cond), want)
