@@ -196,3 +196,42 @@ def test_denoiser_mirror_equals_the_oracle_on_cpu(flavour):
     assert c_skip.shape == c_out.shape == (4,)
     assert torch.equal(net * c_out[:, None, None, None] + x * c_skip[:, None, None, None], want)
     assert torch.equal(bound(x, sigma, cond), want)
+
+
+def test_load_xt_and_target_features_read_the_reference_layout_or_the_hbm_store(tmp_path):
+    """sgm/util.py:277-311: ``{folder}/{exp}/feature_maps/{key}.pt``; the ``features`` dict replaces the files."""
+    from vidseg_diffusion_b200.sgm.util import load_target_features, load_xt
+    fm = tmp_path / "exp" / "feature_maps"
+    fm.mkdir(parents=True)
+    xt, q = torch.randn(2, 4, 8, 8), torch.randn(4, 64, 32)
+    torch.save(xt, fm / "xt_time_7.pt")
+    torch.save(q, fm / "output_block_8_spatial_self_attn_q_time_7.pt")
+    assert torch.equal(load_xt(str(tmp_path), "exp", 7, "cpu"), xt)
+    got = load_target_features(str(tmp_path), "exp", 7, "output", ["spatial_self_attn_q", "spatial_self_attn_k"], 8, "cpu")
+    assert list(got) == ["output_block_8_spatial_self_attn_q_time_7"] and torch.equal(got[list(got)[0]], q)
+    store = {"xt_time_7": xt + 1, "output_block_8_spatial_self_attn_q_time_7": q + 1}
+    assert torch.equal(load_xt(None, None, 7, "cpu", features=store), xt + 1)
+    assert torch.equal(load_target_features(None, None, 7, "output", ["spatial_self_attn_q"], 8, "cpu", features=store)
+                       ["output_block_8_spatial_self_attn_q_time_7"], q + 1)
+    for call in (lambda: load_xt(str(tmp_path), "exp", 8, "cpu"), lambda: load_xt(None, None, 8, "cpu", features=store),
+                 lambda: load_target_features(str(tmp_path), "exp", 7, "input", ["spatial_self_attn_q"], 8, "cpu"),
+                 lambda: load_target_features(None, None, 9, "output", ["spatial_self_attn_q"], 8, "cpu", features=store)):
+        with pytest.raises(ValueError):
+            call()
+
+
+def test_sampler_options_outside_the_scope_fail_loudly():
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    smp = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"num_steps": 4, "device": "cpu", "discretization_config": {
+            "target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization"}}})
+    x = torch.zeros(2, 4, 8, 8)
+    with pytest.raises(NotImplementedError):
+        smp.sampler_step(torch.ones(2), torch.ones(2), None, x, {}, {}, is_smooth_latent=True)
+    with pytest.raises(NotImplementedError):
+        smp.null_text_optimization()
+    with pytest.raises(KeyError):
+        instantiate_from_config({"params": {}})
+    with pytest.raises(AttributeError):
+        instantiate_from_config({"target": "sgm.modules.diffusionmodules.sampling.HeunEDMSampler", "params": {}})
