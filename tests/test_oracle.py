@@ -78,3 +78,22 @@ def test_oracle_refine_vote_rules():
     all_w2 = np.array([[0, 0], [0, 2], [0, 0], [0, 0]])
     _, keep2 = oref.refine_labels(np.zeros((4, 1, 3), dtype=int), np.zeros((4, 2), dtype=int), all_w2)
     assert keep2.tolist() == [True, False]
+
+
+def test_vae_oracle_matches_reference_goldens():
+    """Next row, oracle first: the SD-2.1 first stage restated in oracle/vae.py against
+    the reference Encoder / Decoder (tests/golden/make_vae_goldens.py).  No product code on this row yet."""
+    import torch
+    from oracle import vae as ovae
+    from synth import synthetic_unet_weights
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae_tiny.npz"))
+    seed, _ = (int(v) for v in g["meta"])
+    cfg = ovae.TINY_VAE_CONFIG
+    shapes = ovae.param_shapes(cfg)
+    assert list(g["keys"]) == sorted(shapes)
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(shapes, seed).items()}
+    z = ovae.encode_first_stage(sd, cfg, torch.from_numpy(g["x"]), 0.18215, torch.from_numpy(g["noise"]))
+    img = ovae.decode_first_stage(sd, cfg, torch.from_numpy(g["z"]), 0.18215)
+    rel = lambda a, b: float((a - torch.from_numpy(b)).abs().max() / np.abs(b).max())
+    assert rel(z, g["z"]) < 2e-5 and rel(img, g["image"]) < 2e-5
+    assert z.shape == (2, 4, 4, 4) and img.shape == (2, 3, 32, 32)
