@@ -1,47 +1,2 @@
-"""Pre-conditioning of the denoiser (reference sgm/modules/diffusionmodules/denoiser_scaling.py): the four
-per-sample coefficients c_skip, c_out, c_in, c_noise as functions of sigma.  A handful of scalars per step: plain
-torch on the device, in the reference's operation order (the fused sampler step consumes c_skip / c_out as given)."""
-import torch
-
-
-class EDMScaling:
-    def __init__(self, sigma_data=0.5):
-        self.sigma_data = sigma_data
-
-    def __call__(self, sigma):
-        c_skip = self.sigma_data**2 / (sigma**2 + self.sigma_data**2)
-        c_out = sigma * self.sigma_data / (sigma**2 + self.sigma_data**2) ** 0.5
-        c_in = 1 / (sigma**2 + self.sigma_data**2) ** 0.5
-        c_noise = 0.25 * sigma.log()
-        return c_skip, c_out, c_in, c_noise
-
-
-class EpsScaling:
-    """SD-2.1 (configs/inference/sd_2_1.yaml): the network predicts the noise."""
-
-    def __call__(self, sigma):
-        c_skip = torch.ones_like(sigma, device=sigma.device)
-        c_out = -sigma
-        c_in = 1 / (sigma**2 + 1.0) ** 0.5
-        c_noise = sigma.clone()
-        return c_skip, c_out, c_in, c_noise
-
-
-class VScaling:
-    def __call__(self, sigma):
-        c_skip = 1.0 / (sigma**2 + 1.0)
-        c_out = -sigma / (sigma**2 + 1.0) ** 0.5
-        c_in = 1.0 / (sigma**2 + 1.0) ** 0.5
-        c_noise = sigma.clone()
-        return c_skip, c_out, c_in, c_noise
-
-
-class VScalingWithEDMcNoise:
-    """SVD (configs/inference/svd.yaml)."""
-
-    def __call__(self, sigma):
-        c_skip = 1.0 / (sigma**2 + 1.0)
-        c_out = -sigma / (sigma**2 + 1.0) ** 0.5
-        c_in = 1.0 / (sigma**2 + 1.0) ** 0.5
-        c_noise = 0.25 * sigma.log()
-        return c_skip, c_out, c_in, c_noise
+"""``target:`` names of the reference's sgm/modules/diffusionmodules/denoiser_scaling.py; defined in edm_glue.py."""
+from .edm_glue import EDMScaling, EpsScaling, Preconditioner, VScaling, VScalingWithEDMcNoise  # noqa: F401

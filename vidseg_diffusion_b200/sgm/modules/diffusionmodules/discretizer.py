@@ -1,52 +1,4 @@
-"""Noise-level schedules (reference sgm/modules/diffusionmodules/discretizer.py)."""
-import numpy as np
-import torch
-
-from ...util import append_zero
-
-
-def generate_roughly_equally_spaced_steps(num_substeps, max_step):
-    return np.linspace(max_step - 1, 0, num_substeps, endpoint=False).astype(int)[::-1]
-
-
-class Discretization:
-    def __call__(self, n, do_append_zero=True, device="cpu", flip=False):
-        sigmas = self.get_sigmas(n, device=device)
-        sigmas = append_zero(sigmas) if do_append_zero else sigmas
-        return sigmas if not flip else torch.flip(sigmas, (0,))
-
-    def get_sigmas(self, n, device):
-        raise NotImplementedError
-
-
-class EDMDiscretization(Discretization):
-    """SVD: sigma_max = 700 in svd.yaml."""
-
-    def __init__(self, sigma_min=0.002, sigma_max=80.0, rho=7.0):
-        self.sigma_min, self.sigma_max, self.rho = sigma_min, sigma_max, rho
-
-    def get_sigmas(self, n, device="cpu"):
-        ramp = torch.linspace(0, 1, n, device=device)
-        min_inv_rho = self.sigma_min ** (1 / self.rho)
-        max_inv_rho = self.sigma_max ** (1 / self.rho)
-        return (max_inv_rho + ramp * (min_inv_rho - max_inv_rho)) ** self.rho
-
-
-class LegacyDDPMDiscretization(Discretization):
-    """SD-2.1: the 1000-step linear-beta DDPM schedule, sub-sampled (discretizer.py:44-70; the beta schedule is
-    ``make_beta_schedule("linear")`` of diffusionmodules/util.py: linspace(sqrt(start), sqrt(end), n, float64) ** 2)."""
-
-    def __init__(self, linear_start=0.00085, linear_end=0.0120, num_timesteps=1000):
-        self.num_timesteps = num_timesteps
-        betas = (torch.linspace(linear_start**0.5, linear_end**0.5, num_timesteps, dtype=torch.float64) ** 2).numpy()
-        self.alphas_cumprod = np.cumprod(1.0 - betas, axis=0)
-
-    def get_sigmas(self, n, device="cpu"):
-        if n < self.num_timesteps:
-            alphas_cumprod = self.alphas_cumprod[generate_roughly_equally_spaced_steps(n, self.num_timesteps)]
-        elif n == self.num_timesteps:
-            alphas_cumprod = self.alphas_cumprod
-        else:
-            raise ValueError
-        sigmas = torch.tensor((1 - alphas_cumprod) / alphas_cumprod, dtype=torch.float32, device=device) ** 0.5
-        return torch.flip(sigmas, (0,))
+"""``target:`` names of the reference's sgm/modules/diffusionmodules/discretizer.py; defined in edm_glue.py."""
+from .edm_glue import DDPMSubsampledSchedule as LegacyDDPMDiscretization  # noqa: F401
+from .edm_glue import KarrasSchedule as EDMDiscretization  # noqa: F401
+from .edm_glue import SigmaSchedule as Discretization  # noqa: F401
