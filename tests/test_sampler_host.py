@@ -235,3 +235,128 @@ def test_sampler_options_outside_the_scope_fail_loudly():
         instantiate_from_config({"params": {}})
     with pytest.raises(AttributeError):
         instantiate_from_config({"target": "sgm.modules.diffusionmodules.sampling.HeunEDMSampler", "params": {}})
+
+
+def _eager_step(x, net, c_skip, c_out, scales, sigma_hat, sigma_next, mask=None, ori_xt=None):
+    """The definition of vidseg_sampler_step in torch (the chain the kernel replaces), for host-logic tests on the CPU."""
+    ap = lambda t: t[(...,) + (None,) * 3]
+    inp = torch.cat([x] * 2) if scales is not None else x
+    den = net * ap(c_out) + inp * ap(c_skip)
+    if scales is not None:
+        x_u, x_c = den.chunk(2)
+        den = x_u + ap(scales) * (x_c - x_u)
+    out = x + ap(sigma_next - sigma_hat) * ((x - den) / ap(sigma_hat))
+    if mask is not None:
+        fm = torch.nn.functional.interpolate(mask.unsqueeze(1), size=x.shape[-2:], mode="nearest")
+        out = (out * fm + ori_xt.to(out.dtype) * (1 - fm)).float()
+    return out
+
+
+def test_sampler_host_logic_on_cpu_with_the_step_kernel_replaced_by_its_definition(monkeypatch):
+    """The mirror's control flow (step range, modulation / injection switches, feature store, blending arguments, bound
+    and opaque denoisers) end to end on the CPU: the oracle UNet is the network and the fused step is monkeypatched with
+    its eager definition.  Must land on the reference sampler's goldens."""
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules import sampling
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    monkeypatch.setattr(sampling, "fused_step", _eager_step)
+    g = np.load(GOLDEN)
+    seed, F, hw, L, steps, t_start = (int(v) for v in g["meta"])
+    cfg = ounet.TINY_CONFIG
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ounet.param_shapes(cfg), seed).items()}
+    ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    smp = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"discretization_config": ddpm, "num_steps": steps, "s_churn": 0, "s_tmin": 0, "s_tmax": 999, "s_noise": 1,
+                   "device": "cpu",
+                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 5.0}}}})
+    den = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.denoiser.DiscreteDenoiser",
+        "params": {"num_idx": 1000, "discretization_config": ddpm,
+                   "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}}})
+    store, last = {}, {}
+
+    class Net(torch.nn.Module):   # stands in for OpenAIWrapper(UNetModel): same call signature
+        def forward(self, x_in, c_noise, cond, is_modulate_step=False, is_injected_step=False, modulate_params=None):
+            inj = None
+            if is_injected_step:
+                mp = modulate_params
+                inj = dict(block_types=mp["injected_block_types"], input_block_indices=mp["input_block_indices"],
+                           output_block_indices=mp["output_block_indices"], feature_types=mp["injected_feature_types"],
+                           timestep=mp["timestep"], features=mp["features"])
+            last.clear()
+            return ounet.unet_forward(sd, cfg, x_in, c_noise, cond["crossattn"], last,
+                                      modulate_params=modulate_params if is_modulate_step else None, injection=inj)
+
+    def save_cb(xt, i):
+        for b in BLOCKS:
+            for n in ("q", "k"):
+                store[f"output_block_{b}_spatial_self_attn_{n}_time_{i}"] = last[(f"output_block_{b}", f"spatial_self_attn_{n}")].clone()
+        store[f"xt_time_{i}"] = xt.clone()
+
+    latent, ctx, uctx = (torch.from_numpy(g[k]) for k in ("latent", "ctx", "uctx"))
+    c, uc = {"crossattn": ctx}, {"crossattn": uctx}
+    net = Net()
+    bound = den.bind(net)
+    out_a = smp(bound, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=t_start)
+    assert relerr(out_a, g["out_a"]) < 2e-5
+    opaque = smp(lambda inp, sigma, cc, **kw: den(net, inp, sigma, cc, **kw), latent.clone(), cond=c, uc=uc, t_start=t_start)
+    assert torch.equal(opaque, out_a)
+    mp = modulate_params_for(seed, F, (hw // 2) ** 2, features=store)
+    for key, masks in (("out_b", [torch.from_numpy(m) for m in mp["feature_masks"]]),
+                       ("out_b64", [torch.from_numpy(m.astype(np.float64) * 0.75) for m in mp["feature_masks"]])):
+        out = smp(bound, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=dict(mp, feature_masks=masks),
+                  t_start=t_start, is_latent_blending=True, feature_height=hw // 2, feature_width=hw // 2)
+        assert relerr(out, g[key]) < 5e-5, key
+
+
+def test_sampler_host_logic_on_cpu_svd_flavour(monkeypatch):
+    """Same as above for the SVD configuration: Denoiser + VScalingWithEDMcNoise, Karras schedule, per-frame guidance ramp,
+    the conditioning adapter (OpenAIWrapper: "concat" / "vector" entries) and the extra model inputs fixed by ``bind``."""
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules import sampling
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.wrappers import OpenAIWrapper
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    monkeypatch.setattr(sampling, "fused_step", _eager_step)
+    mk, ov, cfg = video_case()
+    g = np.load(VGOLDEN)
+    seed, F, hw, steps, t_start = (int(v) for v in g["meta"])
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ov.param_shapes(cfg), seed).items()}
+    store, last = {}, {}
+
+    class VideoNet(torch.nn.Module):   # stands in for VideoUNet: the signature OpenAIWrapper calls
+        def forward(self, x, timesteps=None, context=None, y=None, num_video_frames=None, image_only_indicator=None,
+                    is_modulate_step=False, is_injected_step=False, modulate_params=None):
+            inj = None
+            if is_injected_step:
+                mp = modulate_params
+                inj = dict(block_types=mp["injected_block_types"], input_block_indices=mp["input_block_indices"],
+                           output_block_indices=mp["output_block_indices"], feature_types=mp["injected_feature_types"],
+                           timestep=mp["timestep"], features=mp["features"])
+            last.clear()
+            return ov.video_unet_forward(sd, cfg, x, timesteps, context, y, num_video_frames, image_only_indicator, last,
+                                         modulate_params=modulate_params if is_modulate_step else None, injection=inj)
+
+    smp = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"num_steps": steps, "device": "cpu",
+                   "discretization_config": {"target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization",
+                                             "params": {"sigma_max": 700.0}},
+                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.LinearPredictionGuider",
+                                     "params": {"max_scale": 2.5, "min_scale": 1.0, "num_frames": F}}}})
+    den = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.denoiser.Denoiser",
+        "params": {"scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.VScalingWithEDMcNoise"}}})
+    bound = den.bind(OpenAIWrapper(VideoNet()), image_only_indicator=torch.zeros(2, F), num_video_frames=F)
+    latent, c, uc = mk.video_inputs(cfg)
+
+    def save_cb(xt, i):
+        for ft in V_TYPES:
+            store[f"output_block_7_{ft}_time_{i}"] = last[("output_block_7", ft)].clone()
+        store[f"xt_time_{i}"] = xt.clone()
+
+    out_a = smp(bound, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=t_start)
+    assert relerr(out_a, g["out_a"]) < 5e-5
+    mp = mk.video_modulate_params(seed, F, (hw // 2) ** 2, features=store)
+    mp["feature_masks"] = [torch.from_numpy(m) for m in mp["feature_masks"]]
+    out_b = smp(bound, latent.clone(), cond=c, uc=uc, is_modulate=True, modulate_params=mp, t_start=t_start,
+                is_latent_blending=True, feature_height=hw // 2, feature_width=hw // 2)
+    assert relerr(out_b, g["out_b"]) < 5e-5
