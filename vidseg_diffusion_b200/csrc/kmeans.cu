@@ -1854,13 +1854,16 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
   if (changed == nullptr) changed = at<int>(ws, L.changed);
-  if (L.use_mq) {
+  // the int8 product splits its row range over kMqSplit CTAs per tile: ranges shorter than that many 128-row blocks
+  // (tiny shards) take the float64 kernels below, which produce the same `partial`
+  const bool mq_range_ok = (row_end + kMqBK - 1) / kMqBK - row_begin / kMqBK >= kMqSplit || row_end == row_begin;
+  if (L.use_mq && mq_range_ok) {
     VS_LAUNCH(km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
               L.k, row_begin, row_end, at<int>(ws, L.flags), at<int8_t>(ws, L.mq_onehot), at<int>(ws, L.mq_cnt));
     VS_POST_LAUNCH();
     MqParams mp{};
-    mp.kb_lo = row_begin / kMqBK;
-    mp.kb_hi = (row_end + kMqBK - 1) / kMqBK;
+    mp.kb_lo = (row_end > row_begin) ? row_begin / kMqBK : 0;
+    mp.kb_hi = (row_end > row_begin) ? (row_end + kMqBK - 1) / kMqBK : 0;   // empty range: zero sums (memset below)
     mp.kb_per_split = (mp.kb_hi - mp.kb_lo + kMqSplit - 1) / kMqSplit;
     mp.rk = L.r * L.k;
     mp.d = L.d;
