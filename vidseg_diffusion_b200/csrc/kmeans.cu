@@ -1892,20 +1892,12 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
   }
   const size_t smem1 = (size_t)L.k * kColTile * 8;
   VS_REQUIRE(smem1 <= 200 * 1024, "k too large for the M-step kernel");
-  if (false && 2 * smem1 <= 96 * 1024) {   // two runs per pass over X: measured slower (83 vs 72 us) -- the adds bound it
-    const size_t smem = 2 * smem1;
-    static cudaError_t attr2 = cudaFuncSetAttribute(km_partial_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-    VS_CHECK_CUDA(attr2);
-    dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, (L.r + 1) / 2);
-    VS_LAUNCH(km_partial_kernel<2>, grid, kColTile, smem, stream, at<float>(ws, L.xc), L.n, L.d, L.k, L.r, row_begin, row_end,
-              at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
-  } else {
-    static cudaError_t attr1 = cudaFuncSetAttribute(km_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    VS_CHECK_CUDA(attr1);
-    dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, L.r);
-    VS_LAUNCH(km_partial_kernel<1>, grid, kColTile, smem1, stream, at<float>(ws, L.xc), L.n, L.d, L.k, L.r, row_begin, row_end,
-              at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
-  }
+  // (two runs per pass over X were measured slower, 83 vs 72 us: the shared-memory adds bound the kernel, not the reads)
+  static cudaError_t attr1 = cudaFuncSetAttribute(km_partial_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  VS_CHECK_CUDA(attr1);
+  dim3 grid(kSlabs, (L.d + kColTile - 1) / kColTile, L.r);
+  VS_LAUNCH(km_partial_kernel<1>, grid, kColTile, smem1, stream, at<float>(ws, L.xc), L.n, L.d, L.k, L.r, row_begin, row_end,
+            at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
   VS_POST_LAUNCH();
   VS_LAUNCH(km_reduce_kernel, dim3(L.k, L.r), 256, 0, stream, at<double>(ws, L.part), at<int>(ws, L.partcnt), L.d, L.k,
             at<int>(ws, L.flags), partial, at<int>(ws, L.changed), changed);
