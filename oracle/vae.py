@@ -14,7 +14,13 @@ Follows, in the reference tree:
   sgm/models/autoencoder.py :440-506      quant_conv after the encoder, post_quant_conv before the decoder
   sgm/modules/distributions/distributions.py :24-41   mean | logvar split, logvar clamped to [-30, 20], sample
   sgm/models/diffusion.py :117-151        scale_factor around encode / decode
-Pinned by tests/golden/make_vae_goldens.py against the reference Encoder / Decoder modules.
+  sgm/modules/autoencoding/temporal_ae.py (SVD's decoder, svd.yaml: VideoDecoder, time_mode "conv-only")
+    VideoResBlock :18-83    the 2-D ResnetBlock, then a 3-D ResBlock over (t, h, w) with kernel (3,1,1)
+                            (openaimodel.py ResBlock: GroupNorm32 eps 1e-5 + SiLU + conv3d, twice, + x; no embedding),
+                            merged as sigmoid(mix_factor) * temporal + (1 - sigmoid(mix_factor)) * spatial
+    AE3DConv :86-110        conv_out: the 2-D conv followed by a Conv3d (3,1,1) over the frames
+    VideoDecoder :293-349   Decoder with those factories; the mid attention stays the 2-D AttnBlock
+Pinned by tests/golden/make_vae_goldens.py against the reference Encoder / Decoder / VideoDecoder modules.
 """
 import torch
 import torch.nn.functional as F
@@ -69,23 +75,53 @@ def encoder_forward(sd, cfg, x, prefix="encoder"):
     return _conv(sd, f"{prefix}.conv_out", _gn_swish(sd, f"{prefix}.norm_out", h))
 
 
-def decoder_forward(sd, cfg, z, prefix="decoder"):
-    """Decoder.forward (model.py:716-748): image [B, out_ch, 8H, 8W] from the post_quant_conv output."""
+def _frames_first(x, t):
+    """"(b t) c h w -> b c t h w" """
+    bt, c, hh, ww = x.shape
+    return x.reshape(bt // t, t, c, hh, ww).permute(0, 2, 1, 3, 4)
+
+
+def _frames_last(x):
+    b, c, t, hh, ww = x.shape
+    return x.permute(0, 2, 1, 3, 4).reshape(b * t, c, hh, ww)
+
+
+def video_resnet_block(sd, p, x, timesteps):
+    """VideoResBlock.forward (temporal_ae.py:62-83)."""
+    x = resnet_block(sd, p, x)
+    v = _frames_first(x, timesteps)
+    ts = p + ".time_stack"
+    h = F.silu(F.group_norm(v, 32, sd[ts + ".in_layers.0.weight"], sd[ts + ".in_layers.0.bias"], eps=1e-5))
+    h = F.conv3d(h, sd[ts + ".in_layers.2.weight"], sd[ts + ".in_layers.2.bias"], padding=(1, 0, 0))
+    h = F.silu(F.group_norm(h, 32, sd[ts + ".out_layers.0.weight"], sd[ts + ".out_layers.0.bias"], eps=1e-5))
+    h = F.conv3d(h, sd[ts + ".out_layers.3.weight"], sd[ts + ".out_layers.3.bias"], padding=(1, 0, 0))
+    alpha = torch.sigmoid(sd[p + ".mix_factor"])
+    return _frames_last(alpha * (v + h) + (1.0 - alpha) * v)
+
+
+def decoder_forward(sd, cfg, z, prefix="decoder", timesteps=None):
+    """Decoder.forward (model.py:716-748): image [B, out_ch, 8H, 8W] from the post_quant_conv output.
+    ``timesteps`` (frames per clip) selects the VideoDecoder of SVD (temporal_ae.py:293-349, "conv-only")."""
     n_res, nrb = len(cfg["ch_mult"]), cfg["num_res_blocks"]
     res = cfg["resolution"] // 2 ** (n_res - 1)
+    resnet = resnet_block if timesteps is None else (lambda sd_, p_, x_: video_resnet_block(sd_, p_, x_, timesteps))
     h = _conv(sd, f"{prefix}.conv_in", z)
-    h = resnet_block(sd, f"{prefix}.mid.block_1", h)
+    h = resnet(sd, f"{prefix}.mid.block_1", h)
     h = attn_block(sd, f"{prefix}.mid.attn_1", h)
-    h = resnet_block(sd, f"{prefix}.mid.block_2", h)
+    h = resnet(sd, f"{prefix}.mid.block_2", h)
     for lvl in reversed(range(n_res)):
         for blk in range(nrb + 1):
-            h = resnet_block(sd, f"{prefix}.up.{lvl}.block.{blk}", h)
+            h = resnet(sd, f"{prefix}.up.{lvl}.block.{blk}", h)
             if res in cfg["attn_resolutions"]:
                 h = attn_block(sd, f"{prefix}.up.{lvl}.attn.{blk}", h)
         if lvl != 0:
             h = _conv(sd, f"{prefix}.up.{lvl}.upsample.conv", F.interpolate(h, scale_factor=2.0, mode="nearest"))
             res *= 2
-    return _conv(sd, f"{prefix}.conv_out", _gn_swish(sd, f"{prefix}.norm_out", h))
+    out = _conv(sd, f"{prefix}.conv_out", _gn_swish(sd, f"{prefix}.norm_out", h))
+    if timesteps is not None:   # AE3DConv (temporal_ae.py:102-110)
+        tm = f"{prefix}.conv_out.time_mix_conv"
+        out = _frames_last(F.conv3d(_frames_first(out, timesteps), sd[tm + ".weight"], sd[tm + ".bias"], padding=(1, 0, 0)))
+    return out
 
 
 def encode_first_stage(sd, cfg, x, scale_factor, noise=None):
@@ -98,10 +134,31 @@ def encode_first_stage(sd, cfg, x, scale_factor, noise=None):
     return scale_factor * z
 
 
-def decode_first_stage(sd, cfg, z, scale_factor):
-    """diffusion.py:117-134 + AutoencoderKL.decode (autoencoder.py:489-506)."""
+def decode_first_stage(sd, cfg, z, scale_factor, timesteps=None):
+    """diffusion.py:117-134 + AutoencoderKL.decode (autoencoder.py:489-506).  SVD's autoencoder
+    (AutoencodingEngine with a VideoDecoder, svd.yaml) has no post_quant_conv: it is applied only when present."""
     z = 1.0 / scale_factor * z
-    return decoder_forward(sd, cfg, F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"]))
+    if "post_quant_conv.weight" in sd:
+        z = F.conv2d(z, sd["post_quant_conv.weight"], sd["post_quant_conv.bias"])
+    return decoder_forward(sd, cfg, z, timesteps=timesteps)
+
+
+def video_decoder_param_shapes(cfg):
+    """State-dict key -> shape of VideoDecoder(**cfg, video_kernel_size=[3,1,1]) (prefix ``decoder.``)."""
+    base = {k: v for k, v in param_shapes(cfg).items() if k.startswith("decoder.")}
+    out = dict(base)
+    for k, shape in base.items():
+        if k.endswith(".norm1.weight"):     # one entry per ResnetBlock: add its time stack
+            p = k[: -len(".norm1.weight")]
+            c = base[p + ".conv2.weight"][0]
+            for n in ("in_layers.0", "out_layers.0"):
+                out[f"{p}.time_stack.{n}.weight"], out[f"{p}.time_stack.{n}.bias"] = (c,), (c,)
+            for n in ("in_layers.2", "out_layers.3"):
+                out[f"{p}.time_stack.{n}.weight"], out[f"{p}.time_stack.{n}.bias"] = (c, c, 3, 1, 1), (c,)
+            out[p + ".mix_factor"] = (1,)
+    oc = cfg["out_ch"]
+    out["decoder.conv_out.time_mix_conv.weight"], out["decoder.conv_out.time_mix_conv.bias"] = (oc, oc, 3, 1, 1), (oc,)
+    return out
 
 
 def param_shapes(cfg, embed_dim=4):

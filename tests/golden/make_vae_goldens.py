@@ -56,5 +56,34 @@ def main():
                         keys=np.array(sorted(shapes)), meta=np.array([SEED, B]))
 
 
+def main_video():
+    """SVD's VideoDecoder (svd.yaml: temporal_ae.VideoDecoder, video_kernel_size [3,1,1], time_mode "conv-only")."""
+    ta = import_reference("sgm.modules.autoencoding.temporal_ae")
+    cfg = ovae.TINY_VAE_CONFIG
+    T = 3
+    dec = ta.VideoDecoder(**cfg, video_kernel_size=[3, 1, 1]).eval()
+    shapes = ovae.video_decoder_param_shapes(cfg)
+    ref_shapes = {f"decoder.{k}": tuple(v.shape) for k, v in dec.state_dict().items()}
+    assert ref_shapes == shapes, sorted(set(ref_shapes) ^ set(shapes))[:10]
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(shapes, SEED + 1).items()}
+    dec.load_state_dict({k[len("decoder."):]: v for k, v in sd.items()}, strict=True)
+    g = torch.Generator().manual_seed(SEED + 1)
+    z = torch.randn(2 * T, 4, cfg["resolution"] // 8, cfg["resolution"] // 8, generator=g)
+    with torch.no_grad():
+        img = dec(1.0 / SCALE * z, timesteps=T)
+        img_or = ovae.decode_first_stage(sd, cfg, z, SCALE, timesteps=T)
+        img_flat = ovae.decode_first_stage({k: v for k, v in sd.items()}, cfg, z, SCALE, timesteps=1)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    print("video decoder: oracle vs reference", f"{rel(img_or, img):.2e}", "| frames mix: changed the image by",
+          f"{rel(img_flat, img):.2e}", "| image absmax", float(img.abs().max()))
+    assert rel(img_or, img) < 2e-5 and rel(img_flat, img) > 1e-3
+    np.savez_compressed(os.path.join(HERE, "vae_video_tiny.npz"), z=z.numpy(), image=img.numpy(), keys=np.array(sorted(shapes)),
+                        meta=np.array([SEED + 1, T]))
+
+
 if __name__ == "__main__":
-    main()
+    which = sys.argv[1:] or ["image", "video"]
+    if "image" in which:
+        main()
+    if "video" in which:
+        main_video()

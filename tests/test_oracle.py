@@ -97,3 +97,21 @@ def test_vae_oracle_matches_reference_goldens():
     rel = lambda a, b: float((a - torch.from_numpy(b)).abs().max() / np.abs(b).max())
     assert rel(z, g["z"]) < 2e-5 and rel(img, g["image"]) < 2e-5
     assert z.shape == (2, 4, 4, 4) and img.shape == (2, 3, 32, 32)
+
+
+def test_video_decoder_oracle_matches_reference_golden():
+    """SVD's first-stage decoder (temporal_ae.VideoDecoder, "conv-only"): oracle/vae.py against the reference module."""
+    import torch
+    from oracle import vae as ovae
+    from synth import synthetic_unet_weights
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vae_video_tiny.npz"))
+    seed, T = (int(v) for v in g["meta"])
+    cfg = ovae.TINY_VAE_CONFIG
+    shapes = ovae.video_decoder_param_shapes(cfg)
+    assert list(g["keys"]) == sorted(shapes)
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(shapes, seed).items()}
+    img = ovae.decode_first_stage(sd, cfg, torch.from_numpy(g["z"]), 0.18215, timesteps=T)
+    assert float((img - torch.from_numpy(g["image"])).abs().max() / np.abs(g["image"]).max()) < 2e-5
+    # clips are independent: decoding the second clip alone gives its frames again
+    alone = ovae.decode_first_stage(sd, cfg, torch.from_numpy(g["z"][T:]), 0.18215, timesteps=T)
+    assert torch.allclose(alone, img[T:], atol=1e-5)
