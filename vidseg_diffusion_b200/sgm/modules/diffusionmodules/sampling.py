@@ -61,6 +61,40 @@ def _check(t, n, name, device):
     return t
 
 
+class _ModulationSchedule:
+    """Which sampler steps modulate, and from which step on features are injected (reference sampling.py:153-196).
+
+    ``modulate_timestep_frames`` ({step: [frames]}; empty -> every frame on the steps of ``modulate_timestep``) decides
+    the steps; injection, when ``is_injected_features`` is set, starts at the first of them and lasts to the end, and the
+    image callback of a modulated run only fires from that step on."""
+
+    def __init__(self, params):
+        self.params = params
+        self.per_step_frames = {}
+        self.steps = ()
+        self.inject = False
+        if params is not None:
+            self.per_step_frames = params["modulate_timestep_frames"]
+            self.steps = tuple(self.per_step_frames.keys()) if len(self.per_step_frames) else tuple(params["modulate_timestep"])
+            self.inject = bool(params["is_injected_features"])
+
+    def _first(self):
+        return min(self.steps)   # ValueError on an empty list, as in the reference
+
+    def enter(self, i):
+        """-> (modulate on step i, inject on step i); records the frames this step modulates."""
+        if self.params is None:
+            return False, False
+        modulate = i in self.steps
+        if modulate:
+            frames = self.per_step_frames[i] if len(self.per_step_frames) else list(range(self.params["num_frames"]))
+            self.params["modulate_timestep_frames_group"] = frames
+        return modulate, bool(self.inject and i >= self._first())
+
+    def reports(self, i):
+        return self.params is None or i >= self._first()
+
+
 class BaseDiffusionSampler:
     def __init__(self, discretization_config, num_steps=None, guider_config=None, verbose=False, device="cuda"):
         self.num_steps = num_steps
@@ -146,53 +180,38 @@ class EDMSampler(SingleStepDiffusionSampler):
     def __call__(self, denoiser, x, cond, uc=None, num_steps=None, callback=None, img_callback=None, is_modulate=False,
                  modulate_params=None, uc_list=None, t_start=None, t_end=None, is_latent_blending=False,
                  feature_height=None, feature_width=None, is_smooth_latent=False, model=None):
-        """reference sampling.py:146-262"""
+        """reference sampling.py:146-262: steps t_start..t_end of the schedule; on the steps named by ``modulate_params``
+        the UNet modulates its attention / feed-forward outputs with the feature masks, from the first of them on it
+        takes the source run's q / k, and inside [latent_mask_start, latent_mask_end] the latent is blended with the
+        source run's x_t outside the masks.  The per-step bookkeeping written into ``modulate_params`` ("timestep",
+        "modulate_timestep_frames_group") is what the UNet mirrors read, as in the reference."""
         x, s_in, sigmas, num_sigmas, cond, uc = self.prepare_sampling_loop(x, cond, uc, num_steps)
-        if is_modulate:
-            if len(modulate_params["modulate_timestep_frames"]) == 0:
-                modulate_timestep = modulate_params["modulate_timestep"]
-            else:
-                modulate_timestep = modulate_params["modulate_timestep_frames"].keys()
-            is_injected_features = modulate_params["is_injected_features"]
-        else:
-            is_injected_features = False
-        if t_start is None:
-            t_start = 0
-        if t_end is None:
-            t_end = num_sigmas
-        for i in list(self.get_sigma_gen(num_sigmas))[t_start:(t_end + 1)]:
-            gamma = min(self.s_churn / (num_sigmas - 1), 2**0.5 - 1) if self.s_tmin <= sigmas[i] <= self.s_tmax else 0.0
-            is_modulate_step = bool(is_modulate and i in modulate_timestep)
-            is_injected_step = bool(is_modulate and is_injected_features and i >= min(modulate_timestep))
+        schedule = _ModulationSchedule(modulate_params if is_modulate else None)
+        first, last = (0 if t_start is None else t_start), (num_sigmas if t_end is None else t_end)
+        mask_hw = (28 if feature_height is None else feature_height, 52 if feature_width is None else feature_width)
+        for i in range(num_sigmas - 1)[first:last + 1]:
+            churn = self.s_tmin <= sigmas[i] <= self.s_tmax
+            gamma = min(self.s_churn / (num_sigmas - 1), 2 ** 0.5 - 1) if churn else 0.0
             if modulate_params is not None:
                 modulate_params["timestep"] = i
-            if is_modulate and i in modulate_timestep:
-                if len(modulate_params["modulate_timestep_frames"]) > 0:
-                    modulate_params["modulate_timestep_frames_group"] = modulate_params["modulate_timestep_frames"][i]
-                else:
-                    modulate_params["modulate_timestep_frames_group"] = list(range(modulate_params["num_frames"]))
+            modulate_now, inject_now = schedule.enter(i)
             if uc_list is not None:
                 uc = uc_list[i]
             if is_smooth_latent and i in (23, 24):
                 raise NotImplementedError("is_smooth_latent needs the VAE (SURVEY.md section 8f rank 3)")
             blend_mask = blend_xt = None
             if is_latent_blending and modulate_params["latent_mask_start"] <= i <= modulate_params["latent_mask_end"]:
-                blend_xt = load_xt(modulate_params.get("feature_folder"), modulate_params.get("exp_name"),
-                                   modulate_params["timestep"], x.device, features=modulate_params.get("features")).to(x.dtype)
+                blend_xt = load_xt(modulate_params.get("feature_folder"), modulate_params.get("exp_name"), i, x.device,
+                                   features=modulate_params.get("features")).to(x.dtype)
                 masks = torch.stack(list(modulate_params["feature_masks"]), dim=0)
-                blend_mask = masks.reshape(masks.shape[0], 28 if feature_height is None else feature_height,
-                                           52 if feature_width is None else feature_width)
+                blend_mask = masks.reshape(masks.shape[0], *mask_hw)
             x = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], denoiser, x, cond, uc, gamma,
-                                  is_modulate_step=is_modulate_step, is_injected_step=is_injected_step,
+                                  is_modulate_step=modulate_now, is_injected_step=inject_now,
                                   modulate_params=modulate_params, blend_mask=blend_mask, blend_xt=blend_xt)
             if callback:
                 callback(i)
-            if img_callback:
-                if is_modulate:
-                    if i >= min(modulate_timestep):
-                        img_callback(x, i)
-                else:
-                    img_callback(x, i)
+            if img_callback and schedule.reports(i):
+                img_callback(x, i)
         return x
 
     def inversion(self, denoiser, x, cond, uc=None, num_steps=None):
