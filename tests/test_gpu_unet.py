@@ -91,19 +91,31 @@ def test_unet_frames_are_independent(cuda):
 
 def test_cuda_graph_replay_matches_eager_launches(cuda):
     """ClipSegmenter(use_cuda_graph=True): the UNet stage replayed as one CUDA graph gives the same bits as the eager
-    launches, on first use and on a second clip with different inputs (static buffers refreshed)."""
+    launches, on first use and on a second clip with different inputs (static buffers refreshed).  An eager forward on
+    OTHER inputs runs on the same model between the expected result and the graphed call, so a refinement that read the
+    module's q7 attribute instead of the replayed graph's own buffer would track stale features and fail here."""
     from vidseg_diffusion_b200.pipeline import ClipSegmenter
     cfg = ounet.TINY_CONFIG
     model, _ = build(cfg, 5, cuda)
     eager = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True)
     graphed = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, use_cuda_graph=True)
+    other = tuple(torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(77, 2, 16, cfg["in_channels"], 7, cfg["context_dim"]))
     for seed in (5, 6):
         x, t, ctx = (torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(seed, 2, 16, cfg["in_channels"], 7, cfg["context_dim"]))
         want, out_e = eager.segment(x, t, ctx, 2, seed=seed)
         want, out_e = want.clone(), out_e.clone()
+        model(other[0], timesteps=other[1], context=other[2])     # the module attributes now point at another clip's stash
         got, out_g = graphed.segment(x, t, ctx, 2, seed=seed)
         assert torch.equal(out_g, out_e) and torch.equal(got, want)
     assert graphed.graph_replays == 2 and graphed.graph_kernel_launches > 0
+    # a larger batch through a second graph signature, then the first graph again (its scratch must still be alive)
+    xb, tb, cb = (torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(9, 5, 16, cfg["in_channels"], 7, cfg["context_dim"]))
+    want_b = eager.segment(xb, tb, cb, 5, seed=9)[0].clone()
+    assert torch.equal(graphed.segment(xb, tb, cb, 5, seed=9)[0], want_b)
+    x, t, ctx = (torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(5, 2, 16, cfg["in_channels"], 7, cfg["context_dim"]))
+    want = eager.segment(x, t, ctx, 2, seed=5)[0].clone()
+    model(other[0], timesteps=other[1], context=other[2])
+    assert torch.equal(graphed.segment(x, t, ctx, 2, seed=5)[0], want)
 
 
 def test_unet_mask_modulation_matches_reference_golden(cuda, operand_mode):

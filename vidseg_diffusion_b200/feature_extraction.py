@@ -13,7 +13,7 @@ GPU (aggregate/normalise, K-means, nearest-neighbour tracking + voting).  Differ
   * ``write_pngs=False`` skips the per-(frame,label) PNG tree when the caller only wants the label
     maps; the default writes the same mode-L 0/255 PNGs in the same folders.
 
-``match_gt_mask`` (:546-643) is the next row of the scope table and is not built yet.
+``match_gt_mask`` (:546-643) lives in match_gt.py.
 """
 import os
 
@@ -26,9 +26,24 @@ from .features import aggregate_normalize
 from .kmeans import KMeans
 from .refine import refine_masks
 
-# label maps of the most recent kmeans_masks call per mask folder, kept on the device so that
-# correct_low_res_mask does not have to rebuild them from the PNG tree
+# Hand-over of label maps between ``kmeans_masks`` / ``match_gt_mask`` and ``correct_low_res_mask`` for callers that
+# asked for ``write_pngs=False``: with no PNG tree on disk the maps wait here, keyed by mask folder and stamped with the
+# window they belong to; the consumer checks the stamp and removes the entry.  Whenever the PNG tree IS written the
+# refinement re-reads it, exactly like the reference (:380-389).
 _LABEL_CACHE = {}
+
+
+def _stamp(num_frames, frame_name_list, feature_height, feature_width):
+    names = None if frame_name_list is None else tuple(str(n) for n in list(frame_name_list)[:num_frames])
+    return (int(num_frames), names, int(feature_height), int(feature_width))
+
+
+def register_label_maps(masks_folder, labels, num_frames, frame_name_list, feature_height, feature_width):
+    _LABEL_CACHE[os.path.normpath(masks_folder)] = (labels, _stamp(num_frames, frame_name_list, feature_height, feature_width))
+
+
+def invalidate_label_maps(masks_folder):
+    _LABEL_CACHE.pop(os.path.normpath(masks_folder), None)
 
 
 def _device():
@@ -105,7 +120,10 @@ def save_inidividual_masks_kmeans(feature_blocks, selected_timestep, output_fold
     kmeans = KMeans(n_clusters=num_clusters, n_init=10)
     labels = kmeans.fit_predict(x).reshape(num_frames, feature_height, feature_width)
     out_folder = _masks_folder(output_folder, num_clusters)
-    _LABEL_CACHE[os.path.normpath(out_folder)] = (labels, selected_timestep)
+    if write_pngs:
+        invalidate_label_maps(out_folder)   # the PNG tree is the hand-over, as in the reference
+    else:
+        register_label_maps(out_folder, labels, num_frames, frame_name_list, feature_height, feature_width)
     if write_pngs:
         labels_np = labels.cpu().numpy()
         for i in range(num_frames):
@@ -131,8 +149,8 @@ def correct_low_res_mask(feature_maps, mask_folder, output_folder=None, num_clus
         raise _lib.VidsegError("correct_low_res_mask: only the reference's default configuration is built")
     fm = _to_device_f32(feature_maps)
     if label_maps is None:
-        cached = _LABEL_CACHE.get(os.path.normpath(mask_folder))
-        if cached is not None:
+        cached = _LABEL_CACHE.pop(os.path.normpath(mask_folder), None)
+        if cached is not None and cached[1] == _stamp(num_frames, frame_name_list, feature_height, feature_width):
             label_maps = cached[0]
         else:
             # rebuild from the PNG tree exactly like the reference (:380-389; timestep 24 is hard-coded there)

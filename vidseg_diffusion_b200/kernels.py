@@ -15,7 +15,6 @@ from . import _lib
 from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, packed8, split
 
 _WEIGHT_CACHE = {}
-_WORKSPACES = {}
 
 
 def _cached(param, tag, make):
@@ -55,12 +54,9 @@ def conv_weight_split(param, cin_pad=None):
 
 
 def _workspace(device, nbytes):
-    key = (device.type, device.index)
-    ws = _WORKSPACES.get(key)
-    if ws is None or ws.numel() < nbytes:
-        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-        _WORKSPACES[key] = ws
-    return ws
+    """Scratch of ONE call.  Allocated per call from torch's caching allocator (stream-ordered, so concurrent streams
+    never share it; during CUDA-graph capture it lands in the graph's private pool and lives as long as the graph)."""
+    return torch.empty(max(nbytes, 256), dtype=torch.uint8, device=device)
 
 
 def _require(x, name):

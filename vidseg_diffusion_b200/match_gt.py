@@ -74,7 +74,13 @@ def match_gt_mask(feature_blocks, gt_mask_path, feature_height, feature_width, o
     """reference :546-643, same argument meaning and return triple (unique_labels, ref_mask, ref_feature_map); the two
     references are CUDA tensors (int32 [F*hw], fp32 [F*hw, C]) that the caller passes back for the next window.
 
-    ``feature_blocks``: one tensor [2F, hw, C] or the list of per-block tensors to average."""
+    ``feature_blocks``: one tensor [2F, hw, C] or the list of per-block tensors to average.
+
+    Departures from the reference, all on the host side: ``kmeans_cluster_labels.png`` (a matplotlib debug plot, :596-600)
+    is not written; ground-truth labels must lie in [0, 1024) (the majority kernel's histogram; PNG masks are uint8);
+    ``majority_map`` / ``knn_predict`` read one error flag back from the device each (a host sync the reference does not
+    have); with ``write_pngs=False`` the label maps reach a following ``correct_low_res_mask`` through
+    ``feature_extraction.register_label_maps`` instead of the PNG tree."""
     if isinstance(feature_blocks, torch.Tensor):
         feature_blocks = [feature_blocks]
     blocks = [_lib.require_cuda_tensor(b.float().contiguous() if b.is_cuda else b, torch.float32, "feature_maps")
@@ -104,8 +110,12 @@ def match_gt_mask(feature_blocks, gt_mask_path, feature_height, feature_width, o
     if ref_unique_labels is None:
         ref_unique_labels = unique_labels
     labels = knn_predict(ref_feature_map, ref_mask, tokens, 4)
+    from .feature_extraction import generate_binary_mask, invalidate_label_maps, register_label_maps
     if write_pngs:
-        from .feature_extraction import generate_binary_mask
+        invalidate_label_maps(output_folder)
+    else:   # no PNG tree: a following correct_low_res_mask takes the maps from the hand-over cache
+        register_label_maps(output_folder, labels.reshape(num_frames, h, w), num_frames, frame_name_list, h, w)
+    if write_pngs:
         labels_np = labels.cpu().numpy().reshape(num_frames, h, w)
         for frame_id in range(num_frames):
             frame_name = frame_name_list[frame_id] if frame_name_list is not None else frame_id

@@ -82,8 +82,11 @@ class ClipSegmenter:
             with torch.cuda.graph(graph):
                 out = self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
                 feats = self._features(num_frames)
-            ent = self._graphs[key] = (graph, static, out, feats, _lib.launch_count() - n0)
-        graph, static, out, feats, n_launches = ent
+                # the stash the refinement reads: the graph's own buffer, not whatever the module attribute points at
+                # after a later eager forward or another capture
+                q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0] if self.is_refine_mask else None
+            ent = self._graphs[key] = (graph, static, out, feats, _lib.launch_count() - n0, q7)
+        graph, static, out, feats, n_launches, q7 = ent
         self.graph_replays += 1
         self.graph_kernel_launches += n_launches   # library kernels inside the replayed graph (not counted by the host-side counter)
         static["x"].copy_(x, non_blocking=True)
@@ -92,7 +95,7 @@ class ClipSegmenter:
         for k, v in tens.items():
             static["kw_" + k].copy_(v, non_blocking=True)
         graph.replay()
-        return out, feats
+        return out, feats, q7
 
     def cluster(self, num_frames, feature_height, feature_width, seed=None, features=None):
         """K-means label maps [F, h, w] (int32, device) from the features stashed by the last UNet call."""
@@ -113,15 +116,15 @@ class ClipSegmenter:
     @torch.no_grad()
     def segment(self, x, timesteps, context, num_frames, seed=None, **unet_kwargs):
         """Whole path on device tensors.  Returns (label maps int32 [F, h, w], UNet output)."""
-        feats = None
+        feats = q7 = None
         if self.use_cuda_graph:
-            out, feats = self._graphed_unet_features(x, timesteps, context, num_frames, unet_kwargs)
+            out, feats, q7 = self._graphed_unet_features(x, timesteps, context, num_frames, unet_kwargs)
         else:
             out = self.unet_step(x, timesteps, context, **unet_kwargs)
         fh, fw = x.shape[-2] // 2, x.shape[-1] // 2   # H // (8 * 2): feature grid of output blocks 6-8
         labels = self.cluster(num_frames, fh, fw, seed, features=feats)
         if self.is_refine_mask:
-            labels = self.refine(labels, num_frames, fh, fw)
+            labels = self.refine(labels, num_frames, fh, fw, features=q7)
         return labels, out
 
     @torch.no_grad()
@@ -170,18 +173,21 @@ class ClipSegmenter:
         for clip in clips:
             x, t, c = (to_dev(v) for v in clip[:3])
             kw = {k: to_dev(v) for k, v in (clip[3] if len(clip) > 3 else {}).items()}
+            q7 = None
             if self.use_cuda_graph:
-                _, feats = self._graphed_unet_features(x, t, c, num_frames, kw)
+                _, feats, q7 = self._graphed_unet_features(x, t, c, num_frames, kw)
             else:
                 self.unet_step(x, t, c, **kw)
                 feats = self._features(num_frames)
+                if self.is_refine_mask:
+                    q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0]
             # the graph's buffers (and the modules' stash) are overwritten by the next clip: snapshot what the second
             # stream will read
             feats = feats.clone()
             feats.record_stream(side)
             fm7 = None
             if self.is_refine_mask:
-                fm7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0].clone()
+                fm7 = q7.clone()
                 fm7.record_stream(side)
             ready = torch.cuda.Event()
             ready.record(main)

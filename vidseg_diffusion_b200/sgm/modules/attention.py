@@ -113,7 +113,7 @@ class CrossAttention(nn.Module):
         # the reference's SDPA class ignores injected_v (attention.py:316), its xformers class uses it (:435-444);
         # BasicTransformerBlock sets this from attn_mode
         self.inject_v = False
-        self._stash = {"q": None, "k": None}
+        self._stash = {"q": None, "k": None, "v": None}
 
     # the Q/K "hook" (reference :330-331): plain attributes there; here the temporal layers keep their activations in
     # the frame-major layout and hand out the reference's '(b s) t c' view on first access
@@ -125,6 +125,9 @@ class CrossAttention(nn.Module):
 
     q = property(lambda self: self._get_stash("q"), lambda self, v: self._stash.__setitem__("q", v))
     k = property(lambda self: self._get_stash("k"), lambda self, v: self._stash.__setitem__("k", v))
+    # the reference's xformers class also keeps ``self.v`` (:446-448).  Nothing on the path reads it, so it is decoded
+    # from the attention kernel's fp16-pair operand (22 significant bits) on first access instead of costing an fp32 write
+    v = property(lambda self: self._get_stash("v"), lambda self, v: self._stash.__setitem__("v", v))
 
     def forward_single_token(self, xs, context):
         """Cross-attention to a context of ONE token (SVD: the CLIP image embedding, svd.yaml): softmax over a single
@@ -135,6 +138,8 @@ class CrossAttention(nn.Module):
         _, vs = K.linear(context, self.to_v.weight, want_f32=False, want_split=True)
         self.q = q
         self.k = k
+        if self.inject_v:
+            self.v = vs.float
         lin = self.to_out[0]
         out, _ = K.linear(vs, lin.weight, lin.bias, want_f32=True)
         return out.reshape(out.shape[0], out.shape[-1])
@@ -159,6 +164,8 @@ class CrossAttention(nn.Module):
             _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True, split_pair16=True)
         self.q = q
         self.k = k
+        if self.inject_v:   # "softmax-xformers" layers only, as in the reference
+            self.v = vs.float
         _, os_ = K.attention(qs, ks, vs, self.heads, self.scale)
         lin = self.to_out[0]
         out, _ = K.linear(os_, lin.weight, lin.bias, residual=residual, want_f32=True, row_scalar=row_scalar)

@@ -128,6 +128,8 @@ class VideoTransformerBlock(nn.Module):
         v = inj["v"] if ("v" in inj and a1.inject_v) else K.linear(hs, a1.to_v.weight, want_f32=True)[0]
         a1.q = lambda: _to_site_major(q, videos, T)
         a1.k = lambda: _to_site_major(k, videos, T)
+        if a1.inject_v:   # the xformers class also keeps v (attention.py:446-448)
+            a1.v = lambda: _to_site_major(v, videos, T)
         o = K.temporal_attention(q, k, v, videos, T, a1.heads, a1.scale)
         lin = a1.to_out[0]
         h, _ = K.linear(o, lin.weight, lin.bias, residual=h, want_f32=True, row_scalar=mod["self_attn"])
@@ -142,6 +144,8 @@ class VideoTransformerBlock(nn.Module):
             _, v2 = K.linear(context, a2.to_v.weight, want_f32=False, want_split=True)
             a2.q = lambda: _to_site_major(q2, videos, T)
             a2.k = lambda: k2.repeat_interleave(s, dim=0)     # [(b s), 1, c]: the repeated time context's keys
+            if a1.inject_v:
+                a2.v = lambda: v2.float().repeat_interleave(s, dim=0)
             lin2 = a2.to_out[0]
             av, _ = K.linear(v2, lin2.weight, lin2.bias, want_f32=True)   # one vector per clip (softmax over 1 key = 1)
             if mod["cross_attn"] is not None:
