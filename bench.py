@@ -2,7 +2,7 @@
 """Benchmark of the VidSeg per-clip hot path on B200 (contract: see DESIGN.md section "Measurement").
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port)
+    python bench.py --impl reference --steps K --warmup W    # the UNMODIFIED reference on the host cores (oracle/_ref)
 
 One "step" = one pass of the hot path over one synthetic clip per GPU: SD-2.1 UNet forward at batch 2F
 with the Q/K stash -> aggregate(out 8,7,6)/normalise -> K-means(K, n_init=10) fit+predict
@@ -167,80 +167,151 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-# --------------------------------------------------------------------------------------------------
-# the reference's CPU path (oracle port): bounded sample of the same workload
-# --------------------------------------------------------------------------------------------------
-def cpu_reference_step(wl, cfg, sd, clip, n_frames, seed):
-    """One pass of the reference's CPU implementation over ``n_frames`` frames of the clip: fp32 UNet forward
-    (oracle/unet.py, the same ATen CPU kernels the reference's nn.Modules dispatch to) at batch 2*n_frames,
-    3-block mean + max-abs normalise (numpy, as feature_extraction.py:38-46,745), scikit-learn
-    KMeans(K, n_init=10).fit + .predict (feature_extraction.py:52-55; the oracle's restatement if sklearn is
-    missing), and the nearest-neighbour refinement when the workload has it.  Returns seconds."""
-    import numpy as np
-    import torch
-    from oracle import features as ofeat, kmeans as okm, refine as oref, unet as ounet
+def bench_config(args, wl, world, multi_gpu):
+    """The ``config`` object of the JSON line: what is measured, identical for this repo's arm and the reference arm."""
     F = wl["frames"]
-    idx = list(range(n_frames)) + [F + i for i in range(n_frames)]
-    sub = [a[idx] for a in clip]
-    t0 = time.perf_counter()
-    stash = {}
-    if is_video(cfg):
-        from oracle import video_unet as ovid
-        ocfg = dict(in_channels=cfg["in_channels"], out_channels=cfg["out_channels"], model_channels=cfg["model_channels"],
-                    attention_resolutions=tuple(cfg["attention_resolutions"]), num_res_blocks=cfg["num_res_blocks"],
-                    channel_mult=tuple(cfg["channel_mult"]), num_head_channels=cfg["num_head_channels"],
-                    context_dim=cfg["context_dim"], adm_in_channels=cfg["adm_in_channels"])
-        ovid.video_unet_forward(sd, ocfg, sub[0], sub[1], sub[2], sub[3], n_frames, None, stash)
+    if world == 1:
+        mg, clips = "single GPU", 1
+    elif multi_gpu == "sharded":
+        mg = ("ONE clip per step, frames sharded over the ranks: NCCL all-gather of the feature rows + one all-reduce per "
+              "Lloyd iteration (BASELINE configs[3])")
+        clips = 1
+    elif multi_gpu == "cfg-split":
+        mg = "ONE clip per step, the two guidance halves of the SVD batch on two ranks, feature broadcast + distributed K-means"
+        clips = 1
     else:
-        ounet.unet_forward(sd, cfg, sub[0], sub[1], sub[2], stash)
-    blocks = (8, 7, 6) if wl["aggre"] else (8,)
-    feats = [stash[(f"output_block_{i}", "spatial_self_attn_q")].numpy() for i in blocks]
-    X = ofeat.aggregate_normalize(feats, n_frames)
-    np.random.seed(seed)
-    k = min(wl["num_masks"], X.shape[0])
-    try:
-        import warnings
-        from sklearn.cluster import KMeans
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            km = KMeans(n_clusters=k, n_init=10).fit(X)
-            labels = km.predict(X)
-    except ImportError:
-        labels, _ = okm.kmeans_fit_predict(X, k)
-    if wl["refine"]:
-        fh = wl["latent"] // 2
-        oref.correct_low_res_mask(stash[("output_block_7", "spatial_self_attn_q")].numpy(), labels.reshape(n_frames, fh, fh),
-                                  fh, fh, n_frames)
-    return time.perf_counter() - t0
+        mg, clips = "one clip per GPU per step (replicas), no data-path collective", world
+    return {"workload": args.workload, "desc": wl["desc"], "frames": F, "clips_per_step": clips, "multi_gpu": mg,
+            "l2": "working set (3.5 GB split weights + >4 GB activations per step) exceeds the 126 MB L2; no flush needed",
+            "unet_tflop_per_step": UNET_TFLOP.get(args.workload)}
+
+
+def multi_gpu_mode(args, cfg, world):
+    if world == 1:
+        return "single"
+    if args.multi_gpu != "auto":
+        return args.multi_gpu
+    if is_video(cfg):
+        return "cfg-split" if world == 2 else "replicas"
+    return "sharded"
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's own CPU path (unmodified reference modules, oracle/reference_path.py)
+# --------------------------------------------------------------------------------------------------
+_REF_MODEL = {}
+
+
+def reference_model(cfg, sd):
+    """The reference's nn.Module for ``cfg`` with the bench's weights (built once per process)."""
+    from oracle import reference_path as rp
+    key = id(cfg)
+    if key not in _REF_MODEL:
+        m = rp.build_model(cfg)
+        m.load_state_dict(sd, strict=True)
+        _REF_MODEL[key] = m
+    return _REF_MODEL[key]
+
+
+def cpu_reference_step(wl, cfg, sd, clip, seed, keep=False):
+    """One pass of the UNMODIFIED reference over the whole clip on the host cores: ``UNetModel`` / ``VideoUNet`` forward
+    at batch 2F in fp32, ``torch.save`` of the stashed q tensors, ``feature_extraction_main("kmeans_masks")`` (scikit-learn
+    KMeans + PNG tree) and, with refinement, ``feature_extraction_main("correct_low_res_mask")``."""
+    from oracle import reference_path as rp
+    return rp.clip_step(reference_model(cfg, sd), clip, wl["frames"], wl["num_masks"], aggre=wl["aggre"], refine=wl["refine"],
+                        seed=seed, keep=keep)
+
+
+def reference_sample_text(wl, secs=None):
+    import torch
+    txt = (f"{wl['frames']} of {wl['frames']} frames per step: the unmodified reference (oracle/_ref mirror of sgm + scripts) on the "
+           f"CPU, UNet batch {2 * wl['frames']} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32, torch.save of the stashed q, "
+           f"feature_extraction_main kmeans_masks{' + correct_low_res_mask' if wl['refine'] else ''} (scikit-learn KMeans, PNG tree), "
+           f"torch {torch.__version__}")
+    if secs:
+        txt += "; stages " + ", ".join(f"{k} {v:.1f} s" for k, v in secs.items())
+    return txt
 
 
 def run_reference(args, wl, cfg):
     import torch
     rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     if rank != 0:
+        return
+    from oracle import reference_path as rp
+    if not rp.available():
+        emit({"impl": "reference", "unavailable": "oracle/_ref is missing: run `python oracle/make_ref.py` where /root/reference exists"})
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
     sd = make_state_dict(cfg)
     clip = make_clip(wl, cfg, 1)
-    nf = max(1, min(args.ref_frames, wl["frames"]))
+    t_start = time.perf_counter()
+    # every step is the whole 14-frame clip; if W + K such steps do not fit the wall budget the step COUNT is cut (and
+    # reported), never the workload
+    done_w, per_step = 0, None
     for _ in range(args.warmup):
-        cpu_reference_step(wl, cfg, sd, clip, nf, 1)
-    times = [cpu_reference_step(wl, cfg, sd, clip, nf, 1) for _ in range(args.steps)]
-    total = sum(times)
-    fps = nf * args.steps / total
-    sample = (f"{nf} of {wl['frames']} frames per step (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8}, "
-              f"K-means on {nf} frames' features), fp32, torch {torch.__version__} CPU + scikit-learn")
+        r = cpu_reference_step(wl, cfg, sd, clip, 1)
+        done_w += 1
+        per_step = r["seconds"]["total"]
+        left = args.ref_budget_s - (time.perf_counter() - t_start)
+        if per_step * (args.warmup - done_w + args.steps) > left:
+            break
+    steps = args.steps
+    if per_step is not None:
+        left = args.ref_budget_s - (time.perf_counter() - t_start)
+        steps = max(1, min(args.steps, int(left / per_step)))
+    res = [cpu_reference_step(wl, cfg, sd, clip, 1) for _ in range(steps)]
+    total = sum(r["seconds"]["total"] for r in res)
+    stage = {k: sum(r["seconds"][k] for r in res) / steps for k in res[0]["seconds"]}
+    fps = wl["frames"] * steps / total
+    sample = reference_sample_text(wl, stage)
+    mode = multi_gpu_mode(args, cfg, world)
     line = {
-        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": done_w, "ms_per_step": 1e3 * total / steps, "higher_is_better": True,
+        "scaling": "strong" if mode in ("sharded", "cfg-split") else "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"], "sample": sample},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": bench_config(args, wl, world, mode),
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "threads": {"os_cpu_count": cores, "torch": torch.get_num_threads()},
     }
     emit(line)
+
+
+def relerr(got, want):
+    import torch
+    got, want = torch.as_tensor(got).double().cpu(), torch.as_tensor(want).double().cpu()
+    return float((got - want).abs().max() / want.abs().max())
+
+
+def label_oracle(X, q7, wl, seed):
+    """Label maps the reference's clustering arithmetic gives on the GPU's OWN features: scikit-learn KMeans (the reference's
+    third-party call, feature_extraction.py:52-55; the oracle's restatement when sklearn is missing) and the oracle's
+    correct_low_res_mask."""
+    import numpy as np
+    from oracle import kmeans as okm, refine as oref
+    F, fh = wl["frames"], wl["latent"] // 2
+    np.random.seed(seed)
+    try:
+        import warnings
+        from sklearn.cluster import KMeans
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            km = KMeans(n_clusters=wl["num_masks"], n_init=10).fit(X)
+            labels = km.predict(X)
+        how = "scikit-learn KMeans"
+    except ImportError:
+        labels, _ = okm.kmeans_fit_predict(X, wl["num_masks"])
+        how = "oracle/kmeans.py"
+    if wl["refine"]:
+        labels, _, _, _ = oref.correct_low_res_mask(q7, labels.reshape(F, fh, fh), fh, fh, F)
+        how += " + oracle/refine.py"
+    return np.asarray(labels).reshape(-1), how
 
 
 # --------------------------------------------------------------------------------------------------
@@ -251,7 +322,7 @@ def run_b200(args, wl, cfg):
     import torch
     import torch.distributed as dist
     from vidseg_diffusion_b200 import _lib
-    from vidseg_diffusion_b200.pipeline import ClipSegmenter
+    from vidseg_diffusion_b200.pipeline import ClipSegmenter, harvest_self_attn_q
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -265,6 +336,8 @@ def run_b200(args, wl, cfg):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     _lib.load()
+    mode = multi_gpu_mode(args, cfg, world)
+    one_clip = mode in ("sharded", "cfg-split")
 
     sd = make_state_dict(cfg)
     with torch.device("meta"):
@@ -272,28 +345,34 @@ def run_b200(args, wl, cfg):
     model = model.to_empty(device=dev)
     model.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
     model.eval()
-    seg = ClipSegmenter(model, num_masks=wl["num_masks"], is_aggre_attn=wl["aggre"], is_refine_mask=wl["refine"],
-                        use_cuda_graph=not args.no_graph)
-    seg_eager = ClipSegmenter(model, num_masks=wl["num_masks"], is_aggre_attn=wl["aggre"], is_refine_mask=wl["refine"])
+    seg_kw = dict(num_masks=wl["num_masks"], is_aggre_attn=wl["aggre"], is_refine_mask=wl["refine"])
+    seg = ClipSegmenter(model, use_cuda_graph=not args.no_graph, **seg_kw)
+    seg_eager = ClipSegmenter(model, **seg_kw)
     F = wl["frames"]
-    host = [t.pin_memory() for t in make_clip(wl, cfg, 1 + rank)]     # every rank its own clip (weak scaling)
+    # sharded: every rank holds the SAME clip (its frames are what is distributed); replicas: every rank its own clip
+    host = [t.pin_memory() for t in make_clip(wl, cfg, 1 if one_clip else 1 + rank)]
     devt = [t.to(dev) for t in host]
     seed = 1
+    vkw = dict(num_video_frames=F) if is_video(cfg) else {}
+    kw_of = lambda ts: (dict(vkw, y=ts[3]) if vkw else {})
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph_launches = lambda: seg.graph_kernel_launches + (sh.local.graph_kernel_launches if one_clip else 0)
+
     def timed(fn, steps, profile=False):
         barrier()
         if profile:
             _lib.profile_enable(True)
-        launches0 = _lib.launch_count() + seg.graph_kernel_launches
+        launches0 = _lib.launch_count() + graph_launches()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        out = None
         for _ in range(steps):
-            fn()
+            out = fn()
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -305,45 +384,86 @@ def run_b200(args, wl, cfg):
             tt = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             ms = float(tt.item())
-        return ms, _lib.launch_count() + seg.graph_kernel_launches - launches0, prof
+        return ms, _lib.launch_count() + graph_launches() - launches0, prof, out
 
-    vkw = dict(num_video_frames=F) if is_video(cfg) else {}
-    step_dev = lambda: seg.segment(devt[0], devt[1], devt[2], F, seed, **(dict(vkw, y=devt[3]) if vkw else {}))
-    step_e2e = lambda: seg.segment_host(host[0], host[1], host[2], F, seed, **(dict(vkw, y=host[3]) if vkw else {}))
-    if args.pipelined:
-        # the stream API: K clips per call, the UNet stage of clip i+1 overlaps the clustering of clip i (same kernels,
-        # same results; one step = one clip, every step copies its inputs in and its label maps out in the e2e form)
-        clip_dev = (devt[0], devt[1], devt[2], dict(vkw, y=devt[3]) if vkw else {})
-        clip_host = (host[0], host[1], host[2], dict(vkw, y=host[3]) if vkw else {})
-        many = lambda clip, n, to_host: [r for r in seg.segment_many([clip] * n, F, seed, to_host=to_host)]
-    for _ in range(max(args.warmup, 3)):
-        step_dev()
-    if args.pipelined:
-        many(clip_dev, 2, False)
+    step_dev = lambda: seg.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+    clip_dev = (devt[0], devt[1], devt[2], kw_of(devt))
+    clip_host = (host[0], host[1], host[2], kw_of(host))
+    many = lambda clip, n, to_host: [r for r in seg.segment_many([clip] * n, F, seed, to_host=to_host)]
+    extra = {}
+    parity = {}
+    if one_clip:
+        from vidseg_diffusion_b200.distributed import ShardedClipSegmenter
+        sh = ShardedClipSegmenter(model, use_cuda_graph=not args.no_graph, **seg_kw)
+        sh_eager = ShardedClipSegmenter(model, **seg_kw)
+        sh_dev = lambda: sh.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+
+        def sh_e2e():
+            d = [t.to(dev, non_blocking=True) for t in host]
+            return sh.segment(d[0], d[1], d[2], F, seed, **kw_of(d)).cpu()
+        for _ in range(max(args.warmup, 3)):
+            sh_dev()
         sampler = ClockSampler(local_rank)
         sampler.start()
-        ms, launches, _ = timed(lambda: many(clip_dev, args.steps, False), 1)
+        ms, launches, _, labels_dev = timed(sh_dev, args.steps)
         clocks = sampler.finish()
-        many(clip_host, 2, True)
-        ms_e2e, _, _ = timed(lambda: many(clip_host, args.steps, True), 1)
-        ms_lat, _, _ = timed(step_dev, min(args.steps, 3))
-        ms_lat /= min(args.steps, 3)
-    else:
-        sampler = ClockSampler(local_rank)
-        sampler.start()
-        ms, launches, _ = timed(step_dev, args.steps)
-        clocks = sampler.finish()
-        step_e2e()
-        ms_e2e, _, _ = timed(step_e2e, args.steps)
+        info = dict(sh.last["kmeans_info"])
+        sh_e2e()
+        ms_e2e, _, _, labels = timed(sh_e2e, args.steps)
         ms_lat = ms / args.steps
-    labels = step_e2e()
+        step_prof = lambda: sh_eager.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+        # parity of the split: every rank's label maps equal rank 0's, and equal the single-GPU path on the whole clip
+        ref0 = labels_dev.clone()
+        dist.broadcast(ref0, src=0)
+        single = seg_eager.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))[0]
+        flags = torch.tensor([int(torch.equal(ref0, labels_dev)), int(torch.equal(single, labels_dev))], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        parity = {"labels_identical_on_all_ranks": bool(flags[0].item()),
+                  "labels_identical_to_single_gpu_path": bool(flags[1].item()),
+                  "lloyd_iterations": info.get("iterations"), "allreduces_per_clip": info.get("allreduces"),
+                  "exchange_words": info.get("exchange"), "unsharded_fallback": info.get("unsharded_fallback")}
+        # the zero-communication alternative (one clip per GPU), for comparison: a few pipelined steps
+        rep_host = [t.pin_memory() for t in make_clip(wl, cfg, 1 + rank)]
+        rep_clip = (rep_host[0], rep_host[1], rep_host[2], kw_of(rep_host))
+        n_rep = max(2, min(args.steps, 5))
+        many(rep_clip, 2, True)
+        ms_rep, _, _, _ = timed(lambda: many(rep_clip, n_rep, True), 1)
+        extra["replicas"] = {"value": world * F * n_rep / (ms_rep / 1e3), "unit": UNIT, "steps": n_rep, "clips_per_step": world,
+                             "note": "one clip per GPU per step through segment_many with host buffers (weak scaling, no collective)"}
+        clips_per_step = 1
+    else:
+        for _ in range(max(args.warmup, 3)):
+            step_dev()
+        if args.pipelined:
+            # the stream API: K clips per call, the UNet stage of clip i+1 overlaps the clustering of clip i (same kernels,
+            # same results; one step = one clip, every step copies its inputs in and its label maps out in the e2e form)
+            many(clip_dev, 2, False)
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ms, launches, _, _ = timed(lambda: many(clip_dev, args.steps, False), 1)
+            clocks = sampler.finish()
+            many(clip_host, 2, True)
+            ms_e2e, _, _, outs = timed(lambda: many(clip_host, args.steps, True), 1)
+            labels = outs[-1]
+            ms_lat, _, _, _ = timed(step_dev, min(args.steps, 3))
+            ms_lat /= min(args.steps, 3)
+        else:
+            step_e2e = lambda: seg.segment_host(host[0], host[1], host[2], F, seed, **kw_of(host))
+            sampler = ClockSampler(local_rank)
+            sampler.start()
+            ms, launches, _, _ = timed(step_dev, args.steps)
+            clocks = sampler.finish()
+            step_e2e()
+            ms_e2e, _, _, labels = timed(step_e2e, args.steps)
+            ms_lat = ms / args.steps
+        step_prof = lambda: seg_eager.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+        clips_per_step = world
     # per-kernel pass: the SAME step, launched eagerly with every library launch bracketed by CUDA events on its own
     # stream (vidseg_profile_*); the event pairs add host work, so this pass feeds the roofline / stage split only
-    step_prof = lambda: seg_eager.segment(devt[0], devt[1], devt[2], F, seed, **(dict(vkw, y=devt[3]) if vkw else {}))
     step_prof()
-    ms_prof, _, prof = timed(step_prof, args.steps, profile=True)
-    fps = world * F * args.steps / (ms / 1e3)
-    fps_e2e = world * F * args.steps / (ms_e2e / 1e3)
+    ms_prof, _, prof, _ = timed(step_prof, args.steps, profile=True)
+    fps = clips_per_step * F * args.steps / (ms / 1e3)
+    fps_e2e = clips_per_step * F * args.steps / (ms_e2e / 1e3)
     h2d = sum(t.numel() * t.element_size() for t in host)
     d2h = labels.numel() * labels.element_size()
 
@@ -367,15 +487,17 @@ def run_b200(args, wl, cfg):
                      "launches": sum(prof[f]["launches"] for f in fams)}
     kname = max(agg, key=lambda k: agg[k]["ms"])
     p = agg[kname]
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")
-    if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
-        try:
-            tj = json.load(open(tpath))
-            if tj.get("workload") == args.workload and tj.get("kernel", "") in kname:
-                traffic = tj["dram_bytes_per_launch"]
-        except Exception:
-            traffic = None
+    traffic, traffic_src = None, None
+    for tname in ("r02_dominant_kernel_traffic.json", "r01_dominant_kernel_traffic.json"):
+        tpath = os.path.join(ROOT, "profiles", tname)
+        if os.path.exists(tpath):   # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu capture
+            try:
+                tj = json.load(open(tpath))
+                if tj.get("workload") == args.workload and tj.get("kernel", "") in kname and world == 1:
+                    traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/" + tname
+                    break
+            except Exception:
+                pass
     # MMA units per algorithmic product: 2 with fp16 + fp8-correction operands (the default policy), 3 with fp16 pairs
     mma_units = 2.0 if (_lib.load().vidseg_get_operand_mode() != 0 and "gemm_split" in kname) else 3.0
     if p["bound"] == "tensor":
@@ -391,7 +513,7 @@ def run_b200(args, wl, cfg):
                 avg_launch_us=1e3 * p["ms"] / max(p["launches"], 1), share_of_step=p["ms"] / ms_prof,
                 timed_over=f"{args.steps} eagerly launched steps with per-launch CUDA events ({ms_prof / args.steps:.1f} ms/step; the "
                            f"headline value replays the UNet stage as one CUDA graph)",
-                peak_source=peaks["source"],
+                peak_source=peaks["source"], traffic_source=traffic_src,
                 note="achieved = algorithmic FLOPs (2MNK of the fp32-equivalent product) / CUDA-event time over all "
                      "launches of the kernel in the profiled pass; the parity bar (1e-3 vs the fp32 reference) needs more "
                      f"than one fp16 MMA per product: each product costs {mma_units:.0f} fp16-MMA units (fp16 value + "
@@ -404,34 +526,60 @@ def run_b200(args, wl, cfg):
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    nf = max(1, min(args.ref_frames, F))
-    if args.no_cpu_baseline or world > 1:   # the CPU leg is timed at N=1 only (rank 0)
-        t_cpu, sample = float("nan"), "skipped (--no-cpu-baseline)" if args.no_cpu_baseline else "timed at N=1 only"
-    else:
-        t_cpu = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], nf, seed)
-        sample = (f"{nf} of {F} frames, one pass (UNet batch {2 * nf} at {wl['latent'] * 8}x{wl['latent'] * 8} fp32 + "
-                  f"K-means on those frames), {t_cpu:.1f} s")
+    cpu = {"value": None, "unit": UNIT, "cores": cores, "kind": "reference", "sample": "timed at N=1 only"}
+    if args.no_cpu_baseline:
+        cpu["sample"] = "skipped (--no-cpu-baseline)"
+    elif world == 1:
+        from oracle import reference_path as rp
+        if not rp.available():
+            cpu["sample"] = "oracle/_ref missing (run python oracle/make_ref.py where /root/reference exists)"
+        else:
+            # ONE full pass of the unmodified reference over the SAME clip: the CPU baseline and the feature-level parity
+            ref = cpu_reference_step(wl, cfg, sd, [t.clone() for t in make_clip(wl, cfg, 1)], seed, keep=True)
+            cpu.update(value=F / ref["seconds"]["total"], sample="one pass, " + reference_sample_text(wl, ref["seconds"]))
+            lab_gpu, out_gpu = seg_eager.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+            q_gpu = {i: q.cpu() for i, q in zip((8, 7, 6), harvest_self_attn_q(model, (8, 7, 6)))}
+            feat = {f"attn1.q out_block_{i}": relerr(q_gpu[i], ref["q"][i]) for i in (6, 7, 8)}
+            feat["unet_output"] = relerr(out_gpu, ref["out"])
+            parity.update(features_rel_err_vs_reference=feat, features_max_rel_err=max(feat.values()), features_tol=1e-3,
+                          features_ok=max(feat.values()) <= 1e-3,
+                          labels_gpu_path_vs_reference_path_mismatch_cells=int((lab_gpu.cpu().numpy().reshape(-1) != ref["labels"].reshape(-1)).sum()),
+                          labels_gpu_path_vs_reference_path_note="the two paths cluster DIFFERENT feature tensors (equal to "
+                          "features_max_rel_err, not bit-equal), so this count is information; the bit-exact check is label_mismatches")
+            del ref
+    if world == 1 and not args.no_parity:
+        # integer stage: the label maps of the TIMED call against the reference's clustering arithmetic run on the CPU
+        # on the very features the GPU clustered
+        lab_gpu, _ = seg_eager.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
+        timed_labels = labels.cpu().numpy().reshape(-1)
+        X = seg_eager.last["features"].cpu().numpy()
+        q7 = harvest_self_attn_q(model, (7,))[0].cpu().numpy() if wl["refine"] else None
+        t0 = time.perf_counter()
+        want, how = label_oracle(X, q7, wl, seed)
+        parity.update(label_mismatches=int((timed_labels != want).sum()), label_cells=int(want.size), label_checker=how,
+                      label_checker_seconds=round(time.perf_counter() - t0, 1),
+                      timed_call_equals_eager_call=bool((timed_labels == lab_gpu.cpu().numpy().reshape(-1)).all()))
     line = {
         "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if one_clip else "weak", "vs_baseline": None,
         "dtype": "f32 (fp16 tensor-core operands with fp8/fp16 correction terms, fp32 accumulate; parity 1e-3 vs the fp32 reference)",
         "data": "synthetic",
-        "config": {"workload": args.workload, "desc": wl["desc"], "frames": F, "clips_per_step": world,
-                   "multi_gpu": "one clip per GPU per step, no data-path collective" if world > 1 else "single GPU",
-                   "l2": "working set (3.5 GB split weights + >4 GB activations per step) exceeds the 126 MB L2; no flush needed",
-                   "unet_tflop_per_step": UNET_TFLOP.get(args.workload),
-                   "unet_stage": "eager launches" if args.no_graph else "one CUDA graph (UNet + harvest + aggregate/normalise)",
-                   "schedule": "segment_many: clips software-pipelined over two CUDA streams" if args.pipelined
-                               else "segment: one clip at a time, stages back to back"},
+        "config": bench_config(args, wl, world, mode),
+        "impl_detail": {"unet_stage": "eager launches" if args.no_graph else "one CUDA graph (UNet + harvest + aggregate/normalise)",
+                        "schedule": ("ShardedClipSegmenter.segment: one clip at a time over all ranks" if one_clip else
+                                     "segment_many: clips software-pipelined over two CUDA streams" if args.pipelined
+                                     else "segment: one clip at a time, stages back to back")},
         "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "latency_ms_per_clip": ms_lat,
         "roofline": roof,
         "stage_ms_per_step": breakdown,
-        "cpu_baseline": {"value": (nf / t_cpu if t_cpu == t_cpu else None), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": cpu,
+        "parity": parity,
         "clocks": clocks,
     }
+    line.update(extra)
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -472,7 +620,13 @@ def main():
     ap.add_argument("--no-pipeline", dest="pipelined", action="store_false",
                     help="time ClipSegmenter.segment (one clip at a time) instead of segment_many, where the UNet stage of "
                          "clip i+1 overlaps the clustering of clip i on a second stream")
-    ap.add_argument("--ref-frames", type=int, default=2, help="frames per CPU-reference step (bounded sample)")
+    ap.add_argument("--multi-gpu", default="auto", choices=["auto", "sharded", "cfg-split", "replicas"],
+                    help="N > 1: 'sharded' = ONE clip per step with its frames sharded over the ranks (all-gather + distributed "
+                         "K-means; default for SD-2.1), 'cfg-split' = the two guidance halves of an SVD clip on two ranks "
+                         "(default for SVD at N = 2), 'replicas' = one clip per GPU, no collective")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CPU check of the timed call's label maps")
+    ap.add_argument("--ref-budget-s", type=float, default=1500.0,
+                    help="wall budget of the reference arm: the step COUNT is cut to fit it, never the workload")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     from vidseg_diffusion_b200 import configs

@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);  /* 5: + sampler_step, set/get_kmeans_mstep; 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
+int vidseg_abi_version(void);  /* 6: + kmeans exchange words, flags_async, aggregate_normalize_rows; 5: + sampler_step, set/get_kmeans_mstep; 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -48,6 +48,12 @@ int vidseg_device_arch(void);
 int vidseg_aggregate_normalize(const float* const* blocks_host, int n_blocks,
                                int num_frames, int hw, int channels,
                                float* out, void* stream);
+
+/* Same arithmetic on the row window [first_row, first_row + rows) of every block (blocks are [*, C] row-major): the
+ * CFG-half split of the SVD UNet over two GPUs leaves the conditional rows alone on one rank (first_row = 0). */
+int vidseg_aggregate_normalize_rows(const float* const* blocks_host, int n_blocks,
+                                    long long first_row, long long rows, int channels,
+                                    float* out, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * R2  K-means  (sklearn.cluster.KMeans(n_clusters=K, n_init=R).fit + .predict)
@@ -101,6 +107,25 @@ int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin
  * shift, convergence flags (strict label equality, else sum(shift^2) <= tol). */
 int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double* partial,
                          const int32_t* changed, int local_rows_only, void* stream);
+
+/* Multi-GPU exchange form of one Lloyd iteration ("allreduce inside K-means"): the per-cluster
+ * sums, the counts and the label-change counters of all runs travel as ONE array of 8-byte words
+ *   words[(r*K + j)*(D+1) + c] sums (c < D) | count (c == D),  then words[R*K*(D+1) + r] = changed labels of run r,
+ * so an iteration costs one all-reduce.  words_i64 != 0: the words are the INTEGER fixed-point sums of the int8
+ * tensor-core M-step (int64) -- all-reduce(SUM) over ranks is then exact and order independent and the sharded fit is
+ * bit-identical to the single-GPU fit; words_i64 == 0: float64 words.  vidseg_kmeans_exchange_mode returns 1 when the
+ * row range of a rank can produce integer words (every rank must pass the same words_i64, so the caller ANDs the
+ * answers for all ranks' ranges), 0 when not, negative on error.  update_words with integer words requires
+ * local_rows_only (no empty-cluster relocation in that form; see vidseg_kmeans_status). */
+size_t vidseg_kmeans_exchange_words(void* workspace, size_t workspace_bytes);
+int vidseg_kmeans_exchange_mode(void* workspace, size_t workspace_bytes, int row_begin, int row_end);
+int vidseg_kmeans_partial_words(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                                int words_i64, void* words, void* stream);
+int vidseg_kmeans_update_words(void* workspace, size_t workspace_bytes, int words_i64, void* words,
+                               int local_rows_only, void* stream);
+/* convergence flags int32 [R][4] = {done, strict, n_iter, empty cluster seen} -> (pinned) host memory WITHOUT
+ * synchronising: record an event behind the call and read the flags once it has passed. */
+int vidseg_kmeans_flags_async(void* workspace, size_t workspace_bytes, int32_t* flags_host, void* stream);
 
 /* number of runs still iterating (synchronises the stream). */
 int vidseg_kmeans_active_runs(void* workspace, size_t workspace_bytes, int* n_active_host,

@@ -1,10 +1,12 @@
 """TEST INFRASTRUCTURE ONLY -- import shim for the *unmodified* reference tree.
 
 The reference (QianWangX/VidSeg_diffusion @ 3e96366) lives read-only at
-/root/reference in the authoring container and does NOT exist on the GPU box.
-This module is used only by the golden-vector generators under
-``tests/golden/make_*.py`` (run in the authoring container) to import the
-reference's own modules so that goldens come from the reference code itself.
+/root/reference in the authoring container and does NOT exist on the GPU box;
+``oracle/make_ref.py`` mirrors its ``sgm`` / ``scripts`` packages into the
+git-ignored ``oracle/_ref/`` so that they travel there.  This module imports the
+reference's own modules from whichever of the two exists.  Users: the
+golden-vector generators under ``tests/golden/make_*.py``, ``oracle/reference_path.py``
+(the reference arm / CPU baseline of bench.py and the full-size parity tests).
 
 Packages the reference imports at module scope but which are absent from this
 image are replaced by inert ``sys.modules`` stubs:
@@ -17,7 +19,18 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VIDSEG_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root():
+    env = os.environ.get("VIDSEG_REFERENCE_ROOT")
+    for cand in ([env] if env else []) + ["/root/reference", os.path.join(_HERE, "_ref")]:
+        if os.path.isdir(os.path.join(cand, "sgm")) and os.path.isdir(os.path.join(cand, "scripts")):
+            return cand
+    return env or "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:

@@ -1,6 +1,8 @@
 """CPU, world_size 2 over gloo: the host logic of the frame-sharded path (vidseg_diffusion_b200/distributed.py) --
-frame partition, ragged row all-gather, and the distributed Lloyd driver (per-iteration all-reduce of the fused
-[n_init, K, D+1] sums|counts buffer, redundant seeding / best-of selection, final label all-gather).  The CUDA kernels
+frame partition, ragged row all-gather, and the distributed Lloyd driver (ONE all-reduce per iteration of the fused
+[n_init*K*(D+1) + n_init] exchange words: sums | counts | change counters; convergence flags polled one burst late;
+redundant seeding / best-of selection with inertia and the same-clustering matrix in one collective; final label
+all-gather).  The CUDA kernels
 cannot run here, so the driver is exercised with a numpy stand-in that implements the same split E-step / M-step
 contract as include/vidseg_b200.h (R2) on top of the oracle's primitives; the GPU form of the same driver is covered by
 tests/test_gpu_distributed.py."""
@@ -107,6 +109,25 @@ class NumpyLloydBackend:
     def status(self):
         return int((~self.done).sum()), int(self.empty_seen.sum())
 
+    # exchange-word form of the same contract (one fused float64 array per iteration; this stand-in has no int8 M-step)
+    def exchange_mode(self, ranges):
+        return "f64"
+
+    def partial_words(self, r0, r1, mode):
+        assert mode == "f64"
+        part, ch = self.partial(r0, r1)
+        return torch.cat([part.reshape(-1), ch.double()])
+
+    def update_words(self, words, mode, local_rows_only):
+        nk = self.r * self.k * (self.d + 1)
+        self.update(words[:nk].reshape(self.r, self.k, self.d + 1), words[nk:].round().to(torch.int32), local_rows_only)
+
+    def flags_async(self):
+        return self.status() + (int(self.n_iter.max()),)
+
+    def flags_wait(self, ticket):
+        return ticket
+
     def inertia(self, r0, r1):
         out = np.zeros(self.r)
         for r in range(self.r):
@@ -138,6 +159,9 @@ def _free_port():
     return port
 
 
+rank_known_ranges = True
+
+
 def _worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -156,9 +180,10 @@ def _worker(rank, world, port, q):
         np.random.seed(7)
         info = {}
         row0 = sum(counts[:rank])
-        labels = D.sharded_kmeans_fit_predict(X, K, (row0, row0 + counts[rank]), n_init=3,
-                                              backend=NumpyLloydBackend(K, 3), info=info)
-        q.put((rank, labels.numpy(), info["iterations"], info["allreduces"], info["unsharded_fallback"]))
+        ranges = [(sum(counts[:r]), sum(counts[:r + 1])) for r in range(world)]
+        labels = D.sharded_kmeans_fit_predict(X, K, ranges[rank], n_init=3, backend=NumpyLloydBackend(K, 3), info=info,
+                                              row_ranges=ranges if rank_known_ranges else None)
+        q.put((rank, labels.numpy(), info["iterations_issued"], info["allreduces"], info["unsharded_fallback"]))
     finally:
         dist.destroy_process_group()
 
@@ -195,5 +220,5 @@ def test_sharded_kmeans_two_ranks_gloo_matches_oracle():
     np.random.seed(7)
     want, _ = okm.kmeans_fit_predict(x_full, K, n_init=3)
     assert np.array_equal(lab0, want)
-    # two all-reduces per Lloyd iteration (sums|counts, changed) + inertia + same-clustering matrix
-    assert ar0 == 2 * it0 + 2
+    # ONE all-reduce per issued Lloyd iteration (sums | counts | change counters) + one for inertia | same-clustering
+    assert ar0 == it0 + 1

@@ -64,6 +64,61 @@ def test_two_virtual_ranks_reproduce_reference_labels(cuda, case):
     assert np.array_equal(labels.cpu().numpy(), g["labels"].reshape(-1))
 
 
+@pytest.mark.parametrize("case", ["c1_objects", "c2_objects"])
+def test_two_virtual_ranks_integer_exchange_words_are_bit_identical_to_one_gpu(cuda, case):
+    """The exchange-word form (one fused array per iteration): with integer words the hand-made all-reduce (an int64 add)
+    is exact, so the sharded fit must give the single-GPU fit's centres BIT FOR BIT, not just its labels."""
+    from vidseg_diffusion_b200 import distributed as D
+    from vidseg_diffusion_b200.features import aggregate_normalize
+    from vidseg_diffusion_b200.kmeans import KMeans, draw_kmeanspp_randoms
+    name, seed, F, h, w, C, K, kind = next(c for c in CLUSTER_CASES if c[0] == case)
+    g = np.load(os.path.join(GOLDEN, f"cluster_{name}.npz"))
+    blocks, _ = synthetic_clip_features(seed, F, h, w, C, K, kind=kind)
+    X = aggregate_normalize([torch.from_numpy(b).to(cuda) for b in blocks], F)
+    n = X.shape[0]
+    np.random.seed(seed)
+    km = KMeans(n_clusters=K, n_init=10)
+    want_labels = km.fit_predict(X)
+    parts = D.frame_partition(F, 2)
+    ranges = [(a * h * w, b * h * w) for a, b in parts]
+    np.random.seed(seed)
+    first, rand = draw_kmeanspp_randoms(n, K, 10)
+    bes = [D.CudaLloydBackend(K, 10, 300, 1e-4) for _ in ranges]
+    for be in bes:
+        be.prepare(X)
+        be.seed(first, rand)
+    modes = {be.exchange_mode(ranges) for be in bes}
+    assert modes == {"i64"}
+    state = None
+    for it in range(0, 300, D.BURST):
+        for _ in range(D.BURST):
+            ws = []
+            for be, (r0, r1) in zip(bes, ranges):
+                be.assign(r0, r1)
+                ws.append(be.partial_words(r0, r1, "i64"))
+            assert ws[0].dtype == torch.int64
+            total = ws[0] + ws[1]                        # the all-reduce: exact
+            for be in bes:
+                be.update_words(total.clone(), "i64", local_rows_only=True)
+        st = [be.flags_wait(be.flags_async()) for be in bes]
+        assert st[0] == st[1]
+        assert st[0][1] == 0
+        if st[0][0] == 0:
+            state = st[0]
+            break
+    assert state is not None and state[2] == km.info_["max_iter_run"]
+    inertia = sum(be.inertia(r0, r1) for be, (r0, r1) in zip(bes, ranges))
+    same = torch.minimum(*[be.same_matrix(r0, r1) for be, (r0, r1) in zip(bes, ranges)])
+    best = D.pick_best(inertia.float().cpu().numpy(), same.cpu().numpy())
+    assert best == km.info_["best_run"]
+    centers = [be.finish(best) for be in bes]
+    assert torch.equal(centers[0], centers[1]) and torch.equal(centers[0], km.cluster_centers_)
+    labels = torch.cat([be.predict(X[r0:r1].contiguous(), centers[0]) for be, (r0, r1) in zip(bes, ranges)])
+    for be in bes:
+        be.release()
+    assert torch.equal(labels, want_labels) and np.array_equal(labels.cpu().numpy(), g["labels"].reshape(-1))
+
+
 def test_sharded_segmenter_on_one_rank_equals_clip_segmenter(cuda):
     import torch.distributed as dist
     from oracle import unet as ounet
@@ -88,7 +143,9 @@ def test_sharded_segmenter_on_one_rank_equals_clip_segmenter(cuda):
         created = True
     try:
         got = ShardedClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True).segment(x, t, ctx, F, seed=2)
+        got_graph = ShardedClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True,
+                                         use_cuda_graph=True).segment(x, t, ctx, F, seed=2)
     finally:
         if created:
             dist.destroy_process_group()
-    assert torch.equal(got, want)
+    assert torch.equal(got, want) and torch.equal(got_graph, want)

@@ -25,6 +25,12 @@ SIGNATURES = {
     "vidseg_profile_enable": (c_int, [c_int]),
     "vidseg_profile_read": (c_int, [c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(c_longlong), ctypes.POINTER(ctypes.c_double)]),
     "vidseg_aggregate_normalize": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vidseg_aggregate_normalize_rows": (c_int, [c_void_p, c_int, c_longlong, c_longlong, c_int, c_void_p, c_void_p]),
+    "vidseg_kmeans_exchange_words": (c_size_t, [c_void_p, c_size_t]),
+    "vidseg_kmeans_exchange_mode": (c_int, [c_void_p, c_size_t, c_int, c_int]),
+    "vidseg_kmeans_partial_words": (c_int, [c_void_p, c_size_t, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "vidseg_kmeans_update_words": (c_int, [c_void_p, c_size_t, c_int, c_void_p, c_int, c_void_p]),
+    "vidseg_kmeans_flags_async": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
     "vidseg_kmeans_workspace_bytes": (c_size_t, [c_int] * 5),
     "vidseg_kmeans_prepare": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_float, c_int, c_void_p, c_size_t, c_void_p]),
     "vidseg_kmeans_seed": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -135,3 +135,25 @@ VS_API int vidseg_aggregate_normalize(const float* const* blocks_host, int n_blo
     default: return launch_aggregate<4>(bp, out, rows, rows, channels, stream);
   }
 }
+
+// The same arithmetic on an arbitrary row window [first_row, first_row + rows) of every block: the CFG-half split of the
+// SVD UNet over two GPUs leaves the conditional half alone on one rank, i.e. first_row = 0.
+VS_API int vidseg_aggregate_normalize_rows(const float* const* blocks_host, int n_blocks, long long first_row,
+                                           long long rows_ll, int channels, float* out, void* stream) {
+  VS_REQUIRE(n_blocks >= 1 && n_blocks <= 4, "n_blocks must be 1..4");
+  VS_REQUIRE(first_row >= 0 && first_row < (1ll << 26) && rows_ll >= 0 && rows_ll < (1ll << 26) && channels >= 1, "bad shape");
+  const int rows = (int)rows_ll;
+  if (rows == 0) return 0;
+  VS_REQUIRE(blocks_host != nullptr && out != nullptr, "null pointer");
+  BlockPtrs bp{};
+  for (int b = 0; b < n_blocks; ++b) {
+    VS_REQUIRE(blocks_host[b] != nullptr, "null block pointer");
+    bp.p[b] = blocks_host[b];
+  }
+  switch (n_blocks) {
+    case 1: return launch_aggregate<1>(bp, out, rows, (int)first_row, channels, stream);
+    case 2: return launch_aggregate<2>(bp, out, rows, (int)first_row, channels, stream);
+    case 3: return launch_aggregate<3>(bp, out, rows, (int)first_row, channels, stream);
+    default: return launch_aggregate<4>(bp, out, rows, (int)first_row, channels, stream);
+  }
+}

@@ -1167,16 +1167,28 @@ km_mstep_mma_kernel(const __grid_constant__ CUtensorMap tm_onehot, const __grid_
   if (warp == 1) tc::tmem_dealloc<128>(tmem_base);
 }
 
-// sum over splits and digit planes (exact in int64), back to float64, plus the counts -> partial [R, K, D+1]
+// sum over splits and digit planes (exact in int64), back to float64, plus the counts -> partial [R, K, D+1].
+// I64: the multi-GPU exchange form -- the integer sums themselves (and integer counts) as 8-byte words, so that an
+// all-reduce(SUM) over ranks is exact and order independent; `tail` (R words behind the sums) takes the change counters.
+template <bool I64>
 __global__ void __launch_bounds__(256)
 km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cntpart, int cnt_blocks, int d, int k,
                         int rk, const int* __restrict__ flags, const unsigned* __restrict__ absmax,
-                        double* __restrict__ partial, const int* __restrict__ changed_ws, int* __restrict__ changed_out) {
+                        void* __restrict__ partial_v, const int* __restrict__ changed_ws, int* __restrict__ changed_out,
+                        void* __restrict__ tail) {
   const int r = blockIdx.y, j = blockIdx.x;
-  if (j == 0 && threadIdx.x == 0 && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+  if (j == 0 && threadIdx.x == 0) {
+    if (changed_out != nullptr && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+    if (tail != nullptr) {
+      if (I64) reinterpret_cast<long long*>(tail)[r] = (long long)changed_ws[r];
+      else reinterpret_cast<double*>(tail)[r] = (double)changed_ws[r];
+    }
+  }
   if (flags[r * 4 + 0]) return;
   const double inv = 1.0 / ((double)km_operand_scale(absmax[0]) * (double)(1ll << kMqFracBits));
-  double* o = partial + ((size_t)r * k + j) * (d + 1);
+  const size_t obase = ((size_t)r * k + j) * (d + 1);
+  double* o = reinterpret_cast<double*>(partial_v) + obase;
+  long long* oi = reinterpret_cast<long long*>(partial_v) + obase;
   const size_t row = (size_t)r * k + j;
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
     int v[kMqSplit * kMqPlanes];
@@ -1190,12 +1202,14 @@ km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cn
       for (int s = 0; s < kMqSplit; ++s) dsum += v[s * kMqPlanes + p];
       tot = tot * 256 + dsum;
     }
-    o[c] = (double)tot * inv;   // |tot| < 2^24 * 2^46: the conversion may round once at 2^-53 relative
+    if (I64) oi[c] = tot;
+    else o[c] = (double)tot * inv;   // |tot| < 2^24 * 2^46: the conversion may round once at 2^-53 relative
   }
   if (threadIdx.x == 0) {
     long long cnt = 0;
     for (int b = 0; b < cnt_blocks; ++b) cnt += cntpart[((size_t)r * cnt_blocks + b) * k + j];
-    o[d] = (double)cnt;
+    if (I64) oi[d] = cnt;
+    else o[d] = (double)cnt;
   }
 }
 
@@ -1203,9 +1217,12 @@ km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cn
 __global__ void __launch_bounds__(256)
 km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcnt, int d, int k,
                  const int* __restrict__ flags, double* __restrict__ partial, const int* __restrict__ changed_ws,
-                 int* __restrict__ changed_out) {
+                 int* __restrict__ changed_out, double* __restrict__ tail) {
   const int r = blockIdx.y, j = blockIdx.x;
-  if (j == 0 && threadIdx.x == 0 && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+  if (j == 0 && threadIdx.x == 0) {
+    if (changed_out != nullptr && changed_out != changed_ws) changed_out[r] = changed_ws[r];
+    if (tail != nullptr) tail[r] = (double)changed_ws[r];
+  }
   if (flags[r * 4 + 0]) return;
   double* o = partial + ((size_t)r * k + j) * (d + 1);
   for (int c = threadIdx.x; c < d; c += blockDim.x) {
@@ -1232,6 +1249,7 @@ km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcn
 //                          of a run to finish (ticket counter) adds the K squared shifts in cluster order and sets the
 //                          convergence flags.  (One block per run spent 60 us per iteration on 10 SMs.)
 // ------------------------------------------------------------------------------------------
+template <bool I64>   // I64: `partial` holds the all-reduced integer exchange words (no relocation in that form)
 __global__ void __launch_bounds__(256)
 km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* __restrict__ partial,
                       const int* __restrict__ labels, const float* __restrict__ centers, int* __restrict__ flags,
@@ -1247,7 +1265,8 @@ km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* 
   __shared__ int s_red_i[256];
   double* pr = partial + (size_t)r * k * (d + 1);
   const float* cr = centers + (size_t)r * k * d;
-  for (int j = tid; j < k; j += blockDim.x) cnt[j] = pr[(size_t)j * (d + 1) + d];
+  for (int j = tid; j < k; j += blockDim.x)
+    cnt[j] = I64 ? (double)reinterpret_cast<const long long*>(pr)[(size_t)j * (d + 1) + d] : pr[(size_t)j * (d + 1) + d];
   __syncthreads();
   if (tid == 0) {
     int ne = 0;
@@ -1256,7 +1275,7 @@ km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* 
   }
   __syncthreads();
   if (s_nempty > 0 && !can_relocate && tid == 0) flags[r * 4 + 3] = 1;  // sharded caller must redo the fit unsharded
-  if (s_nempty > 0 && can_relocate) {
+  if (!I64 && s_nempty > 0 && can_relocate) {
     // _relocate_empty_clusters_dense: distances of every point to its (old) centre, the n_empty
     // farthest points (descending) seed the empty clusters (ascending cluster id).
     const int* lab = labels + (size_t)r * n;
@@ -1312,6 +1331,7 @@ km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* 
 }
 
 constexpr int kUpdWarps = 4;
+template <bool I64>
 __global__ void __launch_bounds__(kUpdWarps * 32)
 km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial, const double* __restrict__ cnt_all,
                      const int* __restrict__ argmax_all, const int* __restrict__ changed_in,
@@ -1335,6 +1355,9 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
   const int src = has ? j : am;
   const double div = has ? cnt[j] : ((am < j && cnt[am] > 0.0) ? cnt[am] : 1.0);
   const double* prow = pr + (size_t)src * (d + 1);
+  const long long* irow = reinterpret_cast<const long long*>(prow);
+  // exchange words: the same (double)tot * inv conversion the single-GPU combine kernel applies
+  const double winv = I64 ? 1.0 / ((double)km_operand_scale(absmax[0]) * (double)(1ll << kMqFracBits)) : 1.0;
   float* crow = cr + (size_t)j * d;
   // the tensor-core E-step reads the centres as scaled fp16 pairs: written here instead of by a pass of their own
   const float op_scale = cs_hi ? km_operand_scale(absmax[0]) : 1.f;
@@ -1346,7 +1369,7 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
 #pragma unroll
     for (int u = 0; u < 8; ++u) {
       const int c = c0 + 32 * u;
-      raw[u] = (c < d) ? prow[c] : 0.0;
+      raw[u] = (c < d) ? (I64 ? (double)irow[c] * winv : prow[c]) : 0.0;
       ov[u] = (c < d) ? crow[c] : 0.f;
     }
 #pragma unroll
@@ -1846,18 +1869,18 @@ VS_API int vidseg_kmeans_assign(void* workspace, size_t workspace_bytes, int row
   return km_assign_runs(ws, L, row_begin, row_end, 1, 0, stream);
 }
 
-VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
-                                     double* partial, int32_t* changed, void* stream) {
-  KmLayout L;
-  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
-  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
-  void* ws = workspace;
-  if (partial == nullptr) partial = at<double>(ws, L.partial);
-  if (changed == nullptr) changed = at<int>(ws, L.changed);
+static bool km_mq_range_ok(const KmLayout& L, int row_begin, int row_end) {
   // the int8 product splits its row range over kMqSplit CTAs per tile: ranges shorter than that many 128-row blocks
-  // (tiny shards) take the float64 kernels below, which produce the same `partial`
-  const bool mq_range_ok = (row_end + kMqBK - 1) / kMqBK - row_begin / kMqBK >= kMqSplit || row_end == row_begin;
-  if (L.use_mq && mq_range_ok) {
+  // (tiny shards) take the float64 kernels, which produce the same sums
+  return L.use_mq && ((row_end + kMqBK - 1) / kMqBK - row_begin / kMqBK >= kMqSplit || row_end == row_begin);
+}
+
+// M-step part 1.  words_mode: 0 = `partial` float64 [R,K,D+1] + `changed` int32 [R] (the original pair of buffers);
+// 1 = ONE exchange array of float64 words [R*K*(D+1) + R]; 2 = the same array as int64 words (integer sums, exact).
+static int km_partial_impl(void* ws, const KmLayout& L, int row_begin, int row_end, void* partial, int32_t* changed,
+                           int words_mode, void* stream) {
+  void* tail = words_mode ? static_cast<void*>(reinterpret_cast<char*>(partial) + (size_t)L.r * L.k * (L.d + 1) * 8) : nullptr;
+  if (km_mq_range_ok(L, row_begin, row_end)) {
     VS_LAUNCH(km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
               L.k, row_begin, row_end, at<int>(ws, L.flags), at<int8_t>(ws, L.mq_onehot), at<int>(ws, L.mq_cnt));
     VS_POST_LAUNCH();
@@ -1884,12 +1907,18 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
     } else {
       VS_CHECK_CUDA(cudaMemsetAsync(mp.out, 0, (size_t)kMqSplit * kMqPlanes * mp.rk * L.d * 4, (cudaStream_t)stream));
     }
-    VS_LAUNCH(km_mstep_combine_kernel, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
-              L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
-              changed);
+    if (words_mode == 2)
+      VS_LAUNCH(km_mstep_combine_kernel<true>, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
+                L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
+                changed, tail);
+    else
+      VS_LAUNCH(km_mstep_combine_kernel<false>, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
+                L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
+                changed, tail);
     VS_POST_LAUNCH();
     return 0;
   }
+  VS_REQUIRE(words_mode != 2, "integer exchange words need the int8 tensor-core M-step on this row range");
   const size_t smem1 = (size_t)L.k * kColTile * 8;
   VS_REQUIRE(smem1 <= 200 * 1024, "k too large for the M-step kernel");
   // (two runs per pass over X were measured slower, 83 vs 72 us: the shared-memory adds bound the kernel, not the reads)
@@ -1900,8 +1929,43 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
             at<int>(ws, L.labels), at<int>(ws, L.flags), at<double>(ws, L.part), at<int>(ws, L.partcnt));
   VS_POST_LAUNCH();
   VS_LAUNCH(km_reduce_kernel, dim3(L.k, L.r), 256, 0, stream, at<double>(ws, L.part), at<int>(ws, L.partcnt), L.d, L.k,
-            at<int>(ws, L.flags), partial, at<int>(ws, L.changed), changed);
+            at<int>(ws, L.flags), reinterpret_cast<double*>(partial), at<int>(ws, L.changed), changed,
+            reinterpret_cast<double*>(tail));
   VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int row_begin, int row_end,
+                                     double* partial, int32_t* changed, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n, "bad row range");
+  void* ws = workspace;
+  if (partial == nullptr) partial = at<double>(ws, L.partial);
+  if (changed == nullptr) changed = at<int>(ws, L.changed);
+  return km_partial_impl(ws, L, row_begin, row_end, partial, changed, 0, stream);
+}
+
+// M-step part 2 on `partial` (float64 sums | counts, or, with words_i64, the all-reduced integer exchange words).
+static int km_update_impl(void* ws, const KmLayout& L, void* partial, const int32_t* changed, int local_rows_only,
+                          bool words_i64, void* stream) {
+#define VS_KM_UPDATE(I64)                                                                                                    \
+  do {                                                                                                                       \
+    VS_LAUNCH(km_update_prep_kernel<I64>, L.r, 256, (size_t)L.k * 8, stream, at<float>(ws, L.xc), L.n, L.d, L.k,              \
+              reinterpret_cast<double*>(partial), at<int>(ws, L.labels), at<float>(ws, L.centers), at<int>(ws, L.flags),      \
+              at<float>(ws, L.newdist), local_rows_only ? 0 : 1, at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax));       \
+    VS_POST_LAUNCH();                                                                                                        \
+    VS_LAUNCH(km_update_avg_kernel<I64>, (L.r * L.k + kUpdWarps - 1) / kUpdWarps, kUpdWarps * 32, 0, stream, L.d, L.k, L.r,   \
+              reinterpret_cast<const double*>(partial), at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax), changed,         \
+              at<int>(ws, L.changed), at<float>(ws, L.centers), at<double>(ws, L.cnorm), at<int>(ws, L.flags),                 \
+              at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.upd_shift), at<int>(ws, L.upd_ticket),                          \
+              at<unsigned>(ws, L.absmax), L.use_tc ? at<__half>(ws, L.cs_hi) : nullptr,                                        \
+              L.use_tc ? at<__half>(ws, L.cs_lo) : nullptr);                                                                   \
+    VS_POST_LAUNCH();                                                                                                        \
+  } while (0)
+  if (words_i64) VS_KM_UPDATE(true);
+  else VS_KM_UPDATE(false);
+#undef VS_KM_UPDATE
   return 0;
 }
 
@@ -1912,16 +1976,60 @@ VS_API int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double*
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
   if (changed == nullptr) changed = at<int>(ws, L.changed);
-  VS_LAUNCH(km_update_prep_kernel, L.r, 256, (size_t)L.k * 8, stream, at<float>(ws, L.xc), L.n, L.d, L.k, partial,
-            at<int>(ws, L.labels), at<float>(ws, L.centers), at<int>(ws, L.flags), at<float>(ws, L.newdist),
-            local_rows_only ? 0 : 1, at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax));
+  return km_update_impl(ws, L, partial, changed, local_rows_only, false, stream);
+}
+
+// ---- multi-GPU exchange form: ONE array of 8-byte words per Lloyd iteration (sums | counts | change counters) ----
+__global__ void km_unpack_changed_kernel(const void* __restrict__ tail, int i64, int runs, int* __restrict__ changed) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r < runs)
+    changed[r] = i64 ? (int)reinterpret_cast<const long long*>(tail)[r] : (int)reinterpret_cast<const double*>(tail)[r];
+}
+
+VS_API size_t vidseg_kmeans_exchange_words(void* workspace, size_t workspace_bytes) {
+  KmLayout L;
+  if (km_check_ws(workspace, workspace_bytes, &L)) return 0;
+  return (size_t)L.r * L.k * (L.d + 1) + (size_t)L.r;
+}
+
+VS_API int vidseg_kmeans_exchange_mode(void* workspace, size_t workspace_bytes, int row_begin, int row_end) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e < 0 ? e : -e;
+  if (!(0 <= row_begin && row_begin <= row_end && row_end <= L.n)) return VIDSEG_E_INVALID;
+  return km_mq_range_ok(L, row_begin, row_end) ? 1 : 0;
+}
+
+VS_API int vidseg_kmeans_partial_words(void* workspace, size_t workspace_bytes, int row_begin, int row_end, int words_i64,
+                                       void* words, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(0 <= row_begin && row_begin <= row_end && row_end <= L.n && words != nullptr, "bad row range / null words");
+  return km_partial_impl(workspace, L, row_begin, row_end, words, nullptr, words_i64 ? 2 : 1, stream);
+}
+
+VS_API int vidseg_kmeans_update_words(void* workspace, size_t workspace_bytes, int words_i64, void* words,
+                                      int local_rows_only, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(words != nullptr, "null words");
+  VS_REQUIRE(!words_i64 || local_rows_only, "integer exchange words carry no relocation: local_rows_only must be set");
+  void* ws = workspace;
+  const void* tail = reinterpret_cast<const char*>(words) + (size_t)L.r * L.k * (L.d + 1) * 8;
+  // the all-reduced change counters become the `changed` the averaging kernel tests and then clears
+  VS_LAUNCH(km_unpack_changed_kernel, 1, 64, 0, stream, tail, words_i64 ? 1 : 0, L.r, at<int>(ws, L.changed));
   VS_POST_LAUNCH();
-  VS_LAUNCH(km_update_avg_kernel, (L.r * L.k + kUpdWarps - 1) / kUpdWarps, kUpdWarps * 32, 0, stream, L.d, L.k, L.r, partial,
-            at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax), changed, at<int>(ws, L.changed), at<float>(ws, L.centers),
-            at<double>(ws, L.cnorm), at<int>(ws, L.flags), at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.upd_shift),
-            at<int>(ws, L.upd_ticket), at<unsigned>(ws, L.absmax), L.use_tc ? at<__half>(ws, L.cs_hi) : nullptr,
-            L.use_tc ? at<__half>(ws, L.cs_lo) : nullptr);
-  VS_POST_LAUNCH();
+  return km_update_impl(ws, L, words, at<int>(ws, L.changed), local_rows_only, words_i64 != 0, stream);
+}
+
+// the convergence flags [R][4] = {done, strict, n_iter, empty cluster seen} copied to (pinned) host memory WITHOUT
+// synchronising: the caller records an event behind it and reads the flags when that event has passed, so polling
+// never stalls the launch queue
+VS_API int vidseg_kmeans_flags_async(void* workspace, size_t workspace_bytes, int32_t* flags_host, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(flags_host != nullptr, "null pointer");
+  VS_CHECK_CUDA(cudaMemcpyAsync(flags_host, at<int>(workspace, L.flags), (size_t)L.r * 16, cudaMemcpyDeviceToHost,
+                                (cudaStream_t)stream));
   return 0;
 }
 

@@ -2,23 +2,30 @@
 
 One process per GPU.  The SD-2.1 UNet has no op that mixes batch entries, so rank r runs the UNet on its own
 frames only (both classifier-free-guidance halves of each frame) with replicated weights -- no collective in the
-UNet stage.  The path has exactly two exchange steps:
+UNet stage; that stage (UNet + harvest + aggregate/normalise of the local frames) replays as one CUDA graph per rank.
+The path has exactly two exchange steps:
 
   1. one all-gather of the aggregated, normalised, conditional-half feature rows (F*hw*C fp32 = 36.7 MB for a
      14-frame 512x512 clip), so that the k-means++ seeding sees every point in the reference's row order;
-  2. one all-reduce per Lloyd iteration of the fused [n_init, K, D+1] float64 buffer (per-cluster sums | counts,
-     1.0 MB at K=20) plus the [n_init] label-change counters; every rank then performs the same M-step, so the
-     centres stay bit-identical across ranks without broadcasting them.
+  2. ONE all-reduce per Lloyd iteration of the exchange words of all runs -- per-cluster sums | counts | label-change
+     counters, [n_init*K*(D+1) + n_init] 8-byte words (1.0 MB at K=20).  The words are the INTEGER fixed-point sums of
+     the int8 tensor-core M-step (int64), so the sum over ranks is exact and order independent: every rank performs the
+     same M-step on the same integers and the sharded centres are bit-identical to the single-GPU fit -- no broadcast,
+     no ulp drift (tiny shards fall back to float64 words).
 
-Labels stay sharded and are gathered once at the end (N*4 bytes).  k-means++ and the best-of-n_init selection run
-redundantly on every rank (deterministic, same inputs), costing no communication.  sklearn's relocation of empty
-clusters needs every label of a run; the sharded M-step skips it and raises a flag instead, and the fit is then
-repeated unsharded on every rank (every rank holds the full X after step 1), so the result is always the
-reference's.  Cross-rank summation order differs from the single-GPU order, so centres may differ by an ulp; label
-maps are what is compared.
+Convergence is polled without stalling the launch queue: the flags of burst b are copied to pinned memory behind an
+event and read while burst b+1 is already queued (finished runs make every kernel return early, so the extra burst is
+cheap).  Labels stay sharded and are gathered once at the end (N*4 bytes); the inertia and the same-clustering matrix
+of the best-of-n_init rule share one more all-reduce.  k-means++ runs redundantly on every rank (deterministic, same
+inputs).  sklearn's relocation of empty clusters needs every label of a run; the sharded M-step skips it and raises a
+flag instead, and the fit is then repeated unsharded on every rank (every rank holds the full X after step 1), so the
+result is always the reference's.
 
-The SVD VideoUNet does NOT shard by frame (temporal attention and the (3,1,1) convolutions mix frames); its
-multi-GPU form is one clip per GPU (replicas).
+The SVD VideoUNet does NOT shard by frame (temporal attention and the (3,1,1) convolutions mix frames).  Its two
+classifier-free-guidance halves never interact inside the network (guiders.py:78-86 combines them afterwards), so on
+two GPUs rank 0 runs the unconditional and rank 1 the conditional half (option 1); the
+conditional rank broadcasts its feature rows and both ranks share the Lloyd iterations as above.  More ranks: one clip
+per GPU (replicas).
 """
 import ctypes
 
@@ -102,6 +109,43 @@ class CudaLloydBackend:
         self._call("vidseg_kmeans_update", self.ws.data_ptr(), self.nbytes, partial.data_ptr(), changed.data_ptr(),
                    1 if local_rows_only else 0, _lib.stream_ptr())
 
+    # ---- exchange-word form: one fused array per iteration, non-blocking convergence polling ----
+    def exchange_mode(self, ranges):
+        """"i64" when every rank's row range can produce the exact integer words, else "f64" (all ranks must agree)."""
+        ok = True
+        for a, b in ranges:
+            m = self.lib.vidseg_kmeans_exchange_mode(self.ws.data_ptr(), self.nbytes, int(a), int(b))
+            if m < 0:
+                raise _lib.VidsegError(f"kmeans_exchange_mode failed for rows [{a}, {b})")
+            ok = ok and m == 1
+        return "i64" if ok else "f64"
+
+    def partial_words(self, r0, r1, mode):
+        nwords = self.lib.vidseg_kmeans_exchange_words(self.ws.data_ptr(), self.nbytes)
+        words = torch.empty(nwords, dtype=torch.int64 if mode == "i64" else torch.float64, device=self.dev)
+        self._call("vidseg_kmeans_partial_words", self.ws.data_ptr(), self.nbytes, r0, r1, 1 if mode == "i64" else 0,
+                   words.data_ptr(), _lib.stream_ptr())
+        return words
+
+    def update_words(self, words, mode, local_rows_only):
+        self._call("vidseg_kmeans_update_words", self.ws.data_ptr(), self.nbytes, 1 if mode == "i64" else 0, words.data_ptr(),
+                   1 if local_rows_only else 0, _lib.stream_ptr())
+
+    def flags_async(self):
+        """Enqueue a copy of the convergence flags to pinned memory; returns a ticket for ``flags_wait``."""
+        host = torch.empty((self.r, 4), dtype=torch.int32, pin_memory=True)
+        self._call("vidseg_kmeans_flags_async", self.ws.data_ptr(), self.nbytes, host.data_ptr(), _lib.stream_ptr())
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.dev))
+        return host, ev
+
+    def flags_wait(self, ticket):
+        """(runs still iterating, runs that met an empty cluster, max n_iter) of the ticket's moment."""
+        host, ev = ticket
+        ev.synchronize()
+        f = host.numpy()
+        return int((f[:, 0] == 0).sum()), int((f[:, 3] != 0).sum()), int(f[:, 2].max())
+
     def status(self):
         active, empty = ctypes.c_int(), ctypes.c_int()
         self._call("vidseg_kmeans_status", self.ws.data_ptr(), self.nbytes, ctypes.byref(active), ctypes.byref(empty),
@@ -147,13 +191,17 @@ def pick_best(inertia32, same):
     return best
 
 
+BURST = 8   # Lloyd iterations between two looks at the convergence flags
+
+
 def sharded_kmeans_fit_predict(X, n_clusters, row_range, group=None, n_init=10, max_iter=300, tol=1e-4,
-                               random_state=None, backend=None, info=None):
+                               random_state=None, backend=None, info=None, row_ranges=None):
     """``KMeans(n_clusters, n_init).fit(X).predict(X)`` with the rows of X sharded over the ranks of ``group``.
 
     X: the FULL matrix [N, D] (identical on every rank, i.e. after the feature all-gather); row_range: this rank's
-    (begin, end).  Every rank must have numpy's global RandomState in the same state (the pipelines seed it with the
-    clip seed).  Returns the labels of ALL rows (int32 [N], identical on every rank)."""
+    (begin, end); row_ranges: every rank's (begin, end) in rank order when the caller knows them (saves one collective).
+    Every rank must have numpy's global RandomState in the same state (the pipelines seed it with the clip seed).
+    Returns the labels of ALL rows (int32 [N], identical on every rank)."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     n = X.shape[0]
     if n < n_clusters:
@@ -161,7 +209,13 @@ def sharded_kmeans_fit_predict(X, n_clusters, row_range, group=None, n_init=10, 
     r0, r1 = row_range
     be = backend if backend is not None else CudaLloydBackend(n_clusters, n_init, max_iter, tol)
     first, rand = draw_kmeanspp_randoms(n, n_clusters, n_init, random_state)
-    stats = {"iterations": 0, "allreduces": 0, "unsharded_fallback": False}
+    stats = {"iterations": 0, "allreduces": 0, "unsharded_fallback": False, "exchange": None}
+    sharded = world > 1
+    if sharded and row_ranges is None:
+        mine = torch.tensor([r0, r1], dtype=torch.int64, device=X.device)
+        allr = torch.empty(2 * world, dtype=torch.int64, device=X.device)
+        dist.all_gather_into_tensor(allr, mine, group=group)
+        row_ranges = [(int(a), int(b)) for a, b in allr.cpu().view(world, 2)]
 
     def reduce_(t, op=dist.ReduceOp.SUM):
         if world > 1:
@@ -169,51 +223,52 @@ def sharded_kmeans_fit_predict(X, n_clusters, row_range, group=None, n_init=10, 
             stats["allreduces"] += 1
         return t
 
-    def run(lo, hi, sharded):
+    def run(lo, hi, shard):
         be.prepare(X)
         be.seed(first, rand)
-        it, poll = 0, 4
+        mode = be.exchange_mode(row_ranges) if shard else "f64"
+        stats["exchange"] = mode
+        it, pending, state = 0, None, None
         while it < max_iter:
-            burst = min(poll, max_iter - it)
+            burst = min(BURST, max_iter - it)
             for _ in range(burst):
                 be.assign(lo, hi)
-                partial, changed = be.partial(lo, hi)
-                if sharded:
-                    reduce_(partial)
-                    reduce_(changed)
-                be.update(partial, changed, local_rows_only=sharded)
+                words = be.partial_words(lo, hi, mode)
+                if shard:
+                    reduce_(words)                                  # exchange step 2: the only collective of an iteration
+                be.update_words(words, mode, local_rows_only=shard)
             it += burst
-            active, empty = be.status()
-            if empty:
-                return None
-            if active == 0:
-                break
-            poll = min(poll * 2, 16)
-        stats["iterations"] = it
+            ticket = be.flags_async()
+            if pending is not None:          # flags of the PREVIOUS burst: this one is already queued behind them
+                state = be.flags_wait(pending)
+                if state[1] or state[0] == 0:
+                    break
+            pending = ticket
+        else:
+            state = be.flags_wait(ticket)    # max_iter reached without an early exit: the last burst's own flags
+        if state[1]:
+            return None
+        stats["iterations"] = state[2]
+        stats["iterations_issued"] = it
         inertia = be.inertia(lo, hi)
         same = be.same_matrix(lo, hi)
-        if sharded:
-            reduce_(inertia)
-            reduce_(same, dist.ReduceOp.MIN)
+        if shard:   # one collective for both: a pair of runs is the same clustering iff no rank saw a violation
+            r = inertia.numel()
+            buf = torch.cat([inertia.double().reshape(-1), (1 - same).double().reshape(-1)])
+            reduce_(buf)
+            inertia, same = buf[:r], (buf[r:] == 0).reshape(r, r)
         best = pick_best(inertia.float().cpu().numpy(), same.cpu().numpy())
         return be.finish(best)
 
     try:
-        sharded = world > 1
         centers = run(r0, r1, sharded)
         if centers is None:   # an empty cluster needed sklearn's relocation: repeat the fit unsharded, on every rank
             stats["unsharded_fallback"] = True
             centers = run(0, n, False)
             if centers is None:
                 raise _lib.VidsegError("k-means: unsharded fit reported an unrelocated empty cluster")
-        counts = None
-        if sharded:
-            cnt = torch.tensor([r1 - r0], dtype=torch.int64, device=X.device)
-            allc = torch.empty(world, dtype=torch.int64, device=X.device)
-            dist.all_gather_into_tensor(allc, cnt, group=group)
-            counts = [int(v) for v in allc.cpu()]
         local = be.predict(X[r0:r1].contiguous(), centers)
-        labels = gather_rows(local, counts, group) if sharded else local
+        labels = gather_rows(local, [b - a for a, b in row_ranges], group) if sharded else local
     finally:
         if hasattr(be, "release"):
             be.release()
@@ -223,27 +278,45 @@ def sharded_kmeans_fit_predict(X, n_clusters, row_range, group=None, n_init=10, 
 
 
 class ShardedClipSegmenter:
-    """``pipeline.ClipSegmenter`` with the frames of ONE clip sharded over the ranks of a process group."""
+    """``pipeline.ClipSegmenter`` with ONE clip spread over the ranks of a process group: SD-2.1 by frame (any world
+    size), SVD by classifier-free-guidance half (two ranks).  Same call, same label maps, on every rank."""
 
-    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, group=None):
-        from .pipeline import AGGRE_BLOCKS, SINGLE_BLOCK
-        if "VideoUNet" in str(type(model)):
+    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, group=None,
+                 use_cuda_graph=False):
+        from .pipeline import ClipSegmenter
+        self.video = "VideoUNet" in str(type(model))
+        self.group = group
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.video and world > 2:
             raise NotImplementedError("the SVD VideoUNet does not shard by frame (temporal attention / (3,1,1) convolutions "
-                                      "mix frames, SURVEY.md section 8e): run one clip per GPU instead")
+                                      "mix frames, SURVEY.md section 8e): two ranks split the guidance halves, more ranks "
+                                      "run one clip per GPU")
         self.model = model
         self.num_masks = int(num_masks)
-        self.blocks = AGGRE_BLOCKS if is_aggre_attn else SINGLE_BLOCK
         self.is_refine_mask = bool(is_refine_mask)
         self.n_init = n_init
-        self.group = group
+        # the rank-local UNet stage (eager or one CUDA graph per input signature) is the single-GPU segmenter's
+        self.local = ClipSegmenter(model, num_masks=num_masks, is_aggre_attn=is_aggre_attn, is_refine_mask=is_refine_mask,
+                                   n_init=n_init, use_cuda_graph=use_cuda_graph)
+        self.blocks = self.local.blocks
         self.last = {}
 
+    def _local_stage(self, x, t, c, frames, kw, features):
+        """UNet on this rank's rows -> (output, feature rows or None, stashed q of the refinement block or None)."""
+        from .pipeline import REFINE_BLOCK, harvest_self_attn_q
+        if self.local.use_cuda_graph:
+            return self.local._graphed_unet_features(x, t, c, frames, kw, features=features)
+        out = self.model(x, timesteps=t, context=c, **kw)
+        feats = None if features is None else self.local._features(frames, cond_only=(features == "all_rows"))
+        q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0] if self.is_refine_mask else None
+        return out, feats, q7
+
     @torch.no_grad()
-    def segment(self, x, timesteps, context, num_frames, seed=None):
+    def segment(self, x, timesteps, context, num_frames, seed=None, **unet_kwargs):
         """x [2F, C, h, w], timesteps [2F], context [2F, L, D]: the WHOLE clip batch on every rank (uncond rows first).
         Returns the label maps of all frames, int32 [F, h/2, w/2], identical on every rank."""
-        from .features import aggregate_normalize
-        from .pipeline import REFINE_BLOCK, harvest_self_attn_q
+        if self.video:
+            return self._segment_cfg_split(x, timesteps, context, num_frames, seed, unet_kwargs)
         from .refine import refine_masks
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
@@ -255,11 +328,10 @@ class ShardedClipSegmenter:
         hw = fh * fw
         counts = [(b - a) * hw for a, b in parts]
         dev = x.device
+        q7 = None
         if fl > 0:
             idx = torch.cat([torch.arange(f0, f1, device=dev), torch.arange(F + f0, F + f1, device=dev)])
-            self.model(x[idx], timesteps=timesteps[idx], context=context[idx])
-            feats = harvest_self_attn_q(self.model, self.blocks)
-            x_local = aggregate_normalize(feats, fl)
+            _, x_local, q7 = self._local_stage(x[idx], timesteps[idx], context[idx], fl, {}, "cond_half")
             c = x_local.shape[1]
         else:
             c = self.model.output_blocks[self.blocks[0]][1].in_channels
@@ -268,18 +340,66 @@ class ShardedClipSegmenter:
         if seed is not None:
             np.random.seed(seed)
         info = {}
-        row0 = sum(counts[:rank])
-        labels = sharded_kmeans_fit_predict(X, self.num_masks, (row0, row0 + counts[rank]), self.group, n_init=self.n_init,
-                                            info=info)                     # exchange step 2 (per iteration)
+        ranges = [(sum(counts[:r]), sum(counts[:r + 1])) for r in range(world)]
+        labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
+                                            row_ranges=ranges)             # exchange step 2 (per iteration)
         labels = labels.reshape(F, fh, fw)
         self.last = {"features": X, "kmeans_info": info}
         if self.is_refine_mask:
             if fl > 0:
-                q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0][fl:]          # conditional half of the local frames
+                q7 = q7[fl:]                                                # conditional half of the local frames
             else:
                 q7 = torch.empty((0, hw, c), dtype=torch.float32, device=dev)
             cond = gather_rows(q7.contiguous(), [b - a for a, b in parts], self.group)
             feats7 = torch.cat([torch.zeros_like(cond), cond], 0)   # refine reads rows [F, 2F) only (feature_extraction.py:221)
             labels, traj, keep = refine_masks(feats7, labels, F, fh, fw)
             self.last.update(trajectories=traj, keep=keep)
+        return labels
+
+    def _segment_cfg_split(self, x, timesteps, context, num_frames, seed, unet_kwargs):
+        """SVD on two ranks: rank 0 runs the unconditional rows [0, F) of the batch, rank 1 the conditional rows [F, 2F)
+        (one video each; the halves only meet in the guider).  Clustering needs the conditional features: rank 1
+        broadcasts its [F*hw, C] rows (36.7 MB at 14 x 512 x 512), both ranks share the Lloyd iterations by row range,
+        rank 1 refines and broadcasts the label maps."""
+        from .refine import refine_masks
+        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        F = num_frames
+        fh, fw = x.shape[-2] // 2, x.shape[-1] // 2
+        hw = fh * fw
+        dev = x.device
+        if world == 1:
+            return self.local.segment(x, timesteps, context, F, seed, **unet_kwargs)[0]
+        cond_rank = 1
+        half = slice(rank * F, (rank + 1) * F)
+        kw = {}
+        for k, v in unet_kwargs.items():
+            if isinstance(v, torch.Tensor) and v.shape[0] == 2 * F:
+                kw[k] = v[half]
+            elif k == "image_only_indicator" and isinstance(v, torch.Tensor):
+                kw[k] = v[rank:rank + 1]
+            else:
+                kw[k] = v
+        out, x_rows, q7 = self._local_stage(x[half], timesteps[half], context[half], F, kw,
+                                            "all_rows" if rank == cond_rank else None)
+        c = self.model.output_blocks[self.blocks[0]][1].in_channels
+        X = x_rows if rank == cond_rank else torch.empty((F * hw, c), dtype=torch.float32, device=dev)
+        src = dist.get_global_rank(self.group, cond_rank) if self.group is not None else cond_rank
+        dist.broadcast(X, src=src, group=self.group)                       # exchange step 1
+        if seed is not None:
+            np.random.seed(seed)
+        n = F * hw
+        cut = (n // 2 + 127) // 128 * 128
+        ranges = [(0, min(cut, n)), (min(cut, n), n)]
+        info = {}
+        labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
+                                            row_ranges=ranges).reshape(F, fh, fw)
+        self.last = {"features": X, "kmeans_info": info, "unet_out_half": out}
+        if self.is_refine_mask:
+            if rank == cond_rank:
+                feats7 = torch.cat([torch.zeros_like(q7), q7], 0)
+                labels, traj, keep = refine_masks(feats7, labels, F, fh, fw)
+                self.last.update(trajectories=traj, keep=keep)
+                labels = labels.contiguous()
+            dist.broadcast(labels, src=src, group=self.group)
         return labels

@@ -54,18 +54,21 @@ class ClipSegmenter:
         """x [2F, C, h, w] (uncond rows first, guiders.py:38-42), timesteps [2F], context [2F, L, D]."""
         return self.model(x, timesteps=timesteps, context=context, **unet_kwargs)
 
-    def _features(self, num_frames):
-        return aggregate_normalize(harvest_self_attn_q(self.model, self.blocks), num_frames)
+    def _features(self, num_frames, cond_only=False):
+        return aggregate_normalize(harvest_self_attn_q(self.model, self.blocks), num_frames, cond_only=cond_only)
 
-    def _graphed_unet_features(self, x, timesteps, context, num_frames, unet_kwargs):
+    def _graphed_unet_features(self, x, timesteps, context, num_frames, unet_kwargs, features="cond_half"):
         """UNet step + harvest + aggregate/normalise as ONE CUDA graph per input signature: ~500 kernel launches of
         the step replay without host work in between.  Inputs are copied into the graph's static buffers; the stashed
         q/k tensors, the UNet output and the feature matrix live in the graph's memory pool and are overwritten by
-        every replay (clone what must outlive the next call)."""
+        every replay (clone what must outlive the next call).  ``features``: "cond_half" (the batch holds both guidance
+        halves, rows [F, 2F) are clustered), "all_rows" (the batch IS the conditional half: CFG-half split over two GPUs)
+        or None (the unconditional rank of that split: no features)."""
+        feat = (lambda: None) if features is None else (lambda: self._features(num_frames, cond_only=(features == "all_rows")))
         tens = {k: v for k, v in unet_kwargs.items() if isinstance(v, torch.Tensor)}
         rest = {k: v for k, v in unet_kwargs.items() if not isinstance(v, torch.Tensor)}
         key = (tuple(x.shape), tuple(timesteps.shape), tuple(context.shape), num_frames,
-               tuple(sorted((k, tuple(v.shape)) for k, v in tens.items())), tuple(sorted(rest.items())))
+               tuple(sorted((k, tuple(v.shape)) for k, v in tens.items())), tuple(sorted(rest.items())), features)
         ent = self._graphs.get(key)
         if ent is None:
             static = dict(x=x.clone(), t=timesteps.clone(), c=context.clone(), **{"kw_" + k: v.clone() for k, v in tens.items()})
@@ -75,13 +78,13 @@ class ClipSegmenter:
             with torch.cuda.stream(side):            # warm-up outside capture: weight operand caches, workspaces
                 for _ in range(2):
                     self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
-                    self._features(num_frames)
+                    feat()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
             with torch.cuda.graph(graph):
                 out = self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
-                feats = self._features(num_frames)
+                feats = feat()
                 # the stash the refinement reads: the graph's own buffer, not whatever the module attribute points at
                 # after a later eager forward or another capture
                 q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0] if self.is_refine_mask else None
