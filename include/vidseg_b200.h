@@ -385,6 +385,41 @@ int vidseg_profile_read(int family, double* ms_total_host, long long* launches_h
  * gpu_launches accounting). */
 long long vidseg_launch_count(void);
 
+/* ------------------------------------------------------------------------- *
+ * F4  segmentation-map post-process
+ *
+ * Replaces scripts/sampling/process_output.py: compute_difference :8-28 (uint8 wrap-around difference of the decoded
+ * +lambda / -lambda frames, squared in uint8, colour sum, sqrt, cv2.GaussianBlur 5x5 sigma 3 in float64, Pillow
+ * float64 -> "L"), the JPEG quality-75 save (:19) / load (:122) round trip of the stored difference image,
+ * filter_difference_map :30-38 (Pillow LANCZOS resize of the per-label 0/255 K-means masks) and the normalise +
+ * arg-max of get_seg_map_main :120-160.  Every step is bit-exact with the library routine the reference calls.
+ *   frames_pos / frames_neg : uint8 [images, H, W, 3]  (images = masks * frames, mask-major)
+ *   diff_l   : uint8 [images, H, W]  the image the reference saves as difference_map/original_map/.../{frame}.jpg
+ *   vis_l    : uint8 [images, H, W] or NULL: .../vis_map/.../{frame}.jpg (difference / max * 255)
+ *   back_l   : uint8 [images, H, W]  diff_l after the JPEG round trip;  back_max int32 [images] its per-image maximum
+ *   blur_max : double [images] scratch (maximum of the blurred float64 map)
+ * ------------------------------------------------------------------------- */
+int vidseg_segmap_difference(const uint8_t* frames_pos, const uint8_t* frames_neg, int images,
+                             int height, int width, uint8_t* diff_l, uint8_t* vis_l,
+                             uint8_t* back_l, int32_t* back_max, double* blur_max, void* stream);
+
+/* Pillow Image.resize((width, height), LANCZOS) of every (label, frame) mask 255 * (label_maps[f] == unique_labels[m]):
+ * label_maps int32 [frames, h, w] -> out uint8 [masks, frames, height, width]; tmp uint8 [masks, frames, h, width].
+ * The coefficient windows are Pillow's (precompute_coeffs + normalize_coeffs_8bpc, data independent, computed by the
+ * host mirror): bounds int32 [size, 2] = (first input index, count), coeffs int32 [size, ksize] with 22 fractional bits. */
+int vidseg_lanczos_masks(const int32_t* label_maps, const int32_t* unique_labels, int masks, int frames,
+                         int h, int w, int height, int width,
+                         const int32_t* h_bounds, const int32_t* h_coeffs, int h_ksize,
+                         const int32_t* v_bounds, const int32_t* v_coeffs, int v_ksize,
+                         uint8_t* tmp, uint8_t* out, void* stream);
+
+/* back_l / (back_max + 1e-5), optionally filtered by d*m + filter_s*d*(1-m) with m = mask_resized / 255 (NULL = no
+ * filter), arg-max over masks (first maximum) -> seg_raw uint8 [frames, H, W] = unique_labels[argmax] (the
+ * segmentation_map_raw PNG content); seg_index int32 [frames, H, W] or NULL = the arg-max itself (colour-map index). */
+int vidseg_segmap_argmax(const uint8_t* back_l, const int32_t* back_max, int masks, int frames,
+                         int height, int width, const uint8_t* mask_resized, double filter_s,
+                         const int32_t* unique_labels, uint8_t* seg_raw, int32_t* seg_index, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -126,3 +126,33 @@ def synthetic_modulate_params(seed, num_frames, tokens):
                 modulate_attn_type=["cross_attn", "ff_out"], feature_masks=masks,
                 modulate_timestep_frames_group=list(range(num_frames)), modulate_lambda_start=3.0,
                 modulate_lambda_end=1.0, modulate_schedule="linear", num_frames=num_frames, modulate_uc=True)
+
+
+def synthetic_modulated_frames(seed, num_masks, num_frames, height, width, fh, fw):
+    """Decoded frames of the +lambda / -lambda modulated runs (uint8 [K, F, H, W, 3] each) and the K-means label maps
+    [F, fh, fw] they belong to: a shared random base video; run k pushes the pixels of label k's region up (+lambda) or
+    down (-lambda), every run carries its own small noise.  Integer / elementwise arithmetic only."""
+    r = np.random.RandomState(seed)
+    K, F = num_masks, num_frames
+    labels = r.randint(0, K, (F, fh, fw)).astype(np.int32)
+    # blocky regions: repeat a coarse random map so that every label owns connected patches
+    coarse = r.randint(0, K, (F, max(fh // 4, 1), max(fw // 4, 1)))
+    labels = np.repeat(np.repeat(coarse, -(-fh // coarse.shape[1]), axis=1), -(-fw // coarse.shape[2]), axis=2)[:, :fh, :fw].astype(np.int32)
+    yy = (np.arange(height) * fh) // height
+    xx = (np.arange(width) * fw) // width
+    region = labels[:, yy][:, :, xx]                                   # [F, H, W] nearest upsampling
+    base = r.randint(40, 216, (F, height, width, 3)).astype(np.int64)
+    pos = np.zeros((K, F, height, width, 3), dtype=np.uint8)
+    neg = np.zeros_like(pos)
+    for k in range(K):
+        push = (region == k)[..., None] * r.randint(8, 40, (F, 1, 1, 3))
+        pos[k] = np.clip(base + push + r.randint(-3, 4, base.shape), 0, 255).astype(np.uint8)
+        neg[k] = np.clip(base - push + r.randint(-3, 4, base.shape), 0, 255).astype(np.uint8)
+    return pos, neg, labels
+
+
+# (name, seed, K, F, H, W, fh, fw)
+SEGMAP_CASES = [
+    ("small", 11, 3, 2, 40, 56, 5, 7),
+    ("c1", 12, 5, 4, 256, 256, 16, 16),
+]

@@ -75,6 +75,11 @@ SIGNATURES = {
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "vidseg_upsample2x_split": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "vidseg_attention_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vidseg_segmap_difference": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "vidseg_lanczos_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int,
+                                     c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "vidseg_segmap_argmax": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, ctypes.c_double, c_void_p, c_void_p,
+                                     c_void_p, c_void_p]),
     "vidseg_refine_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "vidseg_refine_masks": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_size_t, c_void_p]),
