@@ -32,7 +32,7 @@ extern "C" {
 
 const char* vidseg_last_error(void);
 /* ABI version of this header; bumped on any signature change. */
-int vidseg_abi_version(void);  /* 6: + kmeans exchange words, flags_async, aggregate_normalize_rows; 5: + sampler_step, set/get_kmeans_mstep; 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
+int vidseg_abi_version(void);  /* 7: + first-stage entries (conv2d_down_pad_after, softmax_rows), seg-map post-process; 6: + kmeans exchange words, flags_async, aggregate_normalize_rows; 5: + sampler_step, set/get_kmeans_mstep; 4: + row_scalar in gemm_split_ex, gemm_geglu_split, majority_map / knn_predict (3: operand policy, split_rows) */
 /* Compute capability major*10+minor of the current device (100 on B200). */
 int vidseg_device_arch(void);
 
@@ -384,6 +384,22 @@ int vidseg_profile_read(int family, double* ms_total_host, long long* launches_h
 /* number of kernel launches issued by this library since load (for bench.py's
  * gpu_launches accounting). */
 long long vidseg_launch_count(void);
+
+/* ------------------------------------------------------------------------- *
+ * F3  first stage (VAE) around the UNet: sgm/modules/diffusionmodules/model.py:487-748,
+ *     sgm/modules/autoencoding/temporal_ae.py:18-110, 293-349.  It runs on the convolution / GroupNorm / GEMM entry
+ *     points above plus the two below.
+ * ------------------------------------------------------------------------- */
+/* Downsample (model.py:77-94): F.pad(x, (0,1,0,1)) then a 3x3 stride-2 convolution without padding.  Operands and
+ * outputs as vidseg_conv2d_split; H, W even, Cin % 64 == 0. */
+int vidseg_conv2d_down_pad_after_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                                       const float* bias, float* out_f32, void* out_hi, void* out_lo,
+                                       int batch, int height, int width, int cin, int cout,
+                                       float acc_scale, void* stream);
+/* softmax over the rows of logits * scale (AttnBlock, model.py:183-189: one head over all H*W sites), written as the
+ * split operand [rows, cols] of the following p.v GEMM. */
+int vidseg_softmax_rows_split(const float* logits, float scale, void* out_hi, void* out_lo,
+                              long long rows, int cols, void* stream);
 
 /* ------------------------------------------------------------------------- *
  * F4  segmentation-map post-process

@@ -68,6 +68,8 @@ SIGNATURES = {
     "vidseg_layernorm_bias_split": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_float, c_void_p, c_void_p,
                                             c_longlong, c_int, c_void_p]),
     "vidseg_conv2d_split": (c_int, [c_void_p] * 10 + [c_int] * 7 + [c_float, c_void_p]),
+    "vidseg_conv2d_down_pad_after_split": (c_int, [c_void_p] * 8 + [c_int] * 5 + [c_float, c_void_p]),
+    "vidseg_softmax_rows_split": (c_int, [c_void_p, c_float, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vidseg_layernorm_split": (c_int, [c_void_p, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vidseg_geglu_split": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p]),
     "vidseg_groupnorm_workspace_bytes": (c_size_t, [c_int, c_int]),

@@ -83,7 +83,7 @@ VS_API int vidseg_set_operand_mode(int mode) {
 VS_API int vidseg_get_operand_mode(void) { return vidseg::g_operand_mode.load(); }
 
 VS_API const char* vidseg_last_error(void) { return vidseg::g_last_error; }
-VS_API int vidseg_abi_version(void) { return 6; }
+VS_API int vidseg_abi_version(void) { return 7; }
 VS_API long long vidseg_launch_count(void) { return vidseg::g_launch_count.load(); }
 VS_API int vidseg_device_arch(void) {
   int dev = 0, major = 0, minor = 0;

@@ -250,6 +250,59 @@ upsample2x_split_kernel(const float* __restrict__ x, __half* __restrict__ hi, __
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// row softmax -> split.  s [rows, cols] fp32 logits; out = softmax(s * scale) as the operand of the p.v GEMM of the
+// first-stage AttnBlock (model.py:183-195).  One block per row; the row is read twice from L2 (max, then exp + sum
+// kept in registers is not possible for 4096+ columns), written once.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_split_kernel(const float* __restrict__ s, float scale, __half* __restrict__ hi, __half* __restrict__ lo,
+                          int cols, int packed8) {
+  __shared__ float red[8];
+  __shared__ float bcast;
+  const float* row = s + (size_t)blockIdx.x * cols;
+  const int nq = cols >> 2;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float m = -INFINITY;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + q);
+    m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+  }
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = red[0];
+    for (int w = 1; w < 8; ++w) t = fmaxf(t, red[w]);
+    bcast = t * scale;
+  }
+  __syncthreads();
+  const float mx = bcast;
+  float sum = 0.f;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + q);
+    sum += (expf(v.x * scale - mx) + expf(v.y * scale - mx)) + (expf(v.z * scale - mx) + expf(v.w * scale - mx));
+  }
+  sum = warp_sum(sum);
+  __syncthreads();
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    bcast = 1.0f / t;
+  }
+  __syncthreads();
+  const float inv = bcast;
+  __half* hr = hi + (size_t)blockIdx.x * cols;
+  __half* lr = lo + (size_t)blockIdx.x * cols;
+  for (int q = threadIdx.x; q < nq; q += blockDim.x) {
+    const float4 v = __ldg(reinterpret_cast<const float4*>(row) + q);
+    tc::store_split4(hr, lr, q * 4, expf(v.x * scale - mx) * inv, expf(v.y * scale - mx) * inv, expf(v.z * scale - mx) * inv,
+                     expf(v.w * scale - mx) * inv, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+  }
+}
+
 static int grid_for(long long work_items, int threads) {
   long long blocks = (work_items + threads - 1) / threads;
   const long long cap = (long long)kNumSMs * 16;
@@ -360,6 +413,17 @@ VS_API int vidseg_upsample2x_split(const float* x, void* out_hi, void* out_lo, i
   const long long items = (long long)batch * h * w * (c / 4);
   VS_LAUNCH_W(4.0 * batch * h * w * c * 5.0, upsample2x_split_kernel, grid_for(items, 256), 256, 0, stream, x,
               (__half*)out_hi, (__half*)out_lo, batch, h, w, c, operand_packed8(c) ? 1 : 0);
+  VS_POST_LAUNCH();
+  return 0;
+}
+
+VS_API int vidseg_softmax_rows_split(const float* logits, float scale, void* out_hi, void* out_lo, long long rows, int cols,
+                                     void* stream) {
+  VS_REQUIRE(logits && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(rows >= 0 && rows <= 0x7fffffffLL && cols >= 4 && cols % 4 == 0, "cols must be a multiple of 4");
+  if (rows == 0) return 0;
+  VS_LAUNCH_W(12.0 * rows * cols, softmax_rows_split_kernel, (int)rows, 256, 0, stream, logits, scale, (__half*)out_hi,
+              (__half*)out_lo, cols, operand_packed8(cols) ? 1 : 0);
   VS_POST_LAUNCH();
   return 0;
 }

@@ -693,10 +693,10 @@ VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* 
 
 #undef VS_FAMILY
 #define VS_FAMILY vidseg::kFamConv
-VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                               const float* chan_bias, const float* residual, float* out_f32, void* out_hi, void* out_lo,
-                               int batch, int height, int width, int cin, int cout, int ksize, int stride, float acc_scale,
-                               void* stream) {
+static int conv2d_entry(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                        const float* chan_bias, const float* residual, float* out_f32, void* out_hi, void* out_lo,
+                        int batch, int height, int width, int cin, int cout, int ksize, int stride, int pad_before,
+                        float acc_scale, void* stream) {
   VS_REQUIRE(x_hi && x_lo && w_hi && w_lo, "null operand pointer");
   VS_REQUIRE(out_f32 != nullptr || (out_hi != nullptr && out_lo != nullptr), "no output requested");
   VS_REQUIRE((out_hi == nullptr) == (out_lo == nullptr), "out_hi and out_lo go together");
@@ -733,14 +733,38 @@ VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w
     adims[0] = 2 * (uint64_t)cin; adims[1] = width / 2; adims[2] = 2; adims[3] = height / 2; adims[4] = batch;
     astrides[0] = 2 * px; astrides[1] = px * width; astrides[2] = 2 * px * width; astrides[3] = px * width * height;
     for (int t = 0; t < 9; ++t) {
-      const int dy = t / 3, dx = t % 3;  // input row = 2*ho + dy - 1, column = 2*wo + dx - 1
-      p.p_idx[t] = (dy == 1) ? 0 : 1;
-      p.h_off[t] = (dy == 0) ? -1 : 0;
-      p.c_off[t] = (dx == 1) ? 0 : cin;
-      p.w_off[t] = (dx == 0) ? -1 : 0;
+      const int dy = t / 3, dx = t % 3;
+      if (pad_before) {   // input row = 2*ho + dy - 1, column = 2*wo + dx - 1 (padding 1 on every side)
+        p.p_idx[t] = (dy == 1) ? 0 : 1;
+        p.h_off[t] = (dy == 0) ? -1 : 0;
+        p.c_off[t] = (dx == 1) ? 0 : cin;
+        p.w_off[t] = (dx == 0) ? -1 : 0;
+      } else {            // input row = 2*ho + dy, column = 2*wo + dx (zero row / column AFTER the image only)
+        p.p_idx[t] = (dy == 1) ? 1 : 0;
+        p.h_off[t] = (dy == 2) ? 1 : 0;
+        p.c_off[t] = (dx == 1) ? cin : 0;
+        p.w_off[t] = (dx == 2) ? 1 : 0;
+      }
     }
   }
   return run_gemm(x_hi, x_lo, adims, astrides, p, w_hi, w_lo, kFamConv, stream);
+}
+
+VS_API int vidseg_conv2d_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               const float* chan_bias, const float* residual, float* out_f32, void* out_hi, void* out_lo,
+                               int batch, int height, int width, int cin, int cout, int ksize, int stride, float acc_scale,
+                               void* stream) {
+  return conv2d_entry(x_hi, x_lo, w_hi, w_lo, bias, chan_bias, residual, out_f32, out_hi, out_lo, batch, height, width, cin,
+                      cout, ksize, stride, 1, acc_scale, stream);
+}
+
+// 3x3 stride-2 convolution of F.pad(x, (0, 1, 0, 1)) with padding 0: the Downsample of the first-stage encoder
+// (sgm/modules/diffusionmodules/model.py:77-94)
+VS_API int vidseg_conv2d_down_pad_after_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo,
+                                              const float* bias, float* out_f32, void* out_hi, void* out_lo, int batch,
+                                              int height, int width, int cin, int cout, float acc_scale, void* stream) {
+  return conv2d_entry(x_hi, x_lo, w_hi, w_lo, bias, nullptr, nullptr, out_f32, out_hi, out_lo, batch, height, width, cin,
+                      cout, 3, 2, 0, acc_scale, stream);
 }
 
 

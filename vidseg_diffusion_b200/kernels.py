@@ -41,16 +41,27 @@ def weight_split(param):
     return _cached(param, "lin", lambda w: split(w.float().contiguous(), WEIGHT_SCALE, is_weight=True))
 
 
-def conv_weight_split(param, cin_pad=None):
-    """[Cout, Cin, kh, kw] nn.Conv2d weight -> cached Split of [Cout, kh*kw*Cin'] (tap-major, Cin padded)."""
+def conv_weight_split(param, cin_pad=None, cout_pad=None):
+    """[Cout, Cin, kh, kw] nn.Conv2d weight -> cached Split of [Cout', kh*kw*Cin'] (tap-major, Cin / Cout zero-padded)."""
     def make(w):
         w = w.float().permute(0, 2, 3, 1)  # [Cout, kh, kw, Cin]
         if cin_pad is not None and cin_pad != w.shape[-1]:
             w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
+        if cout_pad is not None and cout_pad != w.shape[0]:
+            w = torch.nn.functional.pad(w, (0, 0, 0, 0, 0, 0, 0, cout_pad - w.shape[0]))
         if packed8(w.shape[-1]):   # same policy as the activation it meets: decided by the channels of one tap
             return split(w.reshape(-1, w.shape[-1]).contiguous(), WEIGHT_SCALE, is_weight=True).reshape(w.shape[0], -1)
         return split(w.reshape(w.shape[0], -1).contiguous(), WEIGHT_SCALE, is_weight=True, pair16=True)
-    return _cached(param, f"conv{cin_pad}", make)
+    return _cached(param, f"conv{cin_pad}_{cout_pad}", make)
+
+
+def _bias_padded(bias, n):
+    """fp32 bias zero-padded to n entries (convolutions whose Cout is not a multiple of 4: the RGB output of the VAE)."""
+    if bias is None:
+        return None
+    if bias.shape[0] == n:
+        return _f32(bias)
+    return _cached(bias, f"bias_pad{n}", lambda b: torch.nn.functional.pad(b.float(), (0, n - b.shape[0])).contiguous())
 
 
 def _workspace(device, nbytes):
@@ -145,8 +156,9 @@ def conv2d(xs, conv, chan_bias=None, residual=None):
     if conv.kernel_size[0] != conv.kernel_size[1] or k not in (1, 3) or conv.padding[0] != k // 2 or stride not in (1, 2):
         raise _lib.VidsegError(f"conv2d: unsupported geometry {conv}")
     b, h, w, cin = xs.hi.shape
-    cout = conv.out_channels
-    ws = conv_weight_split(conv.weight, cin)
+    cout_true = conv.out_channels
+    cout = -(-cout_true // 4) * 4     # zero output channels up to a multiple of 4, sliced off below
+    ws = conv_weight_split(conv.weight, cin, cout)
     if ws.hi.shape[1] != k * k * cin:
         raise _lib.VidsegError(f"conv2d: activation has {cin} channels, weight expects {conv.in_channels}")
     ho, wo = h // stride, w // stride
@@ -160,7 +172,9 @@ def conv2d(xs, conv, chan_bias=None, residual=None):
         _require(chan_bias, "chan_bias")
         if tuple(chan_bias.shape) != (b, cout):
             raise _lib.VidsegError("conv2d: chan_bias must be [B, Cout]")
-    bias = None if conv.bias is None else _f32(conv.bias)
+    if cout != cout_true and (res is not None or chan_bias is not None):
+        raise _lib.VidsegError("conv2d: residual / chan_bias with a padded Cout is not supported")
+    bias = _bias_padded(conv.bias, cout)
     lib = _lib.load()
     with torch.cuda.device(out.device):
         _lib.check(lib.vidseg_conv2d_split(
@@ -169,7 +183,54 @@ def conv2d(xs, conv, chan_bias=None, residual=None):
             chan_bias.data_ptr() if chan_bias is not None else None,
             res.data_ptr() if res is not None else None,
             out.data_ptr(), None, None, b, h, w, cin, cout, k, stride, 1.0 / (xs.scale * ws.scale), _lib.stream_ptr()), "conv2d_split")
+    return as_nchw(out if cout == cout_true else out[..., :cout_true])
+
+
+def conv2d_pad_after(xs, conv):
+    """``Downsample`` of the first-stage encoder (model.py:77-94): F.pad(x, (0, 1, 0, 1)) + 3x3 stride-2 convolution with
+    padding 0, on a Split activation [B, H, W, Cin] -> fp32 [B, Cout, H/2, W/2] (channels_last memory)."""
+    if tuple(conv.kernel_size) != (3, 3) or tuple(conv.stride) != (2, 2) or tuple(conv.padding) != (0, 0):
+        raise _lib.VidsegError(f"conv2d_pad_after: unsupported geometry {conv}")
+    b, h, w, cin = xs.hi.shape
+    cout = conv.out_channels
+    if cin != conv.in_channels or h % 2 or w % 2 or cin % 64 or cout % 4:
+        raise _lib.VidsegError(f"conv2d_pad_after: needs even H, W, Cin % 64 == 0, Cout % 4 == 0; got {tuple(xs.hi.shape)} -> {cout}")
+    ws = conv_weight_split(conv.weight, cin)
+    out = torch.empty((b, h // 2, w // 2, cout), dtype=torch.float32, device=xs.hi.device)
+    bias = None if conv.bias is None else _f32(conv.bias)
+    lib = _lib.load()
+    with torch.cuda.device(out.device):
+        _lib.check(lib.vidseg_conv2d_down_pad_after_split(
+            xs.hi.data_ptr(), xs.lo.data_ptr(), ws.hi.data_ptr(), ws.lo.data_ptr(), bias.data_ptr() if bias is not None else None,
+            out.data_ptr(), None, None, b, h, w, cin, cout, 1.0 / (xs.scale * ws.scale), _lib.stream_ptr()),
+            "conv2d_down_pad_after_split")
     return as_nchw(out)
+
+
+def softmax_rows_split(logits, scale):
+    """softmax(logits * scale) over the last dim of an fp32 [rows, cols] tensor -> Split operand [rows, cols]."""
+    _require(logits, "logits")
+    rows, cols = logits.shape
+    out = _empty_split((rows, cols), logits.device)
+    lib = _lib.load()
+    with torch.cuda.device(logits.device):
+        _lib.check(lib.vidseg_softmax_rows_split(logits.data_ptr(), float(scale), out.hi.data_ptr(), out.lo.data_ptr(), rows, cols,
+                                                 _lib.stream_ptr()), "softmax_rows_split")
+    return out
+
+
+def single_head_attention(q, k, v, scale):
+    """softmax(q k^T * scale) v for ONE head of arbitrary dimension (the first-stage AttnBlock, model.py:160-204: head
+    dimension = channels, 512 at full width, which the 64-wide flash kernel of the UNet does not take).  q, k, v: fp32
+    [n, c].  Two tensor-core GEMMs around the row-softmax kernel; k and v^T take the weight side of their GEMM (the
+    2^8-scaled operand format, so |k|, |v| < 255: activations behind a GroupNorm are far below)."""
+    for t, name in ((q, "q"), (k, "k"), (v, "v")):
+        _require(t, name)
+    n, c = q.shape
+    s, _ = gemm_split(split(q), split(k, WEIGHT_SCALE, is_weight=True), want_f32=True)                      # [n, n] logits
+    p = softmax_rows_split(s, scale)
+    o, _ = gemm_split(p, split(v.t().contiguous(), WEIGHT_SCALE, is_weight=True), want_f32=True)            # [n, c]
+    return o
 
 
 def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blend=None, blend_alpha=None):
@@ -179,15 +240,17 @@ def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blen
     if tuple(conv.kernel_size) != (3, 1, 1) or tuple(conv.padding) != (1, 0, 0) or tuple(conv.stride) != (1, 1, 1):
         raise _lib.VidsegError(f"conv_temporal: unsupported geometry {conv}")
     bt, h, w, cin = xs.hi.shape
-    if bt != videos * frames or cin != conv.in_channels:
+    if bt != videos * frames or cin < conv.in_channels or (cin != conv.in_channels and cin != -(-conv.in_channels // 8) * 8):
         raise _lib.VidsegError("conv_temporal: shape mismatch")
-    cout = conv.out_channels
+    cout_true = conv.out_channels
+    cout = -(-cout_true // 4) * 4
     def make_t(t):
-        w = t.float()[:, :, :, 0, 0].permute(0, 2, 1).contiguous()   # [Cout, 3, Cin], tap-major
+        w = t.float()[:, :, :, 0, 0].permute(0, 2, 1)   # [Cout, 3, Cin], tap-major
+        w = torch.nn.functional.pad(w, (0, cin - w.shape[2], 0, 0, 0, cout - w.shape[0])).contiguous()
         if packed8(cin):
             return split(w.reshape(-1, cin), WEIGHT_SCALE, is_weight=True).reshape(cout, 3 * cin)
         return split(w.reshape(cout, 3 * cin), WEIGHT_SCALE, is_weight=True, pair16=True)
-    ws = _cached(conv.weight, "conv_t", make_t)
+    ws = _cached(conv.weight, f"conv_t{cin}_{cout}", make_t)
     out = torch.empty((bt, h, w, cout), dtype=torch.float32, device=xs.hi.device)
     res = None if residual is None else nhwc(residual, "residual")
     bl = None if blend is None else nhwc(blend, "blend")
@@ -204,7 +267,9 @@ def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blen
         _require(blend_alpha, "blend_alpha")
         if blend_alpha.numel() != bt:
             raise _lib.VidsegError("conv_temporal: blend_alpha must have one entry per frame")
-    bias = None if conv.bias is None else _f32(conv.bias)
+    if cout != cout_true and (res is not None or bl is not None or frame_bias is not None):
+        raise _lib.VidsegError("conv_temporal: epilogue terms with a padded Cout are not supported")
+    bias = _bias_padded(conv.bias, cout)
     ptr = lambda t: t.data_ptr() if t is not None else None
     lib = _lib.load()
     with torch.cuda.device(out.device):
@@ -212,7 +277,7 @@ def conv_temporal(xs, conv, videos, frames, frame_bias=None, residual=None, blen
             xs.hi.data_ptr(), xs.lo.data_ptr(), ws.hi.data_ptr(), ws.lo.data_ptr(), ptr(bias), ptr(frame_bias), ptr(res),
             ptr(bl), ptr(blend_alpha), out.data_ptr(), None, None, videos, frames, h * w, cin, cout,
             1.0 / (xs.scale * ws.scale), _lib.stream_ptr()), "conv_temporal_split")
-    return as_nchw(out)
+    return as_nchw(out if cout == cout_true else out[..., :cout_true])
 
 
 def temporal_attention(q, k, v, videos, frames, heads, scale):

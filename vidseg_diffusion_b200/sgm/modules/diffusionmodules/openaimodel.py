@@ -94,9 +94,11 @@ class ResBlock(TimestepBlock):
                  skip_t_emb=False):
         super().__init__()
         video = dims == 3
-        if up or down or use_scale_shift_norm or skip_t_emb or dims not in (2, 3):
-            _unsupported("ResBlock(up / down / scale-shift / skip_t_emb / dims not in (2, 3))")
-        if video and not (list(kernel_size) == [3, 1, 1] and exchange_temb_dims and not use_conv):
+        if up or down or use_scale_shift_norm or dims not in (2, 3) or (skip_t_emb and not video):
+            _unsupported("ResBlock(up / down / scale-shift / dims not in (2, 3) / skip_t_emb outside a time stack)")
+        # the (3,1,1) time stacks: the UNet's carries the per-frame embedding (exchange_temb_dims), the first-stage
+        # VideoDecoder's has none (skip_t_emb, temporal_ae.py:32-44)
+        if video and not (list(kernel_size) == [3, 1, 1] and (exchange_temb_dims or skip_t_emb) and not use_conv):
             _unsupported("ResBlock(dims=3) other than the (3,1,1) time_stack of VideoResBlock")
         if not video and (kernel_size != 3 or exchange_temb_dims):
             _unsupported("ResBlock(dims=2, kernel != 3 / exchange_temb_dims)")
@@ -111,7 +113,9 @@ class ResBlock(TimestepBlock):
         conv = (lambda ci, co: nn.Conv3d(ci, co, (3, 1, 1), padding=(1, 0, 0))) if video else \
             (lambda ci, co: nn.Conv2d(ci, co, 3, padding=1))
         self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(), conv(channels, self.out_channels))
-        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.skip_t_emb = skip_t_emb
+        if not skip_t_emb:
+            self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
         self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
                                         zero_module(conv(self.out_channels, self.out_channels)))
         if self.out_channels == channels:
