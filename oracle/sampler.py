@@ -77,10 +77,14 @@ def denoise(network, x, sigma, cond, scaling, quantizer=None, **flags):
 
 def euler_edm_sample(network, x, cond, uc, sigmas, scaling, guidance_scale, quantizer=None, t_start=None, t_end=None,
                      is_modulate=False, modulate_params=None, is_latent_blending=False, feature_height=None,
-                     feature_width=None, xt_store=None, img_callback=None, frame_scales=None):
+                     feature_width=None, xt_store=None, img_callback=None, frame_scales=None, is_smooth_latent=False,
+                     first_stage=None):
     """EDMSampler.__call__ with s_churn = 0 (both configs).  ``guidance_scale``: VanillaCFG scale, or None for the
     identity guider; ``frame_scales`` [T]: LinearPredictionGuider.  ``cond`` / ``uc``: dicts whose "crossattn" /
-    "vector" / "concat" entries are concatenated (uc first).  ``xt_store``: {f"xt_time_{i}": latent} for the blending."""
+    "vector" / "concat" entries are concatenated (uc first).  ``xt_store``: {f"xt_time_{i}": latent} for the blending.
+    ``is_smooth_latent`` (sampler_step :116-124, switch :199-210): on sampler steps 23 / 24 the denoised latent is decoded
+    by ``first_stage = (decode, encode)``, every third frame (offset 1 / 2) is replaced by the mean of its neighbours and
+    the clip is encoded again."""
     x = x * torch.sqrt(1.0 + sigmas[0] ** 2.0)
     s_in = x.new_ones([x.shape[0]])
     num_sigmas = len(sigmas)
@@ -118,6 +122,13 @@ def euler_edm_sample(network, x, cond, uc, sigmas, scaling, guidance_scale, quan
                 denoised = x_u + guidance_scale * (x_c - x_u)
         else:
             denoised = denoise(network, x, sigma_hat, cond, scaling, quantizer, **flags)
+        if is_smooth_latent and i in (23, 24):
+            step = 1 if i == 23 else 2
+            frames = first_stage[0](denoised)
+            for f in range(1, frames.shape[0] - 1):
+                if (f - step) % 3 == 0:
+                    frames[f] = 0.5 * (frames[f - 1] + frames[f + 1])
+            denoised = first_stage[1](frames)
         d = (x - denoised) / sigma_hat[(...,) + (None,) * (x.ndim - 1)]
         dt = (next_sigma - sigma_hat)[(...,) + (None,) * (x.ndim - 1)]
         x = x + dt * d

@@ -28,7 +28,7 @@ import torch.nn.functional as F
 SD_VAE_CONFIG = dict(  # configs/inference/sd_2_1.yaml:49-59
     double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128, ch_mult=(1, 2, 4, 4), num_res_blocks=2,
     attn_resolutions=(), dropout=0.0)
-TINY_VAE_CONFIG = dict(SD_VAE_CONFIG, ch=32, resolution=32)   # same topology at toy width
+TINY_VAE_CONFIG = dict(SD_VAE_CONFIG, ch=64, resolution=32)   # same topology at toy width (64: the stride-2 TMA view needs Cin % 64 == 0)
 
 
 def _gn_swish(sd, p, x):

@@ -210,8 +210,75 @@ def main_video():
                         meta=np.array([V_SEED, V_F, HW, V_STEPS, V_T_START]))
 
 
+S_SEED, S_F, S_STEPS, S_T_START, S_SCALE, S_NOISE_SEED = 8, 5, 25, 22, 0.18215, 123
+
+
+def main_smooth():
+    """``is_smooth_latent`` (sampling.py:116-124, 199-210): the reference sampler on the last three steps of a 25-step
+    schedule with a ``model`` whose ``decode_first_stage`` / ``encode_first_stage`` are the reference ``DiffusionEngine``
+    methods (diffusion.py:117-151) over the reference ``AutoencoderKL`` (tiny width, seeded weights).  The posterior noise
+    of the re-encoding comes from torch's global CPU generator, seeded right before the run."""
+    from oracle import vae as ovae
+    om = import_reference("sgm.modules.diffusionmodules.openaimodel")
+    rs = import_reference("sgm.modules.diffusionmodules.sampling")
+    rd = import_reference("sgm.modules.diffusionmodules.denoiser")
+    rw = import_reference("sgm.modules.diffusionmodules.wrappers")
+    ra = import_reference("sgm.models.autoencoder")
+    rdiff = import_reference("sgm.models.diffusion")
+    cfg = ounet.TINY_CONFIG
+    model = om.UNetModel(use_checkpoint=False, use_linear_in_transformer=True, transformer_depth=1, **cfg).eval()
+    sd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ounet.param_shapes(cfg), S_SEED).items()}
+    model.load_state_dict(sd, strict=True)
+    net = rw.OpenAIWrapper(model)
+    vcfg = ovae.TINY_VAE_CONFIG
+    vae = ra.AutoencoderKL(embed_dim=4, monitor="val/rec_loss", ddconfig=dict(vcfg, attn_type="vanilla"),
+                           lossconfig={"target": "torch.nn.Identity"}).eval()
+    vsd = {k: torch.from_numpy(v) for k, v in synthetic_unet_weights(ovae.param_shapes(vcfg), S_SEED + 1).items()}
+    vae.load_state_dict(vsd, strict=True)
+
+    class Engine:   # the attributes the two DiffusionEngine methods read
+        scale_factor, en_and_decode_n_samples_a_time, disable_first_stage_autocast, first_stage_model = S_SCALE, None, True, vae
+        decode_first_stage = rdiff.DiffusionEngine.decode_first_stage
+        encode_first_stage = rdiff.DiffusionEngine.encode_first_stage
+
+    ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    den = rd.DiscreteDenoiser(scaling_config={"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"},
+                              num_idx=1000, discretization_config=ddpm)
+    smp = rs.EulerEDMSampler(discretization_config=ddpm, num_steps=S_STEPS, device="cpu", s_churn=0.0, s_tmin=0.0, s_tmax=999.0,
+                             s_noise=1.0, guider_config={"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG",
+                                                         "params": {"scale": 5.0}})
+    x, _, ctx = synthetic_unet_inputs(S_SEED, S_F, HW, cfg["in_channels"], L, cfg["context_dim"])
+    latent = torch.from_numpy(x)[:S_F].contiguous()
+    ctx = torch.from_numpy(ctx)[:S_F].contiguous()
+    c, uc = {"crossattn": ctx}, {"crossattn": torch.zeros_like(ctx)}
+
+    def denoiser(inp, sigma, cc, **kw):
+        return den(net, inp, sigma, cc, **kw)
+
+    with torch.no_grad():
+        out_plain = smp(denoiser, latent.clone(), cond=c, uc=uc, t_start=S_T_START)
+        torch.manual_seed(S_NOISE_SEED)
+        out_smooth = smp(denoiser, latent.clone(), cond=c, uc=uc, t_start=S_T_START, is_smooth_latent=True, model=Engine())
+        sig = osamp.legacy_ddpm_sigmas(S_STEPS)
+        quant = osamp.make_discrete_quantizer(1000)
+        first_stage = (lambda z: ovae.decode_first_stage(vsd, vcfg, z, S_SCALE),
+                       lambda im: ovae.encode_first_stage(vsd, vcfg, im, S_SCALE, torch.randn(im.shape[0], 4, im.shape[2] // 8, im.shape[3] // 8)))
+        torch.manual_seed(S_NOISE_SEED)
+        o_smooth = osamp.euler_edm_sample(lambda x_in, cn, cond, **fl: net(x_in, cn, cond, **fl), latent.clone(), c, uc, sig,
+                                          osamp.eps_scaling, 5.0, quant, t_start=S_T_START, is_smooth_latent=True,
+                                          first_stage=first_stage)
+    rel = lambda a, b: float((a - b).abs().max() / b.abs().max())
+    print("smooth: oracle vs reference", f"{rel(o_smooth, out_smooth):.2e}", "| smoothing changed the result by",
+          f"{rel(out_smooth, out_plain):.2e}; |x| max {float(out_smooth.abs().max()):.3f}")
+    assert rel(o_smooth, out_smooth) < 2e-5 and rel(out_smooth, out_plain) > 1e-2
+    np.savez_compressed(os.path.join(HERE, "sampler_smooth_tiny.npz"), out_plain=out_plain.numpy(), out_smooth=out_smooth.numpy(),
+                        meta=np.array([S_SEED, S_F, HW, L, S_STEPS, S_T_START, S_NOISE_SEED]))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["sd", "video"]
+    which = sys.argv[1:] or ["sd", "video", "smooth"]
+    if "smooth" in which:
+        main_smooth()
     if "sd" in which:
         main()
     if "video" in which:

@@ -11,7 +11,7 @@ import math
 import torch
 import torch.nn as nn
 
-from .. import _cfg
+from ..util import instantiate_from_config
 from ... import kernels as K
 from ..modules.diffusionmodules.model import Decoder, Encoder
 
@@ -57,10 +57,10 @@ class AutoencodingEngine(nn.Module):
     def __init__(self, *args, encoder_config=None, decoder_config=None, loss_config=None, regularizer_config=None,
                  encoder=None, decoder=None, regularization=None, **kwargs):
         super().__init__()
-        self.encoder = encoder if encoder is not None else _cfg.instantiate_from_config(encoder_config)
-        self.decoder = decoder if decoder is not None else _cfg.instantiate_from_config(decoder_config)
+        self.encoder = encoder if encoder is not None else instantiate_from_config(encoder_config)
+        self.decoder = decoder if decoder is not None else instantiate_from_config(decoder_config)
         self.regularization = regularization if regularization is not None else (
-            _cfg.instantiate_from_config(regularizer_config) if regularizer_config is not None else DiagonalGaussianRegularizer())
+            instantiate_from_config(regularizer_config) if regularizer_config is not None else DiagonalGaussianRegularizer())
 
     def get_last_layer(self):
         return self.decoder.get_last_layer()

@@ -142,14 +142,31 @@ class EDMSampler(SingleStepDiffusionSampler):
                      blend_mask=None, blend_xt=None):
         """reference sampling.py:102-132; ``blend_mask`` / ``blend_xt`` (not in the reference's signature) fold the latent
         blending of ``__call__`` (:229-250) into the same launch."""
-        if is_smooth_latent:
-            raise NotImplementedError("is_smooth_latent decodes / re-encodes through the VAE (SURVEY.md section 8f rank 3), "
-                                      "which this build does not provide")
         sigma_hat = sigma * (gamma + 1.0)
         if gamma > 0:
             eps = torch.randn_like(x) * self.s_noise
             x = x + eps * append_dims(sigma_hat**2 - sigma**2, x.ndim) ** 0.5
         b = x.shape[0]
+        if is_smooth_latent:
+            # reference :116-124: the denoised latent goes through the first stage, every third frame (offset
+            # smooth_step_size) becomes the mean of its neighbours, and the clip is encoded again.  The denoised sample is
+            # needed by itself here, so the denoiser / guider run unfused; the Euler update (+ blending) stays one launch.
+            assert model is not None
+            if sigma_hat.mean() < 1e-6:
+                denoised = x
+            else:
+                denoised = self.denoise(x, denoiser, sigma_hat, cond, uc, is_modulate_step=is_modulate_step,
+                                        is_injected_step=is_injected_step, modulate_params=modulate_params)
+            frames = model.decode_first_stage(denoised)
+            if not frames.is_contiguous():
+                frames = frames.contiguous()
+            for frame_id in range(1, frames.shape[0] - 1):
+                if (frame_id - smooth_step_size) % 3 == 0:
+                    frames[frame_id] = 0.5 * (frames[frame_id - 1] + frames[frame_id + 1])
+            denoised = model.encode_first_stage(frames).to(x.dtype)
+            one, zero = torch.ones(b, device=x.device), torch.zeros(b, device=x.device)
+            x_next = fused_step(x, denoised.contiguous(), zero, one, None, sigma_hat, next_sigma, blend_mask, blend_xt)
+            return self.possible_correction_step(x_next, x, None, None, next_sigma, denoiser, cond, uc)
         if sigma_hat.mean() < 1e-6:
             # denoised = x: no network call
             one, zero = torch.ones(b, device=x.device), torch.zeros(b, device=x.device)
@@ -197,8 +214,9 @@ class EDMSampler(SingleStepDiffusionSampler):
             modulate_now, inject_now = schedule.enter(i)
             if uc_list is not None:
                 uc = uc_list[i]
-            if is_smooth_latent and i in (23, 24):
-                raise NotImplementedError("is_smooth_latent needs the VAE (SURVEY.md section 8f rank 3)")
+            # reference :199-210: sampler steps 23 and 24 are hard-coded there
+            smooth_now = bool(is_smooth_latent and i in (23, 24))
+            smooth_step_size = {23: 1, 24: 2}.get(i) if smooth_now else None
             blend_mask = blend_xt = None
             if is_latent_blending and modulate_params["latent_mask_start"] <= i <= modulate_params["latent_mask_end"]:
                 blend_xt = load_xt(modulate_params.get("feature_folder"), modulate_params.get("exp_name"), i, x.device,
@@ -207,7 +225,8 @@ class EDMSampler(SingleStepDiffusionSampler):
                 blend_mask = masks.reshape(masks.shape[0], *mask_hw)
             x = self.sampler_step(s_in * sigmas[i], s_in * sigmas[i + 1], denoiser, x, cond, uc, gamma,
                                   is_modulate_step=modulate_now, is_injected_step=inject_now,
-                                  modulate_params=modulate_params, blend_mask=blend_mask, blend_xt=blend_xt)
+                                  modulate_params=modulate_params, is_smooth_latent=smooth_now, model=model,
+                                  smooth_step_size=smooth_step_size, blend_mask=blend_mask, blend_xt=blend_xt)
             if callback:
                 callback(i)
             if img_callback and schedule.reports(i):
