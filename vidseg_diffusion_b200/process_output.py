@@ -24,16 +24,34 @@ def _sinc(x):
     return 1.0 if x == 0.0 else math.sin(x * math.pi) / (x * math.pi)
 
 
-def lanczos_windows(in_size, out_size):
-    """Pillow's LANCZOS coefficient windows for one axis (Resample.c precompute_coeffs + normalize_coeffs_8bpc): data
-    independent, so they are computed once per (in, out) on the host with the same libm calls Pillow makes.
+def _lanczos(t):
+    return _sinc(t) * _sinc(t / 3) if -3.0 <= t < 3.0 else 0.0
+
+
+def _bicubic(t, a=-0.5):
+    """Resample.c bicubic_filter (Keys, a = -0.5): Pillow's default filter of Image.resize for mode L."""
+    t = -t if t < 0.0 else t
+    if t < 1.0:
+        return ((a + 2.0) * t - (a + 3.0)) * t * t + 1
+    if t < 2.0:
+        return (((t - 5) * t + 8) * t - 4) * a
+    return 0.0
+
+
+_FILTERS = {"lanczos": (_lanczos, 3.0), "bicubic": (_bicubic, 2.0)}
+
+
+def lanczos_windows(in_size, out_size, filter="lanczos"):
+    """Pillow's resampling coefficient windows for one axis (Resample.c precompute_coeffs + normalize_coeffs_8bpc): data
+    independent, so they are computed once per (in, out, filter) on the host with the same libm calls Pillow makes.
     Returns (bounds int32 [out, 2] = (first input index, count), coeffs int32 [out, ksize], ksize)."""
-    key = (in_size, out_size)
+    key = (in_size, out_size, filter)
     if key in _COEFF_CACHE:
         return _COEFF_CACHE[key]
+    fn, fsupport = _FILTERS[filter]
     scale = in_size / out_size
     filterscale = scale if scale > 1.0 else 1.0
-    support = 3.0 * filterscale
+    support = fsupport * filterscale
     ksize = int(math.ceil(support)) * 2 + 1
     inv = 1.0 / filterscale
     bounds = np.zeros((out_size, 2), dtype=np.int32)
@@ -48,8 +66,7 @@ def lanczos_windows(in_size, out_size):
         n = hi - lo
         w, total = [], 0.0
         for x in range(n):
-            t = (x + lo - center + 0.5) * inv
-            v = _sinc(t) * _sinc(t / 3) if -3.0 <= t < 3.0 else 0.0
+            v = fn((x + lo - center + 0.5) * inv)
             w.append(v)
             total += v
         for x in range(n):
@@ -71,9 +88,10 @@ def _u8(t, name, device):
     return t
 
 
-def resized_masks(label_maps, unique_labels, height, width):
+def resized_masks(label_maps, unique_labels, height, width, filter="lanczos"):
     """uint8 [K, F, H, W]: Pillow ``Image.resize((W, H), LANCZOS)`` of every 0/255 mask ``label_maps[f] == unique_labels[k]``
-    (what filter_difference_map :34 builds from the K-means PNG tree).  label_maps: CUDA int32 [F, h, w]."""
+    (what filter_difference_map :34 builds from the K-means PNG tree); ``filter="bicubic"`` is Pillow's default filter
+    (load_feature_masks, svd_single_video_inference.py:93).  label_maps: CUDA int32 [F, h, w]."""
     lab = _lib.require_cuda_tensor(label_maps.contiguous(), torch.int32, "label_maps")
     F, h, w = lab.shape
     if h == height or w == width:
@@ -81,8 +99,8 @@ def resized_masks(label_maps, unique_labels, height, width):
     dev = lab.device
     ul = torch.as_tensor(np.asarray(unique_labels), dtype=torch.int32).to(dev)
     K = ul.numel()
-    hb, hk, hks = lanczos_windows(w, width)
-    vb, vk, vks = lanczos_windows(h, height)
+    hb, hk, hks = lanczos_windows(w, width, filter)
+    vb, vk, vks = lanczos_windows(h, height, filter)
     d = lambda a: torch.from_numpy(a).to(dev)
     hb, hk, vb, vk = d(hb), d(hk), d(vb), d(vk)
     tmp = torch.empty((K, F, h, width), dtype=torch.uint8, device=dev)
