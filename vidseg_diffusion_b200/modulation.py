@@ -51,7 +51,10 @@ def feature_masks_from_labels(label_maps, mask_id, modulate_block_idx, base_heig
     if (gh, gw) == (h, w):      # the usual case (block 6-8 masks on the block 6-8 grid): Pillow's resize is a copy
         m = (lab == int(mask_id)).to(torch.float64)          # 255 / 255.0 == 1.0 exactly
     elif gh != h and gw != w:
-        m = resized_masks(lab, [int(mask_id)], gh, gw, filter="bicubic")[0].to(torch.float64) / 255.0
+        # v / 255.0 through a table of numpy's own quotients: torch divides by a scalar as a multiplication with its
+        # reciprocal on the GPU, which is not the correctly rounded quotient the reference's numpy division gives
+        table = torch.from_numpy(np.arange(256, dtype=np.float64) / 255.0).to(lab.device)
+        m = table[resized_masks(lab, [int(mask_id)], gh, gw, filter="bicubic")[0].long()]
     else:
         raise _lib.VidsegError("feature_masks_from_labels: a resize of one axis only is not built")
     return [m[f].reshape(-1) for f in range(F)]
