@@ -130,13 +130,15 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 constexpr int kGemmBM = 128, kGemmBK = 64, kGemmAccStages = 2;
 constexpr int kTileABytes = kGemmBM * kGemmBK * 2;  // 16 KB
 constexpr int kMaxTaps = 9;
+constexpr int kKmMaxCols = 256;                                // R*K of the fused K-means E-step epilogue (one N tile)
+constexpr int kKmSmemBytes = kKmMaxCols * 16 + 64 * 4 + 32;   // per-column {cn, tau, meta}, changed[R], per-warp maxima
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kTileBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
   static constexpr int kStages = (BN <= 128) ? 3 : (BN <= 160 ? 3 : 2);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kKmSmemBytes;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
 };
@@ -164,6 +166,8 @@ struct GemmParams {
   float* out_f32;           // [M, N] or null
   __half* out_hi;           // [M, N] or null
   __half* out_lo;
+  int mma_n;                // N of the MMA instruction (multiple of 16, <= BN); 0 = BN
+  KmEpilogue km;            // K-means E-step epilogue (km.on)
 };
 
 constexpr int kGemmThreads = 256;   // TMA warp, MMA warp, TMEM-alloc warp, spare, 4 epilogue warps (8 measured no faster)
@@ -171,6 +175,63 @@ constexpr int kGemmThreads = 256;   // TMA warp, MMA warp, TMEM-alloc warp, spar
 // weight (B) tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per k-block drops
 // from A + B to A + B/2 (the packed8 GEMMs are bound by that traffic, not by the MMA pipe: ncu 69 % tensor-active).
 // A stage may only be refilled when BOTH CTAs have consumed it: the MMA issuer's commit arrives on both empty barriers.
+// State of one epilogue thread (= one point) while it scans the score columns of one K-means run.
+struct KmScan {
+  float best, best_tau, minlow;
+  int best_j, old_label;
+};
+
+// second pass of the K-means epilogue over one run's k score columns (warp-collective TMEM loads, 8 columns at a time):
+// the centres whose lower bound lies inside the final best's band.  Not inlined; compact on purpose -- the epilogue is
+// executed once per tile by one warp per scheduler, so it runs at the speed its code can be fetched.
+__device__ __noinline__ unsigned long long km_candidates(uint32_t taddr, int k, const float4* __restrict__ tab, float m2inv,
+                                                         float xn, float thr) {
+  unsigned long long cand = 0ull;
+#pragma unroll 1
+  for (int q0 = 0; q0 < k; q0 += 8) {
+    uint32_t r2[8];
+    tc::tmem_ld_32x8(taddr + q0, r2);   // may run past the run's last column: masked below
+    tc::tmem_wait_ld();
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 e2 = tab[q0 + q];
+      const float sc2 = fmaf(__uint_as_float(r2[q]), m2inv, e2.x);
+      if (q0 + q < k && sc2 - e2.y * xn <= thr) cand |= 1ull << ((q0 + q) & 63);
+    }
+  }
+  return cand;
+}
+
+// end of a run for one point: take the label, or hand the pair to the resolver with its candidate set
+__device__ __noinline__ void km_run_end(const KmEpilogue& km, const KmScan st, int meta, int col, bool row_ok, int row,
+                                        float xn, float slack, float m2inv, uint32_t t_acc,
+                                        const float4* __restrict__ s_tab, int* __restrict__ s_changed, int lane) {
+  const int run = meta >> 16;
+  const bool take = row_ok && (meta & 0x200);
+  const float thr = st.best + st.best_tau * xn + slack;
+  const bool amb = take && (st.minlow <= thr);
+  bool moved = false;
+  if (take && !amb) {
+    moved = km.count_changes && st.old_label != st.best_j;
+    km.labels[(size_t)run * km.labels_stride + row] = st.best_j;
+  }
+  const unsigned mv = __ballot_sync(0xffffffffu, moved);   // one shared atomic per warp and run
+  if (lane == 0 && mv) atomicAdd(&s_changed[run], __popc(mv));
+  const unsigned am = __ballot_sync(0xffffffffu, amb);
+  if (am) {
+    const int col0 = col - (km.k - 1);
+    unsigned long long cand = km_candidates(t_acc + col0, km.k, s_tab + col0, m2inv, xn, thr);
+    int base_slot = 0;   // one global atomic per warp and run: the counter is a single address for the whole grid
+    if (lane == 0) base_slot = atomicAdd(km.amb_count, __popc(am));
+    base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
+    if (amb) {
+      if (km.k > 64) cand = ~0ull;
+      const int slot = base_slot + __popc(am & ((1u << lane) - 1u));
+      km.amb_list[slot] = make_int4(row, run, (int)(unsigned)cand, (int)(unsigned)(cand >> 32));
+    }
+  }
+}
+
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
@@ -185,6 +246,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   uint64_t* tmem_full_bar = empty_bar + kStages;
   uint64_t* tmem_empty_bar = tmem_full_bar + kGemmAccStages;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + kGemmAccStages);
+  // same bytes as smem + ..., derived from the __shared__ array itself so that the compiler keeps the shared address
+  // space (LDS / ATOMS instead of generic loads and atomics) for the K-means epilogue tables
+  uint8_t* km_smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u) + kStages * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -256,7 +320,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_f16(kGemmBM, BN, 0, 0);
+      const uint32_t idesc = tc::make_idesc_f16(kGemmBM, p.mma_n > 0 ? p.mma_n : BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -318,6 +382,99 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     const int pw = r % p.bw, ph = (r / p.bw) % p.bh, pb = r / (p.bw * p.bh);
     int acc = 0;
     uint32_t acc_phase = 0;
+    if (BN == 256 && p.km.on) {
+      // ===================== K-means E-step epilogue =====================
+      // labels = argmin_j ( ||c_j||^2 - 2 x.c_j ) per run, decided from the tensor-core scores when the best centre is
+      // separated from every other by more than the filter's error band, deferred to the resolver otherwise.
+      // Pass 1, per run, branch-free per column: `best` is the running minimum, `minlow` the smallest lower bound
+      // sc_j - tau_j |x| among the OTHER centres; the point is ambiguous iff minlow <= best + tau_best |x| (+ slack), i.e.
+      // iff some other centre satisfies sc_j <= best + (tau_best + tau_j) |x|.  Pass 2, only for runs in which some
+      // lane of the warp is ambiguous: the run's columns are loaded from TMEM once more and every centre inside the band
+      // of the final best goes into the pair's candidate mask for the resolver.
+      // The test runs in fp32 (float64 issues at ~6 instructions per clock per SM here; 200 columns x 128 rows of it
+      // cost more than the GEMM): the radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the
+      // fp32 test can only flag MORE pairs / candidates than the float64 one -- every flagged pair is settled exactly by
+      // the resolver, every unflagged label is the float64 arg-min.
+      const KmEpilogue& km = p.km;
+      float4* s_tab = reinterpret_cast<float4*>(km_smem);                  // per column {cn, tau, meta, -}
+      int* s_changed = reinterpret_cast<int*>(s_tab + kKmMaxCols);
+      float* s_max = reinterpret_cast<float*>(s_changed + 64);             // per epilogue warp {max cn, max tau}
+      const int et = threadIdx.x - 128;          // 0..127 among the epilogue threads
+      const int rk = km.runs * km.k;
+      float mc = 0.f, mtau = 0.f;
+      for (int i = et; i < kKmMaxCols; i += 128) {
+        float4 e = make_float4(3.0e38f, 0.f, 0.f, 0.f);   // padding columns: never the best, never a candidate
+        if (i < rk) {
+          const double c = km.cnorm[i];
+          const int run = i / km.k, j = i - run * km.k;
+          const int done = km.flags[run * 4 + 0], strict = km.flags[run * 4 + 1];
+          const int live = (km.only_nonstrict ? (strict == 0) : (done == 0)) ? 1 : 0;
+          e.x = (float)c;
+          e.y = (float)(1.01 * km.band * sqrt(c));
+          e.z = __int_as_float(j | ((j == km.k - 1) ? 0x100 : 0) | (live << 9) | ((j == 0) ? 0x400 : 0) | (run << 16));
+          mc = fmaxf(mc, e.x); mtau = fmaxf(mtau, e.y);
+        }
+        s_tab[i] = e;
+      }
+      for (int i = et; i < 64; i += 128) s_changed[i] = 0;
+      mc = warp_max(mc); mtau = warp_max(mtau);
+      if (lane == 0) { s_max[2 * ew] = mc; s_max[2 * ew + 1] = mtau; }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const float cn_max = fmaxf(fmaxf(s_max[0], s_max[2]), fmaxf(s_max[4], s_max[6]));
+      const float sc_f = km_operand_scale(km.absmax[0]);
+      const float m2inv = -2.0f / (sc_f * sc_f);   // a power of two: exact
+      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
+        const int mt = m_tile_of(tile);
+        const int rel = mt * 128 + r;            // Linear form: the tile is 128 consecutive rows
+        const bool row_ok = rel < p.wo;
+        const int row = km.row_begin + rel;
+        const float xn = row_ok ? (float)sqrt(km.xx[row]) * 1.0000002f : 0.f;   // rounded up: radii only grow
+        // |fp32 score - exact score| <= 2^-23 (cn + |x||c|) per centre; two scores meet in every comparison
+        const float slack = 0x1p-21f * (cn_max + xn * sqrtf(cn_max));
+        tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
+        tc::tc_fence_after();
+        const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
+        KmScan st{3.0e38f, 0.f, 3.0e38f, 0, -1};
+        // 8 score columns per TMEM load, the next load in flight while the current eight are scanned (rolled loop:
+        // ~100 instructions of body instead of 32 unrolled columns)
+        uint32_t cur[8], nxt[8];
+        {
+          tc::tmem_ld_32x8(t_acc, cur);
+          tc::tmem_wait_ld();
+#pragma unroll 1
+          for (int c = 0; c < rk; c += 8) {
+            if (c + 8 < rk) tc::tmem_ld_32x8(t_acc + c + 8, nxt);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float4 e = s_tab[c + u];
+              const int meta = __float_as_int(e.z);
+              if ((meta & 0x600) == 0x600 && row_ok && km.count_changes)   // first column of a live run: its old label is
+                st.old_label = km.labels[(size_t)(meta >> 16) * km.labels_stride + row];   // on its way during the scan
+              const float sc = fmaf(__uint_as_float(cur[u]), m2inv, e.x);
+              const float low = sc - e.y * xn;
+              const bool nb = sc < st.best;
+              st.minlow = fminf(st.minlow, nb ? st.best - st.best_tau * xn : low);   // 3e38 on a run's first column
+              st.best_tau = nb ? e.y : st.best_tau;
+              st.best_j = nb ? (meta & 0xff) : st.best_j;
+              st.best = nb ? sc : st.best;
+              if (meta & 0x100) {   // last column of a run (warp-uniform): decide, then start the next run
+                km_run_end(km, st, meta, c + u, row_ok, row, xn, slack, m2inv, t_acc, s_tab, s_changed, lane);
+                st.best = 3.0e38f; st.best_tau = 0.f; st.minlow = 3.0e38f; st.best_j = 0;
+              }
+            }
+            tc::tmem_wait_ld();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
+          }
+        }
+        tc::tc_fence_before();
+        tc::mbar_arrive(&tmem_empty_bar[acc]);
+        if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < km.runs; i += 128)
+        if (s_changed[i]) atomicAdd(&km.changed[i], s_changed[i]);
+    } else
     for (int tile = first_item; tile < num_tiles; tile += item_stride) {
       const int mt = m_tile_of(tile);
       const int n0 = (tile % n_tiles) * BN;
@@ -588,6 +745,41 @@ int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const v
   const uint64_t row = (uint64_t)k * 2;
   const uint64_t astrides[4] = {row, row * m, row * m, row * m};
   return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, family, stream);
+}
+
+// internal entry for kmeans.cu: the score GEMM [m, d] x [d, R*K] of the Lloyd E-step with the arg-min / ambiguity test as
+// its epilogue (KmEpilogue); one 256-wide N tile holds the scores of every run, so R*K <= 256.
+int gemm_km_estep_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int m, int rk_pad, int k,
+                      const KmEpilogue& km, void* stream) {
+  VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null pointer");
+  VS_REQUIRE(m >= 1 && rk_pad >= 8 && rk_pad <= kKmMaxCols && rk_pad % 8 == 0 && k >= 8 && k % 8 == 0, "bad shape");
+  VS_REQUIRE(km.runs * km.k <= rk_pad && km.runs <= 64, "runs * k must fit the padded column count");
+  GemmParams p{};
+  p.n = rk_pad; p.k = k; p.taps = 1; p.cin = k;
+  p.wo = m; p.ho = 1; p.nb = 1;
+  p.acc_scale = 1.0f;
+  p.in_packed8 = 0;   // fp16 pairs: the filter's error band is derived for them
+  p.out_packed8 = 0;
+  p.mma_n = (rk_pad + 15) / 16 * 16;
+  p.km = km;
+  p.km.on = 1;
+  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
+  const uint64_t row = (uint64_t)k * 2;
+  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
+  p.bw = 128; p.bh = 1; p.bb = 1;   // 128 consecutive rows per tile (what the epilogue assumes)
+  p.tiles_w = (m + 127) / 128; p.tiles_h = 1; p.tiles_b = 1;
+  p.kc_per_tap = (k + kGemmBK - 1) / kGemmBK;
+  p.cb_div = 1; p.ba_div = 1;
+  const uint32_t box[5] = {(uint32_t)kGemmBK, 128u, 1u, 1u, 1u};
+  CUtensorMap ta_hi, ta_lo;
+  if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
+  if (int e = encode_tmap_16bit(&ta_lo, a_lo, 5, adims, astrides, box)) return e;
+  const double flops = 2.0 * (double)m * rk_pad * (double)k;
+  // pairs of CTAs share the centre tile through TMA multicast: every CTA would otherwise pull all R*K centre rows from
+  // L2 for each of its k-blocks, and that traffic (not the MMAs) bounds this skinny GEMM
+  static const int cl2 = [] { const char* e = getenv("VIDSEG_KM_CLUSTER"); return e ? atoi(e) : 0; }();
+  if (cl2 && p.tiles_w >= 2) return launch_gemm_cl<256, 2>(ta_hi, ta_lo, w_hi, w_lo, p, flops, kFamKMeans, stream);
+  return launch_gemm_cl<256, 1>(ta_hi, ta_lo, w_hi, w_lo, p, flops, kFamKMeans, stream);
 }
 
 }  // namespace vidseg

@@ -50,12 +50,13 @@ struct KmLayout {
   int max_iter;
   size_t xc, mean, var, xx, closest, newdist, potpart, cand, pot, centers, cnorm, center_idx, labels, part, partcnt,
       partial, changed, flags, tol, inertia_part, inertia, same, rand, first_idx, xs_hi, xs_lo, cs_hi, cs_lo, sdot,
-      absmax, amb_list, upd_cnt, upd_argmax, upd_shift, upd_ticket, mq_planes, mq_onehot, mq_cnt, mq_part, total;
+      absmax, amb_list, upd_cnt, upd_argmax, upd_shift, upd_ticket, mq_planes, mq_onehot, mq_cnt, mq_part, km_cnt, reloc, total;
   int rk_pad;   // R*K rounded up to a multiple of 8 (row length of the tensor-core score matrix)
   int use_tc;   // E-step on the tensor cores (needs D % 8 == 0)
   int use_mq;   // M-step sums as an exact int8 tensor-core product (fixed-point digit planes x one-hot labels)
   int n_pad;    // rows rounded up to the 128-row reduction block of that product
   int mq_blocks;  // one-hot blocks per run (count partials)
+  int fused_e;    // E-step decided in the epilogue of its score GEMM (R*K <= 256): no score matrix, no one-hot pass
   CUtensorMap tm_onehot, tm_planes;
 };
 
@@ -114,7 +115,7 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
     L.cs_hi = take((size_t)L.rk_pad * d * 2);
     L.cs_lo = take((size_t)L.rk_pad * d * 2);
     L.sdot = take((size_t)n * L.rk_pad * 4);
-    L.amb_list = take((size_t)n * r * 8);
+    L.amb_list = take((size_t)n * r * 16);   // int4 entries (fused E-step), int2 in the unfused form
   }
   L.n_pad = (n + kMqBK - 1) / kMqBK * kMqBK;
   L.mq_blocks = (L.n_pad / kOhRows + kOhThreads - 1) / kOhThreads;
@@ -125,6 +126,15 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
     L.mq_cnt = take((size_t)r * L.mq_blocks * k * 4);
     L.mq_part = take((size_t)kMqSplit * kMqPlanes * r * k * d * 4);
   }
+  L.km_cnt = take((size_t)r * k * 4);
+  L.reloc = take((size_t)r * 2 * 4);   // relocation ticket | done flag per run (fused update kernel)
+  // Measured on B200 (tools/km_estep_probe.py, N = 14336, R*K = 200): the fused form is correct (same labels) but NOT
+  // faster -- 47.6 us against 49.4 us per E-step.  Its score GEMM alone takes 19.7 us, but one tile per CTA leaves the
+  // epilogue to four warps, one per scheduler, which run their dependent compare / select chains at ~6 cycles per
+  // instruction (16 us for the column scan, 12 us for run ends and candidate sets), while the separate assign kernel does
+  // the same arithmetic at full occupancy.  It stays opt-in (VIDSEG_KMEANS_FUSED_E=1).
+  static const int fused_env = [] { const char* e = getenv("VIDSEG_KMEANS_FUSED_E"); return e ? atoi(e) : 0; }();
+  L.fused_e = (fused_env && L.use_tc && L.rk_pad <= 224 && r <= 64) ? 1 : 0;   // 224: the candidate pass may read 31 TMEM columns past R*K
   L.total = off;
   return L;
 }
@@ -770,14 +780,6 @@ km_assign_kernel(const float* __restrict__ x, int n, int d, int k, int row_begin
 // Operands are carried scaled by s = 2^(11 - exponent(max |xc|)) so that the fp16 pairs keep 22 bits; centres are
 // means of rows, hence bounded by the same maximum.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float km_operand_scale(unsigned absmax_bits) {
-  const float m = __uint_as_float(absmax_bits);
-  if (!(m > 0.f) || !isfinite(m)) return 1.f;
-  int e;
-  frexpf(m, &e);               // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(11-e) < 2048
-  return ldexpf(1.f, 11 - e);
-}
-
 __global__ void __launch_bounds__(256)
 km_split_scaled_kernel(const float* __restrict__ x, size_t n_valid, size_t n_total, const unsigned* __restrict__ absmax,
                        __half* __restrict__ hi, __half* __restrict__ lo) {
@@ -791,20 +793,35 @@ km_split_scaled_kernel(const float* __restrict__ x, size_t n_valid, size_t n_tot
   }
 }
 
+// One thread per (point, run).  The filter arithmetic is fp32: float64 issues at ~6 instructions per clock per SM on this
+// part, and the 2 x K score evaluations per pair in float64 made this kernel as expensive as the GEMM that feeds it.
+// The error radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the fp32 test can only
+// flag MORE pairs / candidates than the float64 test would -- every flagged pair is settled exactly by the resolver,
+// every unflagged label is the float64 arg-min.  Single pass: `best` is the running minimum, `minlow` the smallest
+// lower bound sc_j - tau_j |x| among the other centres; the pair is ambiguous iff minlow <= best + tau_best |x| + slack.
+// An ambiguous pair re-reads its K scores once and hands the resolver the set of centres inside the band as a bit mask.
 __global__ void __launch_bounds__(256)
 km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* __restrict__ cnorm,
                     const double* __restrict__ xx, const float* __restrict__ sdot, int ld,
                     const unsigned* __restrict__ absmax, int* __restrict__ labels, int labels_stride,
                     int* __restrict__ changed, const int* __restrict__ flags, int count_changes, int only_nonstrict,
-                    double band, int* __restrict__ amb_count, int2* __restrict__ amb_list) {
-  extern __shared__ double sm_cn[];  // [runs*k] squared centre norms, then [runs*k] error radii per unit |x|
-  double* sm_tau = sm_cn + runs * k;
+                    double band, int* __restrict__ amb_count, int4* __restrict__ amb_list) {
+  extern __shared__ float sm_f[];  // [runs*k] squared centre norms, [runs*k] error radii per unit |x|, [8] partial maxima
+  float* sm_cn = sm_f;
+  float* sm_tau = sm_f + runs * k;
+  float* sm_red = sm_tau + runs * k;
+  float mc = 0.f;
   for (int i = threadIdx.x; i < runs * k; i += blockDim.x) {
     const double c = cnorm[i];
-    sm_cn[i] = c;
-    sm_tau[i] = band * sqrt(c);
+    sm_cn[i] = (float)c;
+    sm_tau[i] = (float)(1.01 * band * sqrt(c));
+    mc = fmaxf(mc, (float)c);
   }
+  mc = warp_max(mc);
+  if ((threadIdx.x & 31) == 0) sm_red[threadIdx.x >> 5] = mc;
   __syncthreads();
+  float cn_max = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) cn_max = fmaxf(cn_max, sm_red[w]);
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)(row_end - row_begin) * runs;
   if (idx >= total) return;
@@ -815,25 +832,34 @@ km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* _
     if (only_nonstrict ? (strict != 0) : (done != 0)) return;
   }
   const float s = km_operand_scale(absmax[0]);
-  const double inv = 1.0 / ((double)s * (double)s);
+  const float m2inv = -2.0f / (s * s);   // a power of two: exact
   const float* sr = sdot + (size_t)row * ld + (size_t)r * k;
-  const double* cn = sm_cn + r * k;
-  const double* tau = sm_tau + r * k;
-  const double xn = sqrt(xx[row]);
-  double best = 1e300, best_tau = 0.0;
+  const float* cn = sm_cn + r * k;
+  const float* tau = sm_tau + r * k;
+  const float xn = (float)sqrt(xx[row]) * 1.0000002f;   // rounded up: radii only grow
+  // |fp32 score - exact score| <= 2^-23 (cn + |x||c|) per centre; two scores meet in every comparison
+  const float slack = 0x1p-21f * (cn_max + xn * sqrtf(cn_max));
+  float best = 3.0e38f, best_tau = 0.f, minlow = 3.0e38f;
   int best_j = 0;
   for (int j = 0; j < k; ++j) {
-    const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
-    if (sc < best) { best = sc; best_tau = tau[j]; best_j = j; }
+    const float sc = fmaf(sr[j], m2inv, cn[j]);
+    const float low = sc - tau[j] * xn;
+    const bool nb = sc < best;
+    minlow = fminf(minlow, nb ? best - best_tau * xn : low);
+    best_tau = nb ? tau[j] : best_tau;
+    best_j = nb ? j : best_j;
+    best = nb ? sc : best;
   }
-  int ncand = 0;
-  for (int j = 0; j < k; ++j) {
-    const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
-    ncand += (sc <= best + (best_tau + tau[j]) * xn) ? 1 : 0;
-  }
-  if (ncand > 1) {  // rare: defer to the exact float64 resolver, one warp per pair
+  const float thr = best + best_tau * xn + slack;
+  if (minlow <= thr) {  // not separated: defer to the resolver with the set of centres that can still win
+    unsigned long long cand = ~0ull;
+    if (k <= 64) {
+      cand = 0ull;
+      for (int j = 0; j < k; ++j)
+        if (fmaf(sr[j], m2inv, cn[j]) - tau[j] * xn <= thr) cand |= 1ull << j;
+    }
     const int slot = atomicAdd(amb_count, 1);
-    amb_list[slot] = make_int2(row, r);
+    amb_list[slot] = make_int4(row, r, (int)(unsigned)cand, (int)(unsigned)(cand >> 32));
     return;
   }
   int* lp = labels + (size_t)r * labels_stride + row;
@@ -844,61 +870,160 @@ km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* _
 // float64 evaluation of the candidates of every ambiguous pair: score cn_j - 2 x.c_j with the dot product accumulated
 // in float64 (lane-strided partial sums + butterfly; km_assign_kernel uses one sequential chain -- the two agree to
 // ~1e-16 relative, far below any gap the fp32 data can produce), lowest index wins ties.  One warp per pair.
+// `sdot` (the score matrix of the unfused E-step) narrows the evaluation to the centres inside the filter's error band;
+// the fused E-step (gemm_tc.cu, KmEpilogue) keeps no scores and hands over that set as a bit mask per pair instead (a
+// superset: the arg-min over it is the same).
+constexpr int kRsMaxD = 768;   // the row is held in registers (24 floats per lane) by the fp32 stage of the resolver
+
 __global__ void __launch_bounds__(256)
 km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float* __restrict__ centers,
                          const double* __restrict__ cnorm, const double* __restrict__ xx, const float* __restrict__ sdot,
                          int ld, const unsigned* __restrict__ absmax, int* __restrict__ labels, int labels_stride,
                          int* __restrict__ changed, int count_changes, double band, int* __restrict__ amb_count,
-                         const int2* __restrict__ amb_list) {
+                         const int* __restrict__ amb_list, int entry_ints) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int count = *amb_count;
   const float s = km_operand_scale(absmax[0]);
   const double inv = 1.0 / ((double)s * (double)s);
+  // fp32 stage: a lane-strided fp32 FMA chain of at most 24 terms plus a 5-level butterfly has
+  // |dot32 - dot| <= 30 * 2^-24 * sum |x_i c_i| <= 30 * 2^-24 |x||c| (standard gamma_n bound + Cauchy-Schwarz): two
+  // orders of magnitude tighter than the tensor-core filter, at the fp32 issue rate.  Only centres that this second
+  // band cannot separate either go to the float64 chain.
+  const double band2 = 2.0 * 30.0 * 0x1p-24 * 1.01;
   for (int e = warp; e < count; e += nwarps) {
-    const int row = amb_list[e].x, r = amb_list[e].y;
-    const float* sr = sdot + (size_t)row * ld + (size_t)r * k;
+    const int* ent = amb_list + (size_t)e * entry_ints;
+    const int row = ent[0], r = ent[1];
+    // fused E-step: the set of centres that can still win, as a bit mask (all of them when k > 64)
+    unsigned long long cmask = (entry_ints == 4) ? ((unsigned long long)(unsigned)ent[2] | ((unsigned long long)(unsigned)ent[3] << 32))
+                                                 : ~0ull;
+    const float* sr = sdot ? sdot + (size_t)row * ld + (size_t)r * k : nullptr;
     const double* cn = cnorm + (size_t)r * k;
     const double xn = sqrt(xx[row]);
-    double best = 1e300, best_tau = 0.0;
-    for (int j = 0; j < k; ++j) {
-      const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
-      if (sc < best) { best = sc; best_tau = band * sqrt(cn[j]); }
-    }
     const float* xr = x + (size_t)row * d;
+    if (sr) {   // unfused E-step: the candidate set from the stored scores (k <= 64: as a mask, like the fused form)
+      double best = 1e300, best_tau = 0.0;
+      for (int j = 0; j < k; ++j) {
+        const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+        if (sc < best) { best = sc; best_tau = band * sqrt(cn[j]); }
+      }
+      if (k <= 64) {
+        cmask = 0ull;
+        for (int j0 = 0; j0 < k; j0 += 32) {
+          const int jl = j0 + lane;
+          bool need = false;
+          if (jl < k) {
+            const double sc = cn[jl] - 2.0 * ((double)sr[jl] * inv);
+            need = sc <= best + (best_tau + band * sqrt(cn[jl])) * xn;
+          }
+          cmask |= (unsigned long long)__ballot_sync(0xffffffffu, need) << j0;
+        }
+      }
+    }
     double bs = 1e300;
     int bj = 0x7fffffff;
-    for (int j0 = 0; j0 < k; j0 += 32) {
-      // lanes = candidate centres: which of them fall inside the filter's error band of the best score
-      const int jl = j0 + lane;
-      bool need = false;
-      if (jl < k) {
-        const double sc = cn[jl] - 2.0 * ((double)sr[jl] * inv);
-        need = sc <= best + (best_tau + band * sqrt(cn[jl])) * xn;
-      }
-      unsigned mask = __ballot_sync(0xffffffffu, need);
-      // every candidate in the band: float64 dot product with the 32 lanes striding over the channels (the whole
-      // warp works on one 640-long chain instead of one lane per chain), lowest index wins ties
-      while (mask) {
-        const int j = j0 + __ffs(mask) - 1;
-        mask &= mask - 1;
+    if (k <= 64 && d <= kRsMaxD) {
+      if (k < 64) cmask &= (1ull << k) - 1ull;
+      // ---- stage A: fp32 scores of every candidate; lane (t & 31) keeps candidate t's result in slot t >> 5
+      float xa[kRsMaxD / 32];
+#pragma unroll
+      for (int u = 0; u < kRsMaxD / 32; ++u) { const int c = lane + 32 * u; xa[u] = (c < d) ? xr[c] : 0.f; }
+      double es0 = 1e300, es1 = 1e300, rho0 = 0.0, rho1 = 0.0;
+      int js0 = -1, js1 = -1;
+      double thr = 1e300;   // min over candidates of es + rho: an upper bound of the true minimum score
+      int t = 0;
+      for (unsigned long long m = cmask; m; m &= m - 1, ++t) {
+        const int j = __ffsll((long long)m) - 1;
         const float* cr = centers + ((size_t)r * k + j) * d;
-        double acc = 0.0;
-        for (int c0 = lane; c0 < d; c0 += 8 * 32) {
-          float xa[8], ca[8];
+        float acc = 0.f;
 #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int c = c0 + 32 * u;
-            xa[u] = (c < d) ? xr[c] : 0.f;
-            ca[u] = (c < d) ? cr[c] : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) acc = fma((double)xa[u], (double)ca[u], acc);
-        }
+        for (int u = 0; u < kRsMaxD / 32; ++u) { const int c = lane + 32 * u; acc = fmaf(xa[u], (c < d) ? cr[c] : 0.f, acc); }
         acc = warp_sum(acc);
-        const double es = cn[j] - 2.0 * acc;
-        if (es < bs) { bs = es; bj = j; }   // ascending j: the first minimum is kept
+        const double es = cn[j] - 2.0 * (double)acc;
+        const double rho = band2 * xn * sqrt(cn[j]);
+        thr = fmin(thr, es + rho);
+        if (lane == (t & 31)) {
+          if (t < 32) { es0 = es; rho0 = rho; js0 = j; } else { es1 = es; rho1 = rho; js1 = j; }
+        }
+      }
+      // ---- stage B: survivors of the fp32 band; one survivor is the arg-min, several go to the float64 chain
+      unsigned long long surv = 0ull;
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int js = sl ? js1 : js0;
+        const bool in = js >= 0 && (sl ? es1 - rho1 : es0 - rho0) <= thr;
+        unsigned b = __ballot_sync(0xffffffffu, in);
+        while (b) {   // translate lane positions back to centre indices
+          const int src = __ffs(b) - 1;
+          b &= b - 1;
+          const int j = __shfl_sync(0xffffffffu, js, src);
+          surv |= 1ull << j;
+        }
+      }
+      if (__popcll(surv) == 1) {
+        bj = __ffsll((long long)surv) - 1;
+      } else {
+        for (unsigned long long m = surv; m; m &= m - 1) {   // ascending j: the first minimum is kept
+          const int j = __ffsll((long long)m) - 1;
+          const float* cr = centers + ((size_t)r * k + j) * d;
+          double acc = 0.0;
+          for (int c0 = lane; c0 < d; c0 += 8 * 32) {
+            float ca[8], xv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c = c0 + 32 * u;
+              xv[u] = (c < d) ? xr[c] : 0.f;
+              ca[u] = (c < d) ? cr[c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma((double)xv[u], (double)ca[u], acc);
+          }
+          acc = warp_sum(acc);
+          const double es = cn[j] - 2.0 * acc;
+          if (es < bs) { bs = es; bj = j; }
+        }
+      }
+    } else {
+      // many clusters / very long rows: float64 evaluation of every centre inside the filter's band (or of all of them)
+      double best = 1e300, best_tau = 0.0;
+      if (sr)
+        for (int j = 0; j < k; ++j) {
+          const double sc = cn[j] - 2.0 * ((double)sr[j] * inv);
+          if (sc < best) { best = sc; best_tau = band * sqrt(cn[j]); }
+        }
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int jl = j0 + lane;
+        bool need = false;
+        if (jl < k) {
+          if (sr) {
+            const double sc = cn[jl] - 2.0 * ((double)sr[jl] * inv);
+            need = sc <= best + (best_tau + band * sqrt(cn[jl])) * xn;
+          } else {
+            need = (k > 64) || ((cmask >> jl) & 1ull);
+          }
+        }
+        unsigned mask = __ballot_sync(0xffffffffu, need);
+        while (mask) {
+          const int j = j0 + __ffs(mask) - 1;
+          mask &= mask - 1;
+          const float* cr = centers + ((size_t)r * k + j) * d;
+          double acc = 0.0;
+          for (int c0 = lane; c0 < d; c0 += 8 * 32) {
+            float xv[8], ca[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int c = c0 + 32 * u;
+              xv[u] = (c < d) ? xr[c] : 0.f;
+              ca[u] = (c < d) ? cr[c] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = fma((double)xv[u], (double)ca[u], acc);
+          }
+          acc = warp_sum(acc);
+          const double es = cn[j] - 2.0 * acc;
+          if (es < bs) { bs = es; bj = j; }   // ascending j: the first minimum is kept
+        }
       }
     }
     if (lane == 0) {
@@ -1175,7 +1300,7 @@ __global__ void __launch_bounds__(256)
 km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cntpart, int cnt_blocks, int d, int k,
                         int rk, const int* __restrict__ flags, const unsigned* __restrict__ absmax,
                         void* __restrict__ partial_v, const int* __restrict__ changed_ws, int* __restrict__ changed_out,
-                        void* __restrict__ tail) {
+                        void* __restrict__ tail, int* __restrict__ cnt_direct) {
   const int r = blockIdx.y, j = blockIdx.x;
   if (j == 0 && threadIdx.x == 0) {
     if (changed_out != nullptr && changed_out != changed_ws) changed_out[r] = changed_ws[r];
@@ -1207,7 +1332,12 @@ km_mstep_combine_kernel(const int* __restrict__ part, const int* __restrict__ cn
   }
   if (threadIdx.x == 0) {
     long long cnt = 0;
-    for (int b = 0; b < cnt_blocks; ++b) cnt += cntpart[((size_t)r * cnt_blocks + b) * k + j];
+    if (cnt_direct) {   // fused E-step: one counter per (run, cluster), handed back cleared for the next iteration
+      cnt = cnt_direct[(size_t)r * k + j];
+      cnt_direct[(size_t)r * k + j] = 0;
+    } else {
+      for (int b = 0; b < cnt_blocks; ++b) cnt += cntpart[((size_t)r * cnt_blocks + b) * k + j];
+    }
     if (I64) oi[d] = cnt;
     else o[d] = (double)cnt;
   }
@@ -1242,139 +1372,209 @@ km_reduce_kernel(const double* __restrict__ part, const int* __restrict__ partcn
 }
 
 // ------------------------------------------------------------------------------------------
-// Lloyd M-step, part 2: empty-cluster relocation, averaging, centre shift, convergence flags.
-//   km_update_prep_kernel  one block per run: cluster counts, (rare) relocation of empty clusters -- `partial` is
-//                          updated in place -- and the arg-max count the averaging falls back to;
-//   km_update_avg_kernel   one WARP per (run, cluster): _average_centers + _center_shift of that centre; the last warp
-//                          of a run to finish (ticket counter) adds the K squared shifts in cluster order and sets the
-//                          convergence flags.  (One block per run spent 60 us per iteration on 10 SMs.)
+// Lloyd M-step, part 2: empty-cluster relocation, averaging, centre shift, convergence flags -- ONE launch.
+//   One WARP per (run, cluster).  Every warp reads the K counts of its run (so the number of empty clusters and the
+//   arg-max count need no pass of their own), takes its cluster's sums straight from where the M-step left them -- the
+//   int32 digit-plane partial sums of the tensor-core product (SRC 2: no combine pass), the all-reduced exchange words
+//   of the multi-GPU form (SRC 1) or a float64 [R, K, D+1] array (SRC 0) -- and performs _average_centers +
+//   _center_shift for that centre; the last warp of a run to finish (ticket counter) adds the K squared shifts in
+//   cluster order and sets the convergence flags.
+//   Empty clusters (rare) with relocation allowed: the warps of the run first materialise their float64 rows in
+//   `scratch`, the last one to arrive relocates (_relocate_empty_clusters_dense) while the others wait for its flag,
+//   then all of them average from `scratch`.  All R*K warps are resident (R*K/4 blocks), so the wait cannot deadlock.
 // ------------------------------------------------------------------------------------------
-template <bool I64>   // I64: `partial` holds the all-reduced integer exchange words (no relocation in that form)
-__global__ void __launch_bounds__(256)
-km_update_prep_kernel(const float* __restrict__ x, int n, int d, int k, double* __restrict__ partial,
-                      const int* __restrict__ labels, const float* __restrict__ centers, int* __restrict__ flags,
-                      float* __restrict__ scratch_dist, int can_relocate, double* __restrict__ cnt_out,
-                      int* __restrict__ argmax_out) {
-  extern __shared__ double sm[];  // [k] counts
-  const int r = blockIdx.x;
-  if (flags[r * 4 + 0]) return;
-  const int tid = threadIdx.x;
-  double* cnt = sm;
-  __shared__ int s_nempty;
-  __shared__ double s_red_v[256];
-  __shared__ int s_red_i[256];
-  double* pr = partial + (size_t)r * k * (d + 1);
-  const float* cr = centers + (size_t)r * k * d;
-  for (int j = tid; j < k; j += blockDim.x)
-    cnt[j] = I64 ? (double)reinterpret_cast<const long long*>(pr)[(size_t)j * (d + 1) + d] : pr[(size_t)j * (d + 1) + d];
-  __syncthreads();
-  if (tid == 0) {
-    int ne = 0;
-    for (int j = 0; j < k; ++j) ne += (cnt[j] == 0.0);
-    s_nempty = ne;
+struct UpdArgs {
+  int d, k, runs, n, max_iter, can_relocate, cnt_blocks, rk;
+  const void* sums;            // SRC 0: double [R,K,D+1]; SRC 1: long long [R,K,D+1]; SRC 2: int [split][plane][rk][d]
+  const int* cntpart;          // SRC 2: [R][cnt_blocks][K]
+  const void* tail;            // SRC 0 / 1: change counters of the exchange words (double / long long [R]) or null
+  const int* changed_in;       // used when tail is null
+  int* changed_ws;
+  double* scratch;             // float64 [R,K,D+1] rows of the relocation path (SRC 0: the sums array itself)
+  float* centers; double* cnorm; int* flags; const float* tol; float* shiftsq; int* ticket;
+  const unsigned* absmax; __half* cs_hi; __half* cs_lo;
+  const float* x; const int* labels; float* dist;
+  int* reloc_ticket; int* reloc_done;
+};
+
+constexpr int kUpdThreads = 128;   // one BLOCK per (run, cluster): 200 single warps left the loads of the sums latency-bound
+
+template <int SRC>
+__device__ __forceinline__ double upd_count(const UpdArgs& a, int r, int q) {
+  if (SRC == 0) return reinterpret_cast<const double*>(a.sums)[((size_t)r * a.k + q) * (a.d + 1) + a.d];
+  if (SRC == 1) return (double)reinterpret_cast<const long long*>(a.sums)[((size_t)r * a.k + q) * (a.d + 1) + a.d];
+  long long cnt = 0;
+  for (int b = 0; b < a.cnt_blocks; ++b) cnt += a.cntpart[((size_t)r * a.cnt_blocks + b) * a.k + q];
+  return (double)cnt;
+}
+
+template <int SRC>
+__device__ __forceinline__ double upd_sum(const UpdArgs& a, int r, int q, int c, double winv) {
+  if (SRC == 0) return reinterpret_cast<const double*>(a.sums)[((size_t)r * a.k + q) * (a.d + 1) + c];
+  if (SRC == 1) return (double)reinterpret_cast<const long long*>(a.sums)[((size_t)r * a.k + q) * (a.d + 1) + c] * winv;
+  const int* part = reinterpret_cast<const int*>(a.sums);
+  const size_t row = (size_t)r * a.k + q;
+  int v[kMqSplit * kMqPlanes];
+#pragma unroll
+  for (int e = 0; e < kMqSplit * kMqPlanes; ++e) v[e] = part[((size_t)e * a.rk + row) * a.d + c];   // all in flight
+  long long tot = 0;
+#pragma unroll
+  for (int p = kMqPlanes - 1; p >= 0; --p) {
+    long long dsum = 0;
+#pragma unroll
+    for (int sp = 0; sp < kMqSplit; ++sp) dsum += v[sp * kMqPlanes + p];
+    tot = tot * 256 + dsum;
+  }
+  return (double)tot * winv;   // |tot| < 2^24 * 2^46: the conversion may round once at 2^-53 relative
+}
+
+// counts of the run -> {this cluster's count, number of empty clusters, first arg-max, its count} by warp 0 into shared memory
+template <typename F>
+__device__ __forceinline__ void upd_run_stats(F count_of, int k, int j, double* s_stat) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    double bc = -1.0, mine = 0.0;
+    int bi = 0x7fffffff, ne = 0;
+    for (int q = lane; q < k; q += 32) {
+      const double c = count_of(q);
+      ne += (c == 0.0);
+      if (c > bc) { bc = c; bi = q; }   // ascending q per lane: first maximum
+      if (q == j) mine = c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double oc = __shfl_xor_sync(0xffffffffu, bc, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (oc > bc || (oc == bc && oi < bi)) { bc = oc; bi = oi; }
+      ne += __shfl_xor_sync(0xffffffffu, ne, o);
+      mine += __shfl_xor_sync(0xffffffffu, mine, o);   // exactly one lane holds the value, the rest 0
+    }
+    if (lane == 0) { s_stat[0] = mine; s_stat[1] = (double)ne; s_stat[2] = (double)bi; s_stat[3] = bc; }
   }
   __syncthreads();
-  if (s_nempty > 0 && !can_relocate && tid == 0) flags[r * 4 + 3] = 1;  // sharded caller must redo the fit unsharded
-  if (!I64 && s_nempty > 0 && can_relocate) {
-    // _relocate_empty_clusters_dense: distances of every point to its (old) centre, the n_empty
-    // farthest points (descending) seed the empty clusters (ascending cluster id).
-    const int* lab = labels + (size_t)r * n;
-    float* dist = scratch_dist + (size_t)r * n;
-    for (int i = tid; i < n; i += blockDim.x) {
-      const float* xr = x + (size_t)i * d;
-      const float* cc = cr + (size_t)lab[i] * d;
-      double s = 0.0;
-      for (int c = 0; c < d; ++c) { const double t = (double)xr[c] - (double)cc[c]; s = fma(t, t, s); }
-      dist[i] = (float)s;
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(kUpdThreads)
+km_update_fused_kernel(const UpdArgs a) {
+  __shared__ double s_stat[4];
+  __shared__ double s_red_v[kUpdThreads];
+  __shared__ int s_red_i[kUpdThreads];
+  __shared__ int s_ticket;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int d = a.d, k = a.k;
+  const int r = blockIdx.x / k, j = blockIdx.x - r * k;
+  if (a.flags[r * 4 + 0]) return;   // set only by the finalising block of an EARLIER launch (uniform over the block)
+  const double winv = (SRC == 0) ? 1.0 : 1.0 / ((double)km_operand_scale(a.absmax[0]) * (double)(1ll << kMqFracBits));
+  upd_run_stats([&](int q) { return upd_count<SRC>(a, r, q); }, k, j, s_stat);
+  double my_cnt = s_stat[0];
+  int nempty = (int)s_stat[1], am = (int)s_stat[2];
+  double am_cnt = s_stat[3];
+  if (nempty > 0 && !a.can_relocate && j == 0 && tid == 0) a.flags[r * 4 + 3] = 1;  // sharded caller must redo the fit unsharded
+  const bool reloc = nempty > 0 && a.can_relocate && SRC != 1;
+  double* srow_base = a.scratch + (size_t)r * k * (d + 1);
+  if (reloc) {
+    // ---- rare path: sklearn's _relocate_empty_clusters_dense needs the whole run
+    if (SRC == 2) {
+      double* mine = srow_base + (size_t)j * (d + 1);
+      for (int c = tid; c < d; c += kUpdThreads) mine[c] = upd_sum<SRC>(a, r, j, c, winv);
+      if (tid == 0) mine[d] = my_cnt;
     }
+    __threadfence();
     __syncthreads();
-    const int n_empty = s_nempty;
-    int next_empty = 0;
-    for (int e = 0; e < n_empty; ++e) {
-      double bv = -1.0; int bi = 0x7fffffff;
-      for (int i = tid; i < n; i += blockDim.x) {
-        const double v = (double)dist[i];
-        if (v > bv) { bv = v; bi = i; }
+    if (tid == 0) s_ticket = atomicAdd(&a.reloc_ticket[r], 1);
+    __syncthreads();
+    if (s_ticket == k - 1) {
+      __threadfence();
+      const int* lab = a.labels + (size_t)r * a.n;
+      const float* cr = a.centers + (size_t)r * k * d;
+      float* dist = a.dist + (size_t)r * a.n;
+      // distances of every point to its (old) centre, the n_empty farthest points (descending, lowest index on ties)
+      // seed the empty clusters (ascending cluster id)
+      for (int i = tid; i < a.n; i += kUpdThreads) {
+        const float* xr = a.x + (size_t)i * d;
+        const float* cc = cr + (size_t)lab[i] * d;
+        double sdist = 0.0;
+        for (int c = 0; c < d; ++c) { const double tt = (double)xr[c] - (double)cc[c]; sdist = fma(tt, tt, sdist); }
+        dist[i] = (float)sdist;
       }
-      s_red_v[tid] = bv; s_red_i[tid] = bi;
       __syncthreads();
-      for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) {
-          const double v2 = s_red_v[tid + o]; const int i2 = s_red_i[tid + o];
-          if (v2 > s_red_v[tid] || (v2 == s_red_v[tid] && i2 < s_red_i[tid])) { s_red_v[tid] = v2; s_red_i[tid] = i2; }
+      int next_empty = 0;
+      for (int e = 0; e < nempty; ++e) {
+        double bv = -1.0;
+        int bi = 0x7fffffff;
+        for (int i = tid; i < a.n; i += kUpdThreads) {
+          const double v = (double)dist[i];
+          if (v > bv) { bv = v; bi = i; }
+        }
+        s_red_v[tid] = bv; s_red_i[tid] = bi;
+        __syncthreads();
+        for (int o = kUpdThreads / 2; o > 0; o >>= 1) {
+          if (tid < o) {
+            const double v2 = s_red_v[tid + o]; const int i2 = s_red_i[tid + o];
+            if (v2 > s_red_v[tid] || (v2 == s_red_v[tid] && i2 < s_red_i[tid])) { s_red_v[tid] = v2; s_red_i[tid] = i2; }
+          }
+          __syncthreads();
+        }
+        const double maxv = s_red_v[0];
+        const int far = s_red_i[0];
+        __syncthreads();
+        if (e == 0 && maxv == 0.0) break;  // np.max(distances) == 0 -> return
+        while (srow_base[(size_t)next_empty * (d + 1) + d] != 0.0) ++next_empty;  // uniform across the block
+        const int new_id = next_empty++;
+        const int old_id = lab[far];
+        for (int c = tid; c < d; c += kUpdThreads) {
+          const double xv = (double)a.x[(size_t)far * d + c];
+          srow_base[(size_t)old_id * (d + 1) + c] -= xv;
+          srow_base[(size_t)new_id * (d + 1) + c] = xv;
+        }
+        __syncthreads();
+        if (tid == 0) {
+          srow_base[(size_t)new_id * (d + 1) + d] = 1.0;
+          srow_base[(size_t)old_id * (d + 1) + d] -= 1.0;
+          dist[far] = -1.f;
         }
         __syncthreads();
       }
-      const double maxv = s_red_v[0];
-      const int far = s_red_i[0];
+      __threadfence();
       __syncthreads();
-      if (e == 0 && maxv == 0.0) break;  // np.max(distances) == 0 -> return
-      while (cnt[next_empty] != 0.0) ++next_empty;  // uniform across the block
-      const int new_id = next_empty++;
-      const int old_id = lab[far];
-      for (int c = tid; c < d; c += blockDim.x) {
-        const double xv = (double)x[(size_t)far * d + c];
-        pr[(size_t)old_id * (d + 1) + c] -= xv;
-        pr[(size_t)new_id * (d + 1) + c] = xv;
-      }
-      __syncthreads();
-      if (tid == 0) { cnt[new_id] = 1.0; cnt[old_id] -= 1.0; dist[far] = -1.f; }
-      __syncthreads();
+      if (tid == 0) atomicExch(&a.reloc_done[r], 1);
+    } else {
+      if (tid == 0)
+        while (atomicAdd(&a.reloc_done[r], 0) == 0) __nanosleep(200);
     }
+    __syncthreads();
+    __threadfence();
+    upd_run_stats([&](int q) { return __ldcg(&srow_base[(size_t)q * (d + 1) + d]); }, k, j, s_stat);
+    my_cnt = s_stat[0]; nempty = (int)s_stat[1]; am = (int)s_stat[2]; am_cnt = s_stat[3];
   }
-  for (int j = tid; j < k; j += blockDim.x) cnt_out[(size_t)r * k + j] = cnt[j];
-  if (tid == 0) {
-    int am = 0;
-    for (int j = 1; j < k; ++j) if (cnt[j] > cnt[am]) am = j;  // np.argmax: first maximum
-    argmax_out[r] = am;
-  }
-}
-
-constexpr int kUpdWarps = 4;
-template <bool I64>
-__global__ void __launch_bounds__(kUpdWarps * 32)
-km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial, const double* __restrict__ cnt_all,
-                     const int* __restrict__ argmax_all, const int* __restrict__ changed_in,
-                     int* __restrict__ changed_ws, float* __restrict__ centers, double* __restrict__ cnorm,
-                     int* __restrict__ flags, const float* __restrict__ tol, int max_iter, float* __restrict__ shiftsq,
-                     int* __restrict__ ticket, const unsigned* __restrict__ absmax, __half* __restrict__ cs_hi,
-                     __half* __restrict__ cs_lo) {
-  const int lane = threadIdx.x & 31;
-  const int w = blockIdx.x * kUpdWarps + (threadIdx.x >> 5);
-  if (w >= runs * k) return;
-  const int r = w / k, j = w - r * k;
-  if (flags[r * 4 + 0]) return;   // set only by the finalising warp of an EARLIER launch
-  const double* pr = partial + (size_t)r * k * (d + 1);
-  const double* cnt = cnt_all + (size_t)r * k;
-  float* cr = centers + (size_t)r * k * d;
-  const int am = argmax_all[r];
+  float* cr = a.centers + (size_t)r * k * d;
   // _average_centers + _center_shift
   double ss = 0.0, nn = 0.0;
-  const bool has = cnt[j] > 0.0;
+  const bool has = my_cnt > 0.0;
   // centers[j] = centers[argmax_weight] for an empty cluster: averaged already if argmax < j, raw sum otherwise
   const int src = has ? j : am;
-  const double div = has ? cnt[j] : ((am < j && cnt[am] > 0.0) ? cnt[am] : 1.0);
-  const double* prow = pr + (size_t)src * (d + 1);
-  const long long* irow = reinterpret_cast<const long long*>(prow);
-  // exchange words: the same (double)tot * inv conversion the single-GPU combine kernel applies
-  const double winv = I64 ? 1.0 / ((double)km_operand_scale(absmax[0]) * (double)(1ll << kMqFracBits)) : 1.0;
+  const double div = has ? my_cnt : ((am < j && am_cnt > 0.0) ? am_cnt : 1.0);
   float* crow = cr + (size_t)j * d;
   // the tensor-core E-step reads the centres as scaled fp16 pairs: written here instead of by a pass of their own
-  const float op_scale = cs_hi ? km_operand_scale(absmax[0]) : 1.f;
-  __half* hrow = cs_hi ? cs_hi + ((size_t)r * k + j) * d : nullptr;
-  __half* lrow = cs_hi ? cs_lo + ((size_t)r * k + j) * d : nullptr;
-  for (int c0 = lane; c0 < d; c0 += 8 * 32) {   // 8 independent loads in flight; accumulation order unchanged
-    double raw[8];
-    float ov[8];
+  const float op_scale = a.cs_hi ? km_operand_scale(a.absmax[0]) : 1.f;
+  __half* hrow = a.cs_hi ? a.cs_hi + ((size_t)r * k + j) * d : nullptr;
+  __half* lrow = a.cs_hi ? a.cs_lo + ((size_t)r * k + j) * d : nullptr;
+  for (int c0 = tid; c0 < d; c0 += 3 * kUpdThreads) {   // three independent elements in flight per thread
+    double raw[3];
+    float ov[3];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + 32 * u;
-      raw[u] = (c < d) ? (I64 ? (double)irow[c] * winv : prow[c]) : 0.0;
-      ov[u] = (c < d) ? crow[c] : 0.f;
+    for (int u = 0; u < 3; ++u) {
+      const int c = c0 + kUpdThreads * u;
+      raw[u] = 0.0; ov[u] = 0.f;
+      if (c < d) {
+        raw[u] = reloc ? __ldcg(&srow_base[(size_t)src * (d + 1) + c]) : upd_sum<SRC>(a, r, src, c, winv);
+        ov[u] = crow[c];
+      }
     }
 #pragma unroll
-    for (int u = 0; u < 8; ++u) {
-      const int c = c0 + 32 * u;
+    for (int u = 0; u < 3; ++u) {
+      const int c = c0 + kUpdThreads * u;
       if (c < d) {
         const float nv = (div == 1.0 && !has) ? (float)raw[u] : (float)(raw[u] / div);
         const double df = (double)nv - (double)ov[u];
@@ -1392,26 +1592,33 @@ km_update_avg_kernel(int d, int k, int runs, const double* __restrict__ partial,
   }
   ss = warp_sum(ss);
   nn = warp_sum(nn);
-  int last = 0;
-  if (lane == 0) {
+  if (lane == 0) { s_red_v[warp] = ss; s_red_v[8 + warp] = nn; }
+  __syncthreads();
+  if (tid == 0) {
+    ss = 0.0; nn = 0.0;
+    for (int w2 = 0; w2 < kUpdThreads / 32; ++w2) { ss += s_red_v[w2]; nn += s_red_v[8 + w2]; }   // fixed order
     const float sh = (float)sqrt(ss);
-    shiftsq[(size_t)r * k + j] = __fmul_rn(sh, sh);
-    cnorm[(size_t)r * k + j] = nn;
+    a.shiftsq[(size_t)r * k + j] = __fmul_rn(sh, sh);
+    a.cnorm[(size_t)r * k + j] = nn;
     __threadfence();
-    last = (atomicAdd(&ticket[r], 1) == k - 1);
-  }
-  last = __shfl_sync(0xffffffffu, last, 0);
-  if (last && lane == 0) {
-    __threadfence();
-    float tot = 0.f;
-    for (int jj = 0; jj < k; ++jj) tot = __fadd_rn(tot, __ldcg(&shiftsq[(size_t)r * k + jj]));
-    const int it = flags[r * 4 + 2] + 1;
-    flags[r * 4 + 2] = it;
-    if (changed_in[r] == 0) { flags[r * 4 + 1] = 1; flags[r * 4 + 0] = 1; }
-    else if (tot <= tol[0]) { flags[r * 4 + 0] = 1; }
-    else if (it >= max_iter) { flags[r * 4 + 0] = 1; }
-    changed_ws[r] = 0;
-    ticket[r] = 0;
+    if (atomicAdd(&a.ticket[r], 1) == k - 1) {
+      __threadfence();
+      float tot = 0.f;
+      for (int jj = 0; jj < k; ++jj) tot = __fadd_rn(tot, __ldcg(&a.shiftsq[(size_t)r * k + jj]));
+      const int it = a.flags[r * 4 + 2] + 1;
+      a.flags[r * 4 + 2] = it;
+      int changed;
+      if (a.tail == nullptr) changed = a.changed_in[r];
+      else if (SRC == 1) changed = (int)reinterpret_cast<const long long*>(a.tail)[r];
+      else changed = (int)reinterpret_cast<const double*>(a.tail)[r];
+      if (changed == 0) { a.flags[r * 4 + 1] = 1; a.flags[r * 4 + 0] = 1; }
+      else if (tot <= a.tol[0]) { a.flags[r * 4 + 0] = 1; }
+      else if (it >= a.max_iter) { a.flags[r * 4 + 0] = 1; }
+      a.changed_ws[r] = 0;
+      a.ticket[r] = 0;
+      a.reloc_ticket[r] = 0;
+      a.reloc_done[r] = 0;
+    }
   }
 }
 
@@ -1515,6 +1722,8 @@ static int km_launch_assign(const float* x, const KmLayout& L, int runs, int row
 // defined in gemm_tc.cu: out[M,N] = acc_scale * A[M,K] . W[N,K]^T on the split operands, tagged with `family`
 int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, float* out_f32, int m, int n,
                    int k, float acc_scale, int family, void* stream);
+int gemm_km_estep_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int m, int rk_pad, int k,
+                      const KmEpilogue& km, void* stream);
 
 // E-step of every unfinished run over rows [row_begin, row_end) of the centred data held in the workspace
 static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_end, int count_changes, int only_nonstrict,
@@ -1525,6 +1734,35 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
     return km_launch_assign(at<float>(ws, L.xc), L, L.r, row_begin, row_end, at<float>(ws, L.centers),
                             at<double>(ws, L.cnorm), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed),
                             at<int>(ws, L.flags), count_changes, only_nonstrict, stream);
+  // error radius of the filter per unit |x||c|: the score is cn - 2 S; S carries the operand split (2^-21) and the
+  // fp32 accumulation of d products inside the tensor core (<= d * 2^-22 with truncating alignment)
+  const double band_f = 2.0 * ((double)L.d * 0x1p-22 + 0x1p-20);
+  int* amb_count_f = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
+  if (L.fused_e) {
+    // the arg-min is the epilogue of the score GEMM: labels and change counters come out of the launch that computes the
+    // scores (no [N, R*K] score matrix, no second pass over it); only the (rare) points inside the error band go to
+    // the resolver
+    KmEpilogue km{};
+    km.k = L.k; km.runs = L.r; km.row_begin = row_begin; km.labels_stride = L.n;
+    km.count_changes = count_changes; km.only_nonstrict = only_nonstrict;
+    km.band = band_f;
+    km.absmax = at<unsigned>(ws, L.absmax);
+    km.cnorm = at<double>(ws, L.cnorm);
+    km.xx = at<double>(ws, L.xx);
+    km.flags = at<int>(ws, L.flags);
+    km.labels = at<int>(ws, L.labels);
+    km.changed = at<int>(ws, L.changed);
+    km.amb_count = amb_count_f;
+    km.amb_list = at<int4>(ws, L.amb_list);
+    if (int e = gemm_km_estep_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
+                                  at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo), rows, L.rk_pad, L.d, km, stream))
+      return e;
+    VS_LAUNCH(km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
+              at<double>(ws, L.cnorm), at<double>(ws, L.xx), (const float*)nullptr, L.rk_pad, at<unsigned>(ws, L.absmax),
+              at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band_f, amb_count_f, at<int>(ws, L.amb_list), 4);
+    VS_POST_LAUNCH();
+    return 0;
+  }
   // cs_hi / cs_lo: the centres as scaled fp16 pairs, kept current by vidseg_kmeans_seed and km_update_avg_kernel
   if (int e = gemm_split_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
                              at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo),
@@ -1535,16 +1773,17 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
   const double band = 2.0 * ((double)L.d * 0x1p-22 + 0x1p-20);
   const long long total = (long long)rows * L.r;
   int* amb_count = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
-  const size_t smem = (size_t)L.r * L.k * 16;   // amb_count {count, ticket} is cleared by prepare and by every resolve
+  const size_t smem = (size_t)L.r * L.k * 8 + 64;   // amb_count {count, ticket} is cleared by prepare and by every resolve
   VS_REQUIRE(smem <= 48 * 1024, "n_init * k too large for the tensor-core E-step");
   VS_LAUNCH(km_assign_tc_kernel, (int)((total + 255) / 256), 256, smem, stream, L.k, L.r, row_begin, row_end,
             at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
             at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), at<int>(ws, L.flags), count_changes, only_nonstrict, band,
-            amb_count, at<int2>(ws, L.amb_list));
+            amb_count, at<int4>(ws, L.amb_list));
   VS_POST_LAUNCH();
   VS_LAUNCH(km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
-            at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
-            at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band, amb_count, at<int2>(ws, L.amb_list));
+            at<double>(ws, L.cnorm), at<double>(ws, L.xx), L.k <= 64 ? (const float*)nullptr : at<float>(ws, L.sdot), L.rk_pad,
+            at<unsigned>(ws, L.absmax), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band, amb_count,
+            at<int>(ws, L.amb_list), 4);
   VS_POST_LAUNCH();
   return 0;
 }
@@ -1795,6 +2034,7 @@ VS_API int vidseg_kmeans_prepare(const float* x, int n, int d, int k, int n_init
   VS_POST_LAUNCH();
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.labels), 0xFF, (size_t)n_init * n * 4, (cudaStream_t)stream));
   VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.upd_ticket), 0, (size_t)n_init * 4, (cudaStream_t)stream));
+  VS_CHECK_CUDA(cudaMemsetAsync(at<int>(ws, L.reloc), 0, (size_t)n_init * 2 * 4, (cudaStream_t)stream));
   if (L.use_mq) {
     VS_LAUNCH(km_quantize_kernel, dim3(L.n_pad / kMqBK, (d + 31) / 32), 256, 0, stream, at<float>(ws, L.xc), n, L.n_pad, d,
               at<unsigned>(ws, L.absmax), at<int8_t>(ws, L.mq_planes));
@@ -1877,10 +2117,9 @@ static bool km_mq_range_ok(const KmLayout& L, int row_begin, int row_end) {
 
 // M-step part 1.  words_mode: 0 = `partial` float64 [R,K,D+1] + `changed` int32 [R] (the original pair of buffers);
 // 1 = ONE exchange array of float64 words [R*K*(D+1) + R]; 2 = the same array as int64 words (integer sums, exact).
-static int km_partial_impl(void* ws, const KmLayout& L, int row_begin, int row_end, void* partial, int32_t* changed,
-                           int words_mode, void* stream) {
-  void* tail = words_mode ? static_cast<void*>(reinterpret_cast<char*>(partial) + (size_t)L.r * L.k * (L.d + 1) * 8) : nullptr;
-  if (km_mq_range_ok(L, row_begin, row_end)) {
+// labels -> one-hot rows + count partials -> digit-plane x one-hot tensor-core product (partial sums in the workspace)
+static int km_mstep_product(void* ws, const KmLayout& L, int row_begin, int row_end, void* stream) {
+  {
     VS_LAUNCH(km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
               L.k, row_begin, row_end, at<int>(ws, L.flags), at<int8_t>(ws, L.mq_onehot), at<int>(ws, L.mq_cnt));
     VS_POST_LAUNCH();
@@ -1907,14 +2146,25 @@ static int km_partial_impl(void* ws, const KmLayout& L, int row_begin, int row_e
     } else {
       VS_CHECK_CUDA(cudaMemsetAsync(mp.out, 0, (size_t)kMqSplit * kMqPlanes * mp.rk * L.d * 4, (cudaStream_t)stream));
     }
+  }
+  return 0;
+}
+
+static int km_partial_impl(void* ws, const KmLayout& L, int row_begin, int row_end, void* partial, int32_t* changed,
+                           int words_mode, void* stream) {
+  void* tail = words_mode ? static_cast<void*>(reinterpret_cast<char*>(partial) + (size_t)L.r * L.k * (L.d + 1) * 8) : nullptr;
+  if (km_mq_range_ok(L, row_begin, row_end)) {
+    int* cnt_direct = nullptr;
+    if (int e = km_mstep_product(ws, L, row_begin, row_end, stream)) return e;
+    const int rk = L.r * L.k;
     if (words_mode == 2)
       VS_LAUNCH(km_mstep_combine_kernel<true>, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
-                L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
-                changed, tail);
+                L.mq_blocks, L.d, L.k, rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
+                changed, tail, cnt_direct);
     else
       VS_LAUNCH(km_mstep_combine_kernel<false>, dim3(L.k, L.r), 256, 0, stream, at<int>(ws, L.mq_part), at<int>(ws, L.mq_cnt),
-                L.mq_blocks, L.d, L.k, mp.rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
-                changed, tail);
+                L.mq_blocks, L.d, L.k, rk, at<int>(ws, L.flags), at<unsigned>(ws, L.absmax), partial, at<int>(ws, L.changed),
+                changed, tail, cnt_direct);
     VS_POST_LAUNCH();
     return 0;
   }
@@ -1946,26 +2196,34 @@ VS_API int vidseg_kmeans_partial(void* workspace, size_t workspace_bytes, int ro
   return km_partial_impl(ws, L, row_begin, row_end, partial, changed, 0, stream);
 }
 
-// M-step part 2 on `partial` (float64 sums | counts, or, with words_i64, the all-reduced integer exchange words).
-static int km_update_impl(void* ws, const KmLayout& L, void* partial, const int32_t* changed, int local_rows_only,
-                          bool words_i64, void* stream) {
-#define VS_KM_UPDATE(I64)                                                                                                    \
-  do {                                                                                                                       \
-    VS_LAUNCH(km_update_prep_kernel<I64>, L.r, 256, (size_t)L.k * 8, stream, at<float>(ws, L.xc), L.n, L.d, L.k,              \
-              reinterpret_cast<double*>(partial), at<int>(ws, L.labels), at<float>(ws, L.centers), at<int>(ws, L.flags),      \
-              at<float>(ws, L.newdist), local_rows_only ? 0 : 1, at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax));       \
-    VS_POST_LAUNCH();                                                                                                        \
-    VS_LAUNCH(km_update_avg_kernel<I64>, (L.r * L.k + kUpdWarps - 1) / kUpdWarps, kUpdWarps * 32, 0, stream, L.d, L.k, L.r,   \
-              reinterpret_cast<const double*>(partial), at<double>(ws, L.upd_cnt), at<int>(ws, L.upd_argmax), changed,         \
-              at<int>(ws, L.changed), at<float>(ws, L.centers), at<double>(ws, L.cnorm), at<int>(ws, L.flags),                 \
-              at<float>(ws, L.tol), L.max_iter, at<float>(ws, L.upd_shift), at<int>(ws, L.upd_ticket),                          \
-              at<unsigned>(ws, L.absmax), L.use_tc ? at<__half>(ws, L.cs_hi) : nullptr,                                        \
-              L.use_tc ? at<__half>(ws, L.cs_lo) : nullptr);                                                                   \
-    VS_POST_LAUNCH();                                                                                                        \
-  } while (0)
-  if (words_i64) VS_KM_UPDATE(true);
-  else VS_KM_UPDATE(false);
-#undef VS_KM_UPDATE
+// M-step part 2 (one launch).  src 0: `sums` = float64 [R,K,D+1] (relocation happens in place); src 1: the all-reduced
+// integer exchange words; src 2: the tensor-core product's own partial sums in the workspace (`sums` ignored).
+// `tail`: change counters stored behind the sums (exchange words), else `changed`.
+static int km_update_fused(void* ws, const KmLayout& L, int src, void* sums, const void* tail, const int32_t* changed,
+                           int local_rows_only, void* stream) {
+  UpdArgs a{};
+  a.d = L.d; a.k = L.k; a.runs = L.r; a.n = L.n; a.max_iter = L.max_iter;
+  a.can_relocate = local_rows_only ? 0 : 1;
+  a.cnt_blocks = L.mq_blocks; a.rk = L.r * L.k;
+  a.sums = (src == 2) ? static_cast<const void*>(at<int>(ws, L.mq_part)) : sums;
+  a.cntpart = at<int>(ws, L.mq_cnt);
+  a.tail = tail;
+  a.changed_in = changed ? changed : at<int>(ws, L.changed);
+  a.changed_ws = at<int>(ws, L.changed);
+  a.scratch = (src == 0) ? reinterpret_cast<double*>(sums) : at<double>(ws, L.partial);
+  a.centers = at<float>(ws, L.centers); a.cnorm = at<double>(ws, L.cnorm); a.flags = at<int>(ws, L.flags);
+  a.tol = at<float>(ws, L.tol); a.shiftsq = at<float>(ws, L.upd_shift); a.ticket = at<int>(ws, L.upd_ticket);
+  a.absmax = at<unsigned>(ws, L.absmax);
+  a.cs_hi = L.use_tc ? at<__half>(ws, L.cs_hi) : nullptr;
+  a.cs_lo = L.use_tc ? at<__half>(ws, L.cs_lo) : nullptr;
+  a.x = at<float>(ws, L.xc); a.labels = at<int>(ws, L.labels); a.dist = at<float>(ws, L.newdist);
+  a.reloc_ticket = at<int>(ws, L.reloc); a.reloc_done = at<int>(ws, L.reloc) + L.r;
+  const int grid = L.r * L.k;   // all blocks are resident (the relocation path waits across the blocks of a run)
+  VS_REQUIRE(grid <= kNumSMs * 16, "n_init * k too large for the fused update kernel");
+  if (src == 0) VS_LAUNCH(km_update_fused_kernel<0>, grid, kUpdThreads, 0, stream, a);
+  else if (src == 1) VS_LAUNCH(km_update_fused_kernel<1>, grid, kUpdThreads, 0, stream, a);
+  else VS_LAUNCH(km_update_fused_kernel<2>, grid, kUpdThreads, 0, stream, a);
+  VS_POST_LAUNCH();
   return 0;
 }
 
@@ -1975,17 +2233,10 @@ VS_API int vidseg_kmeans_update(void* workspace, size_t workspace_bytes, double*
   if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
   void* ws = workspace;
   if (partial == nullptr) partial = at<double>(ws, L.partial);
-  if (changed == nullptr) changed = at<int>(ws, L.changed);
-  return km_update_impl(ws, L, partial, changed, local_rows_only, false, stream);
+  return km_update_fused(ws, L, 0, partial, nullptr, changed, local_rows_only, stream);
 }
 
 // ---- multi-GPU exchange form: ONE array of 8-byte words per Lloyd iteration (sums | counts | change counters) ----
-__global__ void km_unpack_changed_kernel(const void* __restrict__ tail, int i64, int runs, int* __restrict__ changed) {
-  const int r = blockIdx.x * blockDim.x + threadIdx.x;
-  if (r < runs)
-    changed[r] = i64 ? (int)reinterpret_cast<const long long*>(tail)[r] : (int)reinterpret_cast<const double*>(tail)[r];
-}
-
 VS_API size_t vidseg_kmeans_exchange_words(void* workspace, size_t workspace_bytes) {
   KmLayout L;
   if (km_check_ws(workspace, workspace_bytes, &L)) return 0;
@@ -2014,11 +2265,9 @@ VS_API int vidseg_kmeans_update_words(void* workspace, size_t workspace_bytes, i
   VS_REQUIRE(words != nullptr, "null words");
   VS_REQUIRE(!words_i64 || local_rows_only, "integer exchange words carry no relocation: local_rows_only must be set");
   void* ws = workspace;
+  // the all-reduced change counters sit behind the sums: the averaging kernel tests them in place
   const void* tail = reinterpret_cast<const char*>(words) + (size_t)L.r * L.k * (L.d + 1) * 8;
-  // the all-reduced change counters become the `changed` the averaging kernel tests and then clears
-  VS_LAUNCH(km_unpack_changed_kernel, 1, 64, 0, stream, tail, words_i64 ? 1 : 0, L.r, at<int>(ws, L.changed));
-  VS_POST_LAUNCH();
-  return km_update_impl(ws, L, words, at<int>(ws, L.changed), local_rows_only, words_i64 != 0, stream);
+  return km_update_fused(ws, L, words_i64 ? 1 : 0, words, tail, nullptr, local_rows_only, stream);
 }
 
 // the convergence flags [R][4] = {done, strict, n_iter, empty cluster seen} copied to (pinned) host memory WITHOUT
@@ -2175,8 +2424,14 @@ VS_API int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_
     const int burst = (max_iter - it) < poll ? (max_iter - it) : poll;
     for (int b = 0; b < burst; ++b) {
       if (int e = vidseg_kmeans_assign(workspace, workspace_bytes, 0, n, stream)) return e;
-      if (int e = vidseg_kmeans_partial(workspace, workspace_bytes, 0, n, nullptr, nullptr, stream)) return e;
-      if (int e = vidseg_kmeans_update(workspace, workspace_bytes, nullptr, nullptr, 0, stream)) return e;
+      if (km_mq_range_ok(L, 0, n)) {
+        // one-hot labels -> exact int8 tensor-core sums -> averaging straight from the product's partial sums
+        if (int e = km_mstep_product(ws, L, 0, n, stream)) return e;
+        if (int e = km_update_fused(ws, L, 2, nullptr, nullptr, nullptr, 0, stream)) return e;
+      } else {
+        if (int e = vidseg_kmeans_partial(workspace, workspace_bytes, 0, n, nullptr, nullptr, stream)) return e;
+        if (int e = vidseg_kmeans_update(workspace, workspace_bytes, nullptr, nullptr, 0, stream)) return e;
+      }
     }
     it += burst;
     int active = 0;
