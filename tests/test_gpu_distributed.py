@@ -143,9 +143,11 @@ def test_sharded_segmenter_on_one_rank_equals_clip_segmenter(cuda):
         created = True
     try:
         got = ShardedClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True).segment(x, t, ctx, F, seed=2)
-        got_graph = ShardedClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True,
-                                         use_cuda_graph=True).segment(x, t, ctx, F, seed=2)
+        sh_graph = ShardedClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, use_cuda_graph=True)
+        got_graph = sh_graph.segment(x, t, ctx, F, seed=2)
+        got_many = list(sh_graph.segment_many([(x, t, ctx)] * 3, F, seed=2, to_host=True))
     finally:
         if created:
             dist.destroy_process_group()
     assert torch.equal(got, want) and torch.equal(got_graph, want)
+    assert len(got_many) == 3 and all(torch.equal(g, want.cpu()) for g in got_many)

@@ -317,7 +317,10 @@ class ShardedClipSegmenter:
         Returns the label maps of all frames, int32 [F, h/2, w/2], identical on every rank."""
         if self.video:
             return self._segment_cfg_split(x, timesteps, context, num_frames, seed, unet_kwargs)
-        from .refine import refine_masks
+        return self._cluster_stage(self._unet_stage(x, timesteps, context, num_frames), seed)
+
+    def _unet_stage(self, x, timesteps, context, num_frames):
+        """Rank-local part: the UNet on this rank's frames, their feature rows and (for the refinement) stashed q."""
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         F = num_frames
@@ -326,17 +329,27 @@ class ShardedClipSegmenter:
         fl = f1 - f0
         fh, fw = x.shape[-2] // 2, x.shape[-1] // 2
         hw = fh * fw
-        counts = [(b - a) * hw for a, b in parts]
         dev = x.device
         q7 = None
         if fl > 0:
             idx = torch.cat([torch.arange(f0, f1, device=dev), torch.arange(F + f0, F + f1, device=dev)])
             _, x_local, q7 = self._local_stage(x[idx], timesteps[idx], context[idx], fl, {}, "cond_half")
             c = x_local.shape[1]
+            if q7 is not None:
+                q7 = q7[fl:]                                                # conditional half of the local frames
         else:
             c = self.model.output_blocks[self.blocks[0]][1].in_channels
             x_local = torch.empty((0, c), dtype=torch.float32, device=dev)
-        X = gather_rows(x_local, counts, self.group)                       # exchange step 1
+        if self.is_refine_mask and q7 is None:
+            q7 = torch.empty((0, hw, c), dtype=torch.float32, device=dev)
+        return dict(x_local=x_local, q7=q7, parts=parts, rank=rank, world=world, F=F, fh=fh, fw=fw, hw=hw)
+
+    def _cluster_stage(self, st, seed):
+        """The two exchange steps and everything behind them: feature all-gather, distributed K-means, refinement."""
+        from .refine import refine_masks
+        parts, rank, world, F, fh, fw, hw = (st[k] for k in ("parts", "rank", "world", "F", "fh", "fw", "hw"))
+        counts = [(b - a) * hw for a, b in parts]
+        X = gather_rows(st["x_local"], counts, self.group)                 # exchange step 1
         if seed is not None:
             np.random.seed(seed)
         info = {}
@@ -346,15 +359,59 @@ class ShardedClipSegmenter:
         labels = labels.reshape(F, fh, fw)
         self.last = {"features": X, "kmeans_info": info}
         if self.is_refine_mask:
-            if fl > 0:
-                q7 = q7[fl:]                                                # conditional half of the local frames
-            else:
-                q7 = torch.empty((0, hw, c), dtype=torch.float32, device=dev)
-            cond = gather_rows(q7.contiguous(), [b - a for a, b in parts], self.group)
+            cond = gather_rows(st["q7"].contiguous(), [b - a for a, b in parts], self.group)
             feats7 = torch.cat([torch.zeros_like(cond), cond], 0)   # refine reads rows [F, 2F) only (feature_extraction.py:221)
             labels, traj, keep = refine_masks(feats7, labels, F, fh, fw)
             self.last.update(trajectories=traj, keep=keep)
         return labels
+
+    @torch.no_grad()
+    def segment_many(self, clips, num_frames, seed=None, to_host=True):
+        """A stream of clips, software-pipelined like ``ClipSegmenter.segment_many``: the rank-local UNet stage of clip i+1
+        (one CUDA graph launch on the current stream) overlaps the exchange steps and the distributed K-means of clip i
+        (second stream; every collective of the path is issued there, in clip order on every rank).  Same label maps as
+        ``segment`` clip by clip."""
+        if self.video:
+            for clip in clips:
+                kw = clip[3] if len(clip) > 3 else {}
+                lab = self.segment(clip[0], clip[1], clip[2], num_frames, seed, **kw)
+                yield lab.cpu() if to_host else lab
+            return
+        dev = next(self.model.parameters()).device
+        if getattr(self, "_side_stream", None) is None:
+            self._side_stream = torch.cuda.Stream(device=dev, priority=-1)
+        side = self._side_stream
+        main = torch.cuda.current_stream(dev)
+        to_dev = lambda v: v.to(dev, non_blocking=True) if isinstance(v, torch.Tensor) else v
+
+        def finish(pending):
+            st, ready = pending
+            with torch.cuda.stream(side):
+                side.wait_event(ready)
+                labels = self._cluster_stage(st, seed)
+                out = labels.cpu() if to_host else labels
+                done = torch.cuda.Event()
+                done.record(side)
+            if not to_host:
+                main.wait_event(done)
+            return out
+
+        pending = None
+        for clip in clips:
+            x, t, c = (to_dev(v) for v in clip[:3])
+            st = self._unet_stage(x, t, c, num_frames)
+            # the graph's buffers are overwritten by the next clip: snapshot what the second stream will read
+            for key in ("x_local", "q7"):
+                if st[key] is not None:
+                    st[key] = st[key].clone()
+                    st[key].record_stream(side)
+            ready = torch.cuda.Event()
+            ready.record(main)
+            if pending is not None:
+                yield finish(pending)
+            pending = (st, ready)
+        if pending is not None:
+            yield finish(pending)
 
     def _segment_cfg_split(self, x, timesteps, context, num_frames, seed, unet_kwargs):
         """SVD on two ranks: rank 0 runs the unconditional rows [0, F) of the batch, rank 1 the conditional rows [F, 2F)
