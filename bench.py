@@ -35,6 +35,12 @@ WORKLOADS = {
                desc="SVD VideoUNet, 28 frames 768x768, num_masks=50, refinement: ONE clip of BASELINE configs[4] on one GPU (size check)"),
     "c1": dict(cfg="sd21", frames=4, latent=32, ctx_len=77, num_masks=5, aggre=False, refine=False,
                desc="SD-2.1, 4 frames 256x256, num_masks=5 (BASELINE configs[0])"),
+    "c2mod": dict(cfg="sd21", frames=14, latent=64, ctx_len=77, num_masks=20, aggre=True, refine=True, modulated=True,
+                  desc="configs[1] continued to the final maps: source run of sampler steps 17..24 with q / k / x_t kept in HBM, "
+                       "K-means + refinement, then the 2 x 20 modulated sampler runs (8 UNet steps each) + first-stage decode + "
+                       "seg-map post-process (svd_single_video_inference.py:404-508); opt-in, one step is ~330 UNet evaluations"),
+    "tinymod": dict(cfg="tiny", frames=2, latent=16, ctx_len=7, num_masks=3, aggre=True, refine=True, modulated=True,
+                    desc="toy-width plumbing check of the modulated-run workload"),
     "tiny": dict(cfg="tiny", frames=2, latent=16, ctx_len=7, num_masks=3, aggre=True, refine=True,
                  desc="toy-width UNet, plumbing check only"),
     "tinyv": dict(cfg="tinyv", frames=3, latent=16, ctx_len=1, num_masks=3, aggre=True, refine=True,
@@ -287,6 +293,19 @@ def relerr(got, want):
     import torch
     got, want = torch.as_tensor(got).double().cpu(), torch.as_tensor(want).double().cpu()
     return float((got - want).abs().max() / want.abs().max())
+
+
+def partition_agreement(a, b, k):
+    """Fraction of cells on which two label maps agree after the best one-to-one matching of their label ids."""
+    import numpy as np
+    conf = np.zeros((k, k), dtype=np.int64)
+    np.add.at(conf, (a.astype(np.int64), b.astype(np.int64)), 1)
+    try:
+        from scipy.optimize import linear_sum_assignment
+        r, c = linear_sum_assignment(-conf)
+        return float(conf[r, c].sum() / max(a.size, 1))
+    except ImportError:
+        return float(conf.max(axis=1).sum() / max(a.size, 1))
 
 
 def label_oracle(X, q7, wl, seed):
@@ -560,9 +579,12 @@ def run_b200(args, wl, cfg):
             feat["unet_output"] = relerr(out_gpu, ref["out"])
             parity.update(features_rel_err_vs_reference=feat, features_max_rel_err=max(feat.values()), features_tol=1e-3,
                           features_ok=max(feat.values()) <= 1e-3,
-                          labels_gpu_path_vs_reference_path_mismatch_cells=int((lab_gpu.cpu().numpy().reshape(-1) != ref["labels"].reshape(-1)).sum()),
-                          labels_gpu_path_vs_reference_path_note="the two paths cluster DIFFERENT feature tensors (equal to "
-                          "features_max_rel_err, not bit-equal), so this count is information; the bit-exact check is label_mismatches")
+                          partition_agreement_gpu_path_vs_reference_path=partition_agreement(
+                              lab_gpu.cpu().numpy().reshape(-1), ref["labels"].reshape(-1), wl["num_masks"]),
+                          partition_agreement_note="fraction of cells on which the two end-to-end paths agree after the best "
+                          "one-to-one matching of cluster ids; they cluster DIFFERENT feature tensors (equal to "
+                          "features_max_rel_err, not bit-equal) and K-means numbers its clusters arbitrarily, so this is "
+                          "information -- the bit-exact check is label_mismatches (same features in, same labels out)")
             del ref
     if world == 1 and not args.no_parity:
         # integer stage: the label maps of the TIMED call against the reference's clustering arithmetic run on the CPU
@@ -602,6 +624,113 @@ def run_b200(args, wl, cfg):
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_modulated(args, wl, cfg):
+    """Opt-in workload: the whole single-clip pipeline behind the per-clip hot path, everything resident in HBM."""
+    import numpy as np
+    import torch
+    from vidseg_diffusion_b200 import _lib
+    from vidseg_diffusion_b200.features import aggregate_normalize
+    from vidseg_diffusion_b200.kmeans import KMeans
+    from vidseg_diffusion_b200.modulation import modulated_segmentation
+    from vidseg_diffusion_b200.refine import refine_masks
+    from vidseg_diffusion_b200.sgm.models.autoencoder import AutoencoderKL
+    from vidseg_diffusion_b200.sgm.models.diffusion import FirstStage
+    from vidseg_diffusion_b200.sgm.modules.diffusionmodules.wrappers import OpenAIWrapper
+    from vidseg_diffusion_b200.sgm.util import instantiate_from_config
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device")
+    dev = torch.device("cuda", 0)
+    _lib.load()
+    F, K = wl["frames"], wl["num_masks"]
+    sd = make_state_dict(cfg)
+    with torch.device("meta"):
+        model = model_class(cfg)(**cfg)
+    model = model.to_empty(device=dev)
+    model.load_state_dict({k: v.to(dev) for k, v in sd.items()}, strict=True)
+    model.eval()
+    ddconfig = dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128 if wl["cfg"] == "sd21" else 64,
+                    ch_mult=(1, 2, 4, 4), num_res_blocks=2, attn_resolutions=(), dropout=0.0)   # sd_2_1.yaml:49-59
+    with torch.device("meta"):
+        vae = AutoencoderKL(embed_dim=4, ddconfig=ddconfig)
+    g = torch.Generator().manual_seed(7)
+    vsd = {}
+    for key, t in vae.state_dict().items():
+        shape = tuple(t.shape)
+        fan_in = int(np.prod(shape[1:])) if len(shape) >= 2 else 1
+        vsd[key] = (torch.randn(shape, generator=g) * fan_in ** -0.5 if len(shape) >= 2 else
+                    (1.0 + 0.1 * torch.randn(shape, generator=g) if key.endswith(".weight") else 0.05 * torch.randn(shape, generator=g)))
+    vae = vae.to_empty(device=dev)
+    vae.load_state_dict({k: v.to(dev) for k, v in vsd.items()}, strict=True)
+    engine = FirstStage(vae.eval(), scale_factor=0.18215, en_and_decode_n_samples_a_time=F)
+    ddpm = {"target": "sgm.modules.diffusionmodules.discretizer.LegacyDDPMDiscretization"}
+    steps, t_start = 25, 17
+    smp = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.sampling.EulerEDMSampler",
+        "params": {"discretization_config": ddpm, "num_steps": steps, "s_churn": 0, "s_tmin": 0, "s_tmax": 999, "s_noise": 1,
+                   "device": str(dev),
+                   "guider_config": {"target": "sgm.modules.diffusionmodules.guiders.VanillaCFG", "params": {"scale": 5.0}}}})
+    den = instantiate_from_config({
+        "target": "sgm.modules.diffusionmodules.denoiser.DiscreteDenoiser",
+        "params": {"num_idx": 1000, "discretization_config": ddpm,
+                   "scaling_config": {"target": "sgm.modules.diffusionmodules.denoiser_scaling.EpsScaling"}}}).to(dev)
+    denoiser = den.bind(OpenAIWrapper(model))
+    x, _, ctx = make_clip(wl, cfg, 1)
+    latent, ctx = x[:F].to(dev), ctx[F:].to(dev)
+    c, uc = {"crossattn": ctx}, {"crossattn": torch.zeros_like(ctx)}
+    fh = wl["latent"] // 2
+    blocks = (8, 7, 6)
+
+    def one_clip():
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        store = {}
+
+        def save_cb(xt, i):   # svd_single_video_inference.py:113-130 without the .pt files
+            store[f"xt_time_{i}"] = xt.clone()
+            if i == steps - 1:
+                for b in blocks:
+                    store[("q", b)] = model.output_blocks[b][1].transformer_blocks[0].attn1.q.clone()
+
+        ev[0].record()
+        smp(denoiser, latent.clone(), cond=c, uc=uc, img_callback=save_cb, t_start=t_start)          # source run
+        ev[1].record()
+        X = aggregate_normalize([store[("q", b)] for b in blocks], F)
+        np.random.seed(1)
+        labels = KMeans(n_clusters=K, n_init=10).fit_predict(X).reshape(F, fh, fh)
+        labels, _, _ = refine_masks(store[("q", 7)], labels, F, fh, fh)
+        ev[2].record()
+        res = modulated_segmentation(smp, denoiser, engine, latent, c, uc, labels.to(torch.int32).contiguous(), np.arange(K),
+                                     num_steps=steps, t_start=t_start, modulate_block_idx=(8,), modulate_timestep=(17,),
+                                     modulate_layer_type=("spatial", "temporal"), modulate_attn_type=("self_attn",),
+                                     is_latent_blending=True, features=store)
+        ev[3].record()
+        torch.cuda.synchronize()
+        return res, [ev[i].elapsed_time(ev[i + 1]) for i in range(3)]
+
+    for _ in range(args.warmup):
+        one_clip()
+    launches0 = _lib.launch_count()
+    total, stages = 0.0, [0.0, 0.0, 0.0]
+    for _ in range(args.steps):
+        res, ms = one_clip()
+        total += sum(ms)
+        stages = [a + b for a, b in zip(stages, ms)]
+    fps = F * args.steps / (total / 1e3)
+    seg = res["seg_raw"]
+    unet_evals = (steps - t_start) * (1 + 2 * K)
+    emit({"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+          "ms_per_step": total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+          "dtype": "f32 (fp16 tensor-core operands with fp8/fp16 correction terms, fp32 accumulate)", "data": "synthetic",
+          "config": bench_config(args, wl, 1, "single"),
+          "stage_ms_per_step": {"source_run(8 sampler steps)": stages[0] / args.steps,
+                                "kmeans+refine": stages[1] / args.steps,
+                                f"{2 * K} modulated runs + decode + post-process": stages[2] / args.steps},
+          "unet_evaluations_per_step": unet_evals, "gpu_launches": int(_lib.launch_count() - launches0),
+          "result": {"seg_raw_shape": list(seg.shape), "labels_used": int(torch.unique(seg).numel())},
+          "e2e": None, "roofline": None,
+          "cpu_baseline": {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+                           "sample": "not timed: the reference needs ~330 CPU UNet evaluations (hours) for this workload"}})
 
 
 _REAL_STDOUT = None
@@ -651,7 +780,9 @@ def main():
     from vidseg_diffusion_b200 import configs
     cfg = {"sd21": configs.SD21_UNET, "tiny": configs.TINY_UNET, "svd": configs.SVD_UNET,
            "tinyv": configs.TINY_VIDEO_UNET}[wl["cfg"]]
-    if args.impl == "reference":
+    if wl.get("modulated"):
+        run_modulated(args, wl, cfg)
+    elif args.impl == "reference":
         run_reference(args, wl, cfg)
     else:
         run_b200(args, wl, cfg)
