@@ -11,6 +11,8 @@
 //   upsample2x_split  nearest x2 (openaimodel.py:153) fused with the operand conversion of the following conv
 #define VS_FAMILY vidseg::kFamElementwise
 #include "common.cuh"
+#include <cstdlib>
+
 #include "tc_common.cuh"
 
 namespace vidseg {
@@ -30,50 +32,74 @@ __global__ void __launch_bounds__(256)
 layernorm_split_kernel(const float* __restrict__ x, const float* __restrict__ row_bias, long long rows_per_bias,
                        const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                        __half* __restrict__ hi, __half* __restrict__ lo, long long rows, int c, int packed8) {
+  // TWO rows per warp, both loaded before either is reduced: twice the bytes in flight per warp (the one-row form ran
+  // at half of the HBM roof on the C = 320 / 640 layers)
+  constexpr int R = 2;
   const int lane = threadIdx.x & 31;
-  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * R;
+  if (row0 >= rows) return;
   const int nq = c >> 2;  // float4 per row
-  const float4* xr = reinterpret_cast<const float4*>(x + row * c);
-  // optional bias shared by groups of rows_per_bias consecutive rows, added BEFORE the normalisation: the
-  // frame-position embedding / single-token cross-attention output of the temporal layers
-  const float4* br = row_bias ? reinterpret_cast<const float4*>(row_bias + (row / rows_per_bias) * c) : nullptr;
-  float4 v[Q];
-  float s = 0.f;
+  float4 v[R][Q];
+  float s[R];
 #pragma unroll
-  for (int i = 0; i < Q; ++i) {
-    const int q = lane + 32 * i;
-    if (q < nq) {
-      v[i] = ld_stream_f4(xr + q);
-      if (br) {
-        const float4 bb = __ldg(br + q);
-        v[i].x += bb.x; v[i].y += bb.y; v[i].z += bb.z; v[i].w += bb.w;
+  for (int rr = 0; rr < R; ++rr) {
+    const long long row = row0 + rr;
+    s[rr] = 0.f;
+    if (row < rows) {
+      const float4* xr = reinterpret_cast<const float4*>(x + row * c);
+#pragma unroll
+      for (int i = 0; i < Q; ++i) {
+        const int q = lane + 32 * i;
+        if (q < nq) v[rr][i] = ld_stream_f4(xr + q);
       }
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     }
   }
-  const float mean = warp_sum(s) / (float)c;
-  float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < Q; ++i) {
-    const int q = lane + 32 * i;
-    if (q < nq) {
-      const float a = v[i].x - mean, b = v[i].y - mean, cc = v[i].z - mean, d = v[i].w - mean;
-      s2 += (a * a + b * b) + (cc * cc + d * d);
+  for (int rr = 0; rr < R; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) continue;
+    // optional bias shared by groups of rows_per_bias consecutive rows, added BEFORE the normalisation: the
+    // frame-position embedding / single-token cross-attention output of the temporal layers
+    const float4* br = row_bias ? reinterpret_cast<const float4*>(row_bias + (row / rows_per_bias) * c) : nullptr;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nq) {
+        if (br) {
+          const float4 bb = __ldg(br + q);
+          v[rr][i].x += bb.x; v[rr][i].y += bb.y; v[rr][i].z += bb.z; v[rr][i].w += bb.w;
+        }
+        s[rr] += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(s2) / (float)c + eps);
-  __half* hr = hi + row * c;
-  __half* lr = lo + row * c;
 #pragma unroll
-  for (int i = 0; i < Q; ++i) {
-    const int q = lane + 32 * i;
-    if (q < nq) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
-      const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
-      tc::store_split4(hr, lr, q * 4, (v[i].x - mean) * rstd * g.x + bt.x, (v[i].y - mean) * rstd * g.y + bt.y,
-                       (v[i].z - mean) * rstd * g.z + bt.z, (v[i].w - mean) * rstd * g.w + bt.w, packed8 != 0,
-                       tc::kAct8Sx, tc::kAct8Sl);
+  for (int rr = 0; rr < R; ++rr) {
+    const long long row = row0 + rr;
+    if (row >= rows) continue;   // warp-uniform
+    const float mean = warp_sum(s[rr]) / (float)c;
+    float s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nq) {
+        const float a = v[rr][i].x - mean, b = v[rr][i].y - mean, cc = v[rr][i].z - mean, d = v[rr][i].w - mean;
+        s2 += (a * a + b * b) + (cc * cc + d * d);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(s2) / (float)c + eps);
+    __half* hr = hi + row * c;
+    __half* lr = lo + row * c;
+#pragma unroll
+    for (int i = 0; i < Q; ++i) {
+      const int q = lane + 32 * i;
+      if (q < nq) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + q);
+        const float4 bt = __ldg(reinterpret_cast<const float4*>(beta) + q);
+        tc::store_split4(hr, lr, q * 4, (v[rr][i].x - mean) * rstd * g.x + bt.x, (v[rr][i].y - mean) * rstd * g.y + bt.y,
+                         (v[rr][i].z - mean) * rstd * g.z + bt.z, (v[rr][i].w - mean) * rstd * g.w + bt.w, packed8 != 0,
+                         tc::kAct8Sx, tc::kAct8Sl);
+      }
     }
   }
 }
@@ -106,6 +132,7 @@ geglu_split_kernel(const float* __restrict__ h, __half* __restrict__ hi, __half*
 constexpr int kGnMaxChunks = 256; // pixel chunks per sample in pass 1 (chosen per call so that the grid fills the GPU)
 constexpr int kGnThreads = 256;
 constexpr int kGnMaxGroups = 32;
+constexpr int kGnInFlight = 4;    // 16-byte loads in flight per thread in the apply pass
 
 __device__ __forceinline__ float4 gn_load(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
                                           long long pix, int ch) {
@@ -193,8 +220,8 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
   __syncthreads();
   const int p0 = blockIdx.x * pix_per_block, p1 = min(hw, p0 + pix_per_block);
   const int total = (p1 - p0) * nq;
-  // (pixel, quad) of this thread advance incrementally: no division in the loop.  Two items per trip, both loads issued
-  // before either is processed: one 16-byte load in flight per thread left the kernel at ~3.5 TB/s.
+  // (pixel, quad) of this thread advance incrementally: no division in the loop.  kGnInFlight items per trip, all loads
+  // issued before any is processed: one 16-byte load in flight per thread left the kernel at ~3.5 TB/s, two at ~4.5.
   int pp = p0 + threadIdx.x / nq, q = threadIdx.x % nq;
   const int dp = kGnThreads / nq, dq = kGnThreads % nq;
   auto process = [&](int ppx, int qx, const float4& v) {
@@ -208,19 +235,21 @@ groupnorm_apply_kernel(const float* __restrict__ x1, int c1, const float* __rest
     if (raw_hi)
       tc::store_split4(raw_hi + pix * c, raw_lo + pix * c, ch, v.x, v.y, v.z, v.w, packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
   };
-  for (int i = threadIdx.x; i < total; i += 2 * kGnThreads) {
-    const int ppa = pp, qa = q;
-    pp += dp; q += dq;
-    if (q >= nq) { q -= nq; ++pp; }
-    const int ppb = pp, qb = q;
-    pp += dp; q += dq;
-    if (q >= nq) { q -= nq; ++pp; }
-    const bool has_b = i + kGnThreads < total;
-    const float4 va = gn_load(x1, c1, x2, c2, (long long)b * hw + ppa, qa * 4);
-    float4 vb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_b) vb = gn_load(x1, c1, x2, c2, (long long)b * hw + ppb, qb * 4);
-    process(ppa, qa, va);
-    if (has_b) process(ppb, qb, vb);
+  for (int i = threadIdx.x; i < total; i += kGnInFlight * kGnThreads) {
+    int ppi[kGnInFlight], qi[kGnInFlight];
+    float4 v[kGnInFlight];
+#pragma unroll
+    for (int u = 0; u < kGnInFlight; ++u) {
+      ppi[u] = pp; qi[u] = q;
+      pp += dp; q += dq;
+      if (q >= nq) { q -= nq; ++pp; }
+    }
+#pragma unroll
+    for (int u = 0; u < kGnInFlight; ++u)
+      if (i + u * kGnThreads < total) v[u] = gn_load(x1, c1, x2, c2, (long long)b * hw + ppi[u], qi[u] * 4);
+#pragma unroll
+    for (int u = 0; u < kGnInFlight; ++u)
+      if (i + u * kGnThreads < total) process(ppi[u], qi[u], v[u]);
   }
 }
 
@@ -336,7 +365,7 @@ static int layernorm_entry(const float* x, const float* row_bias, long long rows
   VS_REQUIRE(rows >= 0 && channels >= 4 && channels % 4 == 0 && channels <= 128 * kLnMaxQuads, "C must be a multiple of 4, <= 2048");
   if (rows == 0) return 0;
   const int warps = 8;
-  const long long grid = (rows + warps - 1) / warps;
+  const long long grid = (rows + 2 * warps - 1) / (2 * warps);   // two rows per warp
   VS_REQUIRE(grid <= 0x7fffffffLL, "too many rows");
   const int quads = (channels / 4 + 31) / 32;
   const int p8 = operand_packed8(channels) ? 1 : 0;
@@ -393,8 +422,10 @@ VS_API int vidseg_groupnorm_split(const float* x1, int c1, const float* x2, int 
   VS_LAUNCH_W(bytes, groupnorm_stats_kernel, dim3(chunks, batch), kGnThreads, smem, stream, x1, c1, x2, c2, hw, groups,
               partial);
   VS_POST_LAUNCH();
-  // pass 2: ~16K quads per block
-  int pix_per_block = (16384 + nq - 1) / nq;
+  // pass 2: ~8K quads per block (twice the blocks of the first version: 3-4 resident blocks per SM did not cover the
+  // HBM latency)
+  static const int gn_quads = [] { const char* e = getenv("VIDSEG_GN_QUADS"); return e ? atoi(e) : 8192; }();
+  int pix_per_block = (gn_quads + nq - 1) / nq;
   if (pix_per_block > hw) pix_per_block = hw;
   const int blocks = (hw + pix_per_block - 1) / pix_per_block;
   VS_REQUIRE((size_t)c * 8 <= 48 * 1024, "C too large for the group-norm apply kernel");
