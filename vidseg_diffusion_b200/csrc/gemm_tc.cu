@@ -391,8 +391,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       // iff some other centre satisfies sc_j <= best + (tau_best + tau_j) |x|.  Pass 2, only for runs in which some
       // lane of the warp is ambiguous: the run's columns are loaded from TMEM once more and every centre inside the band
       // of the final best goes into the pair's candidate mask for the resolver.
-      // The test runs in fp32 (float64 issues at ~6 instructions per clock per SM here; 200 columns x 128 rows of it
-      // cost more than the GEMM): the radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the
+      // The test runs in fp32 (the scan is one dependent compare / select chain per point, issued by a single warp per
+      // scheduler: fp32 halves its latency): the radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the
       // fp32 test can only flag MORE pairs / candidates than the float64 one -- every flagged pair is settled exactly by
       // the resolver, every unflagged label is the float64 arg-min.
       const KmEpilogue& km = p.km;

@@ -793,8 +793,9 @@ km_split_scaled_kernel(const float* __restrict__ x, size_t n_valid, size_t n_tot
   }
 }
 
-// One thread per (point, run).  The filter arithmetic is fp32: float64 issues at ~6 instructions per clock per SM on this
-// part, and the 2 x K score evaluations per pair in float64 made this kernel as expensive as the GEMM that feeds it.
+// One thread per (point, run).  The filter arithmetic is fp32 (half the issue cost and latency of float64 on this part,
+// FP32 : FP64 = 2 : 1) and single pass: the two float64 passes over the K scores of every pair had made this kernel
+// almost as expensive as the GEMM that feeds it (16.6 us against 22.7 us; now 10.8 us).
 // The error radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the fp32 test can only
 // flag MORE pairs / candidates than the float64 test would -- every flagged pair is settled exactly by the resolver,
 // every unflagged label is the float64 arg-min.  Single pass: `best` is the running minimum, `minlow` the smallest
