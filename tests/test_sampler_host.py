@@ -227,7 +227,7 @@ def test_sampler_options_outside_the_scope_fail_loudly():
         "params": {"num_steps": 4, "device": "cpu", "discretization_config": {
             "target": "sgm.modules.diffusionmodules.discretizer.EDMDiscretization"}}})
     x = torch.zeros(2, 4, 8, 8)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):   # the smoothing pass needs the first stage
         smp.sampler_step(torch.ones(2), torch.ones(2), None, x, {}, {}, is_smooth_latent=True)
     with pytest.raises(NotImplementedError):
         smp.null_text_optimization()

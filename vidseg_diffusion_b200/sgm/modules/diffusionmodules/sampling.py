@@ -151,7 +151,8 @@ class EDMSampler(SingleStepDiffusionSampler):
             # reference :116-124: the denoised latent goes through the first stage, every third frame (offset
             # smooth_step_size) becomes the mean of its neighbours, and the clip is encoded again.  The denoised sample is
             # needed by itself here, so the denoiser / guider run unfused; the Euler update (+ blending) stays one launch.
-            assert model is not None
+            if model is None:
+                raise ValueError("is_smooth_latent needs model= (the first stage that decodes / encodes the latent)")
             if sigma_hat.mean() < 1e-6:
                 denoised = x
             else:
