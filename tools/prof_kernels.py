@@ -43,6 +43,13 @@ if "gemmres" in which:   # the memory-bound projection shape of the first UNet l
         return gemm_split(a, w, bias, res_t)
     ms = ev(run, it=3) - ev(lambda: big.zero_(), it=3)
     res["gemmres_114688x320x320_fr"] = {"ms": ms, "GBs": (m * kk * 4 + 2 * m * n * 4) / ms / 1e6}
+if "proj" in which:   # K = 320 projections: plain fp32 output, then the q / k form (fp32 stash + fp16-pair operand)
+    m, n, kk = 28 * 4096, 320, 320
+    a = split(torch.randn(m, kk, device=dev)); w = split(torch.randn(n, kk, device=dev) / kk ** 0.5, 256.0, is_weight=True)
+    ms = ev(lambda: gemm_split(a, w, want_f32=True))
+    res["proj_f32"] = {"ms": ms, "GBs": (m * kk * 4 + m * n * 4) / ms / 1e6}
+    ms = ev(lambda: gemm_split(a, w, want_f32=True, want_split=True, split_pair16=True))
+    res["proj_f32_split"] = {"ms": ms, "GBs": (m * kk * 4 + 2 * m * n * 4) / ms / 1e6}
 if "conv" in which:
     for (B, H, C, Co) in [(28, 64, 320, 320), (28, 32, 640, 640), (28, 64, 640, 320), (28, 8, 1280, 1280), (28, 8, 2560, 1280), (28, 16, 1280, 1280)]:
         conv = torch.nn.Conv2d(C, Co, 3, padding=1).to(dev)

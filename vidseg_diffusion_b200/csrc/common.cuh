@@ -111,22 +111,4 @@ __device__ __forceinline__ float km_operand_scale(unsigned absmax_bits) {
   return ldexpf(1.f, 11 - e);
 }
 
-// K-means E-step as the EPILOGUE of the score GEMM (gemm_tc.cu): every epilogue thread owns one point (a TMEM lane)
-// and walks the R*K score columns of all runs, so the [N, R*K] score matrix never reaches memory.  See kmeans.cu.
-struct KmEpilogue {
-  int on;                    // 0: ordinary GEMM epilogue
-  int k, runs, row_begin, labels_stride;
-  int count_changes, only_nonstrict;
-  double band;               // error radius of the filter per unit |x||c|
-  const unsigned* absmax;    // operand scale source
-  const double* cnorm;       // [R*K] squared centre norms
-  const double* xx;          // [N] squared point norms
-  const int* flags;          // [R][4]
-  int* labels;               // [R][labels_stride]
-  int* changed;              // [R]
-  int* amb_count;            // {count, ticket}
-  int4* amb_list;            // (row, run, candidate mask lo, hi) of the pairs whose best score is not separated by
-                             // the filter's error band
-};
-
 }  // namespace vidseg

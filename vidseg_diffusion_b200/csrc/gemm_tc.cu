@@ -130,15 +130,28 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
 constexpr int kGemmBM = 128, kGemmBK = 64, kGemmAccStages = 2;
 constexpr int kTileABytes = kGemmBM * kGemmBK * 2;  // 16 KB
 constexpr int kMaxTaps = 9;
-constexpr int kKmMaxCols = 256;                                // R*K of the fused K-means E-step epilogue (one N tile)
-constexpr int kKmSmemBytes = kKmMaxCols * 16 + 64 * 4 + 32;   // per-column {cn, tau, meta}, changed[R], per-warp maxima
+// warps: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 3 = spare, 4..11 = epilogue.  Eight epilogue warps: a
+// TMEM lane quarter (warp id % 4) is shared by two warps that take alternate 32-column chunks of the tile, so that every
+// scheduler has two epilogue warps to interleave (with one warp per scheduler the epilogue ran at one instruction per ~7
+// cycles -- dependent issue, instruction-cache misses on the long unrolled body -- and bounded every GEMM with a short K
+// loop: ncu on the K = 320 projections showed 28 % of the DRAM roof with 24 % of the tensor pipe).
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarps = (kGemmThreads - 128) / 32;
+// Epilogue staging: TMEM hands every thread one ROW of the tile (32 consecutive columns per load), so stores issued from
+// that layout touch 32 different cache lines per instruction with 16 bytes each.  Each epilogue warp therefore turns its
+// 32 x 32 block through a private 8-row x 128-byte shared-memory buffer (four passes of 8 rows, XOR-swizzled float4
+// slots, conflict-free both ways) and reads / writes global memory with 8 lanes per row: every request covers four full
+// 128-byte lines of the fp32 output and residual, full 32-byte sectors of the operand outputs.  All element-wise terms
+// (scale, bias, residual, blend) are applied in that layout, where a lane keeps the same four columns for all rows.
+constexpr int kEpiWarpBytes = 8 * 128;
+constexpr int kEpiStageBytes = kEpiWarps * kEpiWarpBytes;
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kTileBBytes = BN * kGemmBK * 2;
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
   static constexpr int kStages = (BN <= 128) ? 3 : (BN <= 160 ? 3 : 2);
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kKmSmemBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
 };
@@ -167,71 +180,12 @@ struct GemmParams {
   __half* out_hi;           // [M, N] or null
   __half* out_lo;
   int mma_n;                // N of the MMA instruction (multiple of 16, <= BN); 0 = BN
-  KmEpilogue km;            // K-means E-step epilogue (km.on)
 };
 
-constexpr int kGemmThreads = 256;   // TMA warp, MMA warp, TMEM-alloc warp, spare, 4 epilogue warps (8 measured no faster)
 // CL = 2: two CTAs of a thread-block cluster work on two adjacent M tiles of the SAME N tile; each loads half of the
 // weight (B) tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per k-block drops
-// from A + B to A + B/2 (the packed8 GEMMs are bound by that traffic, not by the MMA pipe: ncu 69 % tensor-active).
-// A stage may only be refilled when BOTH CTAs have consumed it: the MMA issuer's commit arrives on both empty barriers.
-// State of one epilogue thread (= one point) while it scans the score columns of one K-means run.
-struct KmScan {
-  float best, best_tau, minlow;
-  int best_j, old_label;
-};
-
-// second pass of the K-means epilogue over one run's k score columns (warp-collective TMEM loads, 8 columns at a time):
-// the centres whose lower bound lies inside the final best's band.  Not inlined; compact on purpose -- the epilogue is
-// executed once per tile by one warp per scheduler, so it runs at the speed its code can be fetched.
-__device__ __noinline__ unsigned long long km_candidates(uint32_t taddr, int k, const float4* __restrict__ tab, float m2inv,
-                                                         float xn, float thr) {
-  unsigned long long cand = 0ull;
-#pragma unroll 1
-  for (int q0 = 0; q0 < k; q0 += 8) {
-    uint32_t r2[8];
-    tc::tmem_ld_32x8(taddr + q0, r2);   // may run past the run's last column: masked below
-    tc::tmem_wait_ld();
-#pragma unroll
-    for (int q = 0; q < 8; ++q) {
-      const float4 e2 = tab[q0 + q];
-      const float sc2 = fmaf(__uint_as_float(r2[q]), m2inv, e2.x);
-      if (q0 + q < k && sc2 - e2.y * xn <= thr) cand |= 1ull << ((q0 + q) & 63);
-    }
-  }
-  return cand;
-}
-
-// end of a run for one point: take the label, or hand the pair to the resolver with its candidate set
-__device__ __noinline__ void km_run_end(const KmEpilogue& km, const KmScan st, int meta, int col, bool row_ok, int row,
-                                        float xn, float slack, float m2inv, uint32_t t_acc,
-                                        const float4* __restrict__ s_tab, int* __restrict__ s_changed, int lane) {
-  const int run = meta >> 16;
-  const bool take = row_ok && (meta & 0x200);
-  const float thr = st.best + st.best_tau * xn + slack;
-  const bool amb = take && (st.minlow <= thr);
-  bool moved = false;
-  if (take && !amb) {
-    moved = km.count_changes && st.old_label != st.best_j;
-    km.labels[(size_t)run * km.labels_stride + row] = st.best_j;
-  }
-  const unsigned mv = __ballot_sync(0xffffffffu, moved);   // one shared atomic per warp and run
-  if (lane == 0 && mv) atomicAdd(&s_changed[run], __popc(mv));
-  const unsigned am = __ballot_sync(0xffffffffu, amb);
-  if (am) {
-    const int col0 = col - (km.k - 1);
-    unsigned long long cand = km_candidates(t_acc + col0, km.k, s_tab + col0, m2inv, xn, thr);
-    int base_slot = 0;   // one global atomic per warp and run: the counter is a single address for the whole grid
-    if (lane == 0) base_slot = atomicAdd(km.amb_count, __popc(am));
-    base_slot = __shfl_sync(0xffffffffu, base_slot, 0);
-    if (amb) {
-      if (km.k > 64) cand = ~0ull;
-      const int slot = base_slot + __popc(am & ((1u << lane) - 1u));
-      km.amb_list[slot] = make_int4(row, run, (int)(unsigned)cand, (int)(unsigned)(cand >> 32));
-    }
-  }
-}
-
+// from A + B to A + B/2.  A stage may only be refilled when BOTH CTAs have consumed it: the MMA issuer's commit arrives
+// on both empty barriers.
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
@@ -247,8 +201,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   uint64_t* tmem_empty_bar = tmem_full_bar + kGemmAccStages;
   uint32_t* tmem_base_ptr = reinterpret_cast<uint32_t*>(tmem_empty_bar + kGemmAccStages);
   // same bytes as smem + ..., derived from the __shared__ array itself so that the compiler keeps the shared address
-  // space (LDS / ATOMS instead of generic loads and atomics) for the K-means epilogue tables
-  uint8_t* km_smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u) + kStages * Cfg::kStageBytes + 256;
+  // space (LDS / STS instead of generic accesses) for the epilogue staging buffers
+  uint8_t* epi_smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u) + kStages * Cfg::kStageBytes + 256;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -271,7 +225,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], CL); }
-    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kGemmThreads - 128); }
+    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kEpiWarps * 32); }
     tc::fence_barrier_init();
   }
   if (warp == 2) tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr);
@@ -280,7 +234,6 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   if (CL > 1) tc::cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
   tc::tc_fence_after();
   const uint32_t tmem_base = *tmem_base_ptr;
-
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
@@ -372,109 +325,17 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     }
   } else if (warp >= 4) {
     // ===================== epilogue =====================
-    // epilogue warps: a TMEM lane quarter (warp id % 4) may be shared by two warps that split the tile's columns
-    // (kGemmThreads = 384); with four warps each one walks all columns
-    const int ew = (warp - 4) & 3;     // TMEM lanes [32*ew, 32*ew+32)
-    const int chalf = (warp - 4) >> 2; // which half of the 32-column chunks
-    constexpr int kChunks = (BN + 31) / 32, kChunks0 = (kGemmThreads > 256) ? (kChunks + 1) / 2 : kChunks;
-    const int c_begin = chalf ? kChunks0 * 32 : 0, c_end = chalf ? BN : kChunks0 * 32;
-    const int r = ew * 32 + lane;  // row of the tile = pixel of the patch
+    const int ew = warp & 3;           // TMEM lanes [32*ew, 32*ew+32) (a warp may only touch the quarter warp id % 4)
+    const int chalf = (warp - 4) >> 2; // which of the alternating column chunks
+    const int r = ew * 32 + lane;      // row of the tile = pixel of the patch (row layout: TMEM loads, prefetches)
     const int pw = r % p.bw, ph = (r / p.bw) % p.bh, pb = r / (p.bw * p.bh);
+    // staged layout (see kEpiWarpBytes): lane = (row quarter qrow, 4 columns at qcol); slot u of a chunk is row
+    // 4 * u + qrow of this warp's 32 rows
+    const int qrow = lane >> 3, qx = lane & 7, qcol = qx * 4;
+    uint4* stage = reinterpret_cast<uint4*>(epi_smem + (warp - 4) * kEpiWarpBytes);
+    const int st_row = (lane & 7) * 8;   // row written by this lane in its pass (rows are 8 float4 slots)
     int acc = 0;
     uint32_t acc_phase = 0;
-    if (BN == 256 && p.km.on) {
-      // ===================== K-means E-step epilogue =====================
-      // labels = argmin_j ( ||c_j||^2 - 2 x.c_j ) per run, decided from the tensor-core scores when the best centre is
-      // separated from every other by more than the filter's error band, deferred to the resolver otherwise.
-      // Pass 1, per run, branch-free per column: `best` is the running minimum, `minlow` the smallest lower bound
-      // sc_j - tau_j |x| among the OTHER centres; the point is ambiguous iff minlow <= best + tau_best |x| (+ slack), i.e.
-      // iff some other centre satisfies sc_j <= best + (tau_best + tau_j) |x|.  Pass 2, only for runs in which some
-      // lane of the warp is ambiguous: the run's columns are loaded from TMEM once more and every centre inside the band
-      // of the final best goes into the pair's candidate mask for the resolver.
-      // The test runs in fp32 (the scan is one dependent compare / select chain per point, issued by a single warp per
-      // scheduler: fp32 halves its latency): the radii are widened by 1 % and `slack` bounds the fp32 rounding of two scores, so the
-      // fp32 test can only flag MORE pairs / candidates than the float64 one -- every flagged pair is settled exactly by
-      // the resolver, every unflagged label is the float64 arg-min.
-      const KmEpilogue& km = p.km;
-      float4* s_tab = reinterpret_cast<float4*>(km_smem);                  // per column {cn, tau, meta, -}
-      int* s_changed = reinterpret_cast<int*>(s_tab + kKmMaxCols);
-      float* s_max = reinterpret_cast<float*>(s_changed + 64);             // per epilogue warp {max cn, max tau}
-      const int et = threadIdx.x - 128;          // 0..127 among the epilogue threads
-      const int rk = km.runs * km.k;
-      float mc = 0.f, mtau = 0.f;
-      for (int i = et; i < kKmMaxCols; i += 128) {
-        float4 e = make_float4(3.0e38f, 0.f, 0.f, 0.f);   // padding columns: never the best, never a candidate
-        if (i < rk) {
-          const double c = km.cnorm[i];
-          const int run = i / km.k, j = i - run * km.k;
-          const int done = km.flags[run * 4 + 0], strict = km.flags[run * 4 + 1];
-          const int live = (km.only_nonstrict ? (strict == 0) : (done == 0)) ? 1 : 0;
-          e.x = (float)c;
-          e.y = (float)(1.01 * km.band * sqrt(c));
-          e.z = __int_as_float(j | ((j == km.k - 1) ? 0x100 : 0) | (live << 9) | ((j == 0) ? 0x400 : 0) | (run << 16));
-          mc = fmaxf(mc, e.x); mtau = fmaxf(mtau, e.y);
-        }
-        s_tab[i] = e;
-      }
-      for (int i = et; i < 64; i += 128) s_changed[i] = 0;
-      mc = warp_max(mc); mtau = warp_max(mtau);
-      if (lane == 0) { s_max[2 * ew] = mc; s_max[2 * ew + 1] = mtau; }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const float cn_max = fmaxf(fmaxf(s_max[0], s_max[2]), fmaxf(s_max[4], s_max[6]));
-      const float sc_f = km_operand_scale(km.absmax[0]);
-      const float m2inv = -2.0f / (sc_f * sc_f);   // a power of two: exact
-      for (int tile = first_item; tile < num_tiles; tile += item_stride) {
-        const int mt = m_tile_of(tile);
-        const int rel = mt * 128 + r;            // Linear form: the tile is 128 consecutive rows
-        const bool row_ok = rel < p.wo;
-        const int row = km.row_begin + rel;
-        const float xn = row_ok ? (float)sqrt(km.xx[row]) * 1.0000002f : 0.f;   // rounded up: radii only grow
-        // |fp32 score - exact score| <= 2^-23 (cn + |x||c|) per centre; two scores meet in every comparison
-        const float slack = 0x1p-21f * (cn_max + xn * sqrtf(cn_max));
-        tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
-        tc::tc_fence_after();
-        const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
-        KmScan st{3.0e38f, 0.f, 3.0e38f, 0, -1};
-        // 8 score columns per TMEM load, the next load in flight while the current eight are scanned (rolled loop:
-        // ~100 instructions of body instead of 32 unrolled columns)
-        uint32_t cur[8], nxt[8];
-        {
-          tc::tmem_ld_32x8(t_acc, cur);
-          tc::tmem_wait_ld();
-#pragma unroll 1
-          for (int c = 0; c < rk; c += 8) {
-            if (c + 8 < rk) tc::tmem_ld_32x8(t_acc + c + 8, nxt);
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float4 e = s_tab[c + u];
-              const int meta = __float_as_int(e.z);
-              if ((meta & 0x600) == 0x600 && row_ok && km.count_changes)   // first column of a live run: its old label is
-                st.old_label = km.labels[(size_t)(meta >> 16) * km.labels_stride + row];   // on its way during the scan
-              const float sc = fmaf(__uint_as_float(cur[u]), m2inv, e.x);
-              const float low = sc - e.y * xn;
-              const bool nb = sc < st.best;
-              st.minlow = fminf(st.minlow, nb ? st.best - st.best_tau * xn : low);   // 3e38 on a run's first column
-              st.best_tau = nb ? e.y : st.best_tau;
-              st.best_j = nb ? (meta & 0xff) : st.best_j;
-              st.best = nb ? sc : st.best;
-              if (meta & 0x100) {   // last column of a run (warp-uniform): decide, then start the next run
-                km_run_end(km, st, meta, c + u, row_ok, row, xn, slack, m2inv, t_acc, s_tab, s_changed, lane);
-                st.best = 3.0e38f; st.best_tau = 0.f; st.minlow = 3.0e38f; st.best_j = 0;
-              }
-            }
-            tc::tmem_wait_ld();
-#pragma unroll
-            for (int u = 0; u < 8; ++u) cur[u] = nxt[u];
-          }
-        }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&tmem_empty_bar[acc]);
-        if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < km.runs; i += 128)
-        if (s_changed[i]) atomicAdd(&km.changed[i], s_changed[i]);
-    } else
     for (int tile = first_item; tile < num_tiles; tile += item_stride) {
       const int mt = m_tile_of(tile);
       const int n0 = (tile % n_tiles) * BN;
@@ -482,22 +343,37 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       const int h = ((mt / p.tiles_w) % p.tiles_h) * p.bh + ph;
       const int b = (mt / (p.tiles_w * p.tiles_h)) * p.bb + pb;
       const bool row_ok = (w < p.wo) && (h < p.ho) && (b < p.nb);
-      const size_t pix = ((size_t)b * p.ho + h) * p.wo + w;
-      const size_t cb_row = p.chan_bias ? (size_t)((long long)pix / p.cb_div) : 0;
-      const float blend_a = (p.blend && row_ok) ? __ldg(p.blend_alpha + (long long)pix / p.ba_div) : 0.f;
-      const float row_add = (p.row_scalar && row_ok) ? __ldg(p.row_scalar + pix) : 0.f;
+      const int my_pix = row_ok ? (b * p.ho + h) * p.wo + w : -1;   // M < 2^31 (checked by the host wrappers)
       // The residual (and blend) rows of this tile come from HBM: start them towards L2 now, while the MMAs of the tile
-      // are still running, and keep the loads of chunk c+1 in flight while chunk c is processed (measured before: the
-      // epilogue of the K=320 projections sat on these loads, 29 % of DRAM bandwidth)
-      const int tile_cols = min(c_end, p.n - n0);
-      if (row_ok) {
-        if (p.residual)
-          for (int j = c_begin; j < tile_cols; j += 32)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + pix * p.n + n0 + j));
-        if (p.blend)
-          for (int j = c_begin; j < tile_cols; j += 32)
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.blend + pix * p.n + n0 + j));
+      // are still running
+      if (row_ok && (p.residual || p.blend)) {
+        const int tile_cols = min(BN, p.n - n0);
+        const size_t o = (size_t)my_pix * p.n + n0;
+        for (int j = chalf * 32; j < tile_cols; j += 64) {
+          if (p.residual) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + o + j));
+          if (p.blend) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.blend + o + j));
+        }
       }
+      int prow[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) prow[u] = __shfl_sync(0xffffffffu, my_pix, 4 * u + qrow);
+      // rr[32] = this thread's row (32 columns, raw accumulator bits) -> fn(u, four columns at qcol of row 4u + qrow)
+      auto staged = [&](const uint32_t (&rr)[32], auto&& fn) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (qrow == q) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) stage[st_row + (j ^ qx)] = make_uint4(rr[4 * j], rr[4 * j + 1], rr[4 * j + 2], rr[4 * j + 3]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int s = 0; s < 2; ++s) {
+            const int rl = 4 * s + qrow;
+            fn(2 * q + s, stage[rl * 8 + (qx ^ rl)]);
+          }
+          __syncwarp();
+        }
+      };
       tc::mbar_wait(&tmem_full_bar[acc], acc_phase);
       tc::tc_fence_after();
       const uint32_t t_acc = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(acc * Cfg::kAccStride);
@@ -507,118 +383,97 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
         // [M, 2D] intermediate (the largest tensor of the UNet) is never written.
         const int dn = p.n >> 1;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = chalf * 64; c < BN; c += 128) {
           const int col0 = n0 + c;
           if (col0 >= p.n) break;  // warp-uniform
           uint32_t rv[32], rg[32];
           tc::tmem_ld_32x32(t_acc + c, rv);
           tc::tmem_ld_32x32(t_acc + c + 32, rg);
           tc::tmem_wait_ld();
-          if (row_ok) {
-            float o[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
-              if (p.bias) {
-                bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                bg = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
-              }
-              const float vb[4] = {bv.x, bv.y, bv.z, bv.w}, gb[4] = {bg.x, bg.y, bg.z, bg.w};
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const float val = fmaf(__uint_as_float(rv[j + u]), p.acc_scale, vb[u]);
-                const float gate = fmaf(__uint_as_float(rg[j + u]), p.acc_scale, gb[u]);
-                o[j + u] = val * (0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f)));
-              }
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+            if (p.bias) {
+              bv = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + 32 + j));
             }
-            __half* hrow = p.out_hi + pix * dn;
-            __half* lrow = p.out_lo + pix * dn;
+            const float vb[4] = {bv.x, bv.y, bv.z, bv.w}, gb[4] = {bg.x, bg.y, bg.z, bg.w};
 #pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              tc::store_split8(hrow, lrow, (col0 >> 1) + j, &o[j], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+            for (int u = 0; u < 4; ++u) {
+              const float val = fmaf(__uint_as_float(rv[j + u]), p.acc_scale, vb[u]);
+              const float gate = fmaf(__uint_as_float(rg[j + u]), p.acc_scale, gb[u]);
+              rv[j + u] = __float_as_uint(val * (0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f))));
+            }
           }
+          staged(rv, [&](int u, uint4 x) {
+            if (prow[u] >= 0) {
+              const size_t ro = (size_t)prow[u] * dn;
+              tc::store_split4(p.out_hi + ro, p.out_lo + ro, (col0 >> 1) + qcol, __uint_as_float(x.x), __uint_as_float(x.y),
+                               __uint_as_float(x.z), __uint_as_float(x.w), p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
+            }
+          });
         }
-        tc::tc_fence_before();
-        tc::mbar_arrive(&tmem_empty_bar[acc]);
-        if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
-      float4 res_cur[8], res_nxt[8];
-      auto load_res = [&](float4 (&dst)[8], int c0) {
-        const int nc = min(32, p.n - c0);
+      } else {
+        int crow[8];   // chan_bias row of every slot
+        if (p.chan_bias) {
+          const int cbd = (int)p.cb_div;
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          dst[j] = (p.residual && row_ok && 4 * j < nc) ? *reinterpret_cast<const float4*>(p.residual + pix * p.n + c0 + 4 * j)
-                                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-      };
-      load_res(res_cur, n0 + c_begin);
+          for (int u = 0; u < 8; ++u) crow[u] = prow[u] >= 0 ? prow[u] / cbd : 0;
+        }
 #pragma unroll 1
-      for (int c = c_begin; c < c_end; c += 32) {
-        const int col0 = n0 + c;
-        if (col0 >= p.n) break;  // warp-uniform
-        uint32_t rr[32];
-        tc::tmem_ld_32x32(t_acc + c, rr);
-        if (c + 32 < c_end && col0 + 32 < p.n) load_res(res_nxt, col0 + 32);
-        tc::tmem_wait_ld();
-        if (row_ok) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(rr[j]) * p.acc_scale;
-          const int ncols = min(32, p.n - col0);  // N % 4 == 0 is required by the host wrapper
-          const size_t off = pix * p.n + col0;
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) {
-                const float4 bb4 = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
-              }
-          }
-          if (p.chan_bias) {
-            const float* cb = p.chan_bias + cb_row * p.n + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) {
-                const float4 bb4 = __ldg(reinterpret_cast<const float4*>(cb + j));
-                v[j] += bb4.x; v[j + 1] += bb4.y; v[j + 2] += bb4.z; v[j + 3] += bb4.w;
-              }
-          }
-          if (p.row_scalar) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] += row_add;
-          }
+        for (int c = chalf * 32; c < BN; c += 64) {
+          const int col0 = n0 + c;
+          if (col0 >= p.n) break;  // warp-uniform
+          uint32_t rr[32];
+          tc::tmem_ld_32x32(t_acc + c, rr);
+          const bool col_ok = col0 + qcol < p.n;   // N % 4 == 0 is required by the host wrapper
+          float4 res[8];
           if (p.residual) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 q = res_cur[j >> 2];   // zero beyond ncols
-              v[j] += q.x; v[j + 1] += q.y; v[j + 2] += q.z; v[j + 3] += q.w;
+            for (int u = 0; u < 8; ++u)
+              res[u] = (prow[u] >= 0 && col_ok) ? *reinterpret_cast<const float4*>(p.residual + (size_t)prow[u] * p.n + col0 + qcol)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          const float4 bias4 = (p.bias && col_ok) ? __ldg(reinterpret_cast<const float4*>(p.bias + col0 + qcol))
+                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          tc::tmem_wait_ld();
+          staged(rr, [&](int u, uint4 raw) {
+            if (prow[u] < 0 || !col_ok) return;
+            const size_t ro = (size_t)prow[u] * p.n;
+            const size_t off = ro + col0 + qcol;
+            // same order of operations as the unfused chain: (acc * scale + bias) + chan_bias + row_scalar + residual
+            // (the scale is a power of two, so the fused multiply-add rounds exactly like multiply, then add)
+            float4 x;
+            if (p.bias) {
+              x = make_float4(fmaf(__uint_as_float(raw.x), p.acc_scale, bias4.x), fmaf(__uint_as_float(raw.y), p.acc_scale, bias4.y),
+                              fmaf(__uint_as_float(raw.z), p.acc_scale, bias4.z), fmaf(__uint_as_float(raw.w), p.acc_scale, bias4.w));
+            } else {
+              x = make_float4(__uint_as_float(raw.x) * p.acc_scale, __uint_as_float(raw.y) * p.acc_scale,
+                              __uint_as_float(raw.z) * p.acc_scale, __uint_as_float(raw.w) * p.acc_scale);
             }
-          }
-          if (p.blend) {
-            const float a = blend_a, na = 1.0f - a;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) {
-                const float4 q = *reinterpret_cast<const float4*>(p.blend + off + j);
-                v[j] = a * q.x + na * v[j]; v[j + 1] = a * q.y + na * v[j + 1];
-                v[j + 2] = a * q.z + na * v[j + 2]; v[j + 3] = a * q.w + na * v[j + 3];
-              }
-          }
-          if (p.out_f32) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              if (j < ncols) *reinterpret_cast<float4*>(p.out_f32 + off + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          }
-          if (p.out_hi) {
-            __half* hrow = p.out_hi + pix * p.n;
-            __half* lrow = p.out_lo + pix * p.n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8)
-              if (j < ncols) tc::store_split8(hrow, lrow, col0 + j, &v[j], p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
-          }
+            if (p.chan_bias) {
+              const float4 q = __ldg(reinterpret_cast<const float4*>(p.chan_bias + (size_t)crow[u] * p.n + col0 + qcol));
+              x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+            }
+            if (p.row_scalar) {
+              const float ra = __ldg(p.row_scalar + prow[u]);
+              x.x += ra; x.y += ra; x.z += ra; x.w += ra;
+            }
+            if (p.residual) {
+              const float4 q = res[u];
+              x.x += q.x; x.y += q.y; x.z += q.z; x.w += q.w;
+            }
+            if (p.blend) {
+              const float a = __ldg(p.blend_alpha + (long long)prow[u] / p.ba_div), na = 1.0f - a;
+              const float4 q = *reinterpret_cast<const float4*>(p.blend + off);
+              x.x = a * q.x + na * x.x; x.y = a * q.y + na * x.y; x.z = a * q.z + na * x.z; x.w = a * q.w + na * x.w;
+            }
+            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
+            if (p.out_hi)
+              tc::store_split4(p.out_hi + ro, p.out_lo + ro, col0 + qcol, x.x, x.y, x.z, x.w, p.out_packed8 != 0, tc::kAct8Sx,
+                               tc::kAct8Sl);
+          });
         }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) res_cur[j] = res_nxt[j];
       }
       tc::tc_fence_before();
       tc::mbar_arrive(&tmem_empty_bar[acc]);
@@ -745,41 +600,6 @@ int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const v
   const uint64_t row = (uint64_t)k * 2;
   const uint64_t astrides[4] = {row, row * m, row * m, row * m};
   return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, family, stream);
-}
-
-// internal entry for kmeans.cu: the score GEMM [m, d] x [d, R*K] of the Lloyd E-step with the arg-min / ambiguity test as
-// its epilogue (KmEpilogue); one 256-wide N tile holds the scores of every run, so R*K <= 256.
-int gemm_km_estep_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int m, int rk_pad, int k,
-                      const KmEpilogue& km, void* stream) {
-  VS_REQUIRE(a_hi && a_lo && w_hi && w_lo, "null pointer");
-  VS_REQUIRE(m >= 1 && rk_pad >= 8 && rk_pad <= kKmMaxCols && rk_pad % 8 == 0 && k >= 8 && k % 8 == 0, "bad shape");
-  VS_REQUIRE(km.runs * km.k <= rk_pad && km.runs <= 64, "runs * k must fit the padded column count");
-  GemmParams p{};
-  p.n = rk_pad; p.k = k; p.taps = 1; p.cin = k;
-  p.wo = m; p.ho = 1; p.nb = 1;
-  p.acc_scale = 1.0f;
-  p.in_packed8 = 0;   // fp16 pairs: the filter's error band is derived for them
-  p.out_packed8 = 0;
-  p.mma_n = (rk_pad + 15) / 16 * 16;
-  p.km = km;
-  p.km.on = 1;
-  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
-  const uint64_t row = (uint64_t)k * 2;
-  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
-  p.bw = 128; p.bh = 1; p.bb = 1;   // 128 consecutive rows per tile (what the epilogue assumes)
-  p.tiles_w = (m + 127) / 128; p.tiles_h = 1; p.tiles_b = 1;
-  p.kc_per_tap = (k + kGemmBK - 1) / kGemmBK;
-  p.cb_div = 1; p.ba_div = 1;
-  const uint32_t box[5] = {(uint32_t)kGemmBK, 128u, 1u, 1u, 1u};
-  CUtensorMap ta_hi, ta_lo;
-  if (int e = encode_tmap_16bit(&ta_hi, a_hi, 5, adims, astrides, box)) return e;
-  if (int e = encode_tmap_16bit(&ta_lo, a_lo, 5, adims, astrides, box)) return e;
-  const double flops = 2.0 * (double)m * rk_pad * (double)k;
-  // pairs of CTAs share the centre tile through TMA multicast: every CTA would otherwise pull all R*K centre rows from
-  // L2 for each of its k-blocks, and that traffic (not the MMAs) bounds this skinny GEMM
-  static const int cl2 = [] { const char* e = getenv("VIDSEG_KM_CLUSTER"); return e ? atoi(e) : 0; }();
-  if (cl2 && p.tiles_w >= 2) return launch_gemm_cl<256, 2>(ta_hi, ta_lo, w_hi, w_lo, p, flops, kFamKMeans, stream);
-  return launch_gemm_cl<256, 1>(ta_hi, ta_lo, w_hi, w_lo, p, flops, kFamKMeans, stream);
 }
 
 }  // namespace vidseg

@@ -56,7 +56,6 @@ struct KmLayout {
   int use_mq;   // M-step sums as an exact int8 tensor-core product (fixed-point digit planes x one-hot labels)
   int n_pad;    // rows rounded up to the 128-row reduction block of that product
   int mq_blocks;  // one-hot blocks per run (count partials)
-  int fused_e;    // E-step decided in the epilogue of its score GEMM (R*K <= 256): no score matrix, no one-hot pass
   CUtensorMap tm_onehot, tm_planes;
 };
 
@@ -128,13 +127,10 @@ static KmLayout km_layout(int n, int d, int k, int r, int t) {
   }
   L.km_cnt = take((size_t)r * k * 4);
   L.reloc = take((size_t)r * 2 * 4);   // relocation ticket | done flag per run (fused update kernel)
-  // Measured on B200 (tools/km_estep_probe.py, N = 14336, R*K = 200): the fused form is correct (same labels) but NOT
-  // faster -- 47.6 us against 49.4 us per E-step.  Its score GEMM alone takes 19.7 us, but one tile per CTA leaves the
-  // epilogue to four warps, one per scheduler, which run their dependent compare / select chains at ~6 cycles per
-  // instruction (16 us for the column scan, 12 us for run ends and candidate sets), while the separate assign kernel does
-  // the same arithmetic at full occupancy.  It stays opt-in (VIDSEG_KMEANS_FUSED_E=1).
-  static const int fused_env = [] { const char* e = getenv("VIDSEG_KMEANS_FUSED_E"); return e ? atoi(e) : 0; }();
-  L.fused_e = (fused_env && L.use_tc && L.rk_pad <= 224 && r <= 64) ? 1 : 0;   // 224: the candidate pass may read 31 TMEM columns past R*K
+  // (Tried and removed: the arg-min as the EPILOGUE of the score GEMM.  Measured on B200, N = 14336, R*K = 200: same labels,
+  // 47.6 us against 49.4 us per E-step for GEMM + assign + resolve as separate full-occupancy kernels -- one tile per CTA
+  // leaves the dependent compare / select chains to a handful of warps -- and it kept 1 400 lines of epilogue in the
+  // instruction stream of every other GEMM.)
   L.total = off;
   return L;
 }
@@ -1723,8 +1719,6 @@ static int km_launch_assign(const float* x, const KmLayout& L, int runs, int row
 // defined in gemm_tc.cu: out[M,N] = acc_scale * A[M,K] . W[N,K]^T on the split operands, tagged with `family`
 int gemm_split_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, float* out_f32, int m, int n,
                    int k, float acc_scale, int family, void* stream);
-int gemm_km_estep_run(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int m, int rk_pad, int k,
-                      const KmEpilogue& km, void* stream);
 
 // E-step of every unfinished run over rows [row_begin, row_end) of the centred data held in the workspace
 static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_end, int count_changes, int only_nonstrict,
@@ -1737,33 +1731,6 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
                             at<int>(ws, L.flags), count_changes, only_nonstrict, stream);
   // error radius of the filter per unit |x||c|: the score is cn - 2 S; S carries the operand split (2^-21) and the
   // fp32 accumulation of d products inside the tensor core (<= d * 2^-22 with truncating alignment)
-  const double band_f = 2.0 * ((double)L.d * 0x1p-22 + 0x1p-20);
-  int* amb_count_f = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
-  if (L.fused_e) {
-    // the arg-min is the epilogue of the score GEMM: labels and change counters come out of the launch that computes the
-    // scores (no [N, R*K] score matrix, no second pass over it); only the (rare) points inside the error band go to
-    // the resolver
-    KmEpilogue km{};
-    km.k = L.k; km.runs = L.r; km.row_begin = row_begin; km.labels_stride = L.n;
-    km.count_changes = count_changes; km.only_nonstrict = only_nonstrict;
-    km.band = band_f;
-    km.absmax = at<unsigned>(ws, L.absmax);
-    km.cnorm = at<double>(ws, L.cnorm);
-    km.xx = at<double>(ws, L.xx);
-    km.flags = at<int>(ws, L.flags);
-    km.labels = at<int>(ws, L.labels);
-    km.changed = at<int>(ws, L.changed);
-    km.amb_count = amb_count_f;
-    km.amb_list = at<int4>(ws, L.amb_list);
-    if (int e = gemm_km_estep_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
-                                  at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo), rows, L.rk_pad, L.d, km, stream))
-      return e;
-    VS_LAUNCH(km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
-              at<double>(ws, L.cnorm), at<double>(ws, L.xx), (const float*)nullptr, L.rk_pad, at<unsigned>(ws, L.absmax),
-              at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band_f, amb_count_f, at<int>(ws, L.amb_list), 4);
-    VS_POST_LAUNCH();
-    return 0;
-  }
   // cs_hi / cs_lo: the centres as scaled fp16 pairs, kept current by vidseg_kmeans_seed and km_update_avg_kernel
   if (int e = gemm_split_run(at<__half>(ws, L.xs_hi) + (size_t)row_begin * L.d, at<__half>(ws, L.xs_lo) + (size_t)row_begin * L.d,
                              at<__half>(ws, L.cs_hi), at<__half>(ws, L.cs_lo),
