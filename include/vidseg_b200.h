@@ -302,6 +302,16 @@ int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* w_hi, c
                          long long rows_per_alpha, const float* row_scalar, float* out_f32, void* out_hi,
                          void* out_lo, int out_pair16, int m, int n, int k, float acc_scale, void* stream);
 
+/* Up to three projections of the SAME activation as one GEMM: to_q | to_k | to_v of a self-attention layer
+ * (sgm/modules/attention.py:308-317: q = self.to_q(x); k = self.to_k(context); v = self.to_v(context) with
+ * context = x).  w_*: the nseg weights stacked along N, [nseg * seg_n, K] split; segment s goes to out_f32[s]
+ * (fp32 [M, seg_n], NULL = not wanted) and / or out_hi[s] / out_lo[s] (operand [M, seg_n], NULL = not wanted); the
+ * three arrays are HOST arrays of nseg device pointers.  The A operand is read once instead of nseg times.
+ * seg_n % 128 == 0 or seg_n % 160 == 0 (an N tile must not straddle two outputs).  out_pair16 as in _ex. */
+int vidseg_gemm_split_seg(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int nseg, int seg_n,
+                          float* const* out_f32, void* const* out_hi, void* const* out_lo, int out_pair16, int m,
+                          int k, float acc_scale, void* stream);
+
 /* nn.Conv2d as an implicit GEMM (no im2col: the taps are shifted TMA boxes, zero padding is the TMA out-of-bounds
  * fill).  Replaces the 3x3 / 1x1 convolutions of ResBlock (openaimodel.py:267-315), Downsample (:202-209, stride 2),
  * Upsample (:145-147), the input conv (:587-593) and the output conv (:825-829).

@@ -86,3 +86,23 @@ def test_fused_geglu_projection(cuda, operand_mode, m, d, k):
     err = (got.float().double() - want).abs().max().item() / want.abs().max().item()
     packed_in = operand_mode == 1 and k % 64 == 0
     assert err < (2e-4 if (packed_in or got.fmt == "packed8") else 1e-5), f"rel err {err:.3e} ({got.fmt})"
+
+
+@pytest.mark.parametrize("m,c,k", [(300, 320, 320), (28 * 64, 1280, 1280), (1000, 640, 640), (77, 128, 64)])
+def test_stacked_projections_equal_separate_gemms(cuda, operand_mode, m, c, k):
+    """to_q | to_k | to_v as ONE GEMM with three output sets: bit-identical to three separate GEMMs (same tiles, same
+    order of accumulation), unwanted outputs skipped."""
+    from vidseg_diffusion_b200.linear import gemm_split, gemm_split_seg, split
+    g = torch.Generator(device="cpu").manual_seed(m + c + k)
+    a = split(torch.randn(m, k, generator=g).to(cuda))
+    ws = [(torch.randn(c, k, generator=g) / k ** 0.5).to(cuda) for _ in range(3)]
+    stacked = split(torch.cat(ws, 0).contiguous(), 256.0, is_weight=True)
+    got = gemm_split_seg(a, stacked, 3, (True, False, True), (True, True, False))
+    assert got[1][0] is None and got[2][1] is None
+    for s, w in enumerate(ws):
+        f, sp = gemm_split(a, split(w, 256.0, is_weight=True), want_f32=True, want_split=True, split_pair16=True)
+        if got[s][0] is not None:
+            assert torch.equal(got[s][0], f), f"segment {s}: fp32 output differs"
+        if got[s][1] is not None:
+            assert got[s][1].fmt == "pair16"
+            assert torch.equal(got[s][1].hi, sp.hi) and torch.equal(got[s][1].lo, sp.lo), f"segment {s}: operand output differs"

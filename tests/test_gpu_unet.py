@@ -187,3 +187,30 @@ def test_segment_many_equals_segment_clip_by_clip(cuda):
         seg = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, use_cuda_graph=graph)
         got = list(seg.segment_many(clips, 2, seed=1, to_host=True))
         assert len(got) == 3 and all(torch.equal(g, w) for g, w in zip(got, want))
+
+
+def test_harvested_stash_policy(cuda):
+    """ClipSegmenter(stash="harvested") (default): the layers it harvests keep the exact fp32 stash, the others hand out
+    q / k decoded from the attention operand (fp16 pair, 22 significant bits); label maps, UNet output and the harvested
+    tensors are bit-identical to stash="all", and the model's flags are restored after the call."""
+    from vidseg_diffusion_b200.pipeline import ClipSegmenter
+    cfg = ounet.TINY_CONFIG
+    model, _ = build(cfg, 5, cuda)
+    x, t, ctx = (torch.from_numpy(a).to(cuda) for a in synthetic_unet_inputs(5, 2, 16, cfg["in_channels"], 7, cfg["context_dim"]))
+    full = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True, stash="all")
+    want, out_all = full.segment(x, t, ctx, 2, seed=5)
+    want, out_all = want.clone(), out_all.clone()
+    attn = lambda blocks, i: blocks[i][1].transformer_blocks[0]
+    q_all = {i: attn(model.output_blocks, i).attn1.q.clone() for i in (4, 6, 7, 8)}
+    k_all = attn(model.output_blocks, 4).attn1.k.clone()
+    q2_all = attn(model.output_blocks, 8).attn2.q.clone()
+    lean = ClipSegmenter(model, num_masks=3, is_aggre_attn=True, is_refine_mask=True)
+    got, out_h = lean.segment(x, t, ctx, 2, seed=5)
+    assert torch.equal(got, want) and torch.equal(out_h, out_all)
+    for i in (6, 7, 8):
+        assert torch.equal(attn(model.output_blocks, i).attn1.q, q_all[i])
+    for got_t, want_t in ((attn(model.output_blocks, 4).attn1.q, q_all[4]), (attn(model.output_blocks, 4).attn1.k, k_all),
+                          (attn(model.output_blocks, 8).attn2.q, q2_all)):
+        assert got_t.dtype == torch.float32 and got_t.shape == want_t.shape
+        assert relerr(got_t, want_t) < 1e-6 and not torch.equal(got_t, want_t)
+    assert all(m.stash_f32 for m in model.modules() if hasattr(m, "stash_f32"))

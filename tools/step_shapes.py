@@ -54,7 +54,7 @@ def wrap(mod, name):
 
 
 # leaf ops only (linear -> gemm_split is wrapped at gemm_split; dense calls linear)
-for n in ("gemm_split", "linear_geglu", "conv2d", "conv_temporal", "attention", "temporal_attention", "layer_norm_split",
+for n in ("gemm_split", "gemm_split_seg", "linear_geglu", "conv2d", "conv_temporal", "attention", "temporal_attention", "layer_norm_split",
           "geglu_split", "group_norm_split", "upsample_nearest2x_split", "image_split", "split"):
     wrap(K, n)
 

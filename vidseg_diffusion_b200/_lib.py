@@ -56,6 +56,8 @@ SIGNATURES = {
     "vidseg_gemm_split": (c_int, [c_void_p] * 9 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_gemm_split_ex": (c_int, [c_void_p] * 7 + [c_longlong, c_void_p, c_void_p, c_longlong, c_void_p, c_void_p, c_void_p,
                                      c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p]),
+    "vidseg_gemm_split_seg": (c_int, [c_void_p] * 4 + [c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_float,
+                                      c_void_p]),
     "vidseg_gemm_geglu_split": (c_int, [c_void_p] * 7 + [c_int, c_int, c_int, c_float, c_void_p]),
     "vidseg_set_operand_mode": (c_int, [c_int]),
     "vidseg_get_operand_mode": (c_int, []),

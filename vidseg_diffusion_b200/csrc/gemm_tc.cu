@@ -180,6 +180,12 @@ struct GemmParams {
   __half* out_hi;           // [M, N] or null
   __half* out_lo;
   int mma_n;                // N of the MMA instruction (multiple of 16, <= BN); 0 = BN
+  // segmented output (the fused q | k | v projection): columns [s * seg_n, (s + 1) * seg_n) go to the s-th set of
+  // [M, seg_n] tensors instead of out_f32 / out_hi / out_lo; seg_n is a multiple of the N tile.  0 = off
+  int seg_n;
+  float* seg_f32[3];
+  __half* seg_hi[3];
+  __half* seg_lo[3];
 };
 
 // CL = 2: two CTAs of a thread-block cluster work on two adjacent M tiles of the SAME N tile; each loads half of the
@@ -357,6 +363,15 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       int prow[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) prow[u] = __shfl_sync(0xffffffffu, my_pix, 4 * u + qrow);
+      float* of32 = p.out_f32;
+      __half* ohi = p.out_hi;
+      __half* olo = p.out_lo;
+      int opitch = p.n, oshift = 0;   // row pitch of the output tensors, first column of the tile's segment
+      if (p.seg_n) {
+        const int sg = n0 / p.seg_n;
+        of32 = p.seg_f32[sg]; ohi = p.seg_hi[sg]; olo = p.seg_lo[sg];
+        opitch = p.seg_n; oshift = sg * p.seg_n;
+      }
       // rr[32] = this thread's row (32 columns, raw accumulator bits) -> fn(u, four columns at qcol of row 4u + qrow)
       auto staged = [&](const uint32_t (&rr)[32], auto&& fn) {
 #pragma unroll
@@ -439,8 +454,9 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           tc::tmem_wait_ld();
           staged(rr, [&](int u, uint4 raw) {
             if (prow[u] < 0 || !col_ok) return;
-            const size_t ro = (size_t)prow[u] * p.n;
-            const size_t off = ro + col0 + qcol;
+            const size_t off = (size_t)prow[u] * p.n + col0 + qcol;             // residual / blend: [M, N]
+            const size_t oro = (size_t)prow[u] * opitch;                         // outputs: [M, N] or the segment's [M, seg_n]
+            const int ocol = col0 - oshift + qcol;
             // same order of operations as the unfused chain: (acc * scale + bias) + chan_bias + row_scalar + residual
             // (the scale is a power of two, so the fused multiply-add rounds exactly like multiply, then add)
             float4 x;
@@ -468,10 +484,8 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
               const float4 q = *reinterpret_cast<const float4*>(p.blend + off);
               x.x = a * q.x + na * x.x; x.y = a * q.y + na * x.y; x.z = a * q.z + na * x.z; x.w = a * q.w + na * x.w;
             }
-            if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + off) = x;
-            if (p.out_hi)
-              tc::store_split4(p.out_hi + ro, p.out_lo + ro, col0 + qcol, x.x, x.y, x.z, x.w, p.out_packed8 != 0, tc::kAct8Sx,
-                               tc::kAct8Sl);
+            if (of32) *reinterpret_cast<float4*>(of32 + oro + ocol) = x;
+            if (ohi) tc::store_split4(ohi + oro, olo + oro, ocol, x.x, x.y, x.z, x.w, p.out_packed8 != 0, tc::kAct8Sx, tc::kAct8Sl);
           });
         }
       }
@@ -576,6 +590,12 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
   // small grids (the 8x8 / 16x16 levels of the UNet): 128-wide N tiles double the number of CTAs when 256-wide ones would
   // leave SMs idle
   const long long m_tiles = (long long)p.tiles_w * p.tiles_h * p.tiles_b;
+  if (p.seg_n) {   // an N tile must not straddle two segments
+    if (p.seg_n % 256 == 0) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+    if (p.seg_n % 160 == 0) return launch_gemm<160>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+    VS_REQUIRE(p.seg_n % 128 == 0, "segment width must be a multiple of 128 or 160");
+    return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
+  }
   const bool underfilled = p.n % 128 == 0 && p.n > 128 && m_tiles * ((p.n + 255) / 256) < (3 * kNumSMs) / 4;
   if (!underfilled && (p.n % 256 == 0 || (p.geglu && p.n > 128)))
     return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
@@ -701,6 +721,35 @@ VS_API int vidseg_gemm_split_ex(const void* a_hi, const void* a_lo, const void* 
                                 float acc_scale, void* stream) {
   return gemm_entry(a_hi, a_lo, w_hi, w_lo, bias, residual, row_bias, rows_per_bias, blend, blend_alpha, rows_per_alpha,
                     row_scalar, out_f32, out_hi, out_lo, out_pair16, m, n, k, acc_scale, stream);
+}
+
+// Several projections of the SAME activation as one GEMM (to_q | to_k | to_v of a self-attention layer, attention.py:308-317):
+// w = the weights stacked along N, [nseg * seg_n, K]; segment s is written to out_f32[s] (fp32 [M, seg_n], may be null) and
+// / or out_hi[s] / out_lo[s] (operand [M, seg_n]).  The A operand is read once instead of nseg times.
+VS_API int vidseg_gemm_split_seg(const void* a_hi, const void* a_lo, const void* w_hi, const void* w_lo, int nseg, int seg_n,
+                                 float* const* out_f32, void* const* out_hi, void* const* out_lo, int out_pair16, int m, int k,
+                                 float acc_scale, void* stream) {
+  VS_REQUIRE(a_hi && a_lo && w_hi && w_lo && out_f32 && out_hi && out_lo, "null pointer");
+  VS_REQUIRE(nseg >= 1 && nseg <= 3, "1 to 3 segments");
+  VS_REQUIRE(m >= 0 && k >= 8 && k % 8 == 0 && seg_n >= 128 && (seg_n % 128 == 0 || seg_n % 160 == 0),
+             "K must be a multiple of 8, the segment width of 128 or 160");
+  if (m == 0) return 0;
+  GemmParams p{};
+  p.n = nseg * seg_n; p.k = k; p.taps = 1; p.cin = k;
+  p.wo = m; p.ho = 1; p.nb = 1;
+  p.acc_scale = acc_scale;
+  p.seg_n = seg_n;
+  for (int s = 0; s < nseg; ++s) {
+    VS_REQUIRE((out_hi[s] == nullptr) == (out_lo[s] == nullptr), "out_hi and out_lo go together");
+    VS_REQUIRE(out_f32[s] != nullptr || out_hi[s] != nullptr, "a segment without output");
+    p.seg_f32[s] = out_f32[s]; p.seg_hi[s] = (__half*)out_hi[s]; p.seg_lo[s] = (__half*)out_lo[s];
+  }
+  p.in_packed8 = -1;
+  p.out_packed8 = out_pair16 ? 0 : (operand_packed8(seg_n) ? 1 : 0);
+  const uint64_t adims[5] = {(uint64_t)k, (uint64_t)m, 1, 1, 1};
+  const uint64_t row = (uint64_t)k * 2;
+  const uint64_t astrides[4] = {row, row * m, row * m, row * m};
+  return run_gemm(a_hi, a_lo, adims, astrides, p, w_hi, w_lo, kFamGemm, stream);
 }
 
 #undef VS_FAMILY

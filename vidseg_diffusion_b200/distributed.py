@@ -306,7 +306,7 @@ class ShardedClipSegmenter:
         from .pipeline import REFINE_BLOCK, harvest_self_attn_q
         if self.local.use_cuda_graph:
             return self.local._graphed_unet_features(x, t, c, frames, kw, features=features)
-        out = self.model(x, timesteps=t, context=c, **kw)
+        out = self.local.unet_step(x, t, c, **kw)
         feats = None if features is None else self.local._features(frames, cond_only=(features == "all_rows"))
         q7 = harvest_self_attn_q(self.model, (REFINE_BLOCK,))[0] if self.is_refine_mask else None
         return out, feats, q7

@@ -12,7 +12,7 @@ import weakref
 import torch
 
 from . import _lib
-from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, packed8, split
+from .linear import WEIGHT_SCALE, Split, attention_split, gemm_split, gemm_split_seg, packed8, split
 
 _WEIGHT_CACHE = {}
 
@@ -114,6 +114,29 @@ def linear(xs, weight, bias=None, residual=None, want_f32=True, want_split=False
     row_bias / blend terms of linear.gemm_split (temporal layers of the SVD UNet)."""
     b = None if bias is None else _f32(bias)
     return gemm_split(xs, weight_split(weight), b, residual, want_f32=want_f32, want_split=want_split, **epilogue)
+
+
+def _stacked_weight_split(params):
+    """Several [N_i, K] nn.Linear weights stacked along N -> one cached Split (keyed on every parameter's storage and
+    version, so that replacing or updating any of them rebuilds it)."""
+    key = (tuple(id(p) for p in params), "stack", _lib.load().vidseg_get_operand_mode())
+    stamp = tuple((p.data_ptr(), p._version, p.device) for p in params)
+    hit = _WEIGHT_CACHE.get(key)
+    if hit is not None and hit[0] == stamp and all(r() is p for r, p in zip(hit[1], params)):
+        return hit[2]
+    val = split(torch.cat([p.detach().float() for p in params], dim=0).contiguous(), WEIGHT_SCALE, is_weight=True)
+    _WEIGHT_CACHE[key] = (stamp, [weakref.ref(p) for p in params], val)
+    return val
+
+
+def linear_stacked(xs, weights, want_f32, want_split):
+    """Bias-free projections of one activation by several equally shaped weights (to_q | to_k | to_v) as ONE GEMM with one
+    output set per weight; the split outputs are fp16 pairs (operands of the attention kernel).  Returns a list of
+    (fp32 or None, Split or None).  Falls back to None when the shapes do not allow the stacked form."""
+    n = weights[0].shape[0]
+    if any(tuple(w.shape) != tuple(weights[0].shape) for w in weights) or not (n % 128 == 0 or n % 160 == 0):
+        return None
+    return gemm_split_seg(xs, _stacked_weight_split(list(weights)), len(weights), want_f32, want_split, split_pair16=True)
 
 
 def _geglu_perm(d, device):

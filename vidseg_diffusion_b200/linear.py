@@ -131,6 +131,40 @@ def gemm_split(a, w, bias=None, residual=None, want_f32=True, want_split=False, 
     return out, (Split(oh, ol, 1.0, "pair16" if split_pair16 else None) if want_split else None)
 
 
+def gemm_split_seg(a, w, nseg, want_f32, want_split, split_pair16=True):
+    """``nseg`` projections of the same activation as one GEMM: w = the weights stacked along N, Split [nseg * seg_n, K].
+    ``want_f32`` / ``want_split``: one flag per segment.  Returns a list of (out_f32 or None, Split or None), each
+    [.., seg_n]."""
+    import ctypes
+    k = a.hi.shape[-1]
+    lead = a.hi.shape[:-1]
+    m = a.hi.numel() // k
+    if w.hi.shape[1] != k or w.hi.shape[0] % nseg:
+        raise _lib.VidsegError(f"gemm_split_seg: weight {tuple(w.hi.shape)} does not stack {nseg} projections of K={k}")
+    seg_n = w.hi.shape[0] // nseg
+    want_fmt = "packed8" if packed8(k) else "pair16"
+    if a.fmt != want_fmt or w.fmt != want_fmt:
+        raise _lib.VidsegError(f"gemm_split_seg: operands are {a.fmt} / {w.fmt}, the policy expects {want_fmt} for K={k}")
+    for t, name in ((a.hi, "a.hi"), (a.lo, "a.lo"), (w.hi, "w.hi"), (w.lo, "w.lo")):
+        _lib.require_cuda_tensor(t, torch.float16, name)
+    dev = a.hi.device
+    outs = []
+    for s in range(nseg):
+        if not (want_f32[s] or want_split[s]):
+            raise _lib.VidsegError("gemm_split_seg: every segment needs an output")
+        o = torch.empty((*lead, seg_n), dtype=torch.float32, device=dev) if want_f32[s] else None
+        oh = torch.empty((*lead, seg_n), dtype=torch.float16, device=dev) if want_split[s] else None
+        ol = torch.empty((*lead, seg_n), dtype=torch.float16, device=dev) if want_split[s] else None
+        outs.append((o, oh, ol))
+    arr = lambda i: (ctypes.c_void_p * nseg)(*[(t[i].data_ptr() if t[i] is not None else None) for t in outs])
+    f32s, his, los = arr(0), arr(1), arr(2)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.load().vidseg_gemm_split_seg(
+            a.hi.data_ptr(), a.lo.data_ptr(), w.hi.data_ptr(), w.lo.data_ptr(), nseg, seg_n, f32s, his, los,
+            1 if split_pair16 else 0, m, k, 1.0 / (a.scale * w.scale), _lib.stream_ptr()), "gemm_split_seg")
+    return [(o, Split(oh, ol, 1.0, "pair16" if split_pair16 else None) if oh is not None else None) for o, oh, ol in outs]
+
+
 def attention_split(q, k, v, heads, scale=None, want_f32=False, want_split=True):
     """softmax(q k^T * scale) v per head.  q: Split [B, Nq, heads*64]; k, v: Split [B, Nk, heads*64].
     Returns (out_f32 or None, Split or None), both [B, Nq, heads*64]."""

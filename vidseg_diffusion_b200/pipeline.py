@@ -6,6 +6,8 @@ between the sampler callback (:113-149, ``torch.save`` of every stashed tensor) 
 HBM and are handed to the clustering kernels directly.  Flag names follow the reference CLI
 (``--num_masks``, ``--is_aggre_attn``, ``--is_refine_mask``, ``--seed``).
 """
+import contextlib
+
 import numpy as np
 import torch
 
@@ -37,7 +39,15 @@ def harvest_self_attn_q(model, blocks):
 class ClipSegmenter:
     """One object per process / GPU.  ``model`` is a ``UNetModel`` (or ``VideoUNet``) on the GPU."""
 
-    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, use_cuda_graph=False):
+    def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, use_cuda_graph=False,
+                 stash="harvested"):
+        """``stash``: "harvested" -- during this object's UNet calls only the attention layers whose q it reads (output
+        blocks 8 / 7 / 6, ``attn1``) write the fp32 stash; every other layer's ``.q`` / ``.k`` is decoded from the
+        fp16-pair operand of the attention kernel on first access (22 significant bits) instead of costing an fp32 write
+        per projection.  "all" -- every layer writes its fp32 stash, as the reference's attributes do."""
+        if stash not in ("harvested", "all"):
+            raise _lib.VidsegError(f"stash must be 'harvested' or 'all', got {stash!r}")
+        self.stash = stash
         self.model = model
         self.use_cuda_graph = bool(use_cuda_graph)
         self._graphs = {}
@@ -49,10 +59,30 @@ class ClipSegmenter:
         self.n_init = n_init
         self.last = {}
 
+    @contextlib.contextmanager
+    def _stash_scope(self):
+        """fp32 stash only where this object harvests it, for the duration of one of its own UNet calls."""
+        if self.stash == "all":
+            yield
+            return
+        keep = set(self.blocks) | ({REFINE_BLOCK} if self.is_refine_mask else set())
+        keep_ids = {id(self.model.output_blocks[i][1].transformer_blocks[0].attn1) for i in keep}
+        touched = []
+        for m in self.model.modules():
+            if hasattr(m, "stash_f32") and id(m) not in keep_ids and m.stash_f32:
+                m.stash_f32 = False
+                touched.append(m)
+        try:
+            yield
+        finally:
+            for m in touched:
+                m.stash_f32 = True
+
     @torch.no_grad()
     def unet_step(self, x, timesteps, context, **unet_kwargs):
         """x [2F, C, h, w] (uncond rows first, guiders.py:38-42), timesteps [2F], context [2F, L, D]."""
-        return self.model(x, timesteps=timesteps, context=context, **unet_kwargs)
+        with self._stash_scope():
+            return self.model(x, timesteps=timesteps, context=context, **unet_kwargs)
 
     def _features(self, num_frames, cond_only=False):
         return aggregate_normalize(harvest_self_attn_q(self.model, self.blocks), num_frames, cond_only=cond_only)
@@ -75,14 +105,14 @@ class ClipSegmenter:
             kw = dict(rest, **{k: static["kw_" + k] for k in tens})
             side = torch.cuda.Stream(device=x.device)
             side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):            # warm-up outside capture: weight operand caches, workspaces
+            with torch.cuda.stream(side), self._stash_scope():   # warm-up outside capture: weight operand caches, workspaces
                 for _ in range(2):
                     self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
                     feat()
             torch.cuda.current_stream().wait_stream(side)
             graph = torch.cuda.CUDAGraph()
             n0 = _lib.launch_count()
-            with torch.cuda.graph(graph):
+            with torch.cuda.graph(graph), self._stash_scope():
                 out = self.model(static["x"], timesteps=static["t"], context=static["c"], **kw)
                 feats = feat()
                 # the stash the refinement reads: the graph's own buffer, not whatever the module attribute points at

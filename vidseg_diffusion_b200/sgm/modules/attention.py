@@ -82,11 +82,11 @@ class FeedForward(nn.Module):
         dim_out = dim if dim_out is None else dim_out
         self.net = nn.Sequential(GEGLU(dim, inner_dim), nn.Dropout(dropout), nn.Linear(inner_dim, dim_out))
 
-    def forward_split(self, xs, residual=None, want_split=False, **epilogue):
+    def forward_split(self, xs, residual=None, want_split=False, want_f32=True, **epilogue):
         """``epilogue``: row_bias / blend terms of the output GEMM (linear.gemm_split).  Returns fp32, or
-        (fp32, Split) with ``want_split``."""
+        (fp32 or None, Split) with ``want_split``."""
         hs = self.net[0].forward_split(xs)
-        out, outs = K.linear(hs, self.net[2].weight, self.net[2].bias, residual=residual, want_f32=True,
+        out, outs = K.linear(hs, self.net[2].weight, self.net[2].bias, residual=residual, want_f32=want_f32,
                              want_split=want_split, **epilogue)
         return (out, outs) if want_split else out
 
@@ -113,6 +113,7 @@ class CrossAttention(nn.Module):
         # the reference's SDPA class ignores injected_v (attention.py:316), its xformers class uses it (:435-444);
         # BasicTransformerBlock sets this from attn_mode
         self.inject_v = False
+        self.stash_f32 = True   # see forward_split
         self._stash = {"q": None, "k": None, "v": None}
 
     # the Q/K "hook" (reference :330-331): plain attributes there; here the temporal layers keep their activations in
@@ -149,21 +150,33 @@ class CrossAttention(nn.Module):
         """xs: Split [B, N, C] (already normalised); context: Split [B, L, Cctx] or None.
         Returns to_out(attention) (+ residual) as fp32 [B, N, C]."""
         cs = xs if context is None else context
-        # q / k / v feed the attention kernel, which takes fp16-pair operands whatever the GEMM operand policy is
-        if injected_q is not None:
-            q, qs = injected_q, K.split(injected_q.float().contiguous(), pair16=True)
+        # q / k / v feed the attention kernel, which takes fp16-pair operands whatever the GEMM operand policy is.
+        # ``stash_f32`` (default): q and k are also written as fp32 by the projection's epilogue -- the reference's
+        # ``self.q`` / ``self.k`` attributes.  A caller that reads only some layers' stash (pipeline.ClipSegmenter) clears
+        # the flag on the others: their q / k are then decoded from the fp16 pair (22 significant bits) on first access.
+        f32 = self.stash_f32
+        no_inj = injected_q is None and injected_k is None and not (injected_v is not None and self.inject_v)
+        fused = None
+        if context is None and no_inj:   # self-attention: ONE GEMM reads the activation once for all three projections
+            fused = K.linear_stacked(xs, (self.to_q.weight, self.to_k.weight, self.to_v.weight), (f32, f32, False),
+                                     (True, True, True))
+        if fused is not None:
+            (q, qs), (k, ks), (_, vs) = fused
         else:
-            q, qs = K.linear(xs, self.to_q.weight, want_f32=True, want_split=True, split_pair16=True)
-        if injected_k is not None:
-            k, ks = injected_k, K.split(injected_k.float().contiguous(), pair16=True)
-        else:
-            k, ks = K.linear(cs, self.to_k.weight, want_f32=True, want_split=True, split_pair16=True)
-        if injected_v is not None and self.inject_v:
-            vs = K.split(injected_v.float().contiguous(), pair16=True)
-        else:
-            _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True, split_pair16=True)
-        self.q = q
-        self.k = k
+            if injected_q is not None:
+                q, qs = injected_q, K.split(injected_q.float().contiguous(), pair16=True)
+            else:
+                q, qs = K.linear(xs, self.to_q.weight, want_f32=f32, want_split=True, split_pair16=True)
+            if injected_k is not None:
+                k, ks = injected_k, K.split(injected_k.float().contiguous(), pair16=True)
+            else:
+                k, ks = K.linear(cs, self.to_k.weight, want_f32=f32, want_split=True, split_pair16=True)
+            if injected_v is not None and self.inject_v:
+                vs = K.split(injected_v.float().contiguous(), pair16=True)
+            else:
+                _, vs = K.linear(cs, self.to_v.weight, want_f32=False, want_split=True, split_pair16=True)
+        self.q = q if q is not None else qs.float
+        self.k = k if k is not None else ks.float
         if self.inject_v:   # "softmax-xformers" layers only, as in the reference
             self.v = vs.float
         _, os_ = K.attention(qs, ks, vs, self.heads, self.scale)
@@ -204,12 +217,14 @@ class BasicTransformerBlock(nn.Module):
         self.checkpoint = checkpoint  # inference only: torch.utils.checkpoint is a no-op without grad
 
     def forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
-                is_modulate_step=False, is_injected_step=False, modulate_params=None):
+                is_modulate_step=False, is_injected_step=False, modulate_params=None, out_split=False):
         return self._forward(x, context, additional_tokens, n_times_crossframe_attn_in_self, is_modulate_step,
-                             is_injected_step, modulate_params)
+                             is_injected_step, modulate_params, out_split)
 
     def _forward(self, x, context=None, additional_tokens=None, n_times_crossframe_attn_in_self=0,
-                 is_modulate_step=False, is_injected_step=False, modulate_params=None):
+                 is_modulate_step=False, is_injected_step=False, modulate_params=None, out_split=False):
+        """``out_split`` (not in the reference's signature): return the block's output as the tensor-core operand of the
+        next GEMM (SpatialTransformer.proj_out) instead of fp32 -- the feed-forward GEMM writes it directly."""
         if additional_tokens is not None or n_times_crossframe_attn_in_self:
             _unsupported("BasicTransformerBlock(additional_tokens / n_times_crossframe_attn_in_self)")
         inj = {"self": [None] * 3, "cross": [None] * 3}
@@ -238,12 +253,13 @@ class BasicTransformerBlock(nn.Module):
             # one context token: attn2's output is one vector per sample, carried as a row bias of norm3 / ff
             n = x.shape[1]
             a = self.attn2.forward_single_token(K.layer_norm_split(x, self.norm2), context)
-            return self.ff.forward_split(K.layer_norm_split(x, self.norm3, row_bias=a, rows_per_bias=n), x,
-                                         row_bias=a, rows_per_bias=n)
+            y = self.ff.forward_split(K.layer_norm_split(x, self.norm3, row_bias=a, rows_per_bias=n), x,
+                                      want_split=out_split, want_f32=not out_split, row_bias=a, rows_per_bias=n)
+            return y[1] if out_split else y
         x = self.attn2.forward_split(K.layer_norm_split(x, self.norm2), context, x, *inj["cross"], row_scalar=mod["cross_attn"])
         ff_kw = {"row_scalar": mod["ff_out"]} if mod["ff_out"] is not None else {}
-        x = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x, **ff_kw)
-        return x
+        y = self.ff.forward_split(K.layer_norm_split(x, self.norm3), x, want_split=out_split, want_f32=not out_split, **ff_kw)
+        return y[1] if out_split else y
 
 
 class SpatialTransformer(nn.Module):
@@ -291,7 +307,8 @@ class SpatialTransformer(nn.Module):
                 else:
                     modulate_params["modulate_layer_frames_group"] = list(range(modulate_params["num_frames"]))
             t = block(t, context=ctx, is_modulate_step=mod_spatial, is_injected_step=is_injected_step,
-                      modulate_params=modulate_params)
+                      modulate_params=modulate_params, out_split=(i == len(self.transformer_blocks) - 1))
         # proj_out + residual x_in, still in token layout; the result is handed on as b c h w (channels_last view)
-        out, _ = K.linear(K.split(t), self.proj_out.weight, self.proj_out.bias, residual=x_tok, want_f32=True)
+        out, _ = K.linear(t if isinstance(t, Split) else K.split(t), self.proj_out.weight, self.proj_out.bias, residual=x_tok,
+                          want_f32=True)
         return K.as_nchw(out.reshape(b, h, w, c))
