@@ -165,6 +165,13 @@ int vidseg_kmeans_select(void* workspace, size_t workspace_bytes, const double* 
 int vidseg_kmeans_predict(const float* x, int n, int d, const float* centers, int k,
                           int32_t* labels_out, double* cnorm_scratch, void* stream);
 
+/* `iterations` Lloyd iterations of every unfinished run over all rows, queued on `stream` without synchronising: the
+ * loop body of vidseg_kmeans_fit_predict (sklearn/cluster/_kmeans.py:_kmeans_single_lloyd, one call of lloyd_iter +
+ * the tolerance / strict-convergence tests per iteration) for callers that poll vidseg_kmeans_flags_async themselves.
+ * Used by the run-sharded multi-GPU fit: the n_init initialisations of KMeans(n_init=10) (feature_extraction.py:52)
+ * are independent, so every rank prepares a workspace for its own subset of the runs and iterates it locally. */
+int vidseg_kmeans_lloyd(void* workspace, size_t workspace_bytes, int iterations, void* stream);
+
 /* Whole single-GPU fit+predict: prepare, seed, Lloyd (polling the convergence
  * flags every few iterations), inertia, select, predict.
  *   first_idx_host int32 [R], rand_host double [R, K-1, T]

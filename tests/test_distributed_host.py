@@ -144,8 +144,15 @@ class NumpyLloydBackend:
                 out[a, b] = okm.is_same_clustering(self.labels[a, r0:r1], self.labels[b, r0:r1], self.k)
         return torch.from_numpy(out)
 
-    def finish(self, best):
-        return torch.from_numpy(self.centers[best] + self.mean)
+    def finish(self, best, want_labels=False):
+        cen = torch.from_numpy((self.centers[best] + self.mean).astype(np.float32))
+        return (cen, torch.from_numpy(self.labels[best].copy())) if want_labels else cen
+
+    def lloyd(self, iterations):
+        for _ in range(iterations):
+            self.assign(0, self.n)
+            part, ch = self.partial(0, self.n)
+            self.update(part, ch, local_rows_only=False)
 
     def predict(self, rows, centers):
         return torch.from_numpy(okm.kmeans_predict(rows.numpy(), centers.numpy()).astype(np.int32))
@@ -184,6 +191,11 @@ def _worker(rank, world, port, q):
         labels = D.sharded_kmeans_fit_predict(X, K, ranges[rank], n_init=3, backend=NumpyLloydBackend(K, 3), info=info,
                                               row_ranges=ranges if rank_known_ranges else None)
         q.put((rank, labels.numpy(), info["iterations_issued"], info["allreduces"], info["unsharded_fallback"]))
+        # the same fit with the INITIALISATIONS spread over the ranks (3 runs on 2 ranks: 2 + 1)
+        np.random.seed(7)
+        info2 = {}
+        labels2 = D.run_sharded_kmeans_fit_predict(X, K, n_init=3, backend_factory=NumpyLloydBackend, info=info2)
+        q.put((rank, labels2.numpy(), info2["runs"], info2["allreduces"], info2["best"]))
     finally:
         dist.destroy_process_group()
 
@@ -207,10 +219,12 @@ def test_sharded_kmeans_two_ranks_gloo_matches_oracle():
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    res = sorted((q.get(timeout=180) for _ in procs), key=lambda t: t[0])
+    got = [q.get(timeout=180) for _ in range(2 * world)]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
+    res = sorted((t for t in got if isinstance(t[4], bool)), key=lambda t: t[0])
+    res_runs = sorted((t for t in got if not isinstance(t[4], bool)), key=lambda t: t[0])
     (_, lab0, it0, ar0, fb0), (_, lab1, it1, ar1, fb1) = res
     assert np.array_equal(lab0, lab1) and it0 == it1 and ar0 == ar1 > 0 and not fb0 and not fb1
     # the reference's answer on the same rows, same seed
@@ -222,3 +236,7 @@ def test_sharded_kmeans_two_ranks_gloo_matches_oracle():
     assert np.array_equal(lab0, want)
     # ONE all-reduce per issued Lloyd iteration (sums | counts | change counters) + one for inertia | same-clustering
     assert ar0 == it0 + 1
+    # run-sharded form: rank 0 iterated runs [0, 2), rank 1 run [2, 3); ONE collective; same labels, same winner everywhere
+    (_, rl0, runs0, rar0, best0), (_, rl1, runs1, rar1, best1) = res_runs
+    assert tuple(runs0) == (0, 2) and tuple(runs1) == (2, 3) and rar0 == rar1 == 1 and best0 == best1
+    assert np.array_equal(rl0, want) and np.array_equal(rl1, want)

@@ -151,3 +151,37 @@ def test_sharded_segmenter_on_one_rank_equals_clip_segmenter(cuda):
             dist.destroy_process_group()
     assert torch.equal(got, want) and torch.equal(got_graph, want)
     assert len(got_many) == 3 and all(torch.equal(g, want.cpu()) for g in got_many)
+
+
+@pytest.mark.parametrize("case,world", [("c1_objects", 4), ("c2_objects", 8), ("c1_iid", 3), ("small_odd", 16)])
+def test_run_sharded_fit_is_bit_identical_to_one_gpu(cuda, case, world):
+    """The n_init initialisations spread over `world` virtual ranks (each iterating its own runs on all rows, then the
+    run records summed as the all-reduce does): winner, centres and labels of the single-GPU fit, bit for bit, and the
+    reference's labels (golden)."""
+    from vidseg_diffusion_b200 import distributed as D
+    from vidseg_diffusion_b200.features import aggregate_normalize
+    from vidseg_diffusion_b200.kmeans import KMeans, draw_kmeanspp_randoms
+    name, seed, F, h, w, C, K, kind = next(c for c in CLUSTER_CASES if c[0] == case)
+    g = np.load(os.path.join(GOLDEN, f"cluster_{name}.npz"))
+    blocks, _ = synthetic_clip_features(seed, F, h, w, C, K, kind=kind)
+    X = aggregate_normalize([torch.from_numpy(b).to(cuda) for b in blocks], F)
+    n = X.shape[0]
+    np.random.seed(seed)
+    km = KMeans(n_clusters=K, n_init=10)
+    want_labels = km.fit_predict(X)
+    np.random.seed(seed)
+    first, rand = draw_kmeanspp_randoms(n, K, 10)
+    parts = D.run_partition(10, world)
+    assert parts[0][0] == 0 and parts[-1][1] == 10 and sum(b - a for a, b in parts) == 10
+    total, iters = None, 0
+    for a, b in parts:
+        st = {}
+        words = D.fit_run_records(X, K, first, rand, a, b, 300, 1e-4, D.CudaLloydBackend, st)
+        assert words.dtype == torch.int32 and bool((words[:a] == 0).all()) and bool((words[b:] == 0).all())
+        iters = max(iters, st.get("iterations", 0))
+        total = words if total is None else total + words      # the all-reduce: every word has exactly one non-zero owner
+    assert iters == km.info_["max_iter_run"]
+    labels, centers, best = D.select_from_run_records(X, total, K)
+    assert best == km.info_["best_run"]
+    assert torch.equal(centers, km.cluster_centers_) and torch.equal(labels, want_labels)
+    assert np.array_equal(labels.cpu().numpy(), g["labels"].reshape(-1))

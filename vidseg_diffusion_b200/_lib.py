@@ -37,6 +37,7 @@ SIGNATURES = {
     "vidseg_kmeans_assign": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p]),
     "vidseg_kmeans_partial": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "vidseg_kmeans_update": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]),
+    "vidseg_kmeans_lloyd": (c_int, [c_void_p, c_size_t, c_int, c_void_p]),
     "vidseg_kmeans_active_runs": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_int), c_void_p]),
     "vidseg_kmeans_status": (c_int, [c_void_p, c_size_t, ctypes.POINTER(c_int), ctypes.POINTER(c_int), c_void_p]),
     "vidseg_kmeans_inertia": (c_int, [c_void_p, c_size_t, c_int, c_int, c_void_p, c_void_p]),

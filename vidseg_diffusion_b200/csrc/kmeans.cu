@@ -2368,6 +2368,29 @@ VS_API int vidseg_kmeans_predict(const float* x, int n, int d, const float* cent
   return km_launch_assign(x, L, 1, 0, n, centers, cnorm_scratch, labels_out, n, nullptr, nullptr, 0, 0, stream);
 }
 
+// `iterations` Lloyd iterations of every unfinished run over ALL rows, queued without synchronising (finished runs make
+// every kernel return early): E-step (tensor-core filter + resolver), one-hot labels -> exact int8 tensor-core sums ->
+// averaging / relocation / convergence flags straight from the product's partial sums.  The loop body of
+// vidseg_kmeans_fit_predict; callers that poll the flags themselves (vidseg_kmeans_flags_async) drive it directly -- the
+// run-sharded multi-GPU fit, where every rank iterates its own subset of the n_init runs.
+VS_API int vidseg_kmeans_lloyd(void* workspace, size_t workspace_bytes, int iterations, void* stream) {
+  KmLayout L;
+  if (int e = km_check_ws(workspace, workspace_bytes, &L)) return e;
+  VS_REQUIRE(iterations >= 0, "negative iteration count");
+  void* ws = workspace;
+  for (int b = 0; b < iterations; ++b) {
+    if (int e = km_assign_runs(ws, L, 0, L.n, 1, 0, stream)) return e;
+    if (km_mq_range_ok(L, 0, L.n)) {
+      if (int e = km_mstep_product(ws, L, 0, L.n, stream)) return e;
+      if (int e = km_update_fused(ws, L, 2, nullptr, nullptr, nullptr, 0, stream)) return e;
+    } else {
+      if (int e = vidseg_kmeans_partial(workspace, workspace_bytes, 0, L.n, nullptr, nullptr, stream)) return e;
+      if (int e = vidseg_kmeans_update(workspace, workspace_bytes, nullptr, nullptr, 0, stream)) return e;
+    }
+  }
+  return 0;
+}
+
 VS_API int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_init, int n_trials, int max_iter,
                                          float tol_rel, const int32_t* first_idx_host, const double* rand_host,
                                          int32_t* labels_out, float* centers_out, int32_t* info_host,
@@ -2390,17 +2413,7 @@ VS_API int vidseg_kmeans_fit_predict(const float* x, int n, int d, int k, int n_
   int poll = 4;
   while (it < max_iter) {
     const int burst = (max_iter - it) < poll ? (max_iter - it) : poll;
-    for (int b = 0; b < burst; ++b) {
-      if (int e = vidseg_kmeans_assign(workspace, workspace_bytes, 0, n, stream)) return e;
-      if (km_mq_range_ok(L, 0, n)) {
-        // one-hot labels -> exact int8 tensor-core sums -> averaging straight from the product's partial sums
-        if (int e = km_mstep_product(ws, L, 0, n, stream)) return e;
-        if (int e = km_update_fused(ws, L, 2, nullptr, nullptr, nullptr, 0, stream)) return e;
-      } else {
-        if (int e = vidseg_kmeans_partial(workspace, workspace_bytes, 0, n, nullptr, nullptr, stream)) return e;
-        if (int e = vidseg_kmeans_update(workspace, workspace_bytes, nullptr, nullptr, 0, stream)) return e;
-      }
-    }
+    if (int e = vidseg_kmeans_lloyd(workspace, workspace_bytes, burst, stream)) return e;
     it += burst;
     int active = 0;
     if (int e = vidseg_kmeans_active_runs(workspace, workspace_bytes, &active, stream)) return e;

@@ -162,11 +162,16 @@ class CudaLloydBackend:
         self._call("vidseg_kmeans_same_matrix", self.ws.data_ptr(), self.nbytes, r0, r1, out.data_ptr(), _lib.stream_ptr())
         return out
 
-    def finish(self, best):
+    def lloyd(self, iterations):
+        """``iterations`` Lloyd iterations over all rows, queued without synchronising (single-GPU form)."""
+        self._call("vidseg_kmeans_lloyd", self.ws.data_ptr(), self.nbytes, int(iterations), _lib.stream_ptr())
+
+    def finish(self, best, want_labels=False):
         centers = torch.empty((self.k, self.d), dtype=torch.float32, device=self.dev)
-        self._call("vidseg_kmeans_finish", self.ws.data_ptr(), self.nbytes, int(best), centers.data_ptr(), None,
-                   _lib.stream_ptr())
-        return centers
+        labels = torch.empty(self.n, dtype=torch.int32, device=self.dev) if want_labels else None
+        self._call("vidseg_kmeans_finish", self.ws.data_ptr(), self.nbytes, int(best), centers.data_ptr(),
+                   labels.data_ptr() if want_labels else None, _lib.stream_ptr())
+        return (centers, labels) if want_labels else centers
 
     def predict(self, rows, centers):
         n = rows.shape[0]
@@ -277,13 +282,121 @@ def sharded_kmeans_fit_predict(X, n_clusters, row_range, group=None, n_init=10, 
     return labels
 
 
+def run_partition(n_init, world):
+    """Contiguous ranges of the n_init initialisations per rank, sizes differing by at most one (10 runs on 4 ranks:
+    3,3,2,2; on 8 ranks: 2,2,1,1,1,1,1,1; ranks beyond n_init get none)."""
+    return frame_partition(n_init, world)
+
+
+def _is_same_clustering(l1, l2, k):
+    """sklearn/cluster/_k_means_common.pyx:_is_same_clustering: labels1 -> labels2 is a function (device tensors)."""
+    pairs = torch.unique(l1.long() * k + l2.long())
+    return bool(pairs.numel() == torch.unique(l1).numel())
+
+
+def run_sharded_kmeans_fit_predict(X, n_clusters, group=None, n_init=10, max_iter=300, tol=1e-4, random_state=None,
+                                   info=None, backend_factory=None):
+    """``KMeans(n_clusters, n_init).fit(X).predict(X)`` with the n_init INITIALISATIONS spread over the ranks of ``group``.
+
+    The runs of ``KMeans(n_init=10)`` are independent until the best-of-n_init rule, so rank r seeds and iterates its own
+    subset of the runs on ALL rows of X (the FULL matrix, identical on every rank after the feature all-gather) with the
+    single-GPU kernels -- no collective inside the Lloyd loop, empty-cluster relocation included -- and ONE all-reduce at
+    the end hands every rank the inertia, the fit labels and the centres of every run (each rank contributes its own
+    runs' words and zeros elsewhere, so the integer sum is a bit-exact gather).  Every rank then applies sklearn's
+    best-of-n_init rule and predicts all rows.  Every run is computed exactly as in the single-GPU fit, so centres and
+    labels are bit-identical to it.  All ranks must have numpy's global RandomState in the same state.
+    ``backend_factory(k, runs, max_iter, tol)``: stand-in for ``CudaLloydBackend`` (host tests).
+    Returns the labels of ALL rows (int32 [N], identical on every rank)."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    make = backend_factory if backend_factory is not None else CudaLloydBackend
+    n, d = X.shape
+    if n < n_clusters:
+        raise ValueError(f"n_samples={n} should be >= n_clusters={n_clusters}.")
+    first, rand = draw_kmeanspp_randoms(n, n_clusters, n_init, random_state)   # same draws, same order, on every rank
+    a, b = run_partition(n_init, world)[rank]
+    stats = {"allreduces": 0, "exchange": "runs", "runs": (a, b)}
+    words = fit_run_records(X, n_clusters, first, rand, a, b, max_iter, tol, make, stats)
+    if world > 1:
+        dist.all_reduce(words, group=group)                                      # the only collective of the fit
+        stats["allreduces"] += 1
+    labels, centers, best = select_from_run_records(X, words, n_clusters, make, max_iter, tol)
+    if info is not None:
+        info.update(stats, centers=centers, best=best)
+    return labels
+
+
+def fit_run_records(X, k, first, rand, a, b, max_iter, tol, make, stats=None):
+    """Runs [a, b) of the n_init initialisations on all rows of X -> int32 words [n_init, 2 + N + K*D]: per run the
+    inertia (one float64), the fit labels and the un-centred centres; rows of other runs are zero."""
+    n, d = X.shape
+    n_init = len(first)
+    words = torch.zeros((n_init, 2 + n + k * d), dtype=torch.int32, device=X.device)
+    if b <= a:
+        return words
+    be = make(k, b - a, max_iter, tol)
+    try:
+        be.prepare(X)
+        be.seed(first[a:b], rand[a:b])
+        it, pending, state = 0, None, None
+        while it < max_iter:
+            burst = min(BURST, max_iter - it)
+            be.lloyd(burst)
+            it += burst
+            ticket = be.flags_async()
+            if pending is not None:          # flags of the PREVIOUS burst: this one is already queued behind them
+                state = be.flags_wait(pending)
+                if state[0] == 0:
+                    break
+            pending = ticket
+        else:
+            state = be.flags_wait(ticket)
+        if stats is not None:
+            stats["iterations"] = state[2]
+            stats["iterations_issued"] = it
+        inertia = be.inertia(0, n)                                               # float64 [runs]
+        words[a:b, :2] = inertia.contiguous().view(torch.int32).reshape(b - a, 2)
+        for j in range(b - a):
+            cen, lab = be.finish(j, want_labels=True)
+            words[a + j, 2:2 + n] = lab
+            words[a + j, 2 + n:] = cen.contiguous().reshape(-1).view(torch.int32)
+    finally:
+        if hasattr(be, "release"):
+            be.release()
+    return words
+
+
+def select_from_run_records(X, words, k, make=None, max_iter=300, tol=1e-4):
+    """Best-of-n_init (sklearn/_kmeans.py:1529-1541) over the gathered run records, then KMeans.predict on all rows.
+    Returns (labels int32 [N], centres fp32 [K, D], index of the winning run)."""
+    n, d = X.shape
+    n_init = words.shape[0]
+    inertia32 = words[:, :2].contiguous().view(torch.float64).reshape(-1).float().cpu().numpy()
+    labels_fit = words[:, 2:2 + n]
+    best = 0
+    for i in range(1, n_init):   # the clustering test only where the inertia is lower
+        if inertia32[i] < inertia32[best] and not _is_same_clustering(labels_fit[i], labels_fit[best], k):
+            best = i
+    centers = words[best, 2 + n:].contiguous().view(torch.float32).reshape(k, d)
+    pred = (make if make is not None else CudaLloydBackend)(k, 1, max_iter, tol)
+    pred.dev, pred.d = X.device, d
+    return pred.predict(X, centers), centers, best
+
+
 class ShardedClipSegmenter:
     """``pipeline.ClipSegmenter`` with ONE clip spread over the ranks of a process group: SD-2.1 by frame (any world
     size), SVD by classifier-free-guidance half (two ranks).  Same call, same label maps, on every rank."""
 
     def __init__(self, model, num_masks=10, is_aggre_attn=False, is_refine_mask=False, n_init=10, group=None,
-                 use_cuda_graph=False):
+                 use_cuda_graph=False, kmeans_split="runs"):
+        """``kmeans_split``: how the ranks share the K-means fit after the feature all-gather.  "runs" (default): the n_init
+        initialisations are spread over the ranks, no collective inside the Lloyd loop, one all-reduce at the end
+        (``run_sharded_kmeans_fit_predict``).  "rows": every rank assigns its own rows and ONE all-reduce per Lloyd
+        iteration sums the exchange words (``sharded_kmeans_fit_predict``).  Both give the single-GPU labels bit for bit."""
         from .pipeline import ClipSegmenter
+        if kmeans_split not in ("runs", "rows"):
+            raise _lib.VidsegError(f"kmeans_split must be 'runs' or 'rows', got {kmeans_split!r}")
+        self.kmeans_split = kmeans_split
         self.video = "VideoUNet" in str(type(model))
         self.group = group
         world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -354,8 +467,11 @@ class ShardedClipSegmenter:
             np.random.seed(seed)
         info = {}
         ranges = [(sum(counts[:r]), sum(counts[:r + 1])) for r in range(world)]
-        labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
-                                            row_ranges=ranges)             # exchange step 2 (per iteration)
+        if self.kmeans_split == "runs":
+            labels = run_sharded_kmeans_fit_predict(X, self.num_masks, self.group, n_init=self.n_init, info=info)   # exchange step 2 (once)
+        else:
+            labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
+                                                row_ranges=ranges)             # exchange step 2 (per iteration)
         labels = labels.reshape(F, fh, fw)
         self.last = {"features": X, "kmeans_info": info}
         if self.is_refine_mask:
@@ -449,8 +565,11 @@ class ShardedClipSegmenter:
         cut = (n // 2 + 127) // 128 * 128
         ranges = [(0, min(cut, n)), (min(cut, n), n)]
         info = {}
-        labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
-                                            row_ranges=ranges).reshape(F, fh, fw)
+        if self.kmeans_split == "runs":
+            labels = run_sharded_kmeans_fit_predict(X, self.num_masks, self.group, n_init=self.n_init, info=info).reshape(F, fh, fw)
+        else:
+            labels = sharded_kmeans_fit_predict(X, self.num_masks, ranges[rank], self.group, n_init=self.n_init, info=info,
+                                                row_ranges=ranges).reshape(F, fh, fw)
         self.last = {"features": X, "kmeans_info": info, "unet_out_half": out}
         if self.is_refine_mask:
             if rank == cond_rank:
