@@ -179,8 +179,10 @@ def bench_config(args, wl, world, multi_gpu):
     if world == 1:
         mg, clips = "single GPU", 1
     elif multi_gpu == "sharded":
-        mg = ("ONE clip per step, frames sharded over the ranks: NCCL all-gather of the feature rows + one all-reduce per "
-              "Lloyd iteration (BASELINE configs[3])")
+        mg = ("ONE clip per step, frames sharded over the ranks (BASELINE configs[3]): NCCL all-gather of the feature rows, then "
+              + ("the n_init K-means initialisations spread over the ranks (no collective inside the Lloyd loop) and one "
+                 "all-reduce of the run records" if args.kmeans_split == "runs" else
+                 "one all-reduce of the exchange words per Lloyd iteration"))
         clips = 1
     elif multi_gpu == "cfg-split":
         mg = "ONE clip per step, the two guidance halves of the SVD batch on two ranks, feature broadcast + distributed K-means"
@@ -413,8 +415,8 @@ def run_b200(args, wl, cfg):
     parity = {}
     if one_clip:
         from vidseg_diffusion_b200.distributed import ShardedClipSegmenter
-        sh = ShardedClipSegmenter(model, use_cuda_graph=not args.no_graph, **seg_kw)
-        sh_eager = ShardedClipSegmenter(model, **seg_kw)
+        sh = ShardedClipSegmenter(model, use_cuda_graph=not args.no_graph, kmeans_split=args.kmeans_split, **seg_kw)
+        sh_eager = ShardedClipSegmenter(model, kmeans_split=args.kmeans_split, **seg_kw)
         sh_dev = lambda: sh.segment(devt[0], devt[1], devt[2], F, seed, **kw_of(devt))
 
         def sh_e2e():
@@ -457,7 +459,8 @@ def run_b200(args, wl, cfg):
         parity = {"labels_identical_on_all_ranks": bool(flags[0].item()),
                   "labels_identical_to_single_gpu_path": bool(flags[1].item()),
                   "lloyd_iterations": info.get("iterations"), "allreduces_per_clip": info.get("allreduces"),
-                  "exchange_words": info.get("exchange"), "unsharded_fallback": info.get("unsharded_fallback")}
+                  "kmeans_split": args.kmeans_split, "exchange_words": info.get("exchange"),
+                  "unsharded_fallback": info.get("unsharded_fallback")}
         # the zero-communication alternative (one clip per GPU), for comparison: a few pipelined steps
         rep_host = [t.pin_memory() for t in make_clip(wl, cfg, 1 + rank)]
         rep_clip = (rep_host[0], rep_host[1], rep_host[2], kw_of(rep_host))
@@ -768,6 +771,9 @@ def main():
     ap.add_argument("--no-pipeline", dest="pipelined", action="store_false",
                     help="time ClipSegmenter.segment (one clip at a time) instead of segment_many, where the UNet stage of "
                          "clip i+1 overlaps the clustering of clip i on a second stream")
+    ap.add_argument("--kmeans-split", default="runs", choices=["runs", "rows"],
+                    help="sharded / cfg-split: 'runs' = the n_init initialisations spread over the ranks, one all-reduce at the "
+                         "end; 'rows' = every rank assigns its own rows, one all-reduce per Lloyd iteration")
     ap.add_argument("--multi-gpu", default="auto", choices=["auto", "sharded", "cfg-split", "replicas"],
                     help="N > 1: 'sharded' = ONE clip per step with its frames sharded over the ranks (all-gather + distributed "
                          "K-means; default for SD-2.1), 'cfg-split' = the two guidance halves of an SVD clip on two ranks "

@@ -596,12 +596,12 @@ static int run_gemm(const void* a_hi, const void* a_lo, const uint64_t* adims, c
     VS_REQUIRE(p.seg_n % 128 == 0, "segment width must be a multiple of 128 or 160");
     return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
   }
-  if (!p.in_packed8 && !p.geglu && p.n <= 256 && p.mma_n == 0 && m_tiles <= 2 * kNumSMs) {
+  if (!p.in_packed8 && !p.geglu && p.n <= 128 && p.mma_n == 0) {
     // one N tile whose MMAs are trimmed to the columns that exist (fp16-pair operands: the K-means score GEMM
-    // [N, D] x [D, R*K], R*K = 200 at n_init = 10 and 20..60 for a rank of the run-sharded fit): every A tile is read
-    // once, and a 128-row tile costs N/16 MMA columns instead of a full 128 or 2 x 128
+    // [N, D] x [D, R*K] of a rank of the run-sharded fit, R*K = 20..60).  (Measured: for 128 < N <= 256 a single 256-wide
+    // tile is SLOWER than two 128-wide ones, 32.7 vs 23.0 us at [14336, 640] x [640, 200] -- two pipeline stages of 96 KB
+    // instead of three of 64 KB -- so those keep the generic choice.)
     p.mma_n = (p.n + 15) / 16 * 16;
-    if (p.n > 128) return launch_gemm<256>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
     return launch_gemm<128>(ta_hi, ta_lo, w_hi, w_lo, p, flops, family, stream);
   }
   const bool underfilled = p.n % 128 == 0 && p.n > 128 && m_tiles * ((p.n + 255) / 256) < (3 * kNumSMs) / 4;
