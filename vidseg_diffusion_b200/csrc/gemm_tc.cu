@@ -146,11 +146,11 @@ constexpr int kEpiWarps = (kGemmThreads - 128) / 32;
 constexpr int kEpiWarpBytes = 8 * 128;
 constexpr int kEpiStageBytes = kEpiWarps * kEpiWarpBytes;
 
-template <int BN>
+template <int BN, int CL = 1>
 struct GemmCfg {
-  static constexpr int kTileBBytes = BN * kGemmBK * 2;
+  static constexpr int kTileBBytes = (BN / CL) * kGemmBK * 2;   // a CTA of a pair holds half of the B rows
   static constexpr int kStageBytes = 2 * kTileABytes + 2 * kTileBBytes;
-  static constexpr int kStages = (BN <= 128) ? 3 : (BN <= 160 ? 3 : 2);
+  static constexpr int kStages = (CL == 2) ? (BN <= 160 ? 4 : 3) : ((BN <= 128) ? 3 : (BN <= 160 ? 3 : 2));
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kEpiStageBytes;
   static constexpr int kAccStride = (BN <= 128) ? 128 : 256;  // TMEM columns per accumulator stage
   static constexpr int kTmemCols = (BN <= 128) ? 256 : 512;
@@ -188,16 +188,19 @@ struct GemmParams {
   __half* seg_lo[3];
 };
 
-// CL = 2: two CTAs of a thread-block cluster work on two adjacent M tiles of the SAME N tile; each loads half of the
-// weight (B) tile and multicasts it into both CTAs' shared memory, so the L2 -> SM operand traffic per k-block drops
-// from A + B to A + B/2.  A stage may only be refilled when BOTH CTAs have consumed it: the MMA issuer's commit arrives
-// on both empty barriers.
+// CL = 2: a CTA PAIR (two CTAs of a cluster on the two SMs of a TPC) works on two adjacent M tiles of the SAME N tile
+// with ONE tcgen05.mma.cta_group::2 of M = 256 per k-slice, issued by the leader (cluster rank 0).  Each CTA loads its own
+// A tile and HALF of the B tile (BN / 2 weight rows) into its own shared memory -- per CTA the operand bytes per k-block
+// drop from A + B to A + B/2, both the L2 -> SM traffic (what bounds the short-K GEMMs) and the shared-memory reads of
+// the tensor core (what bounds the long ones) -- and reads its own 128 accumulator rows from its own TMEM.  The TMA loads
+// of both CTAs complete on the LEADER's full barrier; the leader's commits arrive on both CTAs' empty / tmem_full
+// barriers; the epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
 template <int BN, int CL>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_constant__ CUtensorMap tmap_a_lo,
                   const __grid_constant__ CUtensorMap tmap_b_hi, const __grid_constant__ CUtensorMap tmap_b_lo,
                   const __grid_constant__ GemmParams p) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   constexpr int kStages = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -230,11 +233,12 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
     tc::prefetch_tmap(&tmap_b_lo);
   }
   if (warp == 1 && lane == 0) {
-    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], CL); }
-    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kEpiWarps * 32); }
+    for (int s = 0; s < kStages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    // tmem_empty: one arrival per epilogue warp, of both CTAs of a pair (only the leader's barrier is used then)
+    for (int s = 0; s < kGemmAccStages; ++s) { tc::mbar_init(&tmem_full_bar[s], 1); tc::mbar_init(&tmem_empty_bar[s], kEpiWarps * CL); }
     tc::fence_barrier_init();
   }
-  if (warp == 2) tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr);
+  if (warp == 2) { if (CL == 2) tc::tmem_alloc_pair<Cfg::kTmemCols>(tmem_base_ptr); else tc::tmem_alloc<Cfg::kTmemCols>(tmem_base_ptr); }
   tc::tc_fence_before();
   __syncthreads();
   if (CL > 1) tc::cluster_sync_all();   // the peer's barriers are initialised before anything is multicast to them
@@ -256,18 +260,22 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           for (int kc = 0; kc < p.kc_per_tap; ++kc) {
             tc::mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* st = smem + stage * Cfg::kStageBytes;
-            tc::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
             const int ca = p.c_off[tap] + kc * kGemmBK;
             const int kb0 = tap * p.cin + kc * kGemmBK;
-            tc::tma_load_5d(st, &tmap_a_hi, &full_bar[stage], ca, cw, cp, ch, b0);
-            tc::tma_load_5d(st + kTileABytes, &tmap_a_lo, &full_bar[stage], ca, cw, cp, ch, b0);
-            if (CL > 1) {   // this CTA's half of the B rows, delivered to both CTAs of the pair
-              constexpr int kHalfRows = BN / 2, kHalfBytes = Cfg::kTileBBytes / 2;
-              tc::tma_load_2d_mc(st + 2 * kTileABytes + crank * kHalfBytes, &tmap_b_hi, &full_bar[stage], kb0,
-                                 n0 + crank * kHalfRows, (uint16_t)0x3);
-              tc::tma_load_2d_mc(st + 2 * kTileABytes + Cfg::kTileBBytes + crank * kHalfBytes, &tmap_b_lo, &full_bar[stage],
-                                 kb0, n0 + crank * kHalfRows, (uint16_t)0x3);
+            if (CL == 2) {
+              // both CTAs' bytes are counted by the leader's barrier (armed by the leader alone); this CTA's half of the
+              // B rows goes to its own shared memory
+              if (crank == 0) tc::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+              const uint32_t lead_bar = tc::mapa_u32(tc::smem_u32(&full_bar[stage]), 0);
+              constexpr int kHalfRows = BN / 2;
+              tc::tma_load_5d_pair(st, &tmap_a_hi, lead_bar, ca, cw, cp, ch, b0);
+              tc::tma_load_5d_pair(st + kTileABytes, &tmap_a_lo, lead_bar, ca, cw, cp, ch, b0);
+              tc::tma_load_2d_pair(st + 2 * kTileABytes, &tmap_b_hi, lead_bar, kb0, n0 + crank * kHalfRows);
+              tc::tma_load_2d_pair(st + 2 * kTileABytes + Cfg::kTileBBytes, &tmap_b_lo, lead_bar, kb0, n0 + crank * kHalfRows);
             } else {
+              tc::mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+              tc::tma_load_5d(st, &tmap_a_hi, &full_bar[stage], ca, cw, cp, ch, b0);
+              tc::tma_load_5d(st + kTileABytes, &tmap_a_lo, &full_bar[stage], ca, cw, cp, ch, b0);
               tc::tma_load_2d(st + 2 * kTileABytes, &tmap_b_hi, &full_bar[stage], kb0, n0);
               tc::tma_load_2d(st + 2 * kTileABytes + Cfg::kTileBBytes, &tmap_b_lo, &full_bar[stage], kb0, n0);
             }
@@ -277,15 +285,25 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      const uint32_t idesc = tc::make_idesc_f16(kGemmBM, p.mma_n > 0 ? p.mma_n : BN, 0, 0);
+    // ===================== MMA issuer (the leader's alone in a pair) =====================
+    if (lane == 0 && crank == 0) {
+      constexpr int kMmaM = kGemmBM * CL;
+      const uint32_t idesc = tc::make_idesc_f16(kMmaM, p.mma_n > 0 ? p.mma_n : BN, 0, 0);
+      auto mma16 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+        if (CL == 2) tc::umma_f16_pair(d, a, b, id, accum); else tc::umma_f16(d, a, b, id, accum);
+      };
+      auto mma8 = [](uint32_t d, uint64_t a, uint64_t b, uint32_t id, uint32_t accum) {
+        if (CL == 2) tc::umma_f8_pair(d, a, b, id, accum); else tc::umma_f8(d, a, b, id, accum);
+      };
+      auto commit = [](uint64_t* bar) {   // in a pair: the same barrier of both CTAs
+        if (CL == 2) tc::umma_commit_pair(bar, (uint16_t)0x3); else tc::umma_commit(bar);
+      };
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = first_item; tile < num_tiles; tile += item_stride) {
-        tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
+        if (CL == 2) tc::mbar_wait_cluster(&tmem_empty_bar[acc], acc_phase ^ 1); else tc::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
         tc::tc_fence_after();
         const uint32_t d_acc = tmem_base + (uint32_t)(acc * Cfg::kAccStride);
         for (int kb = 0; kb < k_blocks; ++kb) {
@@ -298,32 +316,31 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           const uint64_t b_lo = tc::make_sw128_desc(sa + 2 * kTileABytes + Cfg::kTileBBytes);
           if (p.in_packed8) {
             // the a_lo / b_lo tiles hold [lo8 | x8] rows: corrections as fp8 MMAs (K = 32 each), small terms first
-            constexpr uint32_t idesc_lx = tc::make_idesc_f8(kGemmBM, BN, 1, 0);  // A e5m2 residual x B e4m3 value
-            constexpr uint32_t idesc_xl = tc::make_idesc_f8(kGemmBM, BN, 0, 1);  // A e4m3 value    x B e5m2 residual
+            constexpr uint32_t idesc_lx = tc::make_idesc_f8(kMmaM, BN, 1, 0);  // A e5m2 residual x B e4m3 value
+            constexpr uint32_t idesc_xl = tc::make_idesc_f8(kMmaM, BN, 0, 1);  // A e4m3 value    x B e5m2 residual
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               const uint64_t adv = (uint64_t)(h * 32 >> 4), xoff = (uint64_t)(64 >> 4);
-              tc::umma_f8(d_acc, a_lo + adv, b_lo + xoff + adv, idesc_lx, (kb > 0 || h > 0) ? 1u : 0u);
-              tc::umma_f8(d_acc, a_lo + xoff + adv, b_lo + adv, idesc_xl, 1u);
+              mma8(d_acc, a_lo + adv, b_lo + xoff + adv, idesc_lx, (kb > 0 || h > 0) ? 1u : 0u);
+              mma8(d_acc, a_lo + xoff + adv, b_lo + adv, idesc_xl, 1u);
             }
 #pragma unroll
             for (int ks = 0; ks < kGemmBK / 16; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 32 >> 4);
-              tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+              mma16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           } else {
 #pragma unroll
             for (int ks = 0; ks < kGemmBK / 16; ++ks) {
               const uint64_t adv = (uint64_t)(ks * 32 >> 4);  // 16 elements = 32 bytes along K inside the swizzle atom
               // small terms first, so that they are not absorbed one by one into a large partial sum
-              tc::umma_f16(d_acc, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
-              tc::umma_f16(d_acc, a_hi + adv, b_lo + adv, idesc, 1u);
-              tc::umma_f16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
+              mma16(d_acc, a_lo + adv, b_hi + adv, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
+              mma16(d_acc, a_hi + adv, b_lo + adv, idesc, 1u);
+              mma16(d_acc, a_hi + adv, b_hi + adv, idesc, 1u);
             }
           }
-          // frees the smem stage once these MMAs have read it (in both CTAs of a pair: either may overwrite it)
-          if (CL > 1) tc::umma_commit_mc(&empty_bar[stage], (uint16_t)0x3); else tc::umma_commit(&empty_bar[stage]);
-          if (kb == k_blocks - 1) tc::umma_commit(&tmem_full_bar[acc]);
+          commit(&empty_bar[stage]);   // frees the smem stage (of both CTAs of a pair) once these MMAs have read it
+          if (kb == k_blocks - 1) commit(&tmem_full_bar[acc]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
@@ -489,15 +506,20 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
           });
         }
       }
+      // this warp has read its share of the accumulator: one arrival per warp on the (leader's) tmem_empty barrier
       tc::tc_fence_before();
-      tc::mbar_arrive(&tmem_empty_bar[acc]);
+      __syncwarp();
+      if (lane == 0) {
+        if (CL == 2) tc::mbar_arrive_cluster(tc::mapa_u32(tc::smem_u32(&tmem_empty_bar[acc]), 0));
+        else tc::mbar_arrive(&tmem_empty_bar[acc]);
+      }
       if (++acc == kGemmAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (CL > 1) tc::cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
-  if (warp == 2) tc::tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  if (CL > 1) tc::cluster_sync_all();   // no CTA leaves (or frees its TMEM) while its peer may still signal / compute into it
+  if (warp == 2) { if (CL == 2) tc::tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base); else tc::tmem_dealloc<Cfg::kTmemCols>(tmem_base); }
 }
 
 // 128-pixel tile = bw x bh x bb patch (powers of two) of the output grid that pads the grid the least;
@@ -515,7 +537,7 @@ static void pick_patch(int wo, int ho, int nb, int* bw_out, int* bh_out, int* bb
 template <int BN, int CL>
 static int launch_gemm_cl(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const void* w_hi, const void* w_lo,
                           const GemmParams& p, double flops, int family, void* stream) {
-  using Cfg = GemmCfg<BN>;
+  using Cfg = GemmCfg<BN, CL>;
   CUtensorMap tb_hi, tb_lo;
   if (int e = encode_tmap_2d_f16(&tb_hi, w_hi, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN / CL)) return e;
   if (int e = encode_tmap_2d_f16(&tb_lo, w_lo, p.k, p.n, (uint64_t)p.k * 2, kGemmBK, BN / CL)) return e;
@@ -551,16 +573,14 @@ static int launch_gemm_cl(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, co
   return 0;
 }
 
-// Measured on B200 (tools/prof_kernels.py, packed8): the 2-CTA multicast form is correct but only 0-3 % faster (3x3 conv
-// 562 vs 556, [28672,5120,640] 455 vs 442 algorithmic TFLOP/s) -- the packed8 GEMMs are bound by the bytes that must be
-// in flight INTO shared memory per k-block (72-96 KB every ~0.34 us against ~1 us of TMA latency with 216 KB of smem),
-// which multicast does not reduce.  It therefore stays opt-in (VIDSEG_GEMM_CLUSTER=1); the cure is the 2-SM MMA
-// (cta_group::2, half of B per SM), a next-round item.
+// The CTA-pair form (cta_group::2) for grids with enough work for 74 pairs; VIDSEG_GEMM_PAIR=0 turns it off.  (The
+// earlier 2-CTA form that only MULTICAST the B halves into both CTAs was measured 0-3 % faster at best: multicast does not
+// reduce the bytes that must land in each SM's shared memory.)
 static bool use_cluster(const GemmParams& p, int bn) {
-  static const int env = [] { const char* e = getenv("VIDSEG_GEMM_CLUSTER"); return e ? atoi(e) : 0; }();
-  if (!env) return false;
+  static const int env = [] { const char* e = getenv("VIDSEG_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  if (!env || p.mma_n != 0) return false;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b, n_tiles = (p.n + bn - 1) / bn;
-  return m_tiles >= 2 && (long long)m_tiles * n_tiles >= 2LL * kNumSMs;
+  return m_tiles >= 2 && (long long)((m_tiles + 1) / 2) * n_tiles >= kNumSMs;
 }
 
 template <int BN>
