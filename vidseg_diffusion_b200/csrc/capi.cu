@@ -1,4 +1,5 @@
 // Library-wide state of libvidseg_b200.so: error string, launch counter, version probes.
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
@@ -9,6 +10,10 @@ namespace vidseg {
 thread_local char g_last_error[512] = "";
 std::atomic<long long> g_launch_count{0};
 std::atomic<int> g_profile_on{0};
+bool pdl_enabled(int link) {
+  static const int mask = [] { const char* e = getenv("VIDSEG_KM_PDL"); return e ? atoi(e) : 0xff; }();
+  return (mask >> link) & 1;
+}
 std::atomic<int> g_operand_mode{1};
 
 namespace {

@@ -66,9 +66,45 @@ void profile_after(cudaStream_t stream);
 #define VS_LAUNCH(kernel, grid, block, smem, stream, ...) \
   VS_LAUNCH_FW(VS_FAMILY, 0.0, kernel, grid, block, smem, stream, __VA_ARGS__)
 
+// Programmatic dependent launch for chains of short, strictly dependent kernels (the Lloyd iteration: six launches of
+// 6-23 us each): the kernel may be scheduled while its predecessor in the stream is still draining, runs its prologue and
+// blocks in pdl_wait() until the predecessor has completed and flushed -- the launch latency and the prologue leave the
+// critical path.  ONLY for kernels that call pdl_wait() before their first access to global memory (and
+// pdl_launch_dependents() to let their own successor in).  Falls back to a plain launch under the per-launch profiler.
+bool pdl_enabled(int link = 0);   // link: bit index of the chain link (debug mask VIDSEG_KM_PDL)
+#define VS_LAUNCH_PDL_L(link, kernel, grid, block, smem, stream, ...)                                      \
+  do {                                                                                               \
+    if (vidseg::g_profile_on.load(std::memory_order_relaxed) != 0 || !vidseg::pdl_enabled(link)) {    \
+      VS_LAUNCH(kernel, grid, block, smem, stream, __VA_ARGS__);                                     \
+    } else {                                                                                         \
+      cudaLaunchConfig_t _cfg = {};                                                                  \
+      _cfg.gridDim = dim3(grid);                                                                     \
+      _cfg.blockDim = dim3(block);                                                                   \
+      _cfg.dynamicSmemBytes = (smem);                                                                \
+      _cfg.stream = (cudaStream_t)(stream);                                                          \
+      cudaLaunchAttribute _at[1];                                                                    \
+      _at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                \
+      _at[0].val.programmaticStreamSerializationAllowed = 1;                                         \
+      _cfg.attrs = _at;                                                                              \
+      _cfg.numAttrs = 1;                                                                             \
+      VS_CHECK_CUDA(cudaLaunchKernelEx(&_cfg, kernel, __VA_ARGS__));                                 \
+      vidseg::g_launch_count.fetch_add(1, std::memory_order_relaxed);                                \
+    }                                                                                                \
+  } while (0)
+
+#define VS_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) VS_LAUNCH_PDL_L(0, kernel, grid, block, smem, stream, __VA_ARGS__)
+
 #define VS_POST_LAUNCH() VS_CHECK_CUDA(cudaGetLastError())
 
 constexpr int kNumSMs = 148;  // B200
+
+// see VS_LAUNCH_PDL; both are no-ops in a kernel launched without the attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// for kernels whose first reads are TMA loads (async proxy) of data the predecessor wrote with ordinary stores
+__device__ __forceinline__ void pdl_wait_async_proxy() {
+  asm volatile("griddepcontrol.wait;\n\tfence.proxy.async;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll

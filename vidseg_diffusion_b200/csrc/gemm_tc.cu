@@ -213,6 +213,11 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
   // space (LDS / STS instead of generic accesses) for the epilogue staging buffers
   uint8_t* epi_smem = smem_raw + ((1024u - (tc::smem_u32(smem_raw) & 1023u)) & 1023u) + kStages * Cfg::kStageBytes + 256;
 
+  // launched as a programmatic dependent (the K-means score GEMM, see VS_LAUNCH_PDL): wait for the predecessor first.
+  // (With the barrier initialisation / TMEM allocation ahead of the wait the fit's iteration count changed from run to run,
+  // measured; only the launch latency is hidden, not the prologue.)
+  pdl_wait_async_proxy();
+  pdl_launch_dependents();
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int m_tiles = p.tiles_w * p.tiles_h * p.tiles_b;
@@ -552,19 +557,26 @@ static int launch_gemm_cl(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, co
   const int grid = std::min(items, kNumSMs / CL) * CL;
   const bool prof = g_profile_on.load(std::memory_order_relaxed) != 0;
   if (prof) profile_before(family, flops, (cudaStream_t)stream);
-  if (CL == 1) {
-    gemm_split_kernel<BN, CL><<<grid, kGemmThreads, Cfg::kSmemBytes, (cudaStream_t)stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, p);
-  } else {
+  {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = Cfg::kSmemBytes;
     cfg.stream = (cudaStream_t)stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
+    if (CL > 1) {
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = CL; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      ++na;
+    }
+    if (family == kFamKMeans && !prof && pdl_enabled(0)) {   // a link of the Lloyd chain (see VS_LAUNCH_PDL)
+      attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[na].val.programmaticStreamSerializationAllowed = 1;
+      ++na;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = na;
     VS_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_split_kernel<BN, CL>, ta_hi, ta_lo, tb_hi, tb_lo, p));
   }
   if (prof) profile_after((cudaStream_t)stream);

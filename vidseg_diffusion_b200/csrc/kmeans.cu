@@ -804,6 +804,8 @@ km_assign_tc_kernel(int k, int runs, int row_begin, int row_end, const double* _
                     int* __restrict__ changed, const int* __restrict__ flags, int count_changes, int only_nonstrict,
                     double band, int* __restrict__ amb_count, int4* __restrict__ amb_list) {
   extern __shared__ float sm_f[];  // [runs*k] squared centre norms, [runs*k] error radii per unit |x|, [8] partial maxima
+  pdl_wait();
+  pdl_launch_dependents();
   float* sm_cn = sm_f;
   float* sm_tau = sm_f + runs * k;
   float* sm_red = sm_tau + runs * k;
@@ -881,6 +883,8 @@ km_assign_resolve_kernel(const float* __restrict__ x, int d, int k, const float*
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  pdl_wait();
+  pdl_launch_dependents();
   const int count = *amb_count;
   const float s = km_operand_scale(absmax[0]);
   const double inv = 1.0 / ((double)s * (double)s);
@@ -1157,6 +1161,8 @@ km_onehot_kernel(const int* __restrict__ labels, int n, int n_pad, int k, int ro
                  const int* __restrict__ flags, int8_t* __restrict__ onehot, int* __restrict__ cntpart) {
   extern __shared__ int hist[];  // [k]
   const int r = blockIdx.y;
+  pdl_wait();
+  pdl_launch_dependents();
   if (flags[r * 4 + 0]) return;
   for (int j = threadIdx.x; j < k; j += blockDim.x) hist[j] = 0;
   __syncthreads();
@@ -1202,6 +1208,8 @@ km_mstep_mma_kernel(const __grid_constant__ CUtensorMap tm_onehot, const __grid_
   const int pl = item % kMqPlanes;
   const int sp = item / kMqPlanes;
   const int m0 = mt * 128, n0 = nt * 128;
+  pdl_wait_async_proxy();
+  pdl_launch_dependents();
   {  // a tile whose runs have all converged has nothing to add (uniform: decided before any barrier exists)
     const int r_lo = m0 / p.k, r_hi = min(p.runs - 1, (m0 + 127) / p.k);
     bool live = false;
@@ -1461,6 +1469,8 @@ km_update_fused_kernel(const UpdArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = a.d, k = a.k;
   const int r = blockIdx.x / k, j = blockIdx.x - r * k;
+  pdl_wait();
+  pdl_launch_dependents();
   if (a.flags[r * 4 + 0]) return;   // set only by the finalising block of an EARLIER launch (uniform over the block)
   const double winv = (SRC == 0) ? 1.0 : 1.0 / ((double)km_operand_scale(a.absmax[0]) * (double)(1ll << kMqFracBits));
   upd_run_stats([&](int q) { return upd_count<SRC>(a, r, q); }, k, j, s_stat);
@@ -1743,12 +1753,12 @@ static int km_assign_runs(void* ws, const KmLayout& L, int row_begin, int row_en
   int* amb_count = reinterpret_cast<int*>(at<unsigned>(ws, L.absmax) + 1);
   const size_t smem = (size_t)L.r * L.k * 8 + 64;   // amb_count {count, ticket} is cleared by prepare and by every resolve
   VS_REQUIRE(smem <= 48 * 1024, "n_init * k too large for the tensor-core E-step");
-  VS_LAUNCH(km_assign_tc_kernel, (int)((total + 255) / 256), 256, smem, stream, L.k, L.r, row_begin, row_end,
+  VS_LAUNCH_PDL_L(1, km_assign_tc_kernel, (int)((total + 255) / 256), 256, smem, stream, L.k, L.r, row_begin, row_end,
             at<double>(ws, L.cnorm), at<double>(ws, L.xx), at<float>(ws, L.sdot), L.rk_pad, at<unsigned>(ws, L.absmax),
             at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), at<int>(ws, L.flags), count_changes, only_nonstrict, band,
             amb_count, at<int4>(ws, L.amb_list));
   VS_POST_LAUNCH();
-  VS_LAUNCH(km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
+  VS_LAUNCH_PDL_L(2, km_assign_resolve_kernel, kNumSMs * 2, 256, 0, stream, at<float>(ws, L.xc), L.d, L.k, at<float>(ws, L.centers),
             at<double>(ws, L.cnorm), at<double>(ws, L.xx), L.k <= 64 ? (const float*)nullptr : at<float>(ws, L.sdot), L.rk_pad,
             at<unsigned>(ws, L.absmax), at<int>(ws, L.labels), L.n, at<int>(ws, L.changed), count_changes, band, amb_count,
             at<int>(ws, L.amb_list), 4);
@@ -2088,7 +2098,7 @@ static bool km_mq_range_ok(const KmLayout& L, int row_begin, int row_end) {
 // labels -> one-hot rows + count partials -> digit-plane x one-hot tensor-core product (partial sums in the workspace)
 static int km_mstep_product(void* ws, const KmLayout& L, int row_begin, int row_end, void* stream) {
   {
-    VS_LAUNCH(km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
+    VS_LAUNCH_PDL_L(3, km_onehot_kernel, dim3(L.mq_blocks, L.r), kOhThreads, (size_t)L.k * 4, stream, at<int>(ws, L.labels), L.n, L.n_pad,
               L.k, row_begin, row_end, at<int>(ws, L.flags), at<int8_t>(ws, L.mq_onehot), at<int>(ws, L.mq_cnt));
     VS_POST_LAUNCH();
     MqParams mp{};
@@ -2108,8 +2118,9 @@ static int km_mstep_product(void* ws, const KmLayout& L, int row_begin, int row_
     VS_CHECK_CUDA(attr_mq);
     if (mp.kb_hi > mp.kb_lo) {
       const double macs = (double)mp.m_tiles * 128 * mp.n_tiles * 128 * kMqPlanes * (double)(mp.kb_hi - mp.kb_lo) * kMqBK;
-      VS_LAUNCH_W(2.0 * macs, km_mstep_mma_kernel, mp.m_tiles * mp.n_tiles * kMqPlanes * kMqSplit, kMqThreads, kMqSmem, stream,
-                  L.tm_onehot, L.tm_planes, mp);
+      (void)macs;
+      VS_LAUNCH_PDL_L(4, km_mstep_mma_kernel, mp.m_tiles * mp.n_tiles * kMqPlanes * kMqSplit, kMqThreads, kMqSmem, stream,
+                    L.tm_onehot, L.tm_planes, mp);
       VS_POST_LAUNCH();
     } else {
       VS_CHECK_CUDA(cudaMemsetAsync(mp.out, 0, (size_t)kMqSplit * kMqPlanes * mp.rk * L.d * 4, (cudaStream_t)stream));
@@ -2188,9 +2199,9 @@ static int km_update_fused(void* ws, const KmLayout& L, int src, void* sums, con
   a.reloc_ticket = at<int>(ws, L.reloc); a.reloc_done = at<int>(ws, L.reloc) + L.r;
   const int grid = L.r * L.k;   // all blocks are resident (the relocation path waits across the blocks of a run)
   VS_REQUIRE(grid <= kNumSMs * 16, "n_init * k too large for the fused update kernel");
-  if (src == 0) VS_LAUNCH(km_update_fused_kernel<0>, grid, kUpdThreads, 0, stream, a);
-  else if (src == 1) VS_LAUNCH(km_update_fused_kernel<1>, grid, kUpdThreads, 0, stream, a);
-  else VS_LAUNCH(km_update_fused_kernel<2>, grid, kUpdThreads, 0, stream, a);
+  if (src == 0) VS_LAUNCH_PDL_L(5, km_update_fused_kernel<0>, grid, kUpdThreads, 0, stream, a);
+  else if (src == 1) VS_LAUNCH_PDL_L(5, km_update_fused_kernel<1>, grid, kUpdThreads, 0, stream, a);
+  else VS_LAUNCH_PDL_L(5, km_update_fused_kernel<2>, grid, kUpdThreads, 0, stream, a);
   VS_POST_LAUNCH();
   return 0;
 }
