@@ -19,9 +19,12 @@ for line in out.splitlines():
             if re.search(r"\b" + op + r"\b|\b" + op + r"\.", line):
                 counts[cur][op] += 1
                 break
+        if re.search(r"\b(UTCHMMA|UTCQMMA|UTMALDG)\S*\.2CTA", line):
+            counts[cur]["2CTA"] += 1
         counts[cur]["_instr"] += bool(re.search(r"/\*[0-9a-f]{4,6}\*/", line))
 print(f"# cuobjdump -sass {os.path.relpath(so, ROOT)}  (architectures in the fatbin: {sorted(arch)})")
-print(f"# {'kernel':70s} " + " ".join(f"{o:>8s}" for o in ops) + "   instr")
+print("# 2CTA = UTCHMMA / UTCQMMA / UTMALDG carrying the .2CTA modifier (tcgen05.mma.cta_group::2 and the pair's TMA loads)")
+print(f"# {'kernel':70s} " + " ".join(f"{o:>8s}" for o in ops) + "     2CTA   instr")
 for k, c in counts.items():
     if any(c[o] for o in ops[:6]):
-        print(f"{k[:72]:72s} " + " ".join(f"{c[o]:8d}" for o in ops) + f" {c['_instr']:7d}")
+        print(f"{k[:72]:72s} " + " ".join(f"{c[o]:8d}" for o in ops) + f" {c['2CTA']:8d} {c['_instr']:7d}")
