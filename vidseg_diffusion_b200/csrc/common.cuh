@@ -106,6 +106,26 @@ __device__ __forceinline__ void pdl_wait_async_proxy() {
 }
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
+// x * Phi(x) with Phi through erf(t) = 1 - exp(-q(t)), t = |x| / sqrt(2), q a degree-6 polynomial without constant term
+// fitted (minimax, scipy) to -ln(erfc(t)) on [0, 4.3]: |erf error| <= 2.8e-7 in fp32, |gelu error| <= 5.8e-7 absolute and
+// 2e-7 |x| (erff() itself is 1 ulp of 1).  One range, no selects: 11 instructions against ~32 for 0.5 x (1 + erff(x / sqrt 2)),
+// which is what bounded the fused GEGLU epilogue (50 instructions per output on eight warps against 5 120 MMA cycles per tile).
+// The coefficients carry -log2(e), so the exponential is one ex2.approx; t is clamped at 6 (erf = 1 in fp32 from 3.9 on; the
+// polynomial turns around near t = 17).
+__device__ __forceinline__ float gelu_erf_fast(float x) {
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 6.0f);
+  float p = 1.420341199e-04f;
+  p = fmaf(p, t, -3.664243535e-03f);
+  p = fmaf(p, t, 3.089613741e-02f);
+  p = fmaf(p, t, -1.496994018e-01f);
+  p = fmaf(p, t, -9.181654774e-01f);
+  p = fmaf(p, t, -1.627925070e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p * t));
+  const float hx = 0.5f * x, a = fabsf(hx);
+  return fmaf(-a, e, hx + a);   // 0.5 x + 0.5 |x| erf(t)
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -439,7 +439,7 @@ gemm_split_kernel(const __grid_constant__ CUtensorMap tmap_a_hi, const __grid_co
             for (int u = 0; u < 4; ++u) {
               const float val = fmaf(__uint_as_float(rv[j + u]), p.acc_scale, vb[u]);
               const float gate = fmaf(__uint_as_float(rg[j + u]), p.acc_scale, gb[u]);
-              rv[j + u] = __float_as_uint(val * (0.5f * gate * (1.0f + erff(gate * 0.70710678118654752440f))));
+              rv[j + u] = __float_as_uint(val * gelu_erf_fast(gate));
             }
           }
           staged(rv, [&](int u, uint4 x) {
