@@ -26,20 +26,24 @@
 namespace vidseg {
 
 constexpr int kAtBQ = 128;        // queries per tile
-constexpr int kAtTiles = 2;       // query tiles per CTA
 constexpr int kAtBK = 128;        // keys per block (128-wide S tiles: the 64-wide ones were bound by operand fetch, 6 KB of smem per 32 math cycles)
 constexpr int kAtD = 64;          // head dim
-constexpr int kAtStages = 2;      // K/V ring depth (64 KB per stage)
 constexpr int kAtQTileBytes = kAtBQ * kAtD * 2;  // 16 KB (one of hi / lo)
 constexpr int kAtKTileBytes = kAtBK * kAtD * 2;  // 16 KB
-constexpr int kAtPTileBytes = kAtBQ * kAtBK * 2; // 16 KB
-constexpr int kAtSmemQ = kAtTiles * 2 * kAtQTileBytes;          // 64 KB
-constexpr int kAtSmemKV = kAtStages * 4 * kAtKTileBytes;        // 128 KB
-constexpr int kAtSmemP = 0;                                     // P lives in TMEM
-constexpr int kAtSmemBytes = kAtSmemQ + kAtSmemKV + kAtSmemP + 1024 + 256;
-constexpr int kAtThreads = 64 + kAtTiles * 128;
-constexpr int kAtTmemCols = 512;       // per tile: S (128 columns; P overwrites it in place) | O (64 columns)
-constexpr int kAtTileCols = 192;
+constexpr int kAtTileCols = 192;       // per tile: S (128 columns; P overwrites it in place) | O (64 columns)
+// Two shapes of CTA.  <2, 2>: 256 queries (two tiles whose softmax / MMA phases interleave), K/V through a two-stage ring,
+// all 512 TMEM columns, one CTA per SM -- the long key loops of self-attention.  <1, 1>: 128 queries, one K/V stage,
+// 256 TMEM columns, 96 KB: TWO CTAs per SM -- cross-attention to the 77 context tokens is a single key block per CTA, i.e.
+// a chain of latencies (Q / K / V load, S, softmax, P V, store) with nothing to overlap it inside the CTA; a second resident
+// CTA does (the 4096 x 77 layer ran at 1.3 TB/s of its 294 MB, one CTA per SM).
+template <int TILES, int STAGES>
+struct AtCfg {
+  static constexpr int kSmemQ = TILES * 2 * kAtQTileBytes;
+  static constexpr int kSmemKV = STAGES * 4 * kAtKTileBytes;
+  static constexpr int kSmemBytes = kSmemQ + kSmemKV + 1024 + 256;
+  static constexpr int kThreads = 64 + TILES * 128;    // producer warp, MMA warp, one softmax warpgroup per tile
+  static constexpr int kTmemCols = TILES == 1 ? 256 : 512;
+};
 constexpr float kAtTau = 3.0f;         // lazy-rescale threshold (log2 units): p <= 2^(12+3) stays inside fp16  // producer warp, MMA warp, 2 softmax warpgroups
 
 // 2^x on the SFU, flush-to-zero: one MUFU.EX2 (exp2f() adds a denormal-range rescale: two FMUL and a compare per call)
@@ -58,17 +62,19 @@ struct AttnParams {
   int out_packed8;   // format of the split output (it feeds the to_out GEMM)
 };
 
-__global__ void __launch_bounds__(kAtThreads, 1)
+template <int kAtTiles, int kAtStages>
+__global__ void __launch_bounds__(AtCfg<kAtTiles, kAtStages>::kThreads, kAtTiles == 1 ? 2 : 1)
 attn_split_kernel(const __grid_constant__ CUtensorMap tm_q_hi, const __grid_constant__ CUtensorMap tm_q_lo,
                   const __grid_constant__ CUtensorMap tm_k_hi, const __grid_constant__ CUtensorMap tm_k_lo,
                   const __grid_constant__ CUtensorMap tm_v_hi, const __grid_constant__ CUtensorMap tm_v_lo,
                   const AttnParams p) {
+  using Cfg = AtCfg<kAtTiles, kAtStages>;
+  constexpr int kAtSmemQ = Cfg::kSmemQ, kAtSmemKV = Cfg::kSmemKV, kAtTmemCols = Cfg::kTmemCols;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* sm_q = smem;                       // [tile][hi|lo][128x64]
-  uint8_t* sm_kv = sm_q + kAtSmemQ;           // [stage][k_hi|k_lo|v_hi|v_lo][64x64]
-  uint8_t* sm_p = sm_kv + kAtSmemKV;          // [tile][hi|lo][128x64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_p + kAtSmemP);
+  uint8_t* sm_kv = sm_q + kAtSmemQ;           // [stage][k_hi|k_lo|v_hi|v_lo][128x64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_kv + kAtSmemKV);
   uint64_t* q_full = bars;                                // 1
   uint64_t* kv_full = bars + 1;                           // [kAtStages]
   uint64_t* kv_empty = kv_full + kAtStages;               // [kAtStages]
@@ -325,16 +331,22 @@ VS_API int vidseg_attention_split(const void* q_hi, const void* q_lo, const void
   if (int e = encode_tmap_3d_f16(&tk_lo, k_lo, c, nk, batch, c * 2, c * 2 * nk, kAtD, kAtBK, 1)) return e;
   if (int e = encode_tmap_3d_f16(&tv_hi, v_hi, c, nk, batch, c * 2, c * 2 * nk, kAtD, kAtBK, 1)) return e;
   if (int e = encode_tmap_3d_f16(&tv_lo, v_lo, c, nk, batch, c * 2, c * 2 * nk, kAtD, kAtBK, 1)) return e;
-  static std::once_flag once;
-  static cudaError_t attr_err = cudaSuccess;
-  std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(attn_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kAtSmemBytes);
-  });
-  VS_CHECK_CUDA(attr_err);
   AttnParams p{batch, heads, nq, nk, scale * 1.4426950408889634f, out_f32, (__half*)out_hi, (__half*)out_lo,
                operand_packed8((long long)heads * kAtD) ? 1 : 0};
-  dim3 grid((nq + kAtBQ * kAtTiles - 1) / (kAtBQ * kAtTiles), heads, batch);
-  VS_LAUNCH_W(4.0 * batch * heads * (double)nq * nk * kAtD, attn_split_kernel, grid, kAtThreads, kAtSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
+  const double flops = 4.0 * batch * heads * (double)nq * nk * kAtD;
+  if (nk <= kAtBK) {   // one key block: the light CTA, two per SM
+    using Cfg = AtCfg<1, 1>;
+    static cudaError_t attr1 = cudaFuncSetAttribute(attn_split_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    VS_CHECK_CUDA(attr1);
+    dim3 grid((nq + kAtBQ - 1) / kAtBQ, heads, batch);
+    VS_LAUNCH_W(flops, (attn_split_kernel<1, 1>), grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
+  } else {
+    using Cfg = AtCfg<2, 2>;
+    static cudaError_t attr2 = cudaFuncSetAttribute(attn_split_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    VS_CHECK_CUDA(attr2);
+    dim3 grid((nq + kAtBQ * 2 - 1) / (kAtBQ * 2), heads, batch);
+    VS_LAUNCH_W(flops, (attn_split_kernel<2, 2>), grid, Cfg::kThreads, Cfg::kSmemBytes, stream, tq_hi, tq_lo, tk_hi, tk_lo, tv_hi, tv_lo, p);
+  }
   VS_POST_LAUNCH();
   return 0;
 }
