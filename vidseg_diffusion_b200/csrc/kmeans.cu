@@ -495,6 +495,121 @@ km_kpp_dist_all_kernel(const float* __restrict__ xc, const double* __restrict__ 
   }
 }
 
+// The same distances on the FP64 tensor cores (mma.sync m8n8k4: 256 multiply-adds per warp instruction instead of 32).
+// The kernel above is bound by instruction issue and latency, not by the FP64 pipe (ncu: 8 warps per SM at 255 registers,
+// 25 % issue utilisation, 20 % FP64 pipe): 5 400 instructions per four rows.  Here a warp owns EIGHT rows and all R*T
+// candidates (NT tiles of eight): per 16 columns one 16-byte load of its row, four conversions and, per candidate tile, two
+// 16-byte shared-memory loads and four DMMAs -- 1 400 instructions per eight rows.  Within a 16-column chunk the K index of
+// the MMA is permuted (sub-step s takes columns kc + 4 q + s of quad lane q) so that both fragments come from contiguous
+// vector loads; A and B use the same permutation, the sum runs over the same products.  The order of the float64
+// additions differs from the shuffle kernel's, i.e. a distance can differ from it in the last float64 bit before it is
+// rounded to fp32 (as both differ from any BLAS); the potentials are float64 sums cast to fp32 by the selection kernel.
+// Candidates sit in shared memory as doubles, rows padded by two: a 16-byte load is served per quarter warp = two fragment
+// rows, each touching every other 16 bytes of a 128-byte line (lane q reads doubles 4q, 4q+1, then 4q+2, 4q+3), so the two
+// rows must be 16 bytes apart modulo 128.
+// Measured (ncu, R*T = 40): 64.8 us against 137 us for the shuffle kernel, 7.5 M instead of 31 M warp instructions; what
+// bounds it now is the DMMA rate itself (1.43 M m8n8k4 per launch, ~12 cycles each per SM on this part).
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+template <int NT>   // candidate tiles of eight: NT * 8 >= runs * T
+__global__ void __launch_bounds__(kPotWarps * 32, 1)
+km_kpp_dist_mma_kernel(const float* __restrict__ xc, const double* __restrict__ xx, int n, int d, int runs, int T,
+                       const int* __restrict__ cand, const float* __restrict__ closest, int use_min,
+                       float* __restrict__ newdist, double* __restrict__ potpart, int t_stride) {
+  extern __shared__ double cs[];   // [NT * 8][d + 2], then the candidate norms [NT * 8]
+  const int dpad = d + 2, nc = runs * T;
+  double* cxx = cs + (size_t)NT * 8 * dpad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int rt = warp; rt < NT * 8; rt += kPotWarps) {   // a warp per candidate row; padding candidates are zero rows
+    const int src = rt < nc ? cand[(rt / T) * kMaxTrials + (rt % T)] : -1;
+    for (int c = lane; c < d; c += 32) cs[(size_t)rt * dpad + c] = src >= 0 ? (double)xc[(size_t)src * d + c] : 0.0;
+    if (lane == 0) cxx[rt] = src >= 0 ? xx[src] : 0.0;
+  }
+  __syncthreads();
+  const int r8 = lane >> 2, q = lane & 3;
+  const int gwarp = blockIdx.x * kPotWarps + warp, nwarps = gridDim.x * kPotWarps;
+  double pot[NT][2];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) pot[t][0] = pot[t][1] = 0.0;
+  for (int g = gwarp; g * 8 < n; g += nwarps) {
+    const int row = g * 8 + r8;
+    const bool valid = row < n;
+    const float* xr = xc + (size_t)(valid ? row : n - 1) * d + 4 * q;
+    double acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int kc = 0; kc < d; kc += 64) {
+      float4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)   // four chunks of the row in flight
+        v[u] = (kc + 16 * u < d) ? __ldg(reinterpret_cast<const float4*>(xr + kc + 16 * u)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kc + 16 * u < d) {   // uniform
+          const double a0 = (double)v[u].x, a1 = (double)v[u].y, a2 = (double)v[u].z, a3 = (double)v[u].w;
+#pragma unroll
+          for (int t = 0; t < NT; ++t) {
+            const double2* bp = reinterpret_cast<const double2*>(cs + (size_t)(t * 8 + r8) * dpad + kc + 16 * u + 4 * q);
+            const double2 b01 = bp[0], b23 = bp[1];
+            dmma_m8n8k4(acc[t][0], acc[t][1], a0, b01.x);
+            dmma_m8n8k4(acc[t][0], acc[t][1], a1, b01.y);
+            dmma_m8n8k4(acc[t][0], acc[t][1], a2, b23.x);
+            dmma_m8n8k4(acc[t][0], acc[t][1], a3, b23.y);
+          }
+        }
+      }
+    }
+    const double xxr = valid ? xx[row] : 0.0;
+#pragma unroll
+    for (int t = 0; t < NT; ++t)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int ci = t * 8 + 2 * q + j;   // the accumulator fragment: row lane / 4, columns 2 (lane % 4) + {0, 1}
+        if (valid && ci < nc) {
+          const int rr = ci / T, tt = ci - rr * T;
+          double dd = -2.0 * acc[t][j];
+          dd += cxx[ci];
+          dd += xxr;
+          float f = (float)dd;
+          f = fmaxf(f, 0.f);
+          if (use_min) f = fminf(closest[(size_t)rr * n + row], f);
+          newdist[((size_t)rr * t_stride + tt) * n + row] = f;
+          pot[t][j] += (double)f;
+        }
+      }
+  }
+  // potential partial of this warp per candidate: over its eight row lanes in a fixed order
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      double v = pot[t][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      const int ci = t * 8 + 2 * q + j;
+      if (r8 == 0 && ci < nc) {
+        const int rr = ci / T, tt = ci - rr * T;
+        potpart[((size_t)rr * t_stride + tt) * kPotParts + gwarp] = v;
+      }
+    }
+}
+
+typedef void (*KppDistMmaFn)(const float*, const double*, int, int, int, int, const int*, const float*, int, float*, double*, int);
+static KppDistMmaFn kpp_dist_mma_fn(int nt) {
+  switch (nt) {
+    case 1: return km_kpp_dist_mma_kernel<1>;
+    case 2: return km_kpp_dist_mma_kernel<2>;
+    case 3: return km_kpp_dist_mma_kernel<3>;
+    case 4: return km_kpp_dist_mma_kernel<4>;
+    case 5: return km_kpp_dist_mma_kernel<5>;
+    default: return nullptr;
+  }
+}
+
 typedef void (*KppDistAllFn)(const float*, const double*, int, int, int, const int*, const float*, int, float*, double*, int);
 template <int CH>
 static KppDistAllFn kpp_dist_all_fn_ch(int t) {
@@ -2043,6 +2158,23 @@ VS_API int vidseg_kmeans_seed(const int32_t* first_idx, const double* rand, void
     const int tc = (c == 0) ? 1 : L.t;
     // all runs from one pass over X when their candidates fit in shared memory
     const size_t smem_all = ((size_t)L.r * tc * L.d + (size_t)L.r * tc + (size_t)kPotWarps * L.r * (kPotRows * tc <= 16 ? 16 : 32)) * 8;
+    // FP64 tensor-core form: all runs' candidates as tiles of eight, rows of X in chunks of 16 columns
+    static const int kpp_mma = [] { const char* e = getenv("VIDSEG_KPP_MMA"); return e ? atoi(e) : 1; }();
+    const int nt = (L.r * tc + 7) / 8;
+    const size_t smem_mma = ((size_t)nt * 8 * (L.d + 2) + (size_t)nt * 8) * 8;
+    KppDistMmaFn fm = (kpp_mma && L.d % 16 == 0 && nt <= 5 && smem_mma <= 220 * 1024) ? kpp_dist_mma_fn(nt) : nullptr;
+    if (fm) {
+      VS_CHECK_CUDA(cudaFuncSetAttribute(fm, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+      VS_LAUNCH(fm, kPotBlocks, kPotWarps * 32, smem_mma, st, at<float>(ws, L.xc), at<double>(ws, L.xx), L.n, L.d, L.r, tc,
+                at<int>(ws, L.cand), at<float>(ws, L.closest), c > 0 ? 1 : 0, at<float>(ws, L.newdist),
+                at<double>(ws, L.potpart), L.t);
+      VS_POST_LAUNCH();
+      VS_LAUNCH(km_kpp_select_scan_kernel, L.r, 1024, 0, st, at<float>(ws, L.xc), L.n, L.d, L.k, L.t, L.t, c, tc,
+                at<double>(ws, L.potpart), at<float>(ws, L.newdist), at<float>(ws, L.closest), at<int>(ws, L.cand),
+                at<float>(ws, L.pot), at<float>(ws, L.centers), at<int>(ws, L.center_idx), rand);
+      VS_POST_LAUNCH();
+      continue;
+    }
     KppDistAllFn fa = (smem_all <= 220 * 1024) ? kpp_dist_all_fn(tc, L.d) : nullptr;
     if (fa) {
       VS_CHECK_CUDA(cudaFuncSetAttribute(fa, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
