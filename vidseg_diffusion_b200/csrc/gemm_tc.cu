@@ -12,10 +12,13 @@
 //
 // Kernel: persistent, one CTA per SM, warp-specialised.  warp 0 = TMA producer (4 tiles per stage:
 // A_hi, A_lo [128x64], B_hi, B_lo [BNx64], 128-byte swizzle), warp 1 = MMA issuer (one elected
-// thread, 12 tcgen05.mma per 64-wide k-block), warp 2 = TMEM allocator, warps 4-7 = epilogue
-// (tcgen05.ld 32x32b -> registers -> bias/residual -> fp32 and/or fp16 hi/lo stores).  3-stage smem
-// ring (mbarrier full/empty), 2-stage TMEM accumulator ring (tmem_full/tmem_empty) so the epilogue of
-// tile i overlaps the MMAs of tile i+1.
+// thread: 12 kind::f16 MMAs per 64-wide k-block with fp16-pair operands, 4 kind::f16 + 4 kind::f8f6f4 with
+// the fp16 + fp8-correction operands), warp 2 = TMEM allocator, warps 4-11 = epilogue (tcgen05.ld 32x32b ->
+// registers -> 1 KB shared-memory transpose per warp -> scale / bias / residual / blend / GEGLU gate in a
+// layout whose global accesses cover full 128-byte lines -> fp32 and/or operand stores).  2-4 stage smem ring
+// (mbarrier full/empty), 2-stage TMEM accumulator ring (tmem_full/tmem_empty) so the epilogue of tile i
+// overlaps the MMAs of tile i+1.  Large grids run as CTA PAIRS (tcgen05.mma.cta_group::2, M = 256 over the
+// two SMs of a TPC, each CTA half of the B tile): see gemm_split_kernel.
 #include <cstdlib>
 #include <mutex>
 
