@@ -2,8 +2,9 @@
 frame partition, ragged row all-gather, and the distributed Lloyd driver (ONE all-reduce per iteration of the fused
 [n_init*K*(D+1) + n_init] exchange words: sums | counts | change counters; convergence flags polled one burst late;
 redundant seeding / best-of selection with inertia and the same-clustering matrix in one collective; final label
-all-gather).  The CUDA kernels
-cannot run here, so the driver is exercised with a numpy stand-in that implements the same split E-step / M-step
+all-gather), and the run-sharded form of the same fit (``run_sharded_kmeans_fit_predict``: each rank iterates its own
+subset of the n_init initialisations on all rows, ONE all-reduce of the run records, best-of-n_init on every rank).  The
+CUDA kernels cannot run here, so the driver is exercised with a numpy stand-in that implements the same split E-step / M-step
 contract as include/vidseg_b200.h (R2) on top of the oracle's primitives; the GPU form of the same driver is covered by
 tests/test_gpu_distributed.py."""
 import os
