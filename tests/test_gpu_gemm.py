@@ -12,6 +12,9 @@ pytestmark = pytest.mark.gpu
     (300, 320, 320, True, False, "fs"), (1000, 1280, 640, False, True, "f"), (4096, 2560, 320, True, False, "s"),
     (77, 640, 1024, False, False, "fs"), (1, 8, 8, True, False, "f"), (28 * 1024, 640, 640, True, True, "f"),
     (513, 5120, 1280, True, False, "f"),
+    # CTA-pair form (>= 148 work items) with an ODD number of M tiles and a ragged last tile: the second CTA of the last pair
+    # works on a tile that does not exist (zero-filled operands, no stores)
+    (9500, 1280, 320, True, True, "fs"), (128 * 75, 640, 640, False, False, "f"),
 ])
 def test_gemm_split_matches_fp64(cuda, operand_mode, m, n, k, bias, res, outs):
     from vidseg_diffusion_b200.linear import gemm_split, split
