@@ -241,3 +241,43 @@ def test_sharded_kmeans_two_ranks_gloo_matches_oracle():
     (_, rl0, runs0, rar0, best0), (_, rl1, runs1, rar1, best1) = res_runs
     assert tuple(runs0) == (0, 2) and tuple(runs1) == (2, 3) and rar0 == rar1 == 1 and best0 == best1
     assert np.array_equal(rl0, want) and np.array_equal(rl1, want)
+
+
+def _worker_runs(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from vidseg_diffusion_b200 import distributed as D
+        F, h, w, C, K = 5, 8, 8, 32, 4
+        blocks, _ = synthetic_clip_features(11, F, h, w, C, K)
+        X = torch.from_numpy(ofeat.aggregate_normalize(blocks, F))
+        np.random.seed(7)
+        info = {}
+        labels = D.run_sharded_kmeans_fit_predict(X, K, n_init=3, backend_factory=NumpyLloydBackend, info=info)
+        q.put((rank, labels.numpy(), tuple(info["runs"]), info["allreduces"], info["best"]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_run_sharded_kmeans_four_ranks_gloo_with_an_idle_rank():
+    """3 initialisations on 4 ranks (1, 1, 1, 0): the rank without a run contributes zeros to the one all-reduce and still
+    applies the best-of-n_init rule and predicts; every rank returns the reference's labels."""
+    world = 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_runs, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted((q.get(timeout=240) for _ in procs), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    F, h, w, C, K = 5, 8, 8, 32, 4
+    blocks, _ = synthetic_clip_features(11, F, h, w, C, K)
+    np.random.seed(7)
+    want, _ = okm.kmeans_fit_predict(ofeat.aggregate_normalize(blocks, F), K, n_init=3)
+    assert [t[2] for t in res] == [(0, 1), (1, 2), (2, 3), (3, 3)]
+    assert len({t[4] for t in res}) == 1 and all(t[3] == 1 for t in res)
+    for t in res:
+        assert np.array_equal(t[1], want)
